@@ -1,0 +1,95 @@
+// Shared helpers for libdmayolo (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <atomic>
+#include "../../include/dmayolo.h"
+
+namespace dmay {
+
+extern std::atomic<long long> g_launches;
+
+inline int finish_launch(int n_kernels = 1) {
+  g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DMAY_OK : (int)e;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// SM count of the current device, cached (immutable after first query).
+int sm_count();
+
+// grid size for a grid-stride elementwise kernel: enough CTAs to fill the chip a few times
+// over, as a multiple of the SM count.
+inline int grid_for(long long items, int threads, int ctas_per_sm = 8) {
+  long long need = (items + threads - 1) / threads;
+  long long cap = (long long)sm_count() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---- 128-bit vector access ----------------------------------------------------------------
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ uint4 ld_nc16(const void* p) {  // streaming read, no L1 allocate
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ld16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ void st_na16(void* p, const uint4& v) {  // streaming write
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float f[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float f[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
+__device__ __forceinline__ float hardswish(float x) {
+  return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case DMAY_ACT_SILU: return silu_fast(x);
+    case DMAY_ACT_HARDSWISH: return hardswish(x);
+    case DMAY_ACT_SIGMOID: return sigmoid_fast(x);
+    default: return x;
+  }
+}
+
+// ATen nearest-neighbour source index (UpSampleNearest, `nearest_idx`): identity and exact 2x
+// shortcuts, otherwise min(int(floorf(dst * (float)in/out)), in-1) in fp32.
+__device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size, float scale) {
+  if (out_size == in_size) return dst;
+  if (out_size == 2 * in_size) return dst >> 1;
+  int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}
+
+}  // namespace dmay

@@ -1,0 +1,540 @@
+// a1/a2: Conv + folded BN + activation (+ residual / SCConv gate) as a persistent, warp-specialised
+// tcgen05 implicit GEMM for sm_100a.
+//
+//   D[m, co] = sum_{tap, ci} A[m, (tap, ci)] * W[co, (tap, ci)]         m = (n*Ho + p)*Wo + q
+//
+//   A operand : activations, NHWC bf16.  3x3 / strided convs use TMA *im2col* tensor maps
+//               (cp.async.bulk.tensor.4d...im2col): one instruction loads the 128 output pixels of a
+//               tile for one filter tap (r,s) and one 16/32/64-channel chunk, zero-filling the padding
+//               halo, straight into the 128B/64B/32B-swizzled K-major layout tcgen05 reads.  1x1 stride-1
+//               convs use a plain 2-D tiled map over [M, Cin].
+//   B operand : packed weights [Cout_pad][kh*kw*Cin] bf16, 2-D tiled map, same swizzle.
+//   D         : fp32 accumulators in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of
+//               tile i overlaps the MMAs of tile i+1.
+//   epilogue  : tcgen05.ld 32x32b (thread == output pixel) -> scale*acc + bias (folded BatchNorm,
+//               utils/torch_utils.py:198-218) -> SiLU / Hardswish -> (+ residual, Bottleneck
+//               models/common.py:136-137) or (* sigmoid(x + up(k2)), SCConv models/common.py:1310-1314)
+//               -> bf16 (or fp32 for the Detect head) -> 16-byte stores into a channel slice of the
+//               destination slab (ldy), which is how torch.cat in C3/SPPFCSPC disappears.
+//
+// Warp roles (256 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quadrant = warp % 4).
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue),
+// static persistent tile scheduler (tile = blockIdx.x + i*gridDim.x; n-tile fastest so CTAs running
+// at the same time share the activation tile in L2 and the weights stay L2-resident).
+#include "common.cuh"
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+
+namespace dmay {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost arrival (bad descriptor, wrong byte count) traps after ~2 s instead of
+// hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("dmayolo conv: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tmap, uint32_t bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int BLOCK_M = 128;
+constexpr int kMaxStages = 8;
+constexpr int kConvThreads = 256;
+
+struct __align__(64) ConvArgs {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const __nv_bfloat16* gate_x;
+  const __nv_bfloat16* gate_k;
+  void* y;
+  int M, n_store, Cout_pad;
+  int num_m_tiles, num_n_tiles;
+  int taps, kw, c_chunks, CK, Cin;
+  int conv_stride, pad, Ho, Wo;
+  int im2col;
+  int block_n, acc_stride, tmem_cols, stages;
+  int ldy, ldr, ldgx, ldgk, gHk, gWk;
+  float g_sh, g_sw;
+  int act, out_f32;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  uint32_t idesc;
+  uint32_t sbo_enc, layout_type;
+};
+
+// smem carve-up (after manual 1024-byte alignment):
+//   [stages][A tile | B tile]   stage_bytes each
+//   full[8], empty[8], tmem_full[2], tmem_empty[2] mbarriers, tmem base ptr, scale[256], bias[256]
+constexpr uint32_t kTailBytes = (2 * kMaxStages + 4) * 8 + 16 + 2 * 256 * 4;
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_enc, uint32_t layout_type) {
+  // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout[61,64)
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)sbo_enc << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)layout_type << 61);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t tail = base + a.stages * a.stage_bytes;
+  uint8_t* tail_ptr = base_ptr + (size_t)a.stages * a.stage_bytes;
+  const uint32_t full_bar = tail, empty_bar = tail + kMaxStages * 8;
+  const uint32_t tfull_bar = tail + 2 * kMaxStages * 8, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_ptr + (2 * kMaxStages + 4) * 8);
+  float* s_scale = reinterpret_cast<float*>(tail_ptr + (2 * kMaxStages + 4) * 8 + 16);
+  float* s_bias = s_scale + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = a.num_m_tiles * a.num_n_tiles;
+  const int k_iters = a.taps * a.c_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&a.tmA);
+    tmap_prefetch(&a.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a.stages; ++i) {
+      mbar_init(full_bar + i * 8, 1);
+      mbar_init(empty_bar + i * 8, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + i * 8, 1);
+      mbar_init(tempty_bar + i * 8, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int HoWo = a.Ho * a.Wo;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.num_n_tiles, n_tile = tile % a.num_n_tiles;
+        const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;
+        int n_img = 0, h0 = 0, w0 = 0;
+        if (a.im2col) {
+          n_img = m0 / HoWo;
+          const int rem = m0 - n_img * HoWo;
+          const int p = rem / a.Wo, q = rem - p * a.Wo;
+          h0 = p * a.conv_stride - a.pad;
+          w0 = q * a.conv_stride - a.pad;
+        }
+        for (int tap = 0; tap < a.taps; ++tap) {
+          const int r = tap / a.kw, s = tap - r * a.kw;
+          for (int cc = 0; cc < a.c_chunks; ++cc) {
+            mbar_wait(empty_bar + stage * 8, phase ^ 1u);
+            const uint32_t fb = full_bar + stage * 8;
+            const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.a_bytes;
+            mbar_expect_tx(fb, a.a_bytes + a.b_bytes);
+            if (a.im2col)
+              tma_load_im2col_4d(sa, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+            else
+              tma_load_2d(sa, &a.tmA, fb, cc * a.CK, m0);
+            tma_load_2d(sb, &a.tmB, fb, tap * a.Cin + cc * a.CK, n0);
+            if (++stage == a.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int kk_n = a.CK / 16;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.acc_stride);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(full_bar + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.a_bytes;
+          const uint64_t da = make_smem_desc(sa, a.sbo_enc, a.layout_type);
+          const uint64_t db = make_smem_desc(sb, a.sbo_enc, a.layout_type);
+          for (int kk = 0; kk < kk_n; ++kk)  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
+            umma_bf16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), a.idesc, (uint32_t)((it | kk) != 0));
+          umma_commit(empty_bar + stage * 8);
+          if (++stage == a.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar + acc * 8);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int quad = warp & 3;
+    const int et = threadIdx.x - 128;  // 0..127
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int HoWo = a.Ho * a.Wo;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / a.num_n_tiles, n_tile = tile % a.num_n_tiles;
+      const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;
+      epi_bar_sync();  // everyone is done reading the previous tile's scale/bias
+      for (int i = et; i < a.block_n; i += 128) {
+        const bool in = n0 + i < a.Cout_pad;
+        s_scale[i] = in ? a.scale[n0 + i] : 0.f;
+        s_bias[i] = in ? a.bias[n0 + i] : 0.f;
+      }
+      epi_bar_sync();
+      mbar_wait(tfull_bar + acc * 8, acc_phase);
+      tc_fence_after();
+      const long long row = (long long)m0 + row_in_tile;
+      const bool valid = row < a.M;
+      const __nv_bfloat16* gk_row = nullptr;
+      if (a.gate_x != nullptr && valid) {
+        const int n_img = (int)(row / HoWo);
+        const int rem = (int)(row - (long long)n_img * HoWo);
+        const int p = rem / a.Wo, q = rem - p * a.Wo;
+        const int hs = nearest_src(p, a.gHk, a.Ho, a.g_sh), ws = nearest_src(q, a.gWk, a.Wo, a.g_sw);
+        gk_row = a.gate_k + (((long long)n_img * a.gHk + hs) * a.gWk + ws) * a.ldgk;
+      }
+      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * a.acc_stride) + ((uint32_t)(quad * 32) << 16);
+      for (int c0 = 0; c0 < a.block_n; c0 += 32) {
+        uint32_t r[32];
+        const int width = a.block_n - c0 >= 32 ? 32 : 16;
+        if (width == 32) tmem_ld32(taddr0 + c0, r);
+        else tmem_ld16(taddr0 + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          const int col0 = n0 + c0;
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            if (v8 * 8 >= width) break;
+            const int col = col0 + v8 * 8;
+            if (col + 8 > a.n_store) break;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              f[j] = fmaf(__uint_as_float(r[v8 * 8 + j]), s_scale[c0 + v8 * 8 + j], s_bias[c0 + v8 * 8 + j]);
+            if (a.gate_x != nullptr) {
+              float gx[8], gk[8];
+              unpack8(ld_nc16(a.gate_x + row * a.ldgx + col), gx);
+              unpack8(ld16(gk_row + col), gk);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] *= sigmoid_fast(gx[j] + gk[j]);
+            } else if (a.act != DMAY_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], a.act);
+            }
+            if (a.residual != nullptr) {
+              float rs[8];
+              unpack8(ld_nc16(a.residual + row * a.ldr + col), rs);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += rs[j];
+            }
+            if (a.out_f32) {
+              float* yo = reinterpret_cast<float*>(a.y) + row * a.ldy + col;
+              *reinterpret_cast<float4*>(yo) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(yo + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              st16(reinterpret_cast<__nv_bfloat16*>(a.y) + row * a.ldy + col, pack8(f));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + acc * 8);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map encoding through the driver entry points (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static bool load_driver_fns() {
+  if (g_encode_tiled && g_encode_im2col) return true;
+  void* f1 = nullptr;
+  void* f2 = nullptr;
+  cudaDriverEntryPointQueryResult q1, q2;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q1) != cudaSuccess || !f1) return false;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q2) != cudaSuccess || !f2) return false;
+  cudaDriverGetVersion(&g_driver_version);
+  g_encode_tiled = (EncodeTiledFn)f1;
+  g_encode_im2col = (EncodeIm2colFn)f2;
+  return true;
+}
+
+static int pow2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
+  if (!p || !p->x || !p->w || !p->scale || !p->bias || !p->y) return DMAY_EINVAL;
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->kh <= 0 || p->kw <= 0 || p->stride <= 0 ||
+      p->pad < 0 || p->Ho <= 0 || p->Wo <= 0)
+    return DMAY_EINVAL;
+  if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y)) return DMAY_EINVAL;
+  if (p->Cin & 15) return DMAY_EUNSUPPORTED;
+  if (p->Cout_pad < p->Cout || (p->Cout_pad & 15)) return DMAY_EUNSUPPORTED;
+  if (p->ldx < p->Cin || (p->ldx & 7) || (p->ldy & 3)) return DMAY_EUNSUPPORTED;
+  const bool out_f32 = p->out_dtype == DMAY_DT_F32;
+  if (p->out_dtype != DMAY_DT_F32 && p->out_dtype != DMAY_DT_BF16) return DMAY_EUNSUPPORTED;
+  if (p->Cout & 7) return DMAY_EUNSUPPORTED;  // store width: whole 16-byte vectors (caller pads the slab)
+  if (!out_f32 && (p->ldy & 7)) return DMAY_EUNSUPPORTED;
+  if (p->ldy < p->Cout) return DMAY_EINVAL;
+  if (p->residual && (!aligned16(p->residual) || (p->ldr & 7) || p->ldr < p->Cout)) return DMAY_EINVAL;
+  if (p->gate_x && (!p->gate_k || !aligned16(p->gate_x) || !aligned16(p->gate_k) || (p->ldgx & 7) || p->gHk <= 0 || p->gWk <= 0))
+    return DMAY_EINVAL;
+  if ((p->Ho != (p->H + 2 * p->pad - p->kh) / p->stride + 1) || (p->Wo != (p->W + 2 * p->pad - p->kw) / p->stride + 1))
+    return DMAY_EINVAL;
+  if (p->pad > 127 || p->kh > 64 || p->kw > 64 || p->stride > 8) return DMAY_EUNSUPPORTED;
+  if (!load_driver_fns()) return DMAY_EDRIVER;
+
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  const long long M = (long long)p->N * p->Ho * p->Wo;
+  if (M > 0x7fffff00LL) return DMAY_EUNSUPPORTED;
+  a.M = (int)M;
+  a.CK = (p->Cin % 64 == 0) ? 64 : (p->Cin % 32 == 0) ? 32 : 16;
+  const CUtensorMapSwizzle swz = a.CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                            : (a.CK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  a.layout_type = a.CK == 64 ? 2u : (a.CK == 32 ? 4u : 6u);
+  a.sbo_enc = (uint32_t)(8 * a.CK * 2) >> 4;  // 8 rows of CK bf16
+  a.Cin = p->Cin;
+  a.c_chunks = p->Cin / a.CK;
+  a.taps = p->kh * p->kw;
+  a.kw = p->kw;
+  a.conv_stride = p->stride;
+  a.pad = p->pad;
+  a.Ho = p->Ho;
+  a.Wo = p->Wo;
+  a.im2col = !(p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0);
+  int bn = p->block_n > 0 ? p->block_n : (p->Cout_pad < 256 ? p->Cout_pad : 256);
+  if ((bn & 15) || bn > 256 || bn < 16) return DMAY_EUNSUPPORTED;
+  a.block_n = bn;
+  a.acc_stride = pow2ceil(bn) < 32 ? 32 : pow2ceil(bn);
+  a.tmem_cols = 2 * a.acc_stride;
+  a.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  a.num_n_tiles = (p->Cout_pad + bn - 1) / bn;
+  a.n_store = p->Cout;
+  a.Cout_pad = p->Cout_pad;
+  a.a_bytes = (uint32_t)(BLOCK_M * a.CK * 2);
+  a.b_bytes = (uint32_t)(bn * a.CK * 2);
+  a.stage_bytes = (a.a_bytes + a.b_bytes + 1023u) & ~1023u;
+  const uint32_t budget = 227u * 1024u - 1024u - kTailBytes - 64u;
+  int stages = (int)(budget / a.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return DMAY_EUNSUPPORTED;
+  a.stages = stages;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
+  // both K-major, N>>3 at [17,23), M>>4 at [24,29)
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  a.scale = (const float*)p->scale;
+  a.bias = (const float*)p->bias;
+  a.residual = (const __nv_bfloat16*)p->residual;
+  a.gate_x = (const __nv_bfloat16*)p->gate_x;
+  a.gate_k = (const __nv_bfloat16*)p->gate_k;
+  a.y = p->y;
+  a.ldy = p->ldy;
+  a.ldr = p->ldr;
+  a.ldgx = p->ldgx;
+  a.ldgk = p->Cout;  // k2 output is a dense [N,Hk,Wk,C] tensor
+  a.gHk = p->gHk;
+  a.gWk = p->gWk;
+  a.g_sh = p->gHk > 0 ? (float)p->gHk / (float)p->Ho : 0.f;
+  a.g_sw = p->gWk > 0 ? (float)p->gWk / (float)p->Wo : 0.f;
+  a.act = p->act;
+  a.out_f32 = out_f32 ? 1 : 0;
+
+  // ---- tensor maps ----
+  CUresult r;
+  if (a.im2col) {
+    cuuint64_t gdim[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t gstr[3] = {(cuuint64_t)p->ldx * 2, (cuuint64_t)p->W * p->ldx * 2, (cuuint64_t)p->H * p->W * p->ldx * 2};
+    int lower[2] = {-p->pad, -p->pad};
+    int upper[2] = {p->pad - (p->kw - 1), p->pad - (p->kh - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
+    r = g_encode_im2col(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), gdim, gstr, lower, upper,
+                        (cuuint32_t)a.CK, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DMAY_EDRIVER;
+    // Same driver work-around CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers <= 13.1
+    // set a descriptor bit that breaks im2col loads from tensors smaller than 128 KiB.
+    const unsigned long long bytes = (unsigned long long)p->N * p->H * p->W * p->ldx * 2ull;
+    if (g_driver_version <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(&a.tmA)[1] &= ~(1ull << 21);
+  } else {
+    cuuint64_t gdim[2] = {(cuuint64_t)p->Cin, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)p->ldx * 2};
+    cuuint32_t box[2] = {(cuuint32_t)a.CK, (cuuint32_t)BLOCK_M};
+    cuuint32_t estr[2] = {1, 1};
+    r = g_encode_tiled(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->x), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DMAY_EDRIVER;
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)a.taps * p->Cin;
+    cuuint64_t gdim[2] = {ktot, (cuuint64_t)p->Cout_pad};
+    cuuint64_t gstr[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)a.CK, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    r = g_encode_tiled(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DMAY_EDRIVER;
+  }
+
+  const size_t smem = 1024 + (size_t)a.stages * a.stage_bytes + kTailBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
+  const long long tiles = (long long)a.num_m_tiles * a.num_n_tiles;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  conv_gemm_kernel<<<grid, kConvThreads, smem, stream>>>(a);
+  return finish_launch();
+}
+
+}  // namespace dmay
+
+extern "C" int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream) {
+  return dmay::conv_launch(p, (cudaStream_t)stream);
+}

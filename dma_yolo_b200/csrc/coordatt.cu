@@ -1,0 +1,187 @@
+// a3: CoordAtt (models/common.py:1183-1207) on NHWC bf16.
+//   pool : pooled[n, h, c] = mean_w x ; pooled[n, H+w, c] = mean_h x            (fp32)
+//   mlp  : y = hardswish(s1*(W1.pooled + b1) + t1) ; gates = sigmoid(W{h,w}.y + b{h,w})  (fp32)
+//   apply: out = (x * a_w) * a_h                                                 (bf16)
+// x is read once by `pool` from HBM and once by `apply` (L2-resident at cfg-2 sizes: 52 MB < 126 MB
+// L2); the gate tensors are (H+W)/(H*W) of the activation.  All reductions are deterministic
+// (no atomics): a CTA owns complete rows (for mean_w) and complete columns (for mean_h).
+#include "common.cuh"
+
+namespace dmay {
+
+// grid = N * groups * bands.  CTA (n, g, b): channel vectors [g*8, g*8+8) (64 channels),
+// rows h === b (mod bands) reduced over w, columns w === b (mod bands) reduced over h.
+// thread = (slot 0..31, lane 0..7): lane picks the 16-byte channel vector, slot the row/column.
+__global__ void __launch_bounds__(256) ca_pool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ pooled,
+                                                      int H, int W, int C, int ldx, int bands) {
+  const int cvec = C >> 3;
+  const int groups = (cvec + 7) >> 3;
+  int bid = blockIdx.x;
+  const int b = bid % bands;
+  bid /= bands;
+  const int g = bid % groups;
+  const int n = bid / groups;
+  const int lane = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const int v = g * 8 + lane;
+  if (v >= cvec) return;
+  const __nv_bfloat16* xb = x + (long long)n * H * W * ldx + v * 8;
+  float* pb = pooled + (long long)n * (H + W) * C + v * 8;
+  const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+  // rows
+  for (int h = b + slot * bands; h < H; h += 32 * bands) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const __nv_bfloat16* row = xb + (long long)h * W * ldx;
+#pragma unroll 4
+    for (int w = 0; w < W; ++w) {
+      float f[8];
+      unpack8(ld16(row + (long long)w * ldx), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    float4* o = reinterpret_cast<float4*>(pb + (long long)h * C);
+    o[0] = make_float4(acc[0] * invW, acc[1] * invW, acc[2] * invW, acc[3] * invW);
+    o[1] = make_float4(acc[4] * invW, acc[5] * invW, acc[6] * invW, acc[7] * invW);
+  }
+  // columns
+  for (int w = b + slot * bands; w < W; w += 32 * bands) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const __nv_bfloat16* col = xb + (long long)w * ldx;
+#pragma unroll 4
+    for (int h = 0; h < H; ++h) {
+      float f[8];
+      unpack8(ld16(col + (long long)h * W * ldx), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    float4* o = reinterpret_cast<float4*>(pb + (long long)(H + w) * C);
+    o[0] = make_float4(acc[0] * invH, acc[1] * invH, acc[2] * invH, acc[3] * invH);
+    o[1] = make_float4(acc[4] * invH, acc[5] * invH, acc[6] * invH, acc[7] * invH);
+  }
+}
+
+// grid = N * ceil((H+W)/PG).  CTA handles PG consecutive positions of one image.
+// w1: [Cm][C] fp32; whT / wwT: [Cm][Cout] fp32 (transposed so consecutive threads read consecutive c).
+constexpr int PG = 8;
+__global__ void __launch_bounds__(256) ca_mlp_kernel(const float* __restrict__ pooled, float* __restrict__ gates,
+                                                     const float* __restrict__ w1, const float* __restrict__ b1,
+                                                     const float* __restrict__ s1, const float* __restrict__ t1,
+                                                     const float* __restrict__ whT, const float* __restrict__ bh,
+                                                     const float* __restrict__ wwT, const float* __restrict__ bw,
+                                                     int H, int W, int C, int Cm, int Cout) {
+  extern __shared__ float sm[];
+  float* sp = sm;            // [PG][C]
+  float* sy = sm + PG * C;   // [PG][Cm]
+  const int P = H + W;
+  const int pgroups = (P + PG - 1) / PG;
+  const int n = blockIdx.x / pgroups;
+  const int p0 = (blockIdx.x % pgroups) * PG;
+  const int np = min(PG, P - p0);
+  for (int i = threadIdx.x; i < PG * C; i += blockDim.x) {
+    int pp = i / C, c = i % C;
+    sp[i] = pp < np ? pooled[((long long)n * P + p0 + pp) * C + c] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < Cm; j += nwarps) {
+    float acc[PG];
+#pragma unroll
+    for (int q = 0; q < PG; ++q) acc[q] = 0.f;
+    const float* wr = w1 + (long long)j * C;
+    for (int c = lane; c < C; c += 32) {
+      float wv = wr[c];
+#pragma unroll
+      for (int q = 0; q < PG; ++q) acc[q] += wv * sp[q * C + c];
+    }
+#pragma unroll
+    for (int q = 0; q < PG; ++q) {
+      float a = acc[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      acc[q] = a;
+    }
+    if (lane == 0) {
+      const float bj = b1[j], sj = s1[j], tj = t1[j];
+#pragma unroll
+      for (int q = 0; q < PG; ++q) sy[q * Cm + j] = hardswish(sj * (acc[q] + bj) + tj);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+    float acc[PG];
+    const float bhc = bh[c], bwc = bw[c];
+#pragma unroll
+    for (int q = 0; q < PG; ++q) acc[q] = (p0 + q < H) ? bhc : bwc;
+    for (int j = 0; j < Cm; ++j) {
+      const float a = whT[(long long)j * Cout + c], b = wwT[(long long)j * Cout + c];
+#pragma unroll
+      for (int q = 0; q < PG; ++q) acc[q] += ((p0 + q < H) ? a : b) * sy[q * Cm + j];
+    }
+    for (int q = 0; q < np; ++q) gates[((long long)n * P + p0 + q) * Cout + c] = sigmoid_acc(acc[q]);
+  }
+}
+
+__global__ void __launch_bounds__(256) ca_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                       const float* __restrict__ gates, __nv_bfloat16* __restrict__ y,
+                                                       int N, int H, int W, int C, int ldx, int ldy) {
+  const int cv = C >> 3;
+  const long long items = (long long)N * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    int v = (int)(i % cv);
+    long long pix = i / cv;
+    int w_ = (int)(pix % W);
+    long long t = pix / W;
+    int h_ = (int)(t % H);
+    int n = (int)(t / H);
+    float f[8];
+    unpack8(ld_nc16(x + pix * ldx + v * 8), f);
+    const float4* gh = reinterpret_cast<const float4*>(gates + ((long long)n * (H + W) + h_) * C + v * 8);
+    const float4* gw = reinterpret_cast<const float4*>(gates + ((long long)n * (H + W) + H + w_) * C + v * 8);
+    const float4 h0 = gh[0], h1 = gh[1], w0 = gw[0], w1 = gw[1];
+    f[0] = (f[0] * w0.x) * h0.x; f[1] = (f[1] * w0.y) * h0.y; f[2] = (f[2] * w0.z) * h0.z; f[3] = (f[3] * w0.w) * h0.w;
+    f[4] = (f[4] * w1.x) * h1.x; f[5] = (f[5] * w1.y) * h1.y; f[6] = (f[6] * w1.z) * h1.z; f[7] = (f[7] * w1.w) * h1.w;
+    st_na16(y + pix * ldy + v * 8, pack8(f));
+  }
+}
+
+}  // namespace dmay
+
+using namespace dmay;
+
+extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream) {
+  if (!p || !p->x || !p->y || !p->pooled || !p->gates || !p->w1 || !p->b1 || !p->s1 || !p->t1 || !p->wh || !p->bh ||
+      !p->ww || !p->bw)
+    return DMAY_EINVAL;
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->C <= 0 || p->Cm <= 0) return DMAY_EINVAL;
+  if ((p->C | p->ldx | p->ldy) & 7) return DMAY_EUNSUPPORTED;
+  if (!aligned16(p->x) || !aligned16(p->y) || !aligned16(p->pooled) || !aligned16(p->gates)) return DMAY_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int cvec = p->C / 8, groups = (cvec + 7) / 8;
+  const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
+  // bands: split rows/columns over more CTAs until the grid covers the chip ~2x (cap at min(H,W))
+  int bands = 1;
+  while ((long long)p->N * groups * bands < 2LL * sms && bands * 2 <= (p->H < p->W ? p->H : p->W)) bands *= 2;
+  long long g1 = (long long)p->N * groups * bands;
+  if (g1 > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  ca_pool_kernel<<<(int)g1, 256, 0, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, p->H, p->W, p->C, p->ldx, bands);
+  const int P = p->H + p->W;
+  const int pgroups = (P + PG - 1) / PG;
+  const size_t smem = (size_t)PG * (p->C + p->Cm) * sizeof(float);
+  if (smem > 200 * 1024) return DMAY_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ca_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  ca_mlp_kernel<<<p->N * pgroups, 256, smem, s>>>((const float*)p->pooled, (float*)p->gates, (const float*)p->w1,
+                                                  (const float*)p->b1, (const float*)p->s1, (const float*)p->t1,
+                                                  (const float*)p->wh, (const float*)p->bh, (const float*)p->ww,
+                                                  (const float*)p->bw, p->H, p->W, p->C, p->Cm, p->C);
+  long long items = (long long)p->N * p->H * p->W * cvec;
+  ca_apply_kernel<<<grid_for(items, 256), 256, 0, s>>>((const __nv_bfloat16*)p->x, (const float*)p->gates,
+                                                       (__nv_bfloat16*)p->y, p->N, p->H, p->W, p->C, p->ldx, p->ldy);
+  return finish_launch(3);
+}

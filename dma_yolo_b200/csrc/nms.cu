@@ -1,0 +1,519 @@
+// a8 + a9: Detect decode (models/yolo.py:81-101) and batched class-aware NMS
+// (utils/general.py:633-725 + torchvision.ops.nms CPU semantics), all on device, whole batch per launch.
+//
+//   filter  : order-preserving candidate generation (count -> scan -> write), reading either a dense
+//             [N,R,5+nc] fp32 prediction or the raw Detect logits (decode fused with the confidence
+//             filter: the dense [N,R,no] tensor is never materialised).
+//   sort    : one stable radix sort of (image, ~score) keys over the whole batch (CUB).
+//   greedy  : one CTA per image walks its sorted candidates in chunks of 128, testing each chunk
+//             against the kept list (<= max_det boxes in shared memory), resolving the chunk's internal
+//             order with a 128x128 bitmask and one warp's serial scan, and stops at max_det keeps.
+//
+// Arithmetic contract (bit-exact keep indices): every fp32 operation that the reference performs on
+// boxes / scores is issued with explicit round-to-nearest intrinsics so nvcc cannot contract a
+// multiply into a following add (no FMA), IoU uses IEEE division and is compared in double.
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace dmay {
+
+struct LevelMeta {  // 16 x 4 bytes per level, see ops.py `_level_meta`
+  int row0, ny, nx, ld, na;
+  float stride;
+  float anchor[10];  // (w,h) px for up to 5 anchors
+};
+
+struct RowSrc {
+  const float* pred;         // dense source or nullptr
+  const float* logits[5];    // fused source
+  const LevelMeta* meta;
+  int levels;
+  int R, nc;
+};
+
+// Loads one prediction row for the whole warp: returns obj and xywh (valid in all lanes); class
+// confidences are fetched by `cls_at`.  Dense rows are read as-is; fused rows are decoded from logits
+// exactly in the reference's operation order: xy = (s*2 - 0.5 + g) * stride ; wh = (s*2)^2 * anchor_px.
+struct RowView {
+  const float* base;  // points at element 0 of the row (dense) or logit 0 (fused)
+  bool fused;
+  float x, y, w, h, obj;
+  __device__ __forceinline__ float cls_at(int c) const {
+    float v = base[5 + c];
+    return fused ? sigmoid_acc(v) : v;
+  }
+};
+
+__device__ __forceinline__ RowView load_row(const RowSrc& s, int img, int r) {
+  RowView v;
+  if (s.levels == 0) {
+    v.fused = false;
+    v.base = s.pred + ((long long)img * s.R + r) * (5 + s.nc);
+    v.x = v.base[0]; v.y = v.base[1]; v.w = v.base[2]; v.h = v.base[3]; v.obj = v.base[4];
+    return v;
+  }
+  v.fused = true;
+  int l = 0;
+  while (l + 1 < s.levels && r >= s.meta[l + 1].row0) ++l;
+  const LevelMeta m = s.meta[l];
+  int rr = r - m.row0;
+  const int gx = rr % m.nx;
+  rr /= m.nx;
+  const int gy = rr % m.ny;
+  const int a = rr / m.ny;
+  const int no = 5 + s.nc;
+  v.base = s.logits[l] + (((long long)img * m.ny + gy) * m.nx + gx) * m.ld + a * no;
+  const float sx = sigmoid_acc(v.base[0]), sy = sigmoid_acc(v.base[1]);
+  const float sw = sigmoid_acc(v.base[2]), sh = sigmoid_acc(v.base[3]);
+  v.obj = sigmoid_acc(v.base[4]);
+  v.x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), m.stride);
+  v.y = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.f), 0.5f), (float)gy), m.stride);
+  const float tw = __fmul_rn(sw, 2.f), th = __fmul_rn(sh, 2.f);
+  v.w = __fmul_rn(__fmul_rn(tw, tw), m.anchor[2 * a]);
+  v.h = __fmul_rn(__fmul_rn(th, th), m.anchor[2 * a + 1]);
+  return v;
+}
+
+// Per-row candidate enumeration by one warp.  Calls emit(k, conf, cls) for the k-th candidate of the
+// row in class order (lane-cooperative: emit is invoked by the lane that owns the class); returns the
+// row's candidate count (uniform across the warp).
+template <bool WRITE, typename Emit>
+__device__ __forceinline__ int row_candidates(const RowView& v, int nc, bool multi_label, float thr,
+                                              const unsigned char* __restrict__ class_mask, int lane, Emit emit) {
+  if (!(v.obj > thr)) return 0;
+  if (multi_label) {
+    int total = 0;
+    for (int c0 = 0; c0 < nc; c0 += 32) {
+      const int c = c0 + lane;
+      bool pass = false;
+      float conf = 0.f;
+      if (c < nc) {
+        conf = __fmul_rn(v.cls_at(c), v.obj);
+        pass = conf > thr && (class_mask == nullptr || class_mask[c]);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      if (WRITE && pass) emit(total + __popc(bal & ((1u << lane) - 1u)), conf, c);
+      total += __popc(bal);
+    }
+    return total;
+  }
+  // best class: first maximum (torch.max on CPU), NaN anywhere -> max is NaN -> `conf > thr` false
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  bool has_nan = false;
+  for (int c = lane; c < nc; c += 32) {
+    const float conf = __fmul_rn(v.cls_at(c), v.obj);
+    if (conf != conf) has_nan = true;
+    if (conf > best) {  // strictly greater keeps the first index within this lane's ascending scan
+      best = conf;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  has_nan = __any_sync(0xffffffffu, has_nan);
+  if (has_nan || !(best > thr) || bi >= nc) return 0;
+  if (class_mask != nullptr && !class_mask[bi]) return 0;
+  if (WRITE && lane == 0) emit(0, best, bi);
+  return 1;
+}
+
+constexpr int kFilterThreads = 256;
+constexpr int kFilterWarps = kFilterThreads / 32;
+
+__global__ void __launch_bounds__(kFilterThreads) filter_count_kernel(RowSrc src, const unsigned char* class_mask,
+                                                                      int* __restrict__ blk_counts, int rows_per_block,
+                                                                      int nblk, int multi_label, float thr) {
+  __shared__ int wsum[kFilterWarps];
+  const int img = blockIdx.x / nblk, blk = blockIdx.x % nblk;
+  const int r0 = blk * rows_per_block, r1 = min(r0 + rows_per_block, src.R);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int local = 0;
+  for (int r = r0 + warp; r < r1; r += kFilterWarps) {
+    RowView v = load_row(src, img, r);
+    local += row_candidates<false>(v, src.nc, multi_label != 0, thr, class_mask, lane, [](int, float, int) {});
+  }
+  if (lane == 0) wsum[warp] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < kFilterWarps; ++i) t += wsum[i];
+    blk_counts[blockIdx.x] = t;
+  }
+}
+
+// one CTA per image: exclusive scan of its nblk block counts
+__global__ void __launch_bounds__(1024) filter_scan_kernel(const int* __restrict__ blk_counts,
+                                                           int* __restrict__ blk_offsets, int* __restrict__ img_counts,
+                                                           int nblk) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s, chunk_tot_s;
+  const int img = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblk ? blk_counts[(long long)img * nblk + i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = lane < nwarps ? warp_tot[lane] : 0;
+      int winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      warp_tot[lane] = winc - w;  // exclusive warp offsets
+      if (lane == 31) chunk_tot_s = winc;
+    }
+    __syncthreads();
+    if (i < nblk) blk_offsets[(long long)img * nblk + i] = carry_s + warp_tot[warp] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += chunk_tot_s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) img_counts[img] = carry_s;
+}
+
+// single CTA: exclusive scan of img_counts -> img_offsets[N+1] (serial over N; N is a batch size)
+__global__ void img_scan_kernel(const int* __restrict__ img_counts, long long* __restrict__ img_offsets, int N) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    long long t = 0;
+    for (int i = 0; i < N; ++i) {
+      img_offsets[i] = t;
+      t += img_counts[i];
+    }
+    img_offsets[N] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kFilterThreads) filter_write_kernel(
+    RowSrc src, const unsigned char* class_mask, const int* __restrict__ blk_offsets,
+    const long long* __restrict__ img_offsets, unsigned long long* __restrict__ keys, float* __restrict__ cand,
+    int rows_per_block, int nblk, int multi_label, float thr, long long capacity) {
+  extern __shared__ int row_off[];  // [rows_per_block + 1]
+  const int img = blockIdx.x / nblk, blk = blockIdx.x % nblk;
+  const int r0 = blk * rows_per_block, r1 = min(r0 + rows_per_block, src.R);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nrows = r1 - r0;
+  // pass 1: per-row counts
+  for (int r = r0 + warp; r < r1; r += kFilterWarps) {
+    RowView v = load_row(src, img, r);
+    int c = row_candidates<false>(v, src.nc, multi_label != 0, thr, class_mask, lane, [](int, float, int) {});
+    if (lane == 0) row_off[r - r0] = c;
+  }
+  __syncthreads();
+  // exclusive scan over <= rows_per_block rows by warp 0 (chunks of 32 with carry)
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < nrows; base += 32) {
+      const int i = base + lane;
+      const int v = i < nrows ? row_off[i] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (i < nrows) row_off[i] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  const long long gbase = img_offsets[img] + blk_offsets[(long long)img * nblk + blk];
+  // pass 2: write
+  for (int r = r0 + warp; r < r1; r += kFilterWarps) {
+    RowView v = load_row(src, img, r);
+    const long long g0 = gbase + row_off[r - r0];
+    // xywh2xyxy, utils/general.py:539-546: x - w/2 etc. (w/2 is exact in fp32)
+    const float hw = __fmul_rn(v.w, 0.5f), hh = __fmul_rn(v.h, 0.5f);
+    const float x1 = __fsub_rn(v.x, hw), y1 = __fsub_rn(v.y, hh), x2 = __fadd_rn(v.x, hw), y2 = __fadd_rn(v.y, hh);
+    row_candidates<true>(v, src.nc, multi_label != 0, thr, class_mask, lane, [&](int k, float conf, int cls) {
+      const long long g = g0 + k;
+      if (g < capacity) {
+        float* c = cand + g * 6;
+        c[0] = x1; c[1] = y1; c[2] = x2; c[3] = y2; c[4] = conf; c[5] = (float)cls;
+        keys[g] = ((unsigned long long)(unsigned)img << 32) | (unsigned long long)(~__float_as_uint(conf));
+      }
+    });
+  }
+}
+
+__global__ void iota_kernel(unsigned* __restrict__ idx, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    idx[i] = (unsigned)i;
+}
+
+// ---- greedy NMS -------------------------------------------------------------------------------------
+// torchvision/csrc/ops/cpu/nms_kernel.cpp semantics.
+__device__ __forceinline__ bool suppresses(float ix1, float iy1, float ix2, float iy2, float iarea, float jx1, float jy1,
+                                           float jx2, float jy2, float jarea, double thr) {
+  const float xx1 = ix1 < jx1 ? jx1 : ix1;  // std::max(ix1, x1[j])
+  const float xx2 = jx2 < ix2 ? jx2 : ix2;  // std::min(ix2, x2[j])
+  const float dw = __fsub_rn(xx2, xx1);
+  const float w = 0.f < dw ? dw : 0.f;  // std::max(0, xx2 - xx1)
+  const float yy1 = iy1 < jy1 ? jy1 : iy1;
+  const float yy2 = jy2 < iy2 ? jy2 : iy2;
+  const float dh = __fsub_rn(yy2, yy1);
+  const float h = 0.f < dh ? dh : 0.f;
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
+  return (double)ovr > thr;
+}
+
+constexpr int kNmsThreads = 512;
+constexpr int kChunk = 128;
+
+__global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float* __restrict__ cand,
+                                                                 const unsigned* __restrict__ sorted_idx,
+                                                                 const int* __restrict__ img_counts,
+                                                                 const long long* __restrict__ img_offsets,
+                                                                 float* __restrict__ out, int* __restrict__ out_counts,
+                                                                 int max_det, int max_nms, float max_wh, int agnostic,
+                                                                 double thr) {
+  extern __shared__ float sm[];
+  float* kept = sm;                                   // [max_det][5]  offset box + area
+  float* cb = kept + (size_t)max_det * 5;             // [kChunk][5]   chunk offset boxes + area
+  float* craw = cb + kChunk * 5;                      // [kChunk][6]   chunk raw rows
+  unsigned* mask = reinterpret_cast<unsigned*>(craw + kChunk * 6);  // [kChunk][4] intra-chunk suppression bits
+  int* dead = reinterpret_cast<int*>(mask + kChunk * 4);            // [kChunk]
+  __shared__ int K_s;
+  __shared__ int newk[kChunk];
+  __shared__ int n_new_s;
+
+  const int img = blockIdx.x;
+  const long long off = img_offsets[img];
+  int n = img_counts[img];
+  if (n > max_nms) n = max_nms;
+  if (threadIdx.x == 0) K_s = 0;
+  __syncthreads();
+
+  for (int c0 = 0; c0 < n; c0 += kChunk) {
+    const int cn = min(kChunk, n - c0);
+    const int K = K_s;
+    if (K >= max_det) break;
+    // 1. load the chunk
+    if (threadIdx.x < kChunk) {
+      const int t = threadIdx.x;
+      dead[t] = t < cn ? 0 : 1;
+      mask[t * 4 + 0] = mask[t * 4 + 1] = mask[t * 4 + 2] = mask[t * 4 + 3] = 0u;
+      if (t < cn) {
+        const float* r = cand + ((long long)sorted_idx[off + c0 + t]) * 6;
+        float b[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          b[j] = r[j];
+          craw[t * 6 + j] = b[j];
+        }
+        // boxes + cls * (0 if agnostic else max_wh), utils/general.py:706-707
+        const float c = __fmul_rn(b[5], agnostic ? 0.f : max_wh);
+        const float x1 = __fadd_rn(b[0], c), y1 = __fadd_rn(b[1], c), x2 = __fadd_rn(b[2], c), y2 = __fadd_rn(b[3], c);
+        cb[t * 5 + 0] = x1; cb[t * 5 + 1] = y1; cb[t * 5 + 2] = x2; cb[t * 5 + 3] = y2;
+        cb[t * 5 + 4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+      }
+    }
+    __syncthreads();
+    // 2. chunk vs kept list: 4 threads per candidate, each strides the kept list by 4
+    {
+      const int t = threadIdx.x & (kChunk - 1), sub = threadIdx.x / kChunk;  // sub in 0..3
+      if (t < cn) {
+        const float x1 = cb[t * 5], y1 = cb[t * 5 + 1], x2 = cb[t * 5 + 2], y2 = cb[t * 5 + 3], ar = cb[t * 5 + 4];
+        bool d = false;
+        for (int k = sub; k < K && !d; k += kNmsThreads / kChunk) {
+          const float* kb = kept + k * 5;
+          d = suppresses(kb[0], kb[1], kb[2], kb[3], kb[4], x1, y1, x2, y2, ar, thr);
+        }
+        if (d) dead[t] = 1;
+      }
+    }
+    // 3a. intra-chunk pair bits: thread (i, word) computes which j in [32*word, 32*word+32), j > i, box i suppresses
+    {
+      const int i = threadIdx.x >> 2, wd = threadIdx.x & 3;
+      if (i < cn) {
+        const float x1 = cb[i * 5], y1 = cb[i * 5 + 1], x2 = cb[i * 5 + 2], y2 = cb[i * 5 + 3], ar = cb[i * 5 + 4];
+        unsigned bits = 0u;
+        const int j0 = wd * 32;
+        for (int jj = 0; jj < 32; ++jj) {
+          const int j = j0 + jj;
+          if (j > i && j < cn) {
+            const float* jb = cb + j * 5;
+            if (suppresses(x1, y1, x2, y2, ar, jb[0], jb[1], jb[2], jb[3], jb[4], thr)) bits |= 1u << jj;
+          }
+        }
+        mask[i * 4 + wd] = bits;
+      }
+    }
+    __syncthreads();
+    // 3b. serial resolution by one thread (<= 128 steps of 4-word bit ops)
+    if (threadIdx.x == 0) {
+      unsigned rem[4] = {0u, 0u, 0u, 0u};
+      int k = K, nn = 0;
+      for (int i = 0; i < cn && k < max_det; ++i) {
+        if (dead[i]) continue;
+        if ((rem[i >> 5] >> (i & 31)) & 1u) continue;
+        newk[nn++] = i;
+        ++k;
+        rem[0] |= mask[i * 4 + 0]; rem[1] |= mask[i * 4 + 1]; rem[2] |= mask[i * 4 + 2]; rem[3] |= mask[i * 4 + 3];
+      }
+      n_new_s = nn;
+    }
+    __syncthreads();
+    // 4. append the new keeps (kept list + output rows), in order
+    const int nn = n_new_s;
+    if (threadIdx.x < nn) {
+      const int i = newk[threadIdx.x];
+      const int k = K + threadIdx.x;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) kept[k * 5 + j] = cb[i * 5 + j];
+      float* o = out + ((long long)img * max_det + k) * 6;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) o[j] = craw[i * 6 + j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) K_s = K + nn;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_counts[img] = K_s;
+}
+
+// ---- dense Detect decode (API-compat materialisation of `pred`) ------------------------------------------
+__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ logits, float* __restrict__ pred, int N,
+                                                     int ny, int nx, int na, int no, int ld, int row0, int rows_total,
+                                                     float stride, float aw0,
+                                                     float ah0, float aw1, float ah1, float aw2, float ah2, float aw3,
+                                                     float ah3, float aw4, float ah4) {
+  const float aw[5] = {aw0, aw1, aw2, aw3, aw4}, ah[5] = {ah0, ah1, ah2, ah3, ah4};
+  const long long items = (long long)N * na * ny * nx * no;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    int o = (int)(i % no);
+    long long t = i / no;
+    int gx = (int)(t % nx);
+    t /= nx;
+    int gy = (int)(t % ny);
+    t /= ny;
+    int a = (int)(t % na);
+    int n = (int)(t / na);
+    const float s = sigmoid_acc(logits[(((long long)n * ny + gy) * nx + gx) * ld + a * no + o]);
+    float v = s;
+    if (o == 0) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.f), 0.5f), (float)gx), stride);
+    else if (o == 1) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.f), 0.5f), (float)gy), stride);
+    else if (o == 2) { float q = __fmul_rn(s, 2.f); v = __fmul_rn(__fmul_rn(q, q), aw[a]); }
+    else if (o == 3) { float q = __fmul_rn(s, 2.f); v = __fmul_rn(__fmul_rn(q, q), ah[a]); }
+    pred[((long long)n * rows_total + row0 + ((long long)a * ny + gy) * nx + gx) * no + o] = v;
+  }
+}
+
+}  // namespace dmay
+
+using namespace dmay;
+
+extern "C" {
+
+int dmay_detect_decode(const dmay_decode_params* p, dmay_stream_t stream) {
+  if (!p || !p->logits || !p->pred) return DMAY_EINVAL;
+  if (p->N <= 0 || p->ny <= 0 || p->nx <= 0 || p->na <= 0 || p->no <= 5) return DMAY_EINVAL;
+  if (p->na > 5 || p->ld < p->na * p->no) return DMAY_EUNSUPPORTED;
+  long long items = (long long)p->N * p->na * p->ny * p->nx * p->no;
+  decode_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)p->logits, (float*)p->pred, p->N, p->ny, p->nx, p->na, p->no, p->ld, p->row0, p->rows_total,
+      p->stride, p->aw0, p->ah0, p->aw1, p->ah1, p->aw2, p->ah2, p->aw3, p->ah3, p->aw4, p->ah4);
+  return finish_launch();
+}
+
+int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream) {
+  if (!p || p->N <= 0 || p->R <= 0 || p->nc <= 0) return DMAY_EINVAL;
+  if (!p->blk_counts || !p->blk_offsets || !p->img_counts || !p->img_offsets) return DMAY_EINVAL;
+  if (p->levels < 0 || p->levels > 5) return DMAY_EUNSUPPORTED;
+  if (p->levels == 0 && !p->pred) return DMAY_EINVAL;
+  if (p->levels > 0 && (!p->lv_meta || !p->lv_logits0)) return DMAY_EINVAL;
+  const int rpb = p->rows_per_block > 0 ? p->rows_per_block : 128;
+  if (rpb > 1024) return DMAY_EUNSUPPORTED;
+  const int nblk = (p->R + rpb - 1) / rpb;
+  const long long grid = (long long)p->N * nblk;
+  if (grid > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  RowSrc src;
+  src.pred = (const float*)p->pred;
+  src.logits[0] = (const float*)p->lv_logits0; src.logits[1] = (const float*)p->lv_logits1;
+  src.logits[2] = (const float*)p->lv_logits2; src.logits[3] = (const float*)p->lv_logits3;
+  src.logits[4] = (const float*)p->lv_logits4;
+  src.meta = (const LevelMeta*)p->lv_meta;
+  src.levels = p->levels;
+  src.R = p->R;
+  src.nc = p->nc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned char* cm = (const unsigned char*)p->class_mask;
+  if (p->phase == 0) {
+    filter_count_kernel<<<(int)grid, kFilterThreads, 0, s>>>(src, cm, (int*)p->blk_counts, rpb, nblk, p->multi_label,
+                                                             p->conf_thres);
+    filter_scan_kernel<<<p->N, 1024, 0, s>>>((const int*)p->blk_counts, (int*)p->blk_offsets, (int*)p->img_counts, nblk);
+    img_scan_kernel<<<1, 32, 0, s>>>((const int*)p->img_counts, (long long*)p->img_offsets, p->N);
+    return finish_launch(3);
+  }
+  if (!p->keys || !p->cand || p->capacity <= 0) return DMAY_EINVAL;
+  filter_write_kernel<<<(int)grid, kFilterThreads, (rpb + 1) * sizeof(int), s>>>(
+      src, cm, (const int*)p->blk_offsets, (const long long*)p->img_offsets, (unsigned long long*)p->keys,
+      (float*)p->cand, rpb, nblk, p->multi_label, p->conf_thres, p->capacity);
+  return finish_launch();
+}
+
+static size_t cub_ws_bytes(long long n, int end_bit) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const unsigned*)nullptr, (unsigned*)nullptr, n, 0, end_bit, (cudaStream_t)0);
+  return (bytes + 255) & ~(size_t)255;
+}
+
+long long dmay_nms_sort_ws(long long n, int img_bits) {
+  if (n <= 0) return 256;
+  return (long long)cub_ws_bytes(n, 32 + img_bits) + (long long)((n * 4 + 255) & ~255LL);
+}
+
+int dmay_nms_sort(const dmay_sort_params* p, dmay_stream_t stream) {
+  if (!p || !p->keys_in || !p->keys_out || !p->idx_out || !p->ws || p->n <= 0) return DMAY_EINVAL;
+  if (p->img_bits < 0 || p->img_bits > 31) return DMAY_EINVAL;
+  const int end_bit = 32 + p->img_bits;
+  size_t cub_bytes = cub_ws_bytes(p->n, end_bit);
+  if ((long long)cub_bytes + p->n * 4 > p->ws_bytes) return DMAY_ETOOBIG;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned* idx_in = reinterpret_cast<unsigned*>((char*)p->ws + cub_bytes);
+  iota_kernel<<<grid_for(p->n, 256), 256, 0, s>>>(idx_in, p->n);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(p->ws, cub_bytes, (const unsigned long long*)p->keys_in,
+                                                  (unsigned long long*)p->keys_out, (const unsigned*)idx_in,
+                                                  (unsigned*)p->idx_out, p->n, 0, end_bit, s);
+  if (e != cudaSuccess) return (int)e;
+  return finish_launch(2);
+}
+
+int dmay_nms_greedy(const dmay_nms_params* p, dmay_stream_t stream) {
+  if (!p || !p->cand || !p->sorted_idx || !p->img_counts || !p->img_offsets || !p->out || !p->out_counts) return DMAY_EINVAL;
+  if (p->N <= 0 || p->max_det <= 0 || p->max_nms <= 0) return DMAY_EINVAL;
+  const size_t smem = ((size_t)p->max_det * 5 + kChunk * 5 + kChunk * 6 + kChunk * 4 + kChunk) * 4;
+  if (smem > 220 * 1024) return DMAY_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  nms_greedy_kernel<<<p->N, kNmsThreads, smem, (cudaStream_t)stream>>>(
+      (const float*)p->cand, (const unsigned*)p->sorted_idx, (const int*)p->img_counts,
+      (const long long*)p->img_offsets, (float*)p->out, (int*)p->out_counts, p->max_det, p->max_nms, p->max_wh,
+      p->agnostic, p->iou_thres);
+  return finish_launch();
+}
+
+}  // extern "C"

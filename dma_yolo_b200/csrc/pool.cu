@@ -1,0 +1,169 @@
+// a7: cascaded stride-1 max-pools of SPPF / SPPFCSPC (models/common.py:1272-1274, 252-258) and the
+// single k x k stride-1 max-pool of SPP / SPPCSPC (models/common.py:212-227, 1237-1255).
+//
+// One CTA owns one image x one group of CB channels and keeps the whole H x W x CB plane in shared
+// memory (20x20x64 bf16 = 51 KB at cfg-2): x is read from HBM exactly once and y1..y3 are written
+// exactly once — the kernel's traffic is the algorithmic (1 in + 3 out).  Each pool is done
+// separably (row max then column max) on packed bf16x2 with __hmax2, which is bit-exact for a max.
+#include "common.cuh"
+
+namespace dmay {
+
+__device__ __forceinline__ uint4 max16(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// smem: bufA[H*W*VL] + bufB[H*W*VL] uint4 (VL = CB/8 vectors per pixel)
+template <int STAGES>
+__global__ void __launch_bounds__(256) pool_plane_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
+                                                         __nv_bfloat16* __restrict__ y3, int H, int W, int C, int ldx,
+                                                         int ldy, int k, int VL) {
+  extern __shared__ uint4 smem[];
+  const int HW = H * W;
+  uint4* A = smem;
+  uint4* B = smem + (size_t)HW * VL;
+  const int groups = (C / 8 + VL - 1) / VL;
+  const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int v0 = g * VL;                              // first channel-vector of this CTA
+  const int vl = min(VL, C / 8 - v0);                 // active vectors per pixel
+  const int items = HW * vl;
+  const int r = k >> 1;
+  const long long pbase = (long long)n * HW;
+
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    int v = i % vl, p = i / vl;
+    A[p * VL + v] = ld_nc16(x + (pbase + p) * ldx + (v0 + v) * 8);
+  }
+  __syncthreads();
+  __nv_bfloat16* outs[3] = {y1, y2, y3};
+#pragma unroll
+  for (int s = 0; s < STAGES; ++s) {
+    // row pass: B[h][w] = max_{|d|<=r} A[h][w+d]
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      int v = i % vl, p = i / vl;
+      int w_ = p % W, h_ = p / W;
+      int lo = max(w_ - r, 0), hi = min(w_ + r, W - 1);
+      uint4 m = A[(h_ * W + lo) * VL + v];
+      for (int ww = lo + 1; ww <= hi; ++ww) m = max16(m, A[(h_ * W + ww) * VL + v]);
+      B[p * VL + v] = m;
+    }
+    __syncthreads();
+    // column pass: A[h][w] = max_{|d|<=r} B[h+d][w]; also the stage output
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      int v = i % vl, p = i / vl;
+      int w_ = p % W, h_ = p / W;
+      int lo = max(h_ - r, 0), hi = min(h_ + r, H - 1);
+      uint4 m = B[(lo * W + w_) * VL + v];
+      for (int hh = lo + 1; hh <= hi; ++hh) m = max16(m, B[(hh * W + w_) * VL + v]);
+      st_na16(outs[s] + (pbase + p) * ldy + (v0 + v) * 8, m);
+      if (s + 1 < STAGES) A[p * VL + v] = m;  // each thread overwrites only the element it owns; A is
+                                              // not read in this pass, so no hazard before the barrier
+    }
+    __syncthreads();
+  }
+}
+
+// Fallback for planes that do not fit in shared memory: nested windows straight from global/L2.
+__global__ void __launch_bounds__(256) pool_direct_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
+                                                          __nv_bfloat16* __restrict__ y3, int N, int H, int W, int C,
+                                                          int ldx, int ldy, int k, int stages) {
+  const int cv = C >> 3, r = k >> 1;
+  const long long items = (long long)N * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    int v = (int)(i % cv);
+    long long pix = i / cv;
+    int w_ = (int)(pix % W);
+    long long t = pix / W;
+    int h_ = (int)(t % H);
+    int n = (int)(t / H);
+    const uint4 c0 = ld16(x + pix * ldx + v * 8);
+    uint4 m1 = c0, m2 = c0, m3 = c0;
+    const int R = r * stages;
+    for (int dy = -R; dy <= R; ++dy) {
+      int hh = h_ + dy;
+      if (hh < 0 || hh >= H) continue;
+      for (int dx = -R; dx <= R; ++dx) {
+        int ww = w_ + dx;
+        if (ww < 0 || ww >= W) continue;
+        uint4 val = ld16(x + (((long long)n * H + hh) * W + ww) * ldx + v * 8);
+        int d = max(abs(dy), abs(dx));
+        if (d <= r) m1 = max16(m1, val);
+        if (d <= 2 * r) m2 = max16(m2, val);
+        m3 = max16(m3, val);
+      }
+    }
+    st_na16(y1 + pix * ldy + v * 8, m1);
+    if (stages > 1) st_na16(y2 + pix * ldy + v * 8, m2);
+    if (stages > 2) st_na16(y3 + pix * ldy + v * 8, m3);
+  }
+}
+
+static int launch_pool(const void* x, void* y1, void* y2, void* y3, int N, int H, int W, int C, int ldx, int ldy,
+                       int k, int stages, cudaStream_t s) {
+  if (!x || !y1 || N <= 0 || H <= 0 || W <= 0 || C <= 0) return DMAY_EINVAL;
+  if (stages == 3 && (!y2 || !y3)) return DMAY_EINVAL;
+  if (!(k & 1) || k < 1) return DMAY_EUNSUPPORTED;
+  if ((C | ldx | ldy) & 7) return DMAY_EUNSUPPORTED;
+  if (!aligned16(x) || !aligned16(y1) || (y2 && !aligned16(y2)) || (y3 && !aligned16(y3))) return DMAY_EINVAL;
+  const long long HW = (long long)H * W;
+  const int cvec = C / 8;
+  // largest VL (vectors per pixel per CTA) whose two planes fit in ~200 KB; prefer >=2 CTAs per SM
+  int VL = 0;
+  for (int cand : {8, 4, 2, 1}) {
+    if (cand > cvec && cand != 1) continue;
+    if (HW * cand * 16 * 2 <= 100 * 1024) { VL = cand; break; }
+  }
+  if (VL == 0)
+    for (int cand : {8, 4, 2, 1}) {
+      if (cand > cvec && cand != 1) continue;
+      if (HW * cand * 16 * 2 <= 200 * 1024) { VL = cand; break; }
+    }
+  if (VL == 0) {
+    long long items = (long long)N * HW * cvec;
+    pool_direct_kernel<<<grid_for(items, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y1,
+                                                            (__nv_bfloat16*)y2, (__nv_bfloat16*)y3, N, H, W, C, ldx,
+                                                            ldy, k, stages);
+    return finish_launch();
+  }
+  const size_t smem = (size_t)HW * VL * 16 * 2;
+  const int groups = (cvec + VL - 1) / VL;
+  const long long grid = (long long)N * groups;
+  if (grid > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  cudaError_t e;
+  if (stages == 3) {
+    e = cudaFuncSetAttribute(pool_plane_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pool_plane_kernel<3><<<(int)grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y1, (__nv_bfloat16*)y2,
+                                                      (__nv_bfloat16*)y3, H, W, C, ldx, ldy, k, VL);
+  } else {
+    e = cudaFuncSetAttribute(pool_plane_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pool_plane_kernel<1><<<(int)grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y1, nullptr, nullptr, H,
+                                                      W, C, ldx, ldy, k, VL);
+  }
+  return finish_launch();
+}
+
+}  // namespace dmay
+
+extern "C" {
+int dmay_sppf_pool3(const dmay_sppf_params* p, dmay_stream_t stream) {
+  if (!p) return DMAY_EINVAL;
+  return dmay::launch_pool(p->x, p->y1, p->y2, p->y3, p->N, p->H, p->W, p->C, p->ldx, p->ldy, p->k, 3,
+                           (cudaStream_t)stream);
+}
+int dmay_maxpool_s1(const dmay_maxpool_params* p, dmay_stream_t stream) {
+  if (!p) return DMAY_EINVAL;
+  return dmay::launch_pool(p->x, p->y, nullptr, nullptr, p->N, p->H, p->W, p->C, p->ldx, p->ldy, p->k, 1,
+                           (cudaStream_t)stream);
+}
+}

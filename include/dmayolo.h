@@ -1,0 +1,431 @@
+/*
+ * dmayolo.h — C-ABI of libdmayolo.so: hand-written sm_100a kernels for the DMA-YOLO
+ * detection-forward hot path (custom blocks + Conv/BN/SiLU + Detect decode + NMS).
+ *
+ * The reference (Yaling-Li/DMA-YOLO) is pure PyTorch and has no FFI for this path
+ * (SURVEY.md F1); every entry point below therefore cites the *Python* reference
+ * symbol (file:line under the reference tree) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no torch types.  All pointers are DEVICE pointers
+ *     unless the field name ends in `_host`.
+ *   - activations: bf16, NHWC ("channels_last"): element (n,h,w,c) of a tensor that lives
+ *     in a channel slice of a wider slab is at  base + ((n*H + h)*W + w)*ld + c,
+ *     `ld` = pixel stride in ELEMENTS (= channels of the slab).  ld and channel offsets
+ *     are multiples of 8 so every pixel row is 16-byte aligned.
+ *   - ownership: the caller allocates every input / output / workspace buffer.  The
+ *     library never allocates or frees device memory and keeps no mutable global state
+ *     except the launch counter.
+ *   - all work is enqueued on the passed stream; no implicit synchronisation.
+ *   - return value: 0 = success, <0 = DMAY_E* (bad argument / unsupported shape),
+ *     >0 = cudaError_t.  Nothing throws across the boundary.
+ *   - structs contain only `const void*`, `void*`, `int`, `long long`, `float`, `double`
+ *     fields (one per line) so the Python side can parse this header into ctypes.
+ */
+#ifndef DMAYOLO_H_
+#define DMAYOLO_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMAY_OK 0
+#define DMAY_EINVAL -1      /* null pointer / non-positive size / misaligned pointer */
+#define DMAY_EUNSUPPORTED -2 /* shape outside what the kernel supports */
+#define DMAY_EDRIVER -3     /* cuTensorMapEncode* entry point missing or failed */
+#define DMAY_ETOOBIG -4     /* workspace / capacity too small */
+
+#define DMAY_ACT_NONE 0
+#define DMAY_ACT_SILU 1
+#define DMAY_ACT_HARDSWISH 2
+#define DMAY_ACT_SIGMOID 3
+
+#define DMAY_DT_BF16 0
+#define DMAY_DT_F32 1
+#define DMAY_DT_F16 2
+#define DMAY_DT_U8 3
+
+/* opaque CUDA stream handle (cudaStream_t) */
+typedef void* dmay_stream_t;
+
+/* ---- library introspection ------------------------------------------------------------ */
+int dmay_version(void);
+/* number of kernels this library has launched since load (bench.py `gpu_launches`) */
+long long dmay_launch_count(void);
+/* human readable text for a return code */
+const char* dmay_strerror(int code);
+
+/* ---- a1/a2: Conv + folded BN + activation (+ residual) as tcgen05 implicit GEMM --------
+ * replaces models/common.py:50-77 Conv.forward / forward_fuse (dup models/cspcm.py:11-23),
+ * BN fold utils/torch_utils.py:198-218, Bottleneck residual models/common.py:136-137,
+ * and (via ldy / channel-slice outputs) the torch.cat in C3.forward models/common.py:181-182.
+ *   y[m, co] = act( scale[co] * sum_{r,s,ci} x[n, p*stride-pad+r, q*stride-pad+s, ci] * w[co,r,s,ci] + bias[co] ) (+ residual[m,co])
+ *   m = (n*Ho + p)*Wo + q.
+ * w is packed [Cout_pad][kh][kw][Cin] bf16 (Cin multiple of 16, Cout_pad multiple of 16).
+ * mode gate (gate_x != NULL): y = (scale*acc+bias) * sigmoid(gate_x[m,co] + gate_k[n, hs, ws, co])
+ *   with nearest index hs=min(floor(p*gate_sh),gHk-1) — SCConv.forward models/common.py:1308-1316. */
+typedef struct dmay_conv_params {
+  const void* x;
+  const void* w;
+  const void* scale;
+  const void* bias;
+  const void* residual;
+  const void* gate_x;
+  const void* gate_k;
+  void* y;
+  int N;
+  int H;
+  int W;
+  int Cin;
+  int ldx;
+  int Cout;
+  int Cout_pad;
+  int kh;
+  int kw;
+  int stride;
+  int pad;
+  int Ho;
+  int Wo;
+  int ldy;
+  int ldr;
+  int ldgx;
+  int gHk;
+  int gWk;
+  int act;
+  int out_dtype;
+  int block_n;
+  int num_sms;
+} dmay_conv_params;
+int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream);
+
+/* ---- input prep: NCHW {f32,f16,bf16,u8} image -> NHWC bf16 ------------------------------
+ * replaces val.py:199-202 (`img.float()/255`) + the layout change the first conv needs.
+ * spd=1 writes the 2x2 pixel-unshuffled form [N,H/2,W/2,Cpad] with channel (dy*2+dx)*C+c
+ * (stem 6x6 s2 p2 conv == 3x3 s1 p1 conv on it); channels >= real are zero.  mul scales
+ * (1/255 for u8 callers that skip the division). */
+typedef struct dmay_prep_params {
+  const void* x;
+  void* y;
+  int N;
+  int C;
+  int H;
+  int W;
+  int Cpad;
+  int spd;
+  int in_dtype;
+  float mul;
+} dmay_prep_params;
+int dmay_input_prep(const dmay_prep_params* p, dmay_stream_t stream);
+
+/* NHWC bf16 (slice, ld) <-> NCHW contiguous {f32,bf16,f16}: glue for modules that stay in
+ * torch ops.  dir=0: nhwc->nchw, dir=1: nchw->nhwc. */
+typedef struct dmay_layout_params {
+  const void* x;
+  void* y;
+  int N;
+  int C;
+  int H;
+  int W;
+  int ld;
+  int dtype;
+  int dir;
+} dmay_layout_params;
+int dmay_layout_convert(const dmay_layout_params* p, dmay_stream_t stream);
+
+/* ---- a4: space_to_depth (SPD-Conv), models/common.py:1457-1458 (same: SM 1466, Focus 94)
+ * y[n,h,w,(dy+2*dx)*C + c] = x[n,2h+dy,2w+dx,c]   (bit-exact copy) */
+typedef struct dmay_spd_params {
+  const void* x;
+  void* y;
+  int N;
+  int H;
+  int W;
+  int C;
+  int ldx;
+  int ldy;
+} dmay_spd_params;
+int dmay_spd(const dmay_spd_params* p, dmay_stream_t stream);
+
+/* ---- a6: AdConcat2/3 (+ fused preceding nn.Upsample nearest), Concat -------------------
+ * models/common.py:1003-1008,1021-1026 (weight = w/(sum w + 1e-4) is computed by the
+ * caller in fp32 and passed as w0..w2), models/common.py:656-664 (Concat: weights 1).
+ * y[n,h,w, off_i + c] = bf16( wi * x_i[n, h>>up_i, w>>up_i, c] ),  i < n_in.
+ * H,W are OUTPUT dims; input i has dims (H>>up_i, W>>up_i). */
+typedef struct dmay_adconcat_params {
+  const void* x0;
+  const void* x1;
+  const void* x2;
+  void* y;
+  int n_in;
+  int N;
+  int H;
+  int W;
+  int C0;
+  int C1;
+  int C2;
+  int ld0;
+  int ld1;
+  int ld2;
+  int up0;
+  int up1;
+  int up2;
+  int ldy;
+  float w0;
+  float w1;
+  float w2;
+} dmay_adconcat_params;
+int dmay_adconcat(const dmay_adconcat_params* p, dmay_stream_t stream);
+
+/* Adapt_Add2 models/common.py:1040-1045: y = silu(w0*x0 + w1*x1) (+ w2*x2 for Adapt_Add3
+ * after its shared 1x1 conv, models/common.py:1047-1061).  Same layout rules. */
+typedef struct dmay_adaptadd_params {
+  const void* x0;
+  const void* x1;
+  const void* x2;
+  void* y;
+  int n_in;
+  long long npix;
+  int C;
+  int ld0;
+  int ld1;
+  int ld2;
+  int ldy;
+  float w0;
+  float w1;
+  float w2;
+} dmay_adaptadd_params;
+int dmay_adaptadd(const dmay_adaptadd_params* p, dmay_stream_t stream);
+
+/* nn.Upsample(None, 2, 'nearest') stand-alone (yaml glue), bit-exact copy;
+ * residual-free elementwise add  y = a + b  (Bottleneck fallback when not fused). */
+typedef struct dmay_upsample_params {
+  const void* x;
+  void* y;
+  int N;
+  int H;
+  int W;
+  int C;
+  int ldx;
+  int ldy;
+  int factor;
+} dmay_upsample_params;
+int dmay_upsample_nearest(const dmay_upsample_params* p, dmay_stream_t stream);
+
+/* ---- a7: cascaded 5x5 s1 p2 max-pools of SPPF / SPPFCSPC -------------------------------
+ * models/common.py:1272-1274 and 252-258:  y1=mp_k(x), y2=mp_k(y1), y3=mp_k(y2)
+ * (== windows k, 2k-1, 3k-2 with -inf padding).  x and y1..y3 may be channel slices of one
+ * slab (the 4C concat input of cv5/cv2): separate base pointers, common ld.  Bit-exact. */
+typedef struct dmay_sppf_params {
+  const void* x;
+  void* y1;
+  void* y2;
+  void* y3;
+  int N;
+  int H;
+  int W;
+  int C;
+  int ldx;
+  int ldy;
+  int k;
+} dmay_sppf_params;
+int dmay_sppf_pool3(const dmay_sppf_params* p, dmay_stream_t stream);
+
+/* generic max-pool kxk stride 1 pad k/2 (SPP / SPPCSPC branches, models/common.py:212-227,1237-1255) */
+typedef struct dmay_maxpool_params {
+  const void* x;
+  void* y;
+  int N;
+  int H;
+  int W;
+  int C;
+  int ldx;
+  int ldy;
+  int k;
+} dmay_maxpool_params;
+int dmay_maxpool_s1(const dmay_maxpool_params* p, dmay_stream_t stream);
+
+/* ---- a5: SCConv pieces, models/common.py:1279-1316 --------------------------------------
+ * avgpool: nn.AvgPool2d(r, r) (floor), fp32 accumulate -> bf16.
+ * gate:    y = k3 * sigmoid(x + k2[n, min(floor(h*Hk/H),Hk-1), min(floor(w*Wk/W),Wk-1), c])
+ *          (F.interpolate default 'nearest', index math in fp32 like ATen). */
+typedef struct dmay_avgpool_params {
+  const void* x;
+  void* y;
+  int N;
+  int H;
+  int W;
+  int C;
+  int ldx;
+  int ldy;
+  int r;
+} dmay_avgpool_params;
+int dmay_avgpool(const dmay_avgpool_params* p, dmay_stream_t stream);
+
+typedef struct dmay_scgate_params {
+  const void* x;
+  const void* k3;
+  const void* k2;
+  void* y;
+  int N;
+  int H;
+  int W;
+  int C;
+  int Hk;
+  int Wk;
+  int ldx;
+  int ld3;
+  int ld2;
+  int ldy;
+} dmay_scgate_params;
+int dmay_scconv_gate(const dmay_scgate_params* p, dmay_stream_t stream);
+
+/* ---- a3: CoordAtt, models/common.py:1183-1207 -------------------------------------------
+ * step 1 (pool):  pooled[n, h, c]   = mean_w x[n,h,w,c]        (h <  H)
+ *                 pooled[n, H+w, c] = mean_h x[n,h,w,c]        (fp32, [N, H+W, C])
+ * step 2 (mlp):   y = hardswish(s1 * (W1 . pooled + b1) + t1)  (W1 [Cm, C] fp32, conv1 bias b1,
+ *                 BN folded into s1/t1);  gates[n,p,:] = sigmoid(Wh . y + bh) for p < H,
+ *                 sigmoid(Ww . y + bw) for p >= H   (Wh/Ww [Cout, Cm] fp32), fp32 [N,H+W,Cout]
+ * step 3 (apply): out = (x * a_w[n,w,c]) * a_h[n,h,c]  -> bf16
+ * dmay_coordatt runs the three steps on the stream. */
+typedef struct dmay_coordatt_params {
+  const void* x;
+  void* y;
+  void* pooled;
+  void* gates;
+  const void* w1;
+  const void* b1;
+  const void* s1;
+  const void* t1;
+  const void* wh;
+  const void* bh;
+  const void* ww;
+  const void* bw;
+  int N;
+  int H;
+  int W;
+  int C;
+  int Cm;
+  int ldx;
+  int ldy;
+  int num_sms;
+} dmay_coordatt_params;
+int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream);
+
+/* ---- a8: Detect grid/anchor decode, models/yolo.py:81-101 -------------------------------
+ * logits: fp32 NHWC [N, ny, nx, ld] per level, channel = a*no + o  (1x1 conv + bias output).
+ * dense:  pred[n, row0 + (a*ny + y)*nx + x, :] = decode(sigmoid(logit)) — rows ordered
+ *         (level, anchor, y, x), out [N, rows_total, no] fp32. anchors_px = anchors*stride. */
+typedef struct dmay_decode_params {
+  const void* logits;
+  void* pred;
+  int N;
+  int ny;
+  int nx;
+  int na;
+  int no;
+  int ld;
+  int row0;
+  int rows_total;
+  float stride;
+  float aw0;
+  float ah0;
+  float aw1;
+  float ah1;
+  float aw2;
+  float ah2;
+  float aw3;
+  float ah3;
+  float aw4;
+  float ah4;
+} dmay_decode_params;
+int dmay_detect_decode(const dmay_decode_params* p, dmay_stream_t stream);
+
+/* ---- a9: batched class-aware NMS, utils/general.py:633-725 (+ torchvision.ops.nms) ------
+ * Candidate generation ("filter"), three launches, order-preserving:
+ *   count : per (image, row-block) number of candidates -> blk_counts[N*nblk]
+ *   scan  : per image exclusive scan -> blk_offsets, img_counts[N], img_offsets[N+1]
+ *   write : candidates in reference row-major order:
+ *           keys[g]   = (img << 32) | ~bits(conf)      (ascending key == descending score)
+ *           cand[g,:] = x1,y1,x2,y2,conf,cls  (fp32; xyxy from xywh exactly as xywh2xyxy
+ *                       utils/general.py:539-546), g = img_offsets[img] + local index
+ * source: either dense `pred` [N, R, 5+nc] fp32 (levels = 0) or the Detect logits of up to
+ * 5 levels (fused decode + confidence filter; nothing dense is materialised).
+ * multi_label=0: best class only (first max), keep conf > thr;  =1: every (row,class) with
+ * obj*cls > thr, row-major.  class_mask: optional [nc] u8 keep-list (`classes=` argument). */
+typedef struct dmay_filter_params {
+  const void* pred;
+  const void* lv_logits0;
+  const void* lv_logits1;
+  const void* lv_logits2;
+  const void* lv_logits3;
+  const void* lv_logits4;
+  const void* lv_meta;
+  const void* class_mask;
+  void* blk_counts;
+  void* blk_offsets;
+  void* img_counts;
+  void* img_offsets;
+  void* keys;
+  void* cand;
+  int N;
+  int R;
+  int nc;
+  int levels;
+  int multi_label;
+  int rows_per_block;
+  int phase;
+  long long capacity;
+  float conf_thres;
+} dmay_filter_params;
+int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream);
+
+/* stable sort of candidate keys (payload = candidate index).  CUB radix sort over the
+ * (img, ~score) composite key: equal scores keep ascending candidate index like
+ * torchvision's stable descending sort.  ws_bytes query: call with ws == NULL. */
+typedef struct dmay_sort_params {
+  const void* keys_in;
+  void* keys_out;
+  void* idx_out;
+  void* ws;
+  long long ws_bytes;
+  long long n;
+  int img_bits;
+} dmay_sort_params;
+long long dmay_nms_sort_ws(long long n, int img_bits);
+int dmay_nms_sort(const dmay_sort_params* p, dmay_stream_t stream);
+
+/* greedy NMS over each image's sorted candidates, stopping after max_det keeps.
+ * IoU exactly as torchvision CPU nms_kernel: fp32 inter/(areaA+areaB-inter), compared in
+ * double against iou_thres; boxes offset by cls*max_wh in fp32 first (agnostic -> 0).
+ * Only the first min(count, max_nms) sorted candidates of an image take part
+ * (utils/general.py:702-703).  out [N, max_det, 6] fp32, out_counts [N] int32. */
+typedef struct dmay_nms_params {
+  const void* cand;
+  const void* sorted_idx;
+  const void* img_counts;
+  const void* img_offsets;
+  void* out;
+  void* out_counts;
+  int N;
+  int max_det;
+  int max_nms;
+  int agnostic;
+  float max_wh;
+  double iou_thres;
+} dmay_nms_params;
+int dmay_nms_greedy(const dmay_nms_params* p, dmay_stream_t stream);
+
+/* ---- measurement helpers ---------------------------------------------------------------
+ * plain vectorised copy (roofline calibration inside bench.py) and L2 flush (memset-like
+ * write of a scratch buffer larger than L2). */
+typedef struct dmay_copy_params {
+  const void* src;
+  void* dst;
+  long long bytes;
+} dmay_copy_params;
+int dmay_copy(const dmay_copy_params* p, dmay_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMAYOLO_H_ */
