@@ -1,0 +1,724 @@
+"""Drop-in mirror of the hot-path classes of the reference's models/common.py.
+
+Class names, constructor signatures, attribute names and state_dict keys are the reference's
+(SURVEY.md 8b / Appendix B), so `parse_model`, YAML configs and pickled checkpoints keep working.
+Every class has two bodies:
+  * the reference torch-op body — used in training mode or on CPU tensors (the stride probe in
+    Model.__init__ is a CPU train-mode forward, models/yolo.py:161-170);
+  * `forward_b200` — CUDA eval: bf16 NHWC activations on the sm_100a kernels of libdmayolo.so
+    (BN folded into the conv epilogue, residual adds fused, concatenations written in place).
+    It raises if the shared library is missing; there is no silent fallback.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..ops import ACT_HSWISH, ACT_NONE, ACT_SIGMOID, ACT_SILU, Up
+
+
+class _State:
+    enabled = True  # False -> reference torch bodies everywhere (debug / A-B comparisons only)
+    fuse_scconv_gate = True  # SCConv gate in the k3 conv epilogue instead of the stand-alone gate kernel
+
+
+def set_backend(name: str):
+    """'b200' (default): CUDA eval runs on the kernels.  'torch': reference torch-op bodies."""
+    assert name in ("b200", "torch")
+    _State.enabled = name == "b200"
+
+
+def _first_tensor(x):
+    t = x[0] if isinstance(x, (list, tuple)) else x
+    return t.src if isinstance(t, Up) else t
+
+
+def kernel_path(mod: nn.Module, x) -> bool:
+    return _State.enabled and not mod.training and _first_tensor(x).is_cuda
+
+
+def _materialize(x):
+    if isinstance(x, Up):
+        return x.materialize()
+    if isinstance(x, (list, tuple)):
+        return [_materialize(t) for t in x]
+    return x
+
+
+def torch_body(mod: nn.Module, fn, x):
+    """Run a torch-op body on CUDA for a module that has no kernel path (dtype-matched to its params)."""
+    p = next(mod.parameters(), None)
+    dt = p.dtype if p is not None else torch.float32
+    x = _materialize(x)
+    cast = lambda t: t if t.dtype == dt else t.to(dt)
+    return fn([cast(t) for t in x] if isinstance(x, list) else cast(x))
+
+
+def autopad(k, p=None):
+    """models/common.py:33-48 — 'same' padding."""
+    if p is None:
+        p = k // 2 if isinstance(k, int) else [x // 2 for x in k]
+    return p
+
+
+def _act_code(act: nn.Module):
+    if isinstance(act, nn.SiLU):
+        return ACT_SILU
+    if isinstance(act, nn.Identity):
+        return ACT_NONE
+    if isinstance(act, nn.Hardswish):
+        return ACT_HSWISH
+    if isinstance(act, nn.Sigmoid):
+        return ACT_SIGMOID
+    return None
+
+
+def _ver(*ts):
+    return tuple((t.data_ptr(), t._version) for t in ts if t is not None)
+
+
+def _conv_supported(conv: nn.Conv2d) -> bool:
+    return (conv.groups == 1 and tuple(conv.dilation) == (1, 1) and conv.stride[0] == conv.stride[1]
+            and conv.padding[0] == conv.padding[1] and isinstance(conv.padding, tuple)
+            and conv.padding_mode == 'zeros')
+
+
+def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device):
+    """Cached ConvPack for (conv, bn); rebuilt when any parameter/buffer changed (data_ptr/_version)."""
+    key = (str(device),) + _ver(conv.weight, conv.bias, *((bn.weight, bn.bias, bn.running_mean, bn.running_var)
+                                                          if bn is not None else ())) + ((bn.eps,) if bn is not None else ())
+    cache = owner.__dict__.setdefault('_b200_packs', {})
+    pk = cache.get(slot)
+    if pk is None or pk.key != key:
+        pk = ops.pack_conv(conv.weight, bn=bn, conv_bias=conv.bias, stride=conv.stride[0], pad=conv.padding[0],
+                           device=device)
+        pk.key = key
+        cache[slot] = pk
+    return pk
+
+
+class _PackMixin:
+    """Packs are derived state: never pickled / deep-copied / saved, dropped on .to()/.half()/load_state_dict."""
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop('_b200_packs', None)
+        return d
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__.pop('_b200_packs', None)
+        return super()._apply(fn, *a, **k)
+
+
+class Conv(_PackMixin, nn.Module):
+    """Standard convolution conv+BN+act — models/common.py:50-77."""
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, autopad(k, p), groups=g, bias=False)
+        self.bn = nn.BatchNorm2d(c2)
+        self.act = nn.SiLU() if act is True else (act if isinstance(act, nn.Module) else nn.Identity())
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        return self.act(self.bn(self.conv(x)))
+
+    def forward_fuse(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        return self.act(self.conv(x))
+
+    def forward_b200(self, x, out=None, residual=None):
+        code = _act_code(self.act)
+        bn = getattr(self, 'bn', None)
+        if not _conv_supported(self.conv):
+            y = torch_body(self, (lambda t: self.act(bn(self.conv(t)))) if bn is not None else (lambda t: self.act(self.conv(t))), x)
+            if residual is not None:
+                y = y + residual.to(y.dtype)
+            if out is not None:
+                out.copy_(y)
+                return out
+            return y
+        pk = get_conv_pack(self, 'conv', self.conv, bn, x.device)
+        if code is None:
+            y = ops.conv(x, pk, ACT_NONE)
+            y = self.act(y)
+            if residual is not None:
+                y = y + residual
+            if out is not None:
+                out.copy_(y)
+                return out
+            return y
+        return ops.conv(x, pk, code, out=out, residual=residual)
+
+
+class DWConv(Conv):
+    """Depth-wise convolution — models/common.py:79-82 (grouped: stays on torch ops)."""
+
+    def __init__(self, c1, c2, k=1, s=1, act=True):
+        super().__init__(c1, c2, k, s, g=math.gcd(c1, c2), act=act)
+
+
+class Focus(nn.Module):
+    """Focus wh information into c-space — models/common.py:84-95."""
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
+        super().__init__()
+        self.conv = Conv(c1 * 4, c2, k, s, p, g, act)
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.conv.forward_b200(ops.spd(x))
+        return self.conv(torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1))
+
+
+class Bottleneck(nn.Module):
+    """Standard bottleneck — models/common.py:119-137."""
+
+    def __init__(self, c1, c2, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_, c2, 3, 1, g=g)
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        return x + self.cv2(self.cv1(x)) if self.add else self.cv2(self.cv1(x))
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        return self.cv2.forward_b200(self.cv1.forward_b200(x), out=out, residual=x if self.add else None)
+
+
+class BottleneckCSP(nn.Module):
+    """CSP Bottleneck — models/common.py:139-157."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = nn.Conv2d(c1, c_, 1, 1, bias=False)
+        self.cv3 = nn.Conv2d(c_, c_, 1, 1, bias=False)
+        self.cv4 = Conv(2 * c_, c2, 1, 1)
+        self.bn = nn.BatchNorm2d(2 * c_)
+        self.act = nn.SiLU()
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)))
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return torch_body(self, self._body, x)
+        return self._body(x)
+
+    def _body(self, x):
+        y1 = self.cv3(self.m(self.cv1(x)))
+        y2 = self.cv2(x)
+        return self.cv4(self.act(self.bn(torch.cat((y1, y2), dim=1))))
+
+
+def _run_chain(mods, t, final_out):
+    """Run a Sequential of blocks; the last one writes into `final_out` when it knows how to."""
+    mods = list(mods)
+    for i, b in enumerate(mods):
+        last = i == len(mods) - 1
+        if hasattr(b, 'forward_b200'):
+            t = b.forward_b200(t, out=final_out if last else None) if last else b.forward_b200(t)
+        else:
+            t = b(t)
+            if last and final_out is not None:
+                final_out.copy_(ops.as_act(t))
+                t = final_out
+    return t
+
+
+class C3(nn.Module):
+    """CSP Bottleneck with 3 convolutions — models/common.py:159-182."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)))
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
+
+    def forward_b200(self, x, out=None):
+        # cv1 -> bottlenecks write the first half of the concat slab, cv2 the second half: no torch.cat
+        x = ops.as_act(x)
+        n, _, h, w = x.shape
+        c_ = self.cv1.conv.out_channels
+        slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
+        first = slab[:, :c_]
+        if isinstance(self.m, nn.Sequential) and len(self.m) > 0:
+            _run_chain(self.m, self.cv1.forward_b200(x), first)
+        elif isinstance(self.m, nn.Sequential):
+            self.cv1.forward_b200(x, out=first)
+        else:  # C3 subclasses with a non-Sequential inner module (torch body)
+            t = self.m(self.cv1.forward_b200(x))
+            first.copy_(ops.as_act(t))
+        self.cv2.forward_b200(x, out=slab[:, c_:])
+        return self.cv3.forward_b200(slab, out=out)
+
+
+class SPP(nn.Module):
+    """Spatial Pyramid Pooling — models/common.py:212-227."""
+
+    def __init__(self, c1, c2, k=(5, 9, 13)):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_ * (len(k) + 1), c2, 1, 1)
+        self.m = nn.ModuleList([nn.MaxPool2d(kernel_size=x, stride=1, padding=x // 2) for x in k])
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        x = self.cv1(x)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            return self.cv2(torch.cat([x] + [m(x) for m in self.m], 1))
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        n, _, h, w = x.shape
+        c_ = self.cv1.conv.out_channels
+        ks = [m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0] for m in self.m]
+        slab = ops.empty_nhwc(n, c_ * (len(ks) + 1), h, w, x.device)
+        x1 = self.cv1.forward_b200(x, out=slab[:, :c_])
+        if len(ks) == 3 and ks[1] == 2 * ks[0] - 1 and ks[2] == 3 * ks[0] - 2:  # (5,9,13): one cascaded pass
+            ops.sppf_pool3(x1, slab[:, c_:2 * c_], slab[:, 2 * c_:3 * c_], slab[:, 3 * c_:], ks[0])
+        else:
+            for i, k in enumerate(ks):
+                ops.maxpool_s1(x1, k, out=slab[:, (i + 1) * c_:(i + 2) * c_])
+        return self.cv2.forward_b200(slab, out=out)
+
+
+class SPPF(nn.Module):
+    """Spatial Pyramid Pooling - Fast — models/common.py:243-258."""
+
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1, 1)
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        x = self.cv1(x)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            y1 = self.m(x)
+            y2 = self.m(y1)
+            return self.cv2(torch.cat([x, y1, y2, self.m(y2)], 1))
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        n, _, h, w = x.shape
+        c_ = self.cv1.conv.out_channels
+        k = self.m.kernel_size if isinstance(self.m.kernel_size, int) else self.m.kernel_size[0]
+        slab = ops.empty_nhwc(n, 4 * c_, h, w, x.device)
+        x1 = self.cv1.forward_b200(x, out=slab[:, :c_])
+        ops.sppf_pool3(x1, slab[:, c_:2 * c_], slab[:, 2 * c_:3 * c_], slab[:, 3 * c_:], k)
+        return self.cv2.forward_b200(slab, out=out)
+
+
+class Contract(nn.Module):
+    """Contract width-height into channels — models/common.py:357-369."""
+
+    def __init__(self, gain=2):
+        super().__init__()
+        self.gain = gain
+
+    def forward(self, x):
+        x = _materialize(x)
+        b, c, h, w = x.size()
+        s = self.gain
+        x = x.view(b, c, h // s, s, w // s, s) if x.is_contiguous() else x.reshape(b, c, h // s, s, w // s, s)
+        x = x.permute(0, 3, 5, 1, 2, 4).contiguous()
+        return x.view(b, c * s * s, h // s, w // s)
+
+
+class Expand(nn.Module):
+    """Expand channels into width-height — models/common.py:371-383."""
+
+    def __init__(self, gain=2):
+        super().__init__()
+        self.gain = gain
+
+    def forward(self, x):
+        x = _materialize(x)
+        b, c, h, w = x.size()
+        s = self.gain
+        x = x.reshape(b, s, s, c // s ** 2, h, w)
+        x = x.permute(0, 3, 4, 1, 5, 2).contiguous()
+        return x.view(b, c // s ** 2, h * s, w * s)
+
+
+class Concat(nn.Module):
+    """Concatenate a list of tensors along dimension — models/common.py:656-664."""
+
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+    def forward(self, x):
+        if kernel_path(self, x) and self.d == 1 and all(_is_act_like(t) for t in x):
+            return ops.concat(x)
+        return torch.cat(_materialize(x), self.d)
+
+
+def _is_act_like(t):
+    t = t.src if isinstance(t, Up) else t
+    return t.dim() == 4 and t.shape[1] % 8 == 0
+
+
+class _AdWeights:
+    """Normalised BiFPN weights w/(sum w + eps), cached on the host per parameter version (one D2H)."""
+
+    def _norm_weights(self):
+        key = _ver(self.w)
+        c = self.__dict__.get('_b200_w')
+        if c is None or c[0] != key:
+            w = self.w.detach().float()
+            c = (key, (w / (torch.sum(w, dim=0) + self.epsilon)).tolist())
+            self.__dict__['_b200_w'] = c
+        return c[1]
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop('_b200_w', None)
+        return d
+
+
+class AdConcat2(_AdWeights, nn.Module):
+    """BiFPN learned-weight fusion of two branches, concatenated — models/common.py:994-1008."""
+
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+        self.w = nn.Parameter(torch.ones(2, dtype=torch.float32), requires_grad=True)
+        self.epsilon = 0.0001
+
+    def forward(self, x):
+        if kernel_path(self, x) and self.d == 1:
+            return ops.adconcat(x, self._norm_weights())
+        x = _materialize(x)
+        w = self.w
+        weight = w / (torch.sum(w, dim=0) + self.epsilon)
+        x = [weight[0] * x[0], weight[1] * x[1]]
+        return torch.cat(x, self.d)
+
+
+class AdConcat3(_AdWeights, nn.Module):
+    """Three-branch variant — models/common.py:1010-1026."""
+
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+        self.w = nn.Parameter(torch.ones(3, dtype=torch.float32), requires_grad=True)
+        self.epsilon = 0.0001
+
+    def forward(self, x):
+        if kernel_path(self, x) and self.d == 1:
+            return ops.adconcat(x, self._norm_weights())
+        x = _materialize(x)
+        w = self.w
+        weight = w / (torch.sum(w, dim=0) + self.epsilon)
+        x = [weight[0] * x[0], weight[1] * x[1], weight[2] * x[2]]
+        return torch.cat(x, self.d)
+
+
+class Adapt_Add2(_AdWeights, nn.Module):
+    """Learned-weight add of two branches + SiLU — models/common.py:1028-1045."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = nn.Parameter(torch.ones(2, dtype=torch.float32), requires_grad=True)
+        self.epsilon = 0.0001
+        self.silu = nn.SiLU()
+
+    def forward(self, x):
+        x = _materialize(x)
+        if kernel_path(self, x):
+            return ops.adapt_add(x, self._norm_weights())
+        w = self.w
+        weight = w / (torch.sum(w, dim=0) + self.epsilon)
+        return self.silu(weight[0] * x[0] + weight[1] * x[1])
+
+
+class Adapt_Add3(_PackMixin, _AdWeights, nn.Module):
+    """Three-branch add with a shared 1x1 conv on the first two — models/common.py:1047-1061."""
+
+    def __init__(self, d1, d2, d3):
+        super().__init__()
+        self.w = nn.Parameter(torch.ones(3, dtype=torch.float32), requires_grad=True)
+        self.epsilon = 0.0001
+        self.conv = nn.Conv2d(d1, d3, kernel_size=1, stride=1, padding=0)
+        self.silu = nn.SiLU()
+
+    def forward(self, x):
+        x = _materialize(x)
+        if kernel_path(self, x):
+            pk = get_conv_pack(self, 'conv', self.conv, None, x[0].device)
+            a, b = ops.conv(x[0], pk, ACT_NONE), ops.conv(x[1], pk, ACT_NONE)
+            return ops.adapt_add([a, b, x[2]], self._norm_weights())
+        w = self.w
+        weight = w / (torch.sum(w, dim=0) + self.epsilon)
+        return self.silu(weight[0] * self.conv(x[0]) + weight[1] * self.conv(x[1]) + weight[2] * x[2])
+
+
+class CoorAttention(nn.Module):
+    """Coordinate Attention — models/common.py:1158-1207."""
+
+    def __init__(self, c1, c2, reduction=32):
+        super().__init__()
+        self.pool_h = nn.AdaptiveAvgPool2d((None, 1))
+        self.pool_w = nn.AdaptiveAvgPool2d((1, None))
+        c_ = max(8, c1 // reduction)
+        self.conv1 = nn.Conv2d(c1, c_, kernel_size=1, stride=1, padding=0)
+        self.bn1 = nn.BatchNorm2d(c_)
+        self.act = nn.Hardswish()
+        self.conv_w = nn.Conv2d(c_, c2, kernel_size=1, stride=1, padding=0)
+        self.conv_h = nn.Conv2d(c_, c2, kernel_size=1, stride=1, padding=0)
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        identity = x
+        n, c, h, w = x.size()
+        x_h = self.pool_h(x)
+        x_w = self.pool_w(x).permute(0, 1, 3, 2)
+        y = torch.cat([x_h, x_w], dim=2)
+        y = self.act(self.bn1(self.conv1(y)))
+        x_h, x_w = torch.split(y, [h, w], dim=2)
+        x_w = x_w.permute(0, 1, 3, 2)
+        a_h = self.conv_h(x_h).sigmoid()
+        a_w = self.conv_w(x_w).sigmoid()
+        return identity * a_w * a_h
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop('_b200_ca', None)
+        return d
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__.pop('_b200_ca', None)
+        return super()._apply(fn, *a, **k)
+
+    def forward_b200(self, x, out=None):
+        if not isinstance(self.act, nn.Hardswish) or self.conv_h.out_channels != self.conv1.in_channels:
+            raise ops.DmayError("CoorAttention kernel path needs Hardswish and c2 == c1")
+        key = (str(x.device),) + _ver(self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias,
+                                      self.bn1.running_mean, self.bn1.running_var, self.conv_h.weight,
+                                      self.conv_h.bias, self.conv_w.weight, self.conv_w.bias) + (self.bn1.eps,)
+        pk = self.__dict__.get('_b200_ca')
+        if pk is None or pk.key != key:
+            pk = ops.pack_coordatt(self.conv1, self.bn1, self.conv_h, self.conv_w, x.device)
+            pk.key = key
+            self.__dict__['_b200_ca'] = pk
+        return ops.coordatt(x, pk, out=out)
+
+
+CA = CoorAttention  # the YAMLs name `CA`; the reference never defines it
+
+
+class CABottleneck(nn.Module):
+    """Bottleneck + CoordAtt — models/common.py:1209-1227."""
+
+    def __init__(self, c1, c2, shortcut=True, g=1, e=0.5, reduction=32):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_, c2, 3, 1, g=g)
+        self.ca = CoorAttention(c2, c2, reduction)
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        return x + self.ca(self.cv2(self.cv1(x))) if self.add else self.ca(self.cv2(self.cv1(x)))
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        y = self.ca.forward_b200(self.cv2.forward_b200(self.cv1.forward_b200(x)), out=None if self.add else out)
+        if self.add:  # x + ca(...): learned-weight add kernel is silu-fused, so use the exact 2-input sum
+            y = _residual_add(x, y, out)
+        return y
+
+
+def _residual_add(a, b, out=None):
+    y = torch.add(a, b) if out is None else torch.add(a, b, out=out)
+    return y
+
+
+class C3CA(C3):
+    """C3 with CABottleneck — models/common.py:1229-1235."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__(c1, c2, n, shortcut, g, e)
+        c_ = int(c2 * e)
+        self.m = nn.Sequential(*(CABottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)))
+
+
+class SPPCSPC(nn.Module):
+    """CSP SPP — models/common.py:1237-1255."""
+
+    def __init__(self, c1, c2, n=1, shortcut=False, g=1, e=0.5, k=(5, 9, 13)):
+        super().__init__()
+        c_ = int(2 * c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(c_, c_, 3, 1)
+        self.cv4 = Conv(c_, c_, 1, 1)
+        self.m = nn.ModuleList([nn.MaxPool2d(kernel_size=x, stride=1, padding=x // 2) for x in k])
+        self.cv5 = Conv(4 * c_, c_, 1, 1)
+        self.cv6 = Conv(c_, c_, 3, 1)
+        self.cv7 = Conv(2 * c_, c2, 1, 1)
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        x1 = self.cv4(self.cv3(self.cv1(x)))
+        y1 = self.cv6(self.cv5(torch.cat([x1] + [m(x1) for m in self.m], 1)))
+        y2 = self.cv2(x)
+        return self.cv7(torch.cat((y1, y2), dim=1))
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        n, _, h, w = x.shape
+        c_ = self.cv1.conv.out_channels
+        ks = [m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0] for m in self.m]
+        slab4 = ops.empty_nhwc(n, (len(ks) + 1) * c_, h, w, x.device)
+        x1 = self.cv4.forward_b200(self.cv3.forward_b200(self.cv1.forward_b200(x)), out=slab4[:, :c_])
+        if len(ks) == 3 and ks[1] == 2 * ks[0] - 1 and ks[2] == 3 * ks[0] - 2:
+            ops.sppf_pool3(x1, slab4[:, c_:2 * c_], slab4[:, 2 * c_:3 * c_], slab4[:, 3 * c_:], ks[0])
+        else:
+            for i, k in enumerate(ks):
+                ops.maxpool_s1(x1, k, out=slab4[:, (i + 1) * c_:(i + 2) * c_])
+        slab2 = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
+        self.cv6.forward_b200(self.cv5.forward_b200(slab4), out=slab2[:, :c_])
+        self.cv2.forward_b200(x, out=slab2[:, c_:])
+        return self.cv7.forward_b200(slab2, out=out)
+
+
+class SPPFCSPC(nn.Module):
+    """CSP SPPF: cascaded 5x5 max-pools — models/common.py:1257-1276."""
+
+    def __init__(self, c1, c2, n=1, shortcut=False, g=1, e=0.5, k=5):
+        super().__init__()
+        c_ = int(2 * c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(c_, c_, 3, 1)
+        self.cv4 = Conv(c_, c_, 1, 1)
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+        self.cv5 = Conv(4 * c_, c_, 1, 1)
+        self.cv6 = Conv(c_, c_, 3, 1)
+        self.cv7 = Conv(2 * c_, c2, 1, 1)
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        x1 = self.cv4(self.cv3(self.cv1(x)))
+        x2 = self.m(x1)
+        x3 = self.m(x2)
+        y1 = self.cv6(self.cv5(torch.cat((x1, x2, x3, self.m(x3)), 1)))
+        y2 = self.cv2(x)
+        return self.cv7(torch.cat((y1, y2), dim=1))
+
+    def forward_b200(self, x, out=None):
+        # cv4 writes x1 into channels [0,c_) of the 4c_ slab cv5 reads; the pool cascade fills the
+        # other three quarters in one pass; cv6 / cv2 write the two halves of cv7's input.
+        x = ops.as_act(x)
+        n, _, h, w = x.shape
+        c_ = self.cv1.conv.out_channels
+        k = self.m.kernel_size if isinstance(self.m.kernel_size, int) else self.m.kernel_size[0]
+        slab4 = ops.empty_nhwc(n, 4 * c_, h, w, x.device)
+        x1 = self.cv4.forward_b200(self.cv3.forward_b200(self.cv1.forward_b200(x)), out=slab4[:, :c_])
+        ops.sppf_pool3(x1, slab4[:, c_:2 * c_], slab4[:, 2 * c_:3 * c_], slab4[:, 3 * c_:], k)
+        slab2 = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
+        self.cv6.forward_b200(self.cv5.forward_b200(slab4), out=slab2[:, :c_])
+        self.cv2.forward_b200(x, out=slab2[:, c_:])
+        return self.cv7.forward_b200(slab2, out=out)
+
+
+class SCConv(_PackMixin, nn.Module):
+    """Self-calibrated convolution (SCNet, CVPR'20) — models/common.py:1279-1316."""
+
+    def __init__(self, c1, c2, stride, groups=1, dilation=1, pooling_r=4):
+        super().__init__()
+        self.k2 = nn.Sequential(
+            nn.AvgPool2d(kernel_size=pooling_r, stride=pooling_r),
+            nn.Conv2d(c1, c1, kernel_size=3, stride=1, padding=autopad(3, None), dilation=dilation, groups=groups,
+                      bias=False),
+            nn.BatchNorm2d(c1),
+        )
+        self.k3 = nn.Sequential(
+            nn.Conv2d(c1, c1, kernel_size=3, stride=1, padding=autopad(3, None), dilation=dilation, groups=groups,
+                      bias=False),
+            nn.BatchNorm2d(c1),
+        )
+        self.k4 = nn.Sequential(
+            nn.Conv2d(c1, c2, kernel_size=3, stride=stride, padding=autopad(3, None), dilation=dilation, groups=groups,
+                      bias=False),
+            nn.BatchNorm2d(c2),
+        )
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        identity = x
+        y_ = F.interpolate(self.k2(x), identity.size()[2:])
+        y_ = torch.add(identity, y_)
+        out = torch.sigmoid(y_)
+        out = torch.mul(self.k3(x), out)
+        return self.k4(out)
+
+    def forward_b200(self, x, out=None):
+        convs = (self.k2[1], self.k3[0], self.k4[0])
+        if not all(_conv_supported(c) for c in convs):
+            self._unsupported()
+        x = ops.as_act(x)
+        r = self.k2[0].kernel_size if isinstance(self.k2[0].kernel_size, int) else self.k2[0].kernel_size[0]
+        k2o = ops.conv(ops.avgpool(x, r), get_conv_pack(self, 'k2', self.k2[1], self.k2[2], x.device), ACT_NONE)
+        pk3 = get_conv_pack(self, 'k3', self.k3[0], self.k3[1], x.device)
+        if _State.fuse_scconv_gate:
+            g = ops.conv(x, pk3, ACT_NONE, gate=(x, k2o))       # k3(x) * sigmoid(x + up(k2)) in the epilogue
+        else:
+            g = ops.scconv_gate(x, ops.conv(x, pk3, ACT_NONE), k2o)
+        return ops.conv(g, get_conv_pack(self, 'k4', self.k4[0], self.k4[1], x.device), ACT_NONE, out=out)
+
+    def _unsupported(self):
+        raise ops.DmayError("SCConv kernel path supports groups=1, dilation=1 only")
+
+
+class space_to_depth(nn.Module):
+    """SPD-Conv pixel-unshuffle — models/common.py:1451-1458."""
+
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+    def forward(self, x):
+        if kernel_path(self, x) and x.shape[1] % 8 == 0:
+            return ops.spd(_materialize(x))
+        x = _materialize(x)
+        return torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)
+
+
+class SM(space_to_depth):
+    """Same arithmetic under a second name — models/common.py:1460-1467."""

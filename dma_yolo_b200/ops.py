@@ -1,0 +1,501 @@
+"""Tensor-level wrappers over the C-ABI (include/dmayolo.h).
+
+Activations are torch tensors with NCHW *shape* and channels_last *strides* (NHWC in memory),
+bf16.  A channel slice `slab[:, a:b]` of such a tensor is also accepted everywhere ("ld" = the
+slab's channel count); that is how concatenations are written in place by their producers.
+PyTorch is used for device memory and streams only; every arithmetic op below is one of our kernels.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+from ._lib import CONSTS, DmayError, call
+
+ACT_NONE, ACT_SILU, ACT_HSWISH, ACT_SIGMOID = 0, 1, 2, 3
+_DT = {torch.bfloat16: CONSTS["DMAY_DT_BF16"], torch.float32: CONSTS["DMAY_DT_F32"],
+       torch.float16: CONSTS["DMAY_DT_F16"], torch.uint8: CONSTS["DMAY_DT_U8"]}
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------------
+# layout helpers
+# --------------------------------------------------------------------------------------------
+def is_nhwc(t: torch.Tensor) -> bool:
+    """NCHW-shaped tensor whose memory is [N,H,W,ld] (dense pixels, channel stride 1)."""
+    if t.dim() != 4:
+        return False
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    if c > 1 and sc != 1:
+        return False
+    ld = sw if w > 1 else (sh if h > 1 else (sn if n > 1 else c))
+    if ld < c:
+        return False
+    if w > 1 and sw != ld:
+        return False
+    if h > 1 and sh != w * ld:
+        return False
+    if n > 1 and sn != h * w * ld:
+        return False
+    return True
+
+
+def ld_of(t: torch.Tensor) -> int:
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    if w > 1:
+        return sw
+    if h > 1:
+        return sh
+    if n > 1:
+        return sn
+    return c
+
+
+def empty_nhwc(n, c, h, w, device, dtype=torch.bfloat16, c_alloc=None) -> torch.Tensor:
+    """NCHW-shaped, NHWC-in-memory tensor; c_alloc > c returns a channel-slice view of a padded slab."""
+    ca = c_alloc or c
+    buf = torch.empty((n, h, w, ca), device=device, dtype=dtype)
+    t = buf.permute(0, 3, 1, 2)
+    return t if ca == c else t[:, :c]
+
+
+def as_act(x: torch.Tensor) -> torch.Tensor:
+    """Any 4-D CUDA tensor -> bf16 NHWC activation (our layout kernel for contiguous NCHW input)."""
+    if x.dtype == torch.bfloat16 and is_nhwc(x) and ld_of(x) % 8 == 0 and x.shape[1] % 8 == 0 and x.data_ptr() % 16 == 0:
+        return x
+    n, c, h, w = x.shape
+    if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        x = x.float()
+    if not x.is_contiguous():
+        x = x.contiguous()
+    cp = round_up(c, 8)
+    if cp != c:
+        y = torch.zeros((n, h, w, cp), device=x.device, dtype=torch.bfloat16).permute(0, 3, 1, 2)
+    else:
+        y = empty_nhwc(n, c, h, w, x.device)
+    call("dmay_layout_convert", _stream(x), x=x.data_ptr(), y=y.data_ptr(), N=n, C=c, H=h, W=w, ld=cp,
+         dtype=_DT[x.dtype], dir=1)
+    return y if cp == c else y[:, :c]
+
+
+def to_nchw(x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """bf16 NHWC activation -> contiguous NCHW tensor of `dtype` (glue for torch-op modules)."""
+    x = as_act(x)
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, h, w), device=x.device, dtype=dtype)
+    call("dmay_layout_convert", _stream(x), x=x.data_ptr(), y=y.data_ptr(), N=n, C=c, H=h, W=w, ld=ld_of(x),
+         dtype=_DT[dtype], dir=0)
+    return y
+
+
+def input_prep(x: torch.Tensor, spd: bool, cpad: int = 16, mul: float = 1.0) -> torch.Tensor:
+    """NCHW image {f32,f16,bf16,u8} -> NHWC bf16 [N,cpad,H(/2),W(/2)], optionally 2x2 pixel-unshuffled."""
+    n, c, h, w = x.shape
+    if not x.is_contiguous():
+        x = x.contiguous()
+    ho, wo = (h // 2, w // 2) if spd else (h, w)
+    y = empty_nhwc(n, cpad, ho, wo, x.device)
+    call("dmay_input_prep", _stream(x), x=x.data_ptr(), y=y.data_ptr(), N=n, C=c, H=h, W=w, Cpad=cpad,
+         spd=int(spd), in_dtype=_DT[x.dtype], mul=float(mul))
+    return y
+
+
+# --------------------------------------------------------------------------------------------
+# a1/a2 conv
+# --------------------------------------------------------------------------------------------
+@dataclass
+class ConvPack:
+    """Device-resident operands of one conv: bf16 weights [Cout_pad][kh][kw][Cin_pad] + fp32 scale/bias."""
+    w: torch.Tensor
+    scale: torch.Tensor
+    bias: torch.Tensor
+    cin: int          # logical input channels the caller passes
+    cin_pad: int      # channels of the tensor the kernel reads
+    cout: int
+    cout_pad: int
+    kh: int
+    kw: int
+    stride: int
+    pad: int
+    stem_spd: bool = False   # 2k x 2k stride-2 conv rewritten as k x k stride-1 over pixel-unshuffled input
+    key: tuple = field(default_factory=tuple)
+
+
+def pack_conv(weight: torch.Tensor, bn=None, conv_bias=None, stride=1, pad=0, device=None,
+              allow_stem_spd=True) -> ConvPack:
+    """Fold BN (utils/torch_utils.py:198-218 arithmetic, kept as fp32 per-channel scale/bias applied to the
+    fp32 accumulator) and re-lay the weights K-major for the implicit GEMM."""
+    device = device or weight.device
+    w = weight.detach().float()
+    cout, cin, kh, kw = w.shape
+    if bn is not None:
+        inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        g = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(inv)
+        b = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(inv)
+        scale = g * inv
+        bias = b - bn.running_mean.detach().float() * scale
+        if conv_bias is not None:
+            bias = bias + conv_bias.detach().float() * scale
+    else:
+        scale = torch.ones(cout, device=w.device)
+        bias = conv_bias.detach().float() if conv_bias is not None else torch.zeros(cout, device=w.device)
+    stem = (allow_stem_spd and cin <= 4 and kh == kw and kh % 2 == 0 and stride == 2 and pad % 2 == 0)
+    wk = w.permute(0, 2, 3, 1)  # [Cout, kh, kw, Cin]
+    if stem:
+        k2 = kh // 2
+        # W2[co, a, b, (dy + 2dx)*cin + c] = W[co, c, 2a+dy, 2b+dx]
+        w6 = wk.reshape(cout, k2, 2, k2, 2, cin)          # co, a, dy, b, dx, c
+        w2 = w6.permute(0, 1, 3, 4, 2, 5).reshape(cout, k2, k2, 4 * cin)  # (dx, dy, c) -> q = dy + 2dx
+        wk, kh, kw, stride, pad = w2, k2, k2, 1, pad // 2
+        cin_eff = 4 * cin
+    else:
+        cin_eff = cin
+    cin_pad = round_up(cin_eff, 16)
+    cout_pad = round_up(cout, 16)
+    wp = torch.zeros((cout_pad, kh, kw, cin_pad), dtype=torch.float32, device=w.device)
+    wp[:cout, :, :, :cin_eff] = wk
+    sp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    sp[:cout] = scale
+    bp[:cout] = bias
+    return ConvPack(w=wp.to(device=device, dtype=torch.bfloat16).contiguous(), scale=sp.to(device).contiguous(),
+                    bias=bp.to(device).contiguous(), cin=cin, cin_pad=cin_pad, cout=cout, cout_pad=cout_pad,
+                    kh=kh, kw=kw, stride=stride, pad=pad, stem_spd=stem)
+
+
+def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor | None = None,
+         residual: torch.Tensor | None = None, gate: tuple | None = None, out_fp32: bool = False,
+         block_n: int = 0, num_sms: int = 0) -> torch.Tensor:
+    """y = act(scale * conv(x, w) + bias) (+ residual) | (* sigmoid(gate_x + up(gate_k)))."""
+    if pk.stem_spd:
+        if x.shape[1] != pk.cin:
+            raise DmayError(f"conv: expected {pk.cin} input channels, got {x.shape[1]}")
+        x = input_prep(x, spd=True, cpad=pk.cin_pad)
+    elif x.shape[1] != pk.cin_pad or not (x.dtype == torch.bfloat16 and is_nhwc(x)):
+        if x.shape[1] != pk.cin:
+            raise DmayError(f"conv: expected {pk.cin} input channels, got {x.shape[1]}")
+        if pk.cin != pk.cin_pad:
+            if x.dtype == torch.bfloat16 and is_nhwc(x):
+                x = to_nchw(x, torch.bfloat16)
+            x = input_prep(x, spd=False, cpad=pk.cin_pad)
+        else:
+            x = as_act(x)
+    n, _, h, w = x.shape
+    ho = (h + 2 * pk.pad - pk.kh) // pk.stride + 1
+    wo = (w + 2 * pk.pad - pk.kw) // pk.stride + 1
+    cstore = round_up(pk.cout, 8)
+    odt = torch.float32 if out_fp32 else torch.bfloat16
+    if out is None:
+        out = empty_nhwc(n, pk.cout, ho, wo, x.device, odt, c_alloc=cstore)
+    else:
+        if tuple(out.shape) != (n, pk.cout, ho, wo) or out.dtype != odt or not is_nhwc(out):
+            raise DmayError(f"conv: bad `out` {tuple(out.shape)} {out.dtype}, want {(n, pk.cout, ho, wo)} {odt} NHWC")
+        if pk.cout % 8:
+            raise DmayError("conv: writing into a slab slice needs Cout % 8 == 0")
+    f = dict(x=x.data_ptr(), w=pk.w.data_ptr(), scale=pk.scale.data_ptr(), bias=pk.bias.data_ptr(), y=out.data_ptr(),
+             N=n, H=h, W=w, Cin=pk.cin_pad, ldx=ld_of(x), Cout=cstore, Cout_pad=pk.cout_pad, kh=pk.kh, kw=pk.kw,
+             stride=pk.stride, pad=pk.pad, Ho=ho, Wo=wo, ldy=ld_of(out), act=act,
+             out_dtype=_DT[odt], block_n=block_n, num_sms=num_sms)
+    if residual is not None:
+        residual = as_act(residual)
+        if tuple(residual.shape) != (n, pk.cout, ho, wo):
+            raise DmayError("conv: residual shape mismatch")
+        f.update(residual=residual.data_ptr(), ldr=ld_of(residual))
+    if gate is not None:
+        gx, gk = gate
+        gx, gk = as_act(gx), as_act(gk)
+        if tuple(gx.shape) != (n, pk.cout, ho, wo) or gk.shape[1] != pk.cout or ld_of(gk) != pk.cout:
+            raise DmayError("conv: gate shape mismatch")
+        f.update(gate_x=gx.data_ptr(), gate_k=gk.data_ptr(), ldgx=ld_of(gx), gHk=gk.shape[2], gWk=gk.shape[3])
+    call("dmay_conv_bn_act", _stream(x), **f)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# memory-bound blocks
+# --------------------------------------------------------------------------------------------
+def spd(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    x = as_act(x)
+    n, c, h, w = x.shape
+    if out is None:
+        out = empty_nhwc(n, 4 * c, h // 2, w // 2, x.device)
+    call("dmay_spd", _stream(x), x=x.data_ptr(), y=out.data_ptr(), N=n, H=h, W=w, C=c, ldx=ld_of(x), ldy=ld_of(out))
+    return out
+
+
+class Up:
+    """A nearest-neighbour 2^k upsample that has not been materialised (fused into its consumer)."""
+
+    def __init__(self, src: torch.Tensor, log2f: int):
+        self.src, self.log2f = src, log2f
+
+    @property
+    def shape(self):
+        n, c, h, w = self.src.shape
+        return torch.Size((n, c, h << self.log2f, w << self.log2f))
+
+    def materialize(self) -> torch.Tensor:
+        return upsample(self.src, 1 << self.log2f)
+
+
+def adconcat(xs, weights, out: torch.Tensor | None = None) -> torch.Tensor:
+    """cat([w_i * x_i], 1); x_i may be an `Up` (read at reduced resolution)."""
+    if not 2 <= len(xs) <= 3:
+        raise DmayError("adconcat takes 2 or 3 inputs")
+    srcs, ups = [], []
+    for t in xs:
+        if isinstance(t, Up):
+            srcs.append(as_act(t.src))
+            ups.append(t.log2f)
+        else:
+            srcs.append(as_act(t))
+            ups.append(0)
+    n, _, h0, w0 = srcs[0].shape
+    h, w = h0 << ups[0], w0 << ups[0]
+    for s, u in zip(srcs, ups):
+        if (s.shape[2] << u, s.shape[3] << u) != (h, w) or s.shape[0] != n:
+            raise DmayError("adconcat: spatial/batch mismatch")
+    ctot = sum(s.shape[1] for s in srcs)
+    if out is None:
+        out = empty_nhwc(n, ctot, h, w, srcs[0].device)
+    f = dict(y=out.data_ptr(), n_in=len(srcs), N=n, H=h, W=w, ldy=ld_of(out))
+    for i, (s, u, wt) in enumerate(zip(srcs, ups, weights)):
+        f[f"x{i}"] = s.data_ptr()
+        f[f"C{i}"] = s.shape[1]
+        f[f"ld{i}"] = ld_of(s)
+        f[f"up{i}"] = u
+        f[f"w{i}"] = float(wt)
+    call("dmay_adconcat", _stream(srcs[0]), **f)
+    return out
+
+
+def concat(xs, out=None):
+    """torch.cat(xs, 1) for 2..3 inputs (weights 1.0: an exact copy); longer lists are folded pairwise."""
+    xs = list(xs)
+    while len(xs) > 3:
+        xs = [adconcat(xs[:3], (1.0, 1.0, 1.0))] + xs[3:]
+    if len(xs) == 1:
+        return xs[0].materialize() if isinstance(xs[0], Up) else xs[0]
+    return adconcat(xs, (1.0,) * len(xs), out=out)
+
+
+def adapt_add(xs, weights, out=None) -> torch.Tensor:
+    xs = [as_act(t) for t in xs]
+    n, c, h, w = xs[0].shape
+    if out is None:
+        out = empty_nhwc(n, c, h, w, xs[0].device)
+    f = dict(y=out.data_ptr(), n_in=len(xs), npix=n * h * w, C=c, ldy=ld_of(out))
+    for i, (s, wt) in enumerate(zip(xs, weights)):
+        f[f"x{i}"] = s.data_ptr()
+        f[f"ld{i}"] = ld_of(s)
+        f[f"w{i}"] = float(wt)
+    call("dmay_adaptadd", _stream(xs[0]), **f)
+    return out
+
+
+def upsample(x: torch.Tensor, factor: int = 2, out=None) -> torch.Tensor:
+    x = as_act(x)
+    n, c, h, w = x.shape
+    if out is None:
+        out = empty_nhwc(n, c, h * factor, w * factor, x.device)
+    call("dmay_upsample_nearest", _stream(x), x=x.data_ptr(), y=out.data_ptr(), N=n, H=h, W=w, C=c, ldx=ld_of(x),
+         ldy=ld_of(out), factor=factor)
+    return out
+
+
+def sppf_pool3(x: torch.Tensor, y1, y2, y3, k: int = 5):
+    n, c, h, w = x.shape
+    call("dmay_sppf_pool3", _stream(x), x=x.data_ptr(), y1=y1.data_ptr(), y2=y2.data_ptr(), y3=y3.data_ptr(), N=n, H=h,
+         W=w, C=c, ldx=ld_of(x), ldy=ld_of(y1), k=k)
+
+
+def maxpool_s1(x: torch.Tensor, k: int, out=None) -> torch.Tensor:
+    x = as_act(x)
+    n, c, h, w = x.shape
+    if out is None:
+        out = empty_nhwc(n, c, h, w, x.device)
+    call("dmay_maxpool_s1", _stream(x), x=x.data_ptr(), y=out.data_ptr(), N=n, H=h, W=w, C=c, ldx=ld_of(x),
+         ldy=ld_of(out), k=k)
+    return out
+
+
+def avgpool(x: torch.Tensor, r: int, out=None) -> torch.Tensor:
+    x = as_act(x)
+    n, c, h, w = x.shape
+    if out is None:
+        out = empty_nhwc(n, c, h // r, w // r, x.device)
+    call("dmay_avgpool", _stream(x), x=x.data_ptr(), y=out.data_ptr(), N=n, H=h, W=w, C=c, ldx=ld_of(x), ldy=ld_of(out),
+         r=r)
+    return out
+
+
+def scconv_gate(x, k3, k2, out=None) -> torch.Tensor:
+    x, k3, k2 = as_act(x), as_act(k3), as_act(k2)
+    n, c, h, w = x.shape
+    if out is None:
+        out = empty_nhwc(n, c, h, w, x.device)
+    call("dmay_scconv_gate", _stream(x), x=x.data_ptr(), k3=k3.data_ptr(), k2=k2.data_ptr(), y=out.data_ptr(), N=n, H=h,
+         W=w, C=c, Hk=k2.shape[2], Wk=k2.shape[3], ldx=ld_of(x), ld3=ld_of(k3), ld2=ld_of(k2), ldy=ld_of(out))
+    return out
+
+
+@dataclass
+class CoordAttPack:
+    w1: torch.Tensor
+    b1: torch.Tensor
+    s1: torch.Tensor
+    t1: torch.Tensor
+    whT: torch.Tensor
+    bh: torch.Tensor
+    wwT: torch.Tensor
+    bw: torch.Tensor
+    c: int
+    cm: int
+    key: tuple = field(default_factory=tuple)
+
+
+def pack_coordatt(conv1, bn1, conv_h, conv_w, device) -> CoordAttPack:
+    """models/common.py:1168-1181 parameters -> fp32 device operands (BN folded to s1/t1; W_h/W_w transposed)."""
+    cm, c = conv1.weight.shape[:2]
+    f = lambda t: t.detach().float().to(device).contiguous()
+    inv = torch.rsqrt(bn1.running_var.detach().float() + bn1.eps)
+    s1 = bn1.weight.detach().float() * inv
+    t1 = bn1.bias.detach().float() - bn1.running_mean.detach().float() * s1
+    b1 = conv1.bias if conv1.bias is not None else torch.zeros(cm)
+    zeros = lambda m: m.bias if m.bias is not None else torch.zeros(m.weight.shape[0])
+    return CoordAttPack(w1=f(conv1.weight.reshape(cm, c)), b1=f(b1), s1=f(s1), t1=f(t1),
+                        whT=f(conv_h.weight.reshape(-1, cm).t()), bh=f(zeros(conv_h)),
+                        wwT=f(conv_w.weight.reshape(-1, cm).t()), bw=f(zeros(conv_w)), c=c, cm=cm)
+
+
+def coordatt(x: torch.Tensor, pk: CoordAttPack, out=None, return_gates=False):
+    x = as_act(x)
+    n, c, h, w = x.shape
+    if c != pk.c or pk.whT.shape[1] != c:
+        raise DmayError("coordatt: channel mismatch (needs c2 == c1)")
+    if out is None:
+        out = empty_nhwc(n, c, h, w, x.device)
+    pooled = torch.empty((n, h + w, c), device=x.device, dtype=torch.float32)
+    gates = torch.empty((n, h + w, c), device=x.device, dtype=torch.float32)
+    call("dmay_coordatt", _stream(x), x=x.data_ptr(), y=out.data_ptr(), pooled=pooled.data_ptr(), gates=gates.data_ptr(),
+         w1=pk.w1.data_ptr(), b1=pk.b1.data_ptr(), s1=pk.s1.data_ptr(), t1=pk.t1.data_ptr(), wh=pk.whT.data_ptr(),
+         bh=pk.bh.data_ptr(), ww=pk.wwT.data_ptr(), bw=pk.bw.data_ptr(), N=n, H=h, W=w, C=c, Cm=pk.cm, ldx=ld_of(x),
+         ldy=ld_of(out), num_sms=0)
+    return (out, pooled, gates) if return_gates else out
+
+
+# --------------------------------------------------------------------------------------------
+# a8 Detect decode + a9 NMS
+# --------------------------------------------------------------------------------------------
+@dataclass
+class DetectLevel:
+    logits: torch.Tensor      # fp32 [N, ny, nx, ld] contiguous (NHWC), channel = a*no + o
+    stride: float
+    anchors_px: list          # [(w, h)] * na, pixels (= anchors * stride)
+    ny: int
+    nx: int
+    ld: int
+
+
+def _level_meta(levels, na, device):
+    words, row0 = [], 0
+    for lv in levels:
+        flat = [float(v) for wh in lv.anchors_px for v in wh] + [0.0] * (10 - 2 * na)
+        words.append(struct.pack("<5if10f", row0, lv.ny, lv.nx, lv.ld, na, float(lv.stride), *flat))
+        row0 += na * lv.ny * lv.nx
+    buf = torch.frombuffer(bytearray(b"".join(words)), dtype=torch.uint8).to(device)
+    return buf, row0
+
+
+def detect_decode(levels, na: int, no: int) -> torch.Tensor:
+    """Dense `pred` [N, sum(na*ny*nx), no] fp32 exactly as Detect.forward returns it (models/yolo.py:81-101)."""
+    n = levels[0].logits.shape[0]
+    rows = sum(na * lv.ny * lv.nx for lv in levels)
+    pred = torch.empty((n, rows, no), device=levels[0].logits.device, dtype=torch.float32)
+    row0 = 0
+    for lv in levels:
+        a = [v for wh in lv.anchors_px for v in wh] + [0.0] * (10 - 2 * na)
+        call("dmay_detect_decode", _stream(pred), logits=lv.logits.data_ptr(), pred=pred.data_ptr(), N=n, ny=lv.ny,
+             nx=lv.nx, na=na, no=no, ld=lv.ld, row0=row0, rows_total=rows, stride=float(lv.stride),
+             aw0=a[0], ah0=a[1], aw1=a[2], ah1=a[3], aw2=a[4], ah2=a[5], aw3=a[6], ah3=a[7], aw4=a[8], ah4=a[9])
+        row0 += na * lv.ny * lv.nx
+    return pred
+
+
+def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, *, levels=None, na=0, nc=None,
+                classes=None, agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=4096.0):
+    """Whole-batch NMS.  Source is a dense fp32 `pred` [N,R,5+nc] or Detect `levels` (fused decode).
+    Returns (out [N,max_det,6] fp32, counts [N] int32) on the device; out[i,:counts[i]] are image i's
+    detections (xyxy, conf, cls) in descending score order — utils/general.py:633-725."""
+    if levels is not None:
+        dev = levels[0].logits.device
+        n = levels[0].logits.shape[0]
+        meta, rows = _level_meta(levels, na, dev)
+        src = dict(levels=len(levels), lv_meta=meta.data_ptr())
+        for i, lv in enumerate(levels):
+            src[f"lv_logits{i}"] = lv.logits.data_ptr()
+        keep_alive = (meta,)
+    else:
+        if pred.dtype != torch.float32 or not pred.is_contiguous():
+            pred = pred.float().contiguous()
+        dev = pred.device
+        n, rows, no = pred.shape
+        nc = no - 5
+        src = dict(levels=0, pred=pred.data_ptr())
+        keep_alive = (pred,)
+    s = torch.cuda.current_stream(dev).cuda_stream
+    multi_label = bool(multi_label) and nc > 1
+    rpb = 128
+    nblk = (rows + rpb - 1) // rpb
+    blk_counts = torch.empty(n * nblk, device=dev, dtype=torch.int32)
+    blk_offsets = torch.empty(n * nblk, device=dev, dtype=torch.int32)
+    img_counts = torch.empty(n, device=dev, dtype=torch.int32)
+    img_offsets = torch.empty(n + 1, device=dev, dtype=torch.int64)
+    common = dict(blk_counts=blk_counts.data_ptr(), blk_offsets=blk_offsets.data_ptr(), img_counts=img_counts.data_ptr(),
+                  img_offsets=img_offsets.data_ptr(), N=n, R=rows, nc=nc, multi_label=int(multi_label),
+                  rows_per_block=rpb, conf_thres=float(conf_thres), **src)
+    if classes is not None:
+        cm = torch.zeros(nc, dtype=torch.uint8)
+        for c in classes:
+            if 0 <= int(c) < nc:
+                cm[int(c)] = 1
+        cm = cm.to(dev)
+        common["class_mask"] = cm.data_ptr()
+        keep_alive += (cm,)
+    call("dmay_nms_filter", s, phase=0, **common)
+    total = int(img_offsets[n].item())  # the one sizing sync of the batch
+    out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
+    out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
+    if total == 0:
+        return out, out_counts
+    keys = torch.empty(total, device=dev, dtype=torch.int64)
+    cand = torch.empty((total, 6), device=dev, dtype=torch.float32)
+    call("dmay_nms_filter", s, phase=1, keys=keys.data_ptr(), cand=cand.data_ptr(), capacity=total, **common)
+    img_bits = max(1, (n - 1).bit_length())
+    ws_bytes = int(_lib.lib().dmay_nms_sort_ws(total, img_bits))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    keys_out = torch.empty_like(keys)
+    idx = torch.empty(total, device=dev, dtype=torch.int32)
+    call("dmay_nms_sort", s, keys_in=keys.data_ptr(), keys_out=keys_out.data_ptr(), idx_out=idx.data_ptr(),
+         ws=ws.data_ptr(), ws_bytes=ws_bytes, n=total, img_bits=img_bits)
+    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=img_counts.data_ptr(),
+         img_offsets=img_offsets.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
+         max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
+    del keep_alive
+    return out, out_counts
+
+
+def device_copy(dst: torch.Tensor, src: torch.Tensor):
+    call("dmay_copy", _stream(src), src=src.data_ptr(), dst=dst.data_ptr(), bytes=src.numel() * src.element_size())

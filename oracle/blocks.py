@@ -1,0 +1,232 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py) — CPU fp32 restatement of the reference blocks.
+
+Plain functional PyTorch on CPU tensors: every function takes the block's weights explicitly (a
+state_dict `sd` + key prefix, Appendix B key names) and cites the reference lines it restates.
+`forward_model` interprets a model YAML with these functions, i.e. it is an independent
+re-derivation of `Model._forward_once` that shares no code with `dma_yolo_b200`.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _bn(x, sd, p, eps):
+    """nn.BatchNorm2d in eval mode with the module's own eps (utils/torch_utils.py:167 sets 1e-3 inside a Model)."""
+    return F.batch_norm(x, sd[p + 'running_mean'], sd[p + 'running_var'], sd[p + 'weight'], sd[p + 'bias'], False, 0.0, eps)
+
+
+def silu(x):
+    return x * torch.sigmoid(x)
+
+
+def conv_bn_act(x, sd, p, k=1, s=1, pad=None, act=True, eps=1e-3):
+    """Conv.forward — models/common.py:50-77: act(bn(conv(x))), conv bias=False, pad=k//2.
+    After Model.fuse() (models/yolo.py:315-323) the module has a biased conv and no bn."""
+    pad = k // 2 if pad is None else pad
+    if p + 'bn.weight' in sd:
+        y = _bn(F.conv2d(x, sd[p + 'conv.weight'], None, s, pad), sd, p + 'bn.', eps)
+    else:
+        y = F.conv2d(x, sd[p + 'conv.weight'], sd.get(p + 'conv.bias'), s, pad)
+    return silu(y) if act else y
+
+
+def bottleneck(x, sd, p, shortcut=True, eps=1e-3):
+    """Bottleneck.forward — models/common.py:119-137 (e=1.0 inside C3): x + cv2(cv1(x))."""
+    y = conv_bn_act(conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps), sd, p + 'cv2.', 3, eps=eps)
+    c1, c2 = sd[p + 'cv1.conv.weight'].shape[1], sd[p + 'cv2.conv.weight'].shape[0]
+    return x + y if (shortcut and c1 == c2) else y
+
+
+def c3(x, sd, p, n=1, shortcut=True, eps=1e-3):
+    """C3.forward — models/common.py:159-182: cv3(cat(m(cv1 x), cv2 x))."""
+    y = conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps)
+    for i in range(n):
+        y = bottleneck(y, sd, f'{p}m.{i}.', shortcut, eps)
+    return conv_bn_act(torch.cat((y, conv_bn_act(x, sd, p + 'cv2.', 1, eps=eps)), 1), sd, p + 'cv3.', 1, eps=eps)
+
+
+def coordatt(x, sd, p, eps=1e-3):
+    """CoorAttention.forward — models/common.py:1183-1207 (restatement SURVEY.md App. D-4)."""
+    n, c, h, w = x.shape
+    ph = x.mean(dim=3, keepdim=True)                       # [n,c,h,1]
+    pw = x.mean(dim=2, keepdim=True).permute(0, 1, 3, 2)   # [n,c,w,1]
+    y = F.conv2d(torch.cat([ph, pw], 2), sd[p + 'conv1.weight'], sd[p + 'conv1.bias'])
+    y = F.hardswish(_bn(y, sd, p + 'bn1.', eps))
+    yh, yw = torch.split(y, [h, w], dim=2)
+    a_h = torch.sigmoid(F.conv2d(yh, sd[p + 'conv_h.weight'], sd[p + 'conv_h.bias']))                      # [n,c,h,1]
+    a_w = torch.sigmoid(F.conv2d(yw.permute(0, 1, 3, 2), sd[p + 'conv_w.weight'], sd[p + 'conv_w.bias']))  # [n,c,1,w]
+    return x * a_w * a_h
+
+
+def space_to_depth(x):
+    """space_to_depth.forward — models/common.py:1457-1458: out[n,(dy+2dx)C+c,h,w] = in[n,c,2h+dy,2w+dx]."""
+    return torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)
+
+
+def nearest_index(dst: int, in_size: int, out_size: int) -> int:
+    """ATen nearest source index: min(floor(dst * float(in)/float(out)), in-1) in fp32."""
+    import numpy as np
+    scale = np.float32(in_size) / np.float32(out_size)
+    return min(int(np.floor(np.float32(dst) * scale)), in_size - 1)
+
+
+def scconv_gate(x, k3o, k2o):
+    """k3(x) * sigmoid(x + nearest_up(k2)) — models/common.py:1310-1314, explicit index form (App. D-7)."""
+    H, W = x.shape[2:]
+    Hk, Wk = k2o.shape[2:]
+    hi = torch.tensor([nearest_index(h, Hk, H) for h in range(H)])
+    wi = torch.tensor([nearest_index(w, Wk, W) for w in range(W)])
+    up = k2o[:, :, hi][:, :, :, wi]
+    return k3o * torch.sigmoid(x + up)
+
+
+def scconv(x, sd, p, stride, pooling_r=4, eps=1e-3):
+    """SCConv.forward — models/common.py:1279-1316 (no activation anywhere inside)."""
+    k2o = _bn(F.conv2d(F.avg_pool2d(x, pooling_r, pooling_r), sd[p + 'k2.1.weight'], None, 1, 1), sd, p + 'k2.2.', eps)
+    k3o = _bn(F.conv2d(x, sd[p + 'k3.0.weight'], None, 1, 1), sd, p + 'k3.1.', eps)
+    g = scconv_gate(x, k3o, k2o)
+    return _bn(F.conv2d(g, sd[p + 'k4.0.weight'], None, stride, 1), sd, p + 'k4.1.', eps)
+
+
+def adconcat(xs, w, epsilon=1e-4):
+    """AdConcat2/3.forward — models/common.py:1003-1008,1021-1026."""
+    weight = w / (torch.sum(w, dim=0) + epsilon)
+    return torch.cat([weight[i] * x for i, x in enumerate(xs)], 1)
+
+
+def adapt_add2(xs, w, epsilon=1e-4):
+    """Adapt_Add2.forward — models/common.py:1040-1045."""
+    weight = w / (torch.sum(w, dim=0) + epsilon)
+    return silu(weight[0] * xs[0] + weight[1] * xs[1])
+
+
+def adapt_add3(xs, sd, p, epsilon=1e-4):
+    """Adapt_Add3.forward — models/common.py:1056-1061 (shared biased 1x1 conv on the first two inputs)."""
+    w = sd[p + 'w']
+    weight = w / (torch.sum(w, dim=0) + epsilon)
+    cv = lambda t: F.conv2d(t, sd[p + 'conv.weight'], sd[p + 'conv.bias'])
+    return silu(weight[0] * cv(xs[0]) + weight[1] * cv(xs[1]) + weight[2] * xs[2])
+
+
+def maxpool_cascade(x, k=5):
+    """x -> (mp_k x, mp_k mp_k x, mp_k mp_k mp_k x), stride 1, -inf padding — models/common.py:1272-1274."""
+    y1 = F.max_pool2d(x, k, 1, k // 2)
+    y2 = F.max_pool2d(y1, k, 1, k // 2)
+    return y1, y2, F.max_pool2d(y2, k, 1, k // 2)
+
+
+def sppf(x, sd, p, k=5, eps=1e-3):
+    """SPPF.forward — models/common.py:252-258."""
+    x1 = conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps)
+    return conv_bn_act(torch.cat((x1,) + maxpool_cascade(x1, k), 1), sd, p + 'cv2.', 1, eps=eps)
+
+
+def spp(x, sd, p, ks=(5, 9, 13), eps=1e-3):
+    """SPP.forward — models/common.py:221-227."""
+    x1 = conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps)
+    return conv_bn_act(torch.cat([x1] + [F.max_pool2d(x1, k, 1, k // 2) for k in ks], 1), sd, p + 'cv2.', 1, eps=eps)
+
+
+def sppfcspc(x, sd, p, k=5, eps=1e-3):
+    """SPPFCSPC.forward — models/common.py:1270-1276."""
+    cba = lambda t, name, kk: conv_bn_act(t, sd, f'{p}{name}.', kk, eps=eps)
+    x1 = cba(cba(cba(x, 'cv1', 1), 'cv3', 3), 'cv4', 1)
+    y1 = cba(cba(torch.cat((x1,) + maxpool_cascade(x1, k), 1), 'cv5', 1), 'cv6', 3)
+    return cba(torch.cat((y1, cba(x, 'cv2', 1)), 1), 'cv7', 1)
+
+
+def sppcspc(x, sd, p, ks=(5, 9, 13), eps=1e-3):
+    """SPPCSPC.forward — models/common.py:1250-1255."""
+    cba = lambda t, name, kk: conv_bn_act(t, sd, f'{p}{name}.', kk, eps=eps)
+    x1 = cba(cba(cba(x, 'cv1', 1), 'cv3', 3), 'cv4', 1)
+    y1 = cba(cba(torch.cat([x1] + [F.max_pool2d(x1, k, 1, k // 2) for k in ks], 1), 'cv5', 1), 'cv6', 3)
+    return cba(torch.cat((y1, cba(x, 'cv2', 1)), 1), 'cv7', 1)
+
+
+def detect(xs, sd, p, anchors_grid, strides, nc):
+    """Detect.forward (eval) — models/yolo.py:68-103.  anchors_grid = the `anchors` buffer (grid units).
+    Returns (pred [bs, rows, no], [x_i (bs,na,ny,nx,no) raw logits])."""
+    no = nc + 5
+    na = anchors_grid.shape[1]
+    z, raw = [], []
+    for i, x in enumerate(xs):
+        t = F.conv2d(x, sd[f'{p}m.{i}.weight'], sd[f'{p}m.{i}.bias'])
+        bs, _, ny, nx = t.shape
+        t = t.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
+        raw.append(t)
+        yv, xv = torch.meshgrid(torch.arange(ny), torch.arange(nx), indexing='ij')
+        grid = torch.stack((xv, yv), 2).view(1, 1, ny, nx, 2).float()
+        ag = (anchors_grid[i].float() * strides[i]).view(1, na, 1, 1, 2)
+        y = t.sigmoid()
+        xy = (y[..., 0:2] * 2 - 0.5 + grid) * strides[i]
+        wh = (y[..., 2:4] * 2) ** 2 * ag
+        z.append(torch.cat((xy, wh, y[..., 4:]), -1).view(bs, -1, no))
+    return torch.cat(z, 1), raw
+
+
+def make_divisible(x, d):
+    return math.ceil(x / d) * d
+
+
+def forward_model(cfg: dict, sd: dict, x: torch.Tensor, strides, eps=1e-3):
+    """Model._forward_once (eval) — models/yolo.py:211-239 + the channel/arg bookkeeping of parse_model
+    (models/yolo.py:353-478), as a functional interpreter over the hot-path module set.
+    `sd` = state_dict of the model (keys `model.{i}....`).  Returns (pred, raw_list, per-layer outputs)."""
+    gd, nc = cfg['depth_multiple'], cfg['nc']
+    ys, outs = [], []
+    for i, (f, n, m, args) in enumerate(cfg['backbone'] + cfg['head']):
+        p = f'model.{i}.'
+        if f != -1:
+            xin = ys[f] if isinstance(f, int) else [x if j == -1 else ys[j] for j in f]
+        else:
+            xin = x
+        n = max(round(n * gd), 1) if n > 1 else n
+        a = [None if v == 'None' else v for v in args]
+        if m == 'Conv':
+            k = a[1] if len(a) > 1 else 1
+            s = a[2] if len(a) > 2 else 1
+            pad = a[3] if len(a) > 3 else None
+            if n > 1:
+                for r in range(n):
+                    xin = conv_bn_act(xin, sd, f'{p}{r}.', k, s, pad, eps=eps)
+                x = xin
+            else:
+                x = conv_bn_act(xin, sd, p, k, s, pad, eps=eps)
+        elif m == 'C3':
+            x = c3(xin, sd, p, n, a[1] if len(a) > 1 else True, eps)
+        elif m == 'SCConv':
+            x = scconv(xin, sd, p, a[1], eps=eps)
+        elif m in ('CA', 'CoorAttention'):
+            x = coordatt(xin, sd, p, eps)
+        elif m == 'SPPFCSPC':
+            x = sppfcspc(xin, sd, p, eps=eps)
+        elif m == 'SPPCSPC':
+            x = sppcspc(xin, sd, p, eps=eps)
+        elif m == 'SPPF':
+            x = sppf(xin, sd, p, a[1] if len(a) > 1 else 5, eps)
+        elif m == 'SPP':
+            x = spp(xin, sd, p, tuple(a[1]) if len(a) > 1 else (5, 9, 13), eps)
+        elif m == 'nn.Upsample':
+            x = F.interpolate(xin, scale_factor=a[1], mode=a[2])
+        elif m in ('AdConcat2', 'AdConcat3'):
+            x = adconcat(xin, sd[p + 'w'])
+        elif m == 'Adapt_Add2':
+            x = adapt_add2(xin, sd[p + 'w'])
+        elif m == 'Concat':
+            x = torch.cat(xin, 1)
+        elif m in ('space_to_depth', 'SM'):
+            x = space_to_depth(xin)
+        elif m == 'Focus':
+            x = conv_bn_act(space_to_depth(xin), sd, p + 'conv.', a[1] if len(a) > 1 else 1, eps=eps)
+        elif m == 'Detect':
+            pred, raw = detect(xin, sd, p, sd[p + 'anchors'], strides, nc)
+            outs.append(pred)
+            return pred, raw, outs
+        else:
+            raise NotImplementedError(f'oracle: layer {i} module {m}')
+        ys.append(x)
+        outs.append(x)
+    return x, None, outs

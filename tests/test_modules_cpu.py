@@ -1,0 +1,131 @@
+"""Drop-in boundary on CPU: same class names / ctor signatures / state_dict keys as the reference, same
+results from the torch-op bodies, same seeded weights from `Model(cfg)` (RNG consumption order)."""
+import numpy as np
+import pytest
+import torch
+import yaml
+
+import dma_yolo_b200 as D
+from dma_yolo_b200.models import common as C
+from dma_yolo_b200.models import yolo as Y
+from dma_yolo_b200.utils.calib import build_calibrated, state_digest
+from oracle import blocks as O
+from tests.util import assert_close, load_golden
+
+CTORS = {
+    'conv_k3s1': lambda: C.Conv(16, 32, 3, 1), 'conv_k3s2_odd': lambda: C.Conv(16, 32, 3, 2),
+    'conv_k1': lambda: C.Conv(32, 16, 1, 1), 'conv_stem_k6s2p2': lambda: C.Conv(3, 32, 6, 2, 2),
+    'conv_c64_k3': lambda: C.Conv(64, 64, 3, 1), 'bottleneck': lambda: C.Bottleneck(32, 32, True, e=1.0),
+    'c3_n2': lambda: C.C3(32, 32, 2), 'c3_n1_noshortcut': lambda: C.C3(64, 32, 1, False),
+    'coordatt_7x5': lambda: C.CoorAttention(64, 64), 'coordatt_20x20': lambda: C.CA(256, 256),
+    'spd': lambda: C.space_to_depth(), 'scconv_38': lambda: C.SCConv(16, 32, 2),
+    'scconv_16x12': lambda: C.SCConv(32, 64, 2), 'scconv_19x23_s1': lambda: C.SCConv(16, 16, 1),
+    'adconcat2': lambda: C.AdConcat2(), 'adconcat3': lambda: C.AdConcat3(), 'adapt_add2': lambda: C.Adapt_Add2(),
+    'adapt_add3': lambda: C.Adapt_Add3(16, 16, 32), 'sppf_20': lambda: C.SPPF(32, 32, 5),
+    'sppfcspc_12x9': lambda: C.SPPFCSPC(32, 32), 'spp': lambda: C.SPP(32, 32), 'sppcspc': lambda: C.SPPCSPC(32, 32),
+}
+
+
+def make_module(name):
+    d, sd, ins = load_golden(name)
+    m = CTORS[name]()
+    if sd:
+        m.load_state_dict(sd, strict=True)
+    for b in m.modules():
+        if isinstance(b, torch.nn.BatchNorm2d):
+            b.eps = 1e-3
+    return m.eval(), d, ins
+
+
+@pytest.mark.parametrize('name', list(CTORS))
+def test_cpu_body_matches_reference(name):
+    m, d, ins = make_module(name)
+    with torch.no_grad():
+        y = m([t.clone() for t in ins] if len(ins) > 1 else ins[0].clone())
+    assert_close(y, d['out'], atol=2e-5, rtol=2e-5, what=name)
+
+
+def test_detect_cpu_and_keys():
+    d, sd, ins = load_golden('detect_nc4')
+    det = Y.Detect(nc=4, anchors=[[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]],
+                   ch=(16, 32, 64))
+    det.stride = torch.tensor([8., 16., 32.])
+    det.load_state_dict(sd, strict=True)
+    det.eval()
+    with torch.no_grad():
+        pred, raw = det([t.clone() for t in ins])
+    assert_close(pred, d['out'], atol=1e-4, rtol=1e-5, what='detect')
+
+
+@pytest.mark.parametrize('cfg', ['yolov5s', 'ablation-ca-scconv-sppfcspc-bifpn'])
+def test_model_seeded_weights_and_forward(cfg):
+    d, _, ins = load_golden('model_' + cfg)
+    m = build_calibrated(cfg + '.yaml', seed=0)
+    assert state_digest(m.state_dict()) == str(d['digest']), 'seeded weights differ from the reference Model'
+    assert torch.equal(m.stride, d['strides'])
+    with torch.no_grad():
+        pred, raw = m(ins[0])
+    assert_close(pred, d['out'], atol=1e-4, rtol=1e-4, what='pred')
+    # oracle interpreter on the same weights
+    cfgd = yaml.safe_load(open(Y.CFG_DIR / (cfg + '.yaml')))
+    with torch.no_grad():
+        po, _, _ = O.forward_model(cfgd, m.state_dict(), ins[0], m.stride.tolist())
+    assert_close(po, d['out'], atol=1e-3, rtol=2e-4, what='oracle pred')  # fp32 re-association over ~100 convs
+    # CPU NMS body == reference outputs
+    for style, kw in (('detect', dict(conf_thres=0.25, iou_thres=0.45, max_det=1000)),
+                      ('val', dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300))):
+        outs = D.non_max_suppression(d['out'].clone(), **kw)
+        for i, o in enumerate(outs):
+            assert torch.equal(o, d[f'nms_{style}_{i}']), (style, i)
+
+
+def test_fuse_only_top_level_convs():
+    """models/yolo.py:315-323 + SURVEY F4: fuse() folds BN only for YAML-level `Conv` (cspcm.Conv)."""
+    m = D.Model('yolov5s.yaml')
+    n_bn = sum(isinstance(x, torch.nn.BatchNorm2d) for x in m.modules())
+    x = torch.rand(1, 3, 64, 64)
+    m.eval()
+    with torch.no_grad():
+        a = m(x)[0]
+        m.fuse()
+        b = m(x)[0]
+    n_bn2 = sum(isinstance(x, torch.nn.BatchNorm2d) for x in m.modules())
+    assert 0 < n_bn2 < n_bn
+    assert_close(a, b, atol=1e-4, rtol=1e-4)
+
+
+def test_unknown_module_is_reported():
+    cfg = dict(nc=2, depth_multiple=1, width_multiple=1, anchors=3, backbone=[[-1, 1, 'C3STR', [64]]],
+               head=[[[0], 1, 'Detect', ['nc', 'anchors']]])
+    with pytest.raises(NotImplementedError):
+        D.Model(cfg)
+
+
+def test_aliases_and_pickle_roundtrip(tmp_path):
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k == 'models' or k.startswith('models.') or k == 'utils' or k.startswith('utils.')}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        D.install_aliases()
+        import models.common as mc
+        import models.yolo as my
+        assert my.Model is D.Model and mc.CA is mc.CoorAttention
+        m = D.Model('yolov5s.yaml').eval()
+        m(torch.rand(1, 3, 64, 64))
+        torch.save({'model': m}, tmp_path / 'ck.pt')
+        m2 = torch.load(tmp_path / 'ck.pt', weights_only=False)['model']
+        assert state_digest(m2.state_dict()) == state_digest(m.state_dict())
+    finally:
+        for k in list(sys.modules):
+            if k == 'models' or k.startswith('models.') or k == 'utils' or k.startswith('utils.'):
+                del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_cuda_path_fails_loudly_without_library(monkeypatch):
+    from dma_yolo_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'SO', _lib.SO.with_name('missing.so'))
+    with pytest.raises(D.DmayError):
+        _lib.lib()

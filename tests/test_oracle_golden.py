@@ -1,0 +1,126 @@
+"""The oracle (CPU restatement) is pinned against outputs of the executed reference (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import blocks as O
+from oracle import nms as ON
+from tests.util import assert_close, load_golden
+
+TOL = dict(atol=2e-5, rtol=2e-5)
+
+
+def run_block(name):
+    d, sd, ins = load_golden(name)
+    x = ins[0]
+    if name.startswith('conv_k3s1'): y = O.conv_bn_act(x, sd, '', 3, 1)
+    elif name.startswith('conv_k3s2'): y = O.conv_bn_act(x, sd, '', 3, 2)
+    elif name.startswith('conv_k1'): y = O.conv_bn_act(x, sd, '', 1, 1)
+    elif name.startswith('conv_stem'): y = O.conv_bn_act(x, sd, '', 6, 2, 2)
+    elif name.startswith('conv_c64'): y = O.conv_bn_act(x, sd, '', 3, 1)
+    elif name == 'bottleneck': y = O.bottleneck(x, sd, '')
+    elif name == 'c3_n2': y = O.c3(x, sd, '', 2, True)
+    elif name == 'c3_n1_noshortcut': y = O.c3(x, sd, '', 1, False)
+    elif name.startswith('coordatt'): y = O.coordatt(x, sd, '')
+    elif name == 'spd': y = O.space_to_depth(x)
+    elif name in ('scconv_38', 'scconv_16x12'): y = O.scconv(x, sd, '', 2)
+    elif name == 'scconv_19x23_s1': y = O.scconv(x, sd, '', 1)
+    elif name in ('adconcat2', 'adconcat3'): y = O.adconcat(ins, sd['w'])
+    elif name == 'adapt_add2': y = O.adapt_add2(ins, sd['w'])
+    elif name == 'adapt_add3': y = O.adapt_add3(ins, sd, '')
+    elif name == 'sppf_20': y = O.sppf(x, sd, '')
+    elif name == 'sppfcspc_12x9': y = O.sppfcspc(x, sd, '')
+    elif name == 'spp': y = O.spp(x, sd, '')
+    elif name == 'sppcspc': y = O.sppcspc(x, sd, '')
+    else: raise KeyError(name)
+    return y, d['out']
+
+
+BLOCKS = ['conv_k3s1', 'conv_k3s2_odd', 'conv_k1', 'conv_stem_k6s2p2', 'conv_c64_k3', 'bottleneck', 'c3_n2',
+          'c3_n1_noshortcut', 'coordatt_7x5', 'coordatt_20x20', 'spd', 'scconv_38', 'scconv_16x12', 'scconv_19x23_s1',
+          'adconcat2', 'adconcat3', 'adapt_add2', 'adapt_add3', 'sppf_20', 'sppfcspc_12x9', 'spp', 'sppcspc']
+
+
+@pytest.mark.parametrize('name', BLOCKS)
+def test_block_oracle_matches_reference(name):
+    y, ref = run_block(name)
+    if name == 'spd':
+        assert torch.equal(y, ref)
+    else:
+        assert_close(y, ref, what=name, **TOL)
+
+
+def test_maxpool_cascade_identity():
+    d, _, ins = load_golden('maxpool_cascade_48')
+    y1, y2, y3 = O.maxpool_cascade(ins[0], 5)
+    assert torch.equal(y1, d['y1']) and torch.equal(y2, d['y2']) and torch.equal(y3, d['y3'])  # mp5∘mp5 == mp9 ...
+
+
+def test_detect_oracle():
+    d, sd, ins = load_golden('detect_nc4')
+    pred, raw = O.detect(ins, sd, '', sd['anchors'], [8., 16., 32.], 4)
+    assert_close(pred, d['out'], what='detect pred', atol=1e-4, rtol=1e-5)
+    for i, r in enumerate(raw):
+        assert_close(r, d[f'raw{i}'], what=f'raw{i}', **TOL)
+
+
+STYLES = {'detect': dict(conf_thres=0.25, iou_thres=0.45, max_det=1000),
+          'val': dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300),
+          'agnostic': dict(conf_thres=0.3, iou_thres=0.5, agnostic=True, max_det=50),
+          'classes': dict(conf_thres=0.2, iou_thres=0.45, classes=[1, 3, 7], max_det=300)}
+
+
+@pytest.mark.parametrize('fixture', ['nms_random', 'nms_clustered'])
+@pytest.mark.parametrize('style', list(STYLES))
+def test_nms_oracle_bit_exact(fixture, style):
+    d, _, _ = load_golden(fixture)
+    kw = dict(STYLES[style])
+    if fixture == 'nms_clustered' and style == 'classes':
+        kw['classes'] = [0, 2]
+    pred = d['pred'].numpy()
+    for i in range(pred.shape[0]):
+        got = ON.non_max_suppression(pred[i:i + 1], **kw)[0]
+        ref = d[f'{style}_{i}'].numpy()
+        assert got.shape == ref.shape, (style, i, got.shape, ref.shape)
+        assert np.array_equal(got, ref), (style, i)
+
+
+def test_nms_truncation_path():
+    d, _, _ = load_golden('nms_truncate')
+    got = ON.non_max_suppression(d['pred'].numpy(), 0.001, 0.6, multi_label=True, max_det=300)[0]
+    assert np.array_equal(got, d['val_0'].numpy())
+
+
+def test_nms_known_answers():
+    """SURVEY.md 8c KATs (probed on the reference's torchvision CPU op)."""
+    import torchvision
+    f = np.float32
+    cases = [
+        (np.array([[0, 0, 10, 10], [100, 100, 110, 110], [0, 0, 10, 10], [200, 200, 210, 210]], f), np.full(4, 0.5, f), 0.5, [0, 1, 3]),
+        (np.array([[0, 0, 2, 2], [0, 0, 2, 1]], f), np.array([0.9, 0.8], f), 0.5, [0, 1]),          # iou == thr kept
+        (np.array([[0, 0, 2, 1], [1, 0, 3, 1]], f), np.array([0.9, 0.8], f), 1 / 3, [0]),           # double vs float thr
+        (np.array([[5, 5, 5, 9], [5, 5, 5, 9]], f), np.array([0.9, 0.8], f), 0.5, [0, 1]),          # 0/0 -> nan -> kept
+    ]
+    for boxes, scores, thr, want in cases:
+        assert ON.nms_reference(boxes, scores, thr).tolist() == want
+        tv = torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).tolist()
+        assert tv == want
+
+
+def test_nms_oracle_vs_torchvision_random():
+    import torchvision
+    g = torch.Generator().manual_seed(3)
+    for trial in range(6):
+        n = 1500
+        xy = torch.rand(n, 2, generator=g) * 300
+        wh = torch.rand(n, 2, generator=g) * 80 + 1
+        boxes = torch.cat([xy, xy + wh], 1)
+        scores = torch.rand(n, generator=g)
+        if trial % 2:
+            scores = (scores * 20).round() / 20          # many ties
+        off = (torch.randint(0, 80, (n, 1), generator=g).float() * 4096) if trial >= 3 else 0
+        b = boxes + off                                 # fp32 rounding of class offsets
+        for thr in (0.45, 0.6):
+            want = torchvision.ops.nms(b, scores, thr).numpy()
+            got = ON.nms_reference(b.numpy(), scores.numpy(), thr)
+            assert np.array_equal(got, want), (trial, thr)
