@@ -1,0 +1,117 @@
+"""-m gpu: the tcgen05 implicit-GEMM conv through the C-ABI vs F.conv2d (fp32, same bf16-rounded operands).
+
+Accumulation is fp32 in TMEM on exact bf16 products, so before the bf16 store the result equals the fp32
+reference up to summation order; tolerance = bf16 output rounding (2^-9 relative) + slack: atol=rtol=1e-2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(t):
+    return t.bfloat16().float()
+
+
+def back(t):
+    return t.float().cpu().contiguous()
+
+
+def run_conv(n, cin, h, w, cout, k, s, p, act=1, residual=False, out_fp32=False, bias=False, seed=0, slab_pad=0):
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+    scale = torch.rand(cout, generator=g) + 0.5
+    b = torch.randn(cout, generator=g) * 0.3
+    bn = torch.nn.BatchNorm2d(cout).eval()
+    bn.weight.data, bn.bias.data = scale.clone(), b.clone()
+    bn.running_mean.zero_(); bn.running_var.fill_(1.0); bn.eps = 0.0
+    conv_bias = bf(torch.randn(cout, generator=g)) if bias else None
+    pk = ops.pack_conv(wt, bn=bn, conv_bias=conv_bias, stride=s, pad=p, device='cuda')
+    ref = F.conv2d(x, wt, conv_bias, s, p) * scale.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+    if act == 1:
+        ref = ref * torch.sigmoid(ref)
+    res = None
+    if residual:
+        res = bf(torch.randn(ref.shape, generator=g))
+        ref = ref + res
+    xin = x.cuda() if cin % 16 else ops.as_act(x.cuda())
+    out = None
+    if slab_pad:
+        ho, wo = ref.shape[2:]
+        slab = ops.empty_nhwc(n, cout + 2 * slab_pad, ho, wo, 'cuda')
+        slab.zero_()
+        out = slab[:, slab_pad:slab_pad + cout]
+    y = ops.conv(xin, pk, act, out=out, residual=None if res is None else ops.as_act(res.cuda()), out_fp32=out_fp32)
+    torch.cuda.synchronize()
+    if slab_pad:
+        assert float(slab[:, :slab_pad].abs().sum()) == 0 and float(slab[:, slab_pad + cout:].abs().sum()) == 0
+    return back(y), ref
+
+
+CASES = [
+    # n, cin, h, w, cout, k, s, p
+    (1, 64, 8, 8, 64, 1, 1, 0),        # plain GEMM, one tile
+    (2, 64, 20, 20, 128, 1, 1, 0),     # M = 800: tail tile
+    (1, 128, 16, 16, 256, 1, 1, 0),    # 2 K chunks, N = 256
+    (1, 256, 12, 10, 512, 1, 1, 0),    # 2 n-tiles
+    (2, 64, 12, 10, 64, 3, 1, 1),      # im2col 3x3
+    (1, 64, 20, 20, 64, 3, 2, 1),      # stride 2
+    (3, 128, 11, 9, 128, 3, 2, 1),     # odd sizes, stride 2, multi image
+    (1, 32, 16, 16, 64, 3, 1, 1),      # Cin = 32 -> 64-byte swizzle
+    (1, 16, 16, 16, 32, 3, 1, 1),      # Cin = 16 -> 32-byte swizzle
+    (1, 512, 10, 10, 1024, 3, 1, 1),   # K = 4608, 4 n-tiles
+    (4, 64, 40, 40, 64, 3, 1, 1),      # 50 m-tiles, persistent loop + double-buffered TMEM
+    (1, 64, 5, 5, 48, 1, 1, 0),        # N = 48 (x16 TMEM tail)
+    (1, 1024, 20, 20, 512, 1, 1, 0),   # K = 1024
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[str(c) for c in CASES])
+def test_conv_bn_silu(case):
+    y, ref = run_conv(*case)
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what=str(case))
+
+
+def test_conv_stem_spd_rewrite():
+    y, ref = run_conv(2, 3, 64, 48, 64, 6, 2, 2)          # 6x6 s2 p2 on RGB == 3x3 s1 p1 on pixel-unshuffled input
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what='stem')
+    y, ref = run_conv(1, 3, 32, 32, 32, 3, 1, 1, seed=3)  # generic small-Cin path (channel padding to 16)
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what='cin3 k3')
+
+
+def test_conv_residual_and_slab_slice():
+    y, ref = run_conv(2, 64, 12, 12, 64, 3, 1, 1, residual=True, slab_pad=16)
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what='residual+slab')
+
+
+def test_conv_detect_head_fp32_255():
+    y, ref = run_conv(2, 128, 10, 10, 255, 1, 1, 0, act=0, out_fp32=True, bias=True)
+    assert y.shape[1] == 255
+    assert_close(y, ref, atol=2e-4, rtol=2e-4, what='fp32 head')   # fp32 store: only summation order differs
+
+
+def test_conv_gate_epilogue():
+    from dma_yolo_b200 import ops
+    from oracle import blocks as O
+    g = torch.Generator().manual_seed(5)
+    n, c, h, w = 2, 64, 19, 23
+    x = bf(torch.randn(n, c, h, w, generator=g))
+    wt = bf(torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5)
+    k2 = bf(torch.randn(n, c, h // 4, w // 4, generator=g))
+    pk = ops.pack_conv(wt, stride=1, pad=1, device='cuda')
+    xa = ops.as_act(x.cuda())
+    y = ops.conv(xa, pk, 0, gate=(xa, ops.as_act(k2.cuda())))
+    ref = O.scconv_gate(x, F.conv2d(x, wt, None, 1, 1), k2)
+    assert_close(back(y), ref, atol=1e-2, rtol=1e-2, what='gate epilogue')
+
+
+def test_conv_rejects_bad_arguments():
+    import dma_yolo_b200 as D
+    from dma_yolo_b200 import ops
+    pk = ops.pack_conv(torch.randn(64, 64, 1, 1), device='cuda')
+    with pytest.raises(D.DmayError):
+        ops.conv(torch.randn(1, 32, 4, 4).cuda(), pk)

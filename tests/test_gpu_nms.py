@@ -1,0 +1,127 @@
+"""-m gpu: batched NMS through the C-ABI.  Keep indices / output rows are BIT-EXACT vs the reference
+(`tests/golden/nms_*.npz` = outputs of the executed reference `non_max_suppression`) and vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nms as ON
+from tests.test_oracle_golden import STYLES
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('fixture', ['nms_random', 'nms_clustered'])
+@pytest.mark.parametrize('style', list(STYLES))
+def test_nms_golden_bit_exact(fixture, style):
+    import dma_yolo_b200 as D
+    d, _, _ = load_golden(fixture)
+    kw = dict(STYLES[style])
+    if fixture == 'nms_clustered' and style == 'classes':
+        kw['classes'] = [0, 2]
+    outs = D.non_max_suppression(d['pred'].cuda(), **kw)           # whole batch in one call
+    assert len(outs) == d['pred'].shape[0]
+    for i, o in enumerate(outs):
+        ref = d[f'{style}_{i}']
+        assert tuple(o.shape) == tuple(ref.shape), (style, i, tuple(o.shape), tuple(ref.shape))
+        assert torch.equal(o.cpu(), ref), (style, i)
+
+
+def test_nms_truncation_over_max_nms():
+    import dma_yolo_b200 as D
+    d, _, _ = load_golden('nms_truncate')
+    o = D.non_max_suppression(d['pred'].cuda(), 0.001, 0.6, multi_label=True, max_det=300)[0]
+    assert torch.equal(o.cpu(), d['val_0'])
+
+
+def test_nms_known_answers_through_api():
+    """tie stability, iou == thr kept, double-vs-float threshold, degenerate boxes (SURVEY 8c KATs)."""
+    import dma_yolo_b200 as D
+
+    def run(boxes_xyxy, scores, thr):
+        b = torch.tensor(boxes_xyxy, dtype=torch.float32)
+        xywh = torch.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], 1)
+        pred = torch.zeros(1, len(b), 6)
+        pred[0, :, :4] = xywh
+        pred[0, :, 4] = 1.0
+        pred[0, :, 5] = torch.tensor(scores)
+        out = D.non_max_suppression(pred.cuda(), 0.01, thr)[0].cpu()
+        ref = ON.non_max_suppression(pred.numpy(), 0.01, thr)[0]
+        assert np.array_equal(out.numpy(), ref)
+        return out
+
+    o = run([[0, 0, 10, 10], [100, 100, 110, 110], [0, 0, 10, 10], [200, 200, 210, 210]], [0.5] * 4, 0.5)
+    assert o.shape[0] == 3 and o[:, 0].tolist() == [0., 100., 200.]
+    assert run([[0, 0, 2, 2], [0, 0, 2, 1]], [0.9, 0.8], 0.5).shape[0] == 2
+    assert run([[0, 0, 2, 1], [1, 0, 3, 1]], [0.9, 0.8], 1 / 3).shape[0] == 1
+    assert run([[5, 5, 5, 9], [5, 5, 5, 9]], [0.9, 0.8], 0.5).shape[0] == 2
+
+
+@pytest.mark.parametrize('style', ['detect', 'val'])
+def test_nms_class_offset_rounding_and_big_random(style):
+    """80 classes: offsets up to 79*4096 round the coordinates in fp32 before IoU; 25,200 rows."""
+    import dma_yolo_b200 as D
+    g = torch.Generator().manual_seed(21)
+    pred = torch.rand(2, 25200, 85, generator=g)
+    pred[..., :2] *= 640
+    pred[..., 2:4] = pred[..., 2:4] * 60 + 4
+    pred[..., 4] = pred[..., 4] ** 4              # fewer candidates (keeps the numpy oracle to seconds)
+    pred[..., 5:] = pred[..., 5:] ** 3
+    kw = dict(STYLES[style])
+    outs = D.non_max_suppression(pred.cuda(), **kw)
+    for i in range(2):
+        ref = ON.non_max_suppression(pred[i:i + 1].numpy(), **kw)[0]
+        assert np.array_equal(outs[i].cpu().numpy(), ref), (style, i)
+
+
+def test_nms_empty_and_ragged():
+    import dma_yolo_b200 as D
+    pred = torch.zeros(3, 100, 9)
+    pred[1, :5, 4] = 0.9
+    pred[1, :5, 5] = 0.8
+    pred[1, :5, :4] = torch.tensor([[10, 10, 4, 4], [11, 11, 4, 4], [50, 50, 6, 6], [90, 10, 3, 3], [10, 90, 3, 3]]).float()
+    outs = D.non_max_suppression(pred.cuda(), 0.25, 0.45)
+    assert [tuple(o.shape) for o in outs] == [(0, 6), tuple(ON.non_max_suppression(pred[1:2].numpy(), 0.25, 0.45)[0].shape), (0, 6)]
+    assert np.array_equal(outs[1].cpu().numpy(), ON.non_max_suppression(pred[1:2].numpy(), 0.25, 0.45)[0])
+    outs = D.non_max_suppression(torch.zeros(2, 10, 7).cuda(), 0.25, 0.45)
+    assert all(tuple(o.shape) == (0, 6) for o in outs)
+
+
+def test_nms_labels_autolabelling_path():
+    import dma_yolo_b200 as D
+    d, _, _ = load_golden('nms_random')
+    pred = d['pred'][:2, :500].contiguous()
+    labels = [torch.tensor([[1., 100., 100., 30., 40.], [3., 300., 200., 50., 20.]]), torch.zeros(0, 5)]
+    outs = D.non_max_suppression(pred.cuda(), 0.25, 0.45, labels=[l.cuda() for l in labels])
+    ref = ON.non_max_suppression(pred.numpy(), 0.25, 0.45, labels=[l.numpy() for l in labels])
+    for o, r in zip(outs, ref):
+        assert np.array_equal(o.cpu().numpy(), r)
+
+
+def test_fused_decode_filter_equals_dense_path():
+    """LazyPred (decode fused with the confidence filter) and the materialised dense tensor must give the
+    same detections: identical decode arithmetic in both kernels."""
+    import dma_yolo_b200 as D
+    from dma_yolo_b200.models import yolo as Y
+    torch.manual_seed(0)
+    det = Y.Detect(nc=10, anchors=[[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]],
+                   ch=(32, 64, 128))
+    det.stride = torch.tensor([8., 16., 32.])
+    det.anchors /= det.stride.view(-1, 1, 1)
+    for mi in det.m:
+        mi.weight.data.mul_(3.0)
+        mi.bias.data.normal_(-1.0, 1.0)
+    det = det.cuda().eval()
+    det.stride = det.stride.cuda()
+    xs = [torch.randn(3, 32, 20, 12).cuda(), torch.randn(3, 64, 10, 6).cuda(), torch.randn(3, 128, 5, 3).cuda()]
+    with torch.no_grad():
+        pred, _ = det(xs)
+        for kw in (dict(conf_thres=0.25, iou_thres=0.45, max_det=1000), dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)):
+            fused = D.non_max_suppression(pred, **kw)
+            assert pred._dense is None, 'fused path must not materialise the dense prediction'
+            dense = D.non_max_suppression(pred.dense().clone(), **kw)
+            oracle = ON.non_max_suppression(pred.dense().cpu().numpy(), **kw)
+            for f, dn, o in zip(fused, dense, oracle):
+                assert torch.equal(f, dn)
+                assert np.array_equal(dn.cpu().numpy(), o)
+            assert sum(len(f) for f in fused) > 0
