@@ -130,14 +130,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int BLOCK_M = 128;
 constexpr int kMaxStages = 8;
-constexpr int kConvThreads = 256;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kConvThreads = 128 + kEpiThreads;    // warps 0-3: TMA / MMA / TMEM alloc / spare
+
+// epilogue flavours (compile-time: keeps the hot loop branch-free and small enough for the I-cache)
+enum EpiMode : int {
+  EPI_SILU = 0,        // bf16( silu(s*acc + b) )
+  EPI_SILU_RES = 1,    // bf16( silu(s*acc + b) + residual )
+  EPI_LINEAR = 2,      // bf16( s*acc + b )
+  EPI_GATE = 3,        // bf16( (s*acc + b) * sigmoid(gate_x + up(gate_k)) )
+  EPI_LINEAR_F32 = 4,  // fp32( s*acc + b )                       (Detect head logits)
+  EPI_GENERIC = 5,     // runtime activation / optional residual / either dtype (rare layers)
+};
 
 struct __align__(64) ConvArgs {
   CUtensorMap tmA;
@@ -173,6 +184,66 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
          ((uint64_t)layout_type << 61);
 }
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// silu(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2   (one MUFU; rel. error 2^-11, below bf16 resolution)
+__device__ __forceinline__ float silu_t(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+__device__ __forceinline__ float sigmoid_t(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// One 8-column group of one output row: registers r[0..7] (fp32 accumulators) -> global.
+template <int MODE>
+__device__ __forceinline__ void epi_store8(const ConvArgs& a, const uint32_t* r, const float* sc, const float* bi,
+                                           long long row, int col, const uint4& aux0, const uint4& aux1) {
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(r[j]), sc[j], bi[j]);
+  if (MODE == EPI_SILU || MODE == EPI_SILU_RES) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = silu_t(f[j]);
+  }
+  if (MODE == EPI_SILU_RES) {
+    float rs[8];
+    unpack8(aux0, rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += rs[j];
+  }
+  if (MODE == EPI_GATE) {
+    float gx[8], gk[8];
+    unpack8(aux0, gx);
+    unpack8(aux1, gk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= sigmoid_t(gx[j] + gk[j]);
+  }
+  if (MODE == EPI_GENERIC) {
+    if (a.act != DMAY_ACT_NONE) {
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], a.act);
+    }
+    if (a.residual != nullptr) {
+      float rs[8];
+      unpack8(ld_nc16(a.residual + row * a.ldr + col), rs);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += rs[j];
+    }
+  }
+  if (MODE == EPI_LINEAR_F32 || (MODE == EPI_GENERIC && a.out_f32)) {
+    float* yo = reinterpret_cast<float*>(a.y) + row * a.ldy + col;
+    *reinterpret_cast<float4*>(yo) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(yo + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    st16(reinterpret_cast<__nv_bfloat16*>(a.y) + row * a.ldy + col, pack8(f));
+  }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -202,7 +273,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i * 8, 1);
-      mbar_init(tempty_bar + i * 8, 128);
+      mbar_init(tempty_bar + i * 8, kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -267,6 +338,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.a_bytes;
           const uint64_t da = make_smem_desc(sa, a.sbo_enc, a.layout_type);
           const uint64_t db = make_smem_desc(sb, a.sbo_enc, a.layout_type);
+#pragma unroll 1
           for (int kk = 0; kk < kk_n; ++kk)  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
             umma_bf16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), a.idesc, (uint32_t)((it | kk) != 0));
           umma_commit(empty_bar + stage * 8);
@@ -281,29 +353,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue =====
+    // ===== epilogue: warp pair (w, w+4) shares TMEM lane quadrant w%4 and interleaves 32-column chunks =====
     const int quad = warp & 3;
-    const int et = threadIdx.x - 128;  // 0..127
+    const int half = (warp - 4) >> 2;  // 0 or 1
+    const int et = threadIdx.x - 128;  // 0..kEpiThreads-1
     const int row_in_tile = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int staged_n0 = -1;
     const int HoWo = a.Ho * a.Wo;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / a.num_n_tiles, n_tile = tile % a.num_n_tiles;
       const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;
-      epi_bar_sync();  // everyone is done reading the previous tile's scale/bias
-      for (int i = et; i < a.block_n; i += 128) {
-        const bool in = n0 + i < a.Cout_pad;
-        s_scale[i] = in ? a.scale[n0 + i] : 0.f;
-        s_bias[i] = in ? a.bias[n0 + i] : 0.f;
+      if (n0 != staged_n0) {  // uniform across the CTA
+        epi_bar_sync();       // everyone is done reading the previous scale/bias
+        for (int i = et; i < a.block_n; i += kEpiThreads) {
+          const bool in = n0 + i < a.Cout_pad;
+          s_scale[i] = in ? a.scale[n0 + i] : 0.f;
+          s_bias[i] = in ? a.bias[n0 + i] : 0.f;
+        }
+        epi_bar_sync();
+        staged_n0 = n0;
       }
-      epi_bar_sync();
-      mbar_wait(tfull_bar + acc * 8, acc_phase);
-      tc_fence_after();
       const long long row = (long long)m0 + row_in_tile;
       const bool valid = row < a.M;
       const __nv_bfloat16* gk_row = nullptr;
-      if (a.gate_x != nullptr && valid) {
+      if (MODE == EPI_GATE && valid) {
         const int n_img = (int)(row / HoWo);
         const int rem = (int)(row - (long long)n_img * HoWo);
         const int p = rem / a.Wo, q = rem - p * a.Wo;
@@ -311,48 +386,45 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         gk_row = a.gate_k + (((long long)n_img * a.gHk + hs) * a.gWk + ws) * a.ldgk;
       }
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * a.acc_stride) + ((uint32_t)(quad * 32) << 16);
-      for (int c0 = 0; c0 < a.block_n; c0 += 32) {
-        uint32_t r[32];
+      bool waited = false;
+      for (int c0 = half * 32; c0 < a.block_n; c0 += 64) {
         const int width = a.block_n - c0 >= 32 ? 32 : 16;
+        const int col0 = n0 + c0;
+        // operands that do not depend on the accumulator are fetched before waiting for it
+        uint4 aux0[4], aux1[4];
+        if (MODE == EPI_SILU_RES || MODE == EPI_GATE) {
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            const int col = col0 + v8 * 8;
+            const bool on = valid && v8 * 8 < width && col + 8 <= a.n_store;
+            if (MODE == EPI_SILU_RES) aux0[v8] = on ? ld_nc16(a.residual + row * a.ldr + col) : make_uint4(0, 0, 0, 0);
+            if (MODE == EPI_GATE) {
+              aux0[v8] = on ? ld_nc16(a.gate_x + row * a.ldgx + col) : make_uint4(0, 0, 0, 0);
+              aux1[v8] = on ? ld16(gk_row + col) : make_uint4(0, 0, 0, 0);
+            }
+          }
+        }
+        if (!waited) {
+          mbar_wait(tfull_bar + acc * 8, acc_phase);
+          tc_fence_after();
+          waited = true;
+        }
+        uint32_t r[32];
         if (width == 32) tmem_ld32(taddr0 + c0, r);
         else tmem_ld16(taddr0 + c0, r);
         tmem_ld_wait();
         if (valid) {
-          const int col0 = n0 + c0;
 #pragma unroll
           for (int v8 = 0; v8 < 4; ++v8) {
-            if (v8 * 8 >= width) break;
             const int col = col0 + v8 * 8;
-            if (col + 8 > a.n_store) break;
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              f[j] = fmaf(__uint_as_float(r[v8 * 8 + j]), s_scale[c0 + v8 * 8 + j], s_bias[c0 + v8 * 8 + j]);
-            if (a.gate_x != nullptr) {
-              float gx[8], gk[8];
-              unpack8(ld_nc16(a.gate_x + row * a.ldgx + col), gx);
-              unpack8(ld16(gk_row + col), gk);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] *= sigmoid_fast(gx[j] + gk[j]);
-            } else if (a.act != DMAY_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], a.act);
-            }
-            if (a.residual != nullptr) {
-              float rs[8];
-              unpack8(ld_nc16(a.residual + row * a.ldr + col), rs);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += rs[j];
-            }
-            if (a.out_f32) {
-              float* yo = reinterpret_cast<float*>(a.y) + row * a.ldy + col;
-              *reinterpret_cast<float4*>(yo) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(yo + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              st16(reinterpret_cast<__nv_bfloat16*>(a.y) + row * a.ldy + col, pack8(f));
-            }
+            if (v8 * 8 < width && col + 8 <= a.n_store)
+              epi_store8<MODE>(a, r + v8 * 8, s_scale + c0 + v8 * 8, s_bias + c0 + v8 * 8, row, col, aux0[v8], aux1[v8]);
           }
         }
+      }
+      if (!waited) {  // this warp had no chunk (block_n <= 32 and half == 1): still consume the phase
+        mbar_wait(tfull_bar + acc * 8, acc_phase);
+        tc_fence_after();
       }
       tc_fence_before();
       mbar_arrive(tempty_bar + acc * 8);
@@ -520,16 +592,37 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   }
 
   const size_t smem = 1024 + (size_t)a.stages * a.stage_bytes + kTailBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
   const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
   const long long tiles = (long long)a.num_m_tiles * a.num_n_tiles;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  conv_gemm_kernel<<<grid, kConvThreads, smem, stream>>>(a);
+  int mode;
+  if (a.gate_x) mode = (!out_f32 && !a.residual) ? EPI_GATE : -1;
+  else if (out_f32) mode = (a.act == DMAY_ACT_NONE && !a.residual) ? EPI_LINEAR_F32 : EPI_GENERIC;
+  else if (a.act == DMAY_ACT_SILU) mode = a.residual ? EPI_SILU_RES : EPI_SILU;
+  else if (a.act == DMAY_ACT_NONE && !a.residual) mode = EPI_LINEAR;
+  else mode = EPI_GENERIC;
+  if (mode < 0) return DMAY_EUNSUPPORTED;
+#define DMAY_LAUNCH_MODE(MODE)                                                                                     \
+  case MODE: {                                                                                                      \
+    static bool attr_set = false;                                                                                   \
+    if (!attr_set) {                                                                                                \
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                           227 * 1024);                                                            \
+      if (e != cudaSuccess) return (int)e;                                                                          \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
+    conv_gemm_kernel<MODE><<<grid, kConvThreads, smem, stream>>>(a);                                                \
+    break;                                                                                                          \
+  }
+  switch (mode) {
+    DMAY_LAUNCH_MODE(EPI_SILU)
+    DMAY_LAUNCH_MODE(EPI_SILU_RES)
+    DMAY_LAUNCH_MODE(EPI_LINEAR)
+    DMAY_LAUNCH_MODE(EPI_GATE)
+    DMAY_LAUNCH_MODE(EPI_LINEAR_F32)
+    DMAY_LAUNCH_MODE(EPI_GENERIC)
+  }
+#undef DMAY_LAUNCH_MODE
   return finish_launch();
 }
 

@@ -9,6 +9,49 @@
 
 namespace dmay {
 
+// ---- pool, plane-in-smem variant: CTA = (image, group of VL channel vectors); the H x W x VL plane is
+// staged with fully coalesced, fully parallel loads, then row / column sums run out of shared memory.
+__global__ void __launch_bounds__(256) ca_pool_plane_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            float* __restrict__ pooled, int H, int W, int C, int ldx,
+                                                            int VL) {
+  extern __shared__ uint4 plane[];  // [H*W][VL]
+  const int cvec = C >> 3;
+  const int groups = (cvec + VL - 1) / VL;
+  const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int v0 = g * VL;
+  const int vl = min(VL, cvec - v0);
+  const int HW = H * W;
+  const __nv_bfloat16* xb = x + (long long)n * HW * ldx + v0 * 8;
+  for (int i = threadIdx.x; i < HW * vl; i += blockDim.x) {
+    const int p = i / vl, v = i - p * vl;
+    plane[p * VL + v] = ld16(xb + (long long)p * ldx + v * 8);  // default caching: `apply` re-reads x from L2
+  }
+  __syncthreads();
+  float* pb = pooled + (long long)n * (H + W) * C + v0 * 8;
+  const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+  // items: (position p in [0, H+W), vector v)
+  for (int i = threadIdx.x; i < (H + W) * vl; i += blockDim.x) {
+    const int p = i / vl, v = i - p * vl;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int start, step, cnt;
+    float inv;
+    if (p < H) { start = p * W; step = 1; cnt = W; inv = invW; }
+    else { start = p - H; step = W; cnt = H; inv = invH; }
+    for (int k = 0; k < cnt; ++k) {
+      float f[8];
+      unpack8(plane[(start + k * step) * VL + v], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    float4* o = reinterpret_cast<float4*>(pb + (long long)p * C + v * 8);
+    o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    o[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+  }
+}
+
+// ---- pool, direct variant for planes that do not fit in shared memory.
 // grid = N * groups * bands.  CTA (n, g, b): channel vectors [g*8, g*8+8) (64 channels),
 // rows h === b (mod bands) reduced over w, columns w === b (mod bands) reduced over h.
 // thread = (slot 0..31, lane 0..7): lane picks the 16-byte channel vector, slot the row/column.
@@ -27,7 +70,6 @@ __global__ void __launch_bounds__(256) ca_pool_kernel(const __nv_bfloat16* __res
   const __nv_bfloat16* xb = x + (long long)n * H * W * ldx + v * 8;
   float* pb = pooled + (long long)n * (H + W) * C + v * 8;
   const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
-  // rows
   for (int h = b + slot * bands; h < H; h += 32 * bands) {
     float acc[8];
 #pragma unroll
@@ -44,7 +86,6 @@ __global__ void __launch_bounds__(256) ca_pool_kernel(const __nv_bfloat16* __res
     o[0] = make_float4(acc[0] * invW, acc[1] * invW, acc[2] * invW, acc[3] * invW);
     o[1] = make_float4(acc[4] * invW, acc[5] * invW, acc[6] * invW, acc[7] * invW);
   }
-  // columns
   for (int w = b + slot * bands; w < W; w += 32 * bands) {
     float acc[8];
 #pragma unroll
@@ -63,11 +104,12 @@ __global__ void __launch_bounds__(256) ca_pool_kernel(const __nv_bfloat16* __res
   }
 }
 
-// grid = N * ceil((H+W)/PG).  CTA handles PG consecutive positions of one image.
-// w1: [Cm][C] fp32; whT / wwT: [Cm][Cout] fp32 (transposed so consecutive threads read consecutive c).
+// ---- mlp.  grid = N * ceil((H+W)/PG); CTA handles PG consecutive positions of one image.
+// w1T: [C][Cm] fp32 (transposed: threads of a warp = consecutive hidden units j -> coalesced);
+// whT / wwT: [Cm][Cout] fp32 (consecutive threads = consecutive output channels -> coalesced).
 constexpr int PG = 8;
 __global__ void __launch_bounds__(256) ca_mlp_kernel(const float* __restrict__ pooled, float* __restrict__ gates,
-                                                     const float* __restrict__ w1, const float* __restrict__ b1,
+                                                     const float* __restrict__ w1T, const float* __restrict__ b1,
                                                      const float* __restrict__ s1, const float* __restrict__ t1,
                                                      const float* __restrict__ whT, const float* __restrict__ bh,
                                                      const float* __restrict__ wwT, const float* __restrict__ bw,
@@ -81,33 +123,25 @@ __global__ void __launch_bounds__(256) ca_mlp_kernel(const float* __restrict__ p
   const int p0 = (blockIdx.x % pgroups) * PG;
   const int np = min(PG, P - p0);
   for (int i = threadIdx.x; i < PG * C; i += blockDim.x) {
-    int pp = i / C, c = i % C;
+    const int pp = i / C, c = i - pp * C;
     sp[i] = pp < np ? pooled[((long long)n * P + p0 + pp) * C + c] : 0.f;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int j = warp; j < Cm; j += nwarps) {
-    float acc[PG];
-#pragma unroll
-    for (int q = 0; q < PG; ++q) acc[q] = 0.f;
-    const float* wr = w1 + (long long)j * C;
-    for (int c = lane; c < C; c += 32) {
-      float wv = wr[c];
-#pragma unroll
-      for (int q = 0; q < PG; ++q) acc[q] += wv * sp[q * C + c];
+  // hidden: one thread per (position q, hidden unit j); 4 independent accumulators hide the load latency
+  for (int o = threadIdx.x; o < PG * Cm; o += blockDim.x) {
+    const int q = o / Cm, j = o - q * Cm;
+    const float* sq = sp + q * C;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+      a0 = fmaf(w1T[(long long)(c + 0) * Cm + j], sq[c + 0], a0);
+      a1 = fmaf(w1T[(long long)(c + 1) * Cm + j], sq[c + 1], a1);
+      a2 = fmaf(w1T[(long long)(c + 2) * Cm + j], sq[c + 2], a2);
+      a3 = fmaf(w1T[(long long)(c + 3) * Cm + j], sq[c + 3], a3);
     }
-#pragma unroll
-    for (int q = 0; q < PG; ++q) {
-      float a = acc[q];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      acc[q] = a;
-    }
-    if (lane == 0) {
-      const float bj = b1[j], sj = s1[j], tj = t1[j];
-#pragma unroll
-      for (int q = 0; q < PG; ++q) sy[q * Cm + j] = hardswish(sj * (acc[q] + bj) + tj);
-    }
+    for (; c < C; ++c) a0 = fmaf(w1T[(long long)c * Cm + j], sq[c], a0);
+    const float acc = (a0 + a1) + (a2 + a3);
+    sy[q * Cm + j] = hardswish(s1[j] * (acc + b1[j]) + t1[j]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
@@ -118,33 +152,33 @@ __global__ void __launch_bounds__(256) ca_mlp_kernel(const float* __restrict__ p
     for (int j = 0; j < Cm; ++j) {
       const float a = whT[(long long)j * Cout + c], b = wwT[(long long)j * Cout + c];
 #pragma unroll
-      for (int q = 0; q < PG; ++q) acc[q] += ((p0 + q < H) ? a : b) * sy[q * Cm + j];
+      for (int q = 0; q < PG; ++q) acc[q] = fmaf((p0 + q < H) ? a : b, sy[q * Cm + j], acc[q]);
     }
     for (int q = 0; q < np; ++q) gates[((long long)n * P + p0 + q) * Cout + c] = sigmoid_acc(acc[q]);
   }
 }
 
+// ---- apply: blockDim = (VX channel vectors, PY pixels), 32-bit pixel index.
 __global__ void __launch_bounds__(256) ca_apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                        const float* __restrict__ gates, __nv_bfloat16* __restrict__ y,
-                                                       int N, int H, int W, int C, int ldx, int ldy) {
+                                                       unsigned npix, int H, int W, int C, int ldx, int ldy) {
   const int cv = C >> 3;
-  const long long items = (long long)N * H * W * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
-       i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % cv);
-    long long pix = i / cv;
-    int w_ = (int)(pix % W);
-    long long t = pix / W;
-    int h_ = (int)(t % H);
-    int n = (int)(t / H);
-    float f[8];
-    unpack8(ld_nc16(x + pix * ldx + v * 8), f);
-    const float4* gh = reinterpret_cast<const float4*>(gates + ((long long)n * (H + W) + h_) * C + v * 8);
-    const float4* gw = reinterpret_cast<const float4*>(gates + ((long long)n * (H + W) + H + w_) * C + v * 8);
-    const float4 h0 = gh[0], h1 = gh[1], w0 = gw[0], w1 = gw[1];
-    f[0] = (f[0] * w0.x) * h0.x; f[1] = (f[1] * w0.y) * h0.y; f[2] = (f[2] * w0.z) * h0.z; f[3] = (f[3] * w0.w) * h0.w;
-    f[4] = (f[4] * w1.x) * h1.x; f[5] = (f[5] * w1.y) * h1.y; f[6] = (f[6] * w1.z) * h1.z; f[7] = (f[7] * w1.w) * h1.w;
-    st_na16(y + pix * ldy + v * 8, pack8(f));
+  for (unsigned pix = blockIdx.x * blockDim.y + threadIdx.y; pix < npix; pix += gridDim.x * blockDim.y) {
+    const unsigned t = pix / (unsigned)W;
+    const int w_ = (int)(pix - t * (unsigned)W);
+    const int n = (int)(t / (unsigned)H);
+    const int h_ = (int)(t - (unsigned)n * (unsigned)H);
+    const float* gh = gates + ((long long)n * (H + W) + h_) * C;
+    const float* gw = gates + ((long long)n * (H + W) + H + w_) * C;
+    for (int v = threadIdx.x; v < cv; v += blockDim.x) {
+      float f[8];
+      unpack8(ld_nc16(x + (long long)pix * ldx + v * 8), f);
+      const float4 h0 = reinterpret_cast<const float4*>(gh + v * 8)[0], h1 = reinterpret_cast<const float4*>(gh + v * 8)[1];
+      const float4 w0 = reinterpret_cast<const float4*>(gw + v * 8)[0], w1 = reinterpret_cast<const float4*>(gw + v * 8)[1];
+      f[0] = (f[0] * w0.x) * h0.x; f[1] = (f[1] * w0.y) * h0.y; f[2] = (f[2] * w0.z) * h0.z; f[3] = (f[3] * w0.w) * h0.w;
+      f[4] = (f[4] * w1.x) * h1.x; f[5] = (f[5] * w1.y) * h1.y; f[6] = (f[6] * w1.z) * h1.z; f[7] = (f[7] * w1.w) * h1.w;
+      st_na16(y + (long long)pix * ldy + v * 8, pack8(f));
+    }
   }
 }
 
@@ -159,15 +193,37 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
   if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->C <= 0 || p->Cm <= 0) return DMAY_EINVAL;
   if ((p->C | p->ldx | p->ldy) & 7) return DMAY_EUNSUPPORTED;
   if (!aligned16(p->x) || !aligned16(p->y) || !aligned16(p->pooled) || !aligned16(p->gates)) return DMAY_EINVAL;
+  const long long npix = (long long)p->N * p->H * p->W;
+  if (npix >= 0x7fffffffLL) return DMAY_EUNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  const int cvec = p->C / 8, groups = (cvec + 7) / 8;
+  const int cvec = p->C / 8;
   const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
-  // bands: split rows/columns over more CTAs until the grid covers the chip ~2x (cap at min(H,W))
-  int bands = 1;
-  while ((long long)p->N * groups * bands < 2LL * sms && bands * 2 <= (p->H < p->W ? p->H : p->W)) bands *= 2;
-  long long g1 = (long long)p->N * groups * bands;
-  if (g1 > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
-  ca_pool_kernel<<<(int)g1, 256, 0, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, p->H, p->W, p->C, p->ldx, bands);
+  const long long HW = (long long)p->H * p->W;
+  // 1. pool
+  int VL = 0;
+  for (int cand : {8, 4, 2, 1}) {
+    if (cand > cvec && cand != 1) continue;
+    if (HW * cand * 16 <= 100 * 1024) { VL = cand; break; }
+  }
+  if (VL > 0) {
+    const int groups = (cvec + VL - 1) / VL;
+    const size_t smem = (size_t)HW * VL * 16;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(ca_pool_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    ca_pool_plane_kernel<<<p->N * groups, 256, smem, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, p->H, p->W,
+                                                          p->C, p->ldx, VL);
+  } else {
+    const int groups = (cvec + 7) / 8;
+    int bands = 1;
+    while ((long long)p->N * groups * bands < 2LL * sms && bands * 2 <= (p->H < p->W ? p->H : p->W)) bands *= 2;
+    long long g1 = (long long)p->N * groups * bands;
+    if (g1 > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+    ca_pool_kernel<<<(int)g1, 256, 0, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, p->H, p->W, p->C, p->ldx,
+                                           bands);
+  }
+  // 2. mlp
   const int P = p->H + p->W;
   const int pgroups = (P + PG - 1) / PG;
   const size_t smem = (size_t)PG * (p->C + p->Cm) * sizeof(float);
@@ -180,8 +236,14 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
                                                   (const float*)p->b1, (const float*)p->s1, (const float*)p->t1,
                                                   (const float*)p->wh, (const float*)p->bh, (const float*)p->ww,
                                                   (const float*)p->bw, p->H, p->W, p->C, p->Cm, p->C);
-  long long items = (long long)p->N * p->H * p->W * cvec;
-  ca_apply_kernel<<<grid_for(items, 256), 256, 0, s>>>((const __nv_bfloat16*)p->x, (const float*)p->gates,
-                                                       (__nv_bfloat16*)p->y, p->N, p->H, p->W, p->C, p->ldx, p->ldy);
+  // 3. apply
+  int vx = 1;
+  while (vx * 2 <= cvec && vx < 32) vx *= 2;
+  const dim3 blk(vx, 256 / vx);
+  long long need = (npix + blk.y - 1) / blk.y;
+  const long long cap = (long long)sms * 8;
+  ca_apply_kernel<<<(int)(need < cap ? need : cap), blk, 0, s>>>((const __nv_bfloat16*)p->x, (const float*)p->gates,
+                                                                 (__nv_bfloat16*)p->y, (unsigned)npix, p->H, p->W, p->C,
+                                                                 p->ldx, p->ldy);
   return finish_launch(3);
 }

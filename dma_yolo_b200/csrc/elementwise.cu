@@ -22,27 +22,52 @@ int sm_count() {
 
 constexpr int kThreads = 256;
 
+// Thread layout of the NHWC streaming kernels: blockDim = (VX, PY) with VX = channel vectors (16 B each)
+// handled side by side (a power of two <= 32) and PY = 256/VX pixels per CTA step.  Pixels are indexed
+// with 32-bit integers (host checks N*H*W < 2^31) and decoded into (n,h,w) once per pixel, so the
+// per-vector cost is one add — 64-bit div/mod per 16-byte item made the first version ALU-bound.
+struct PixGeom {
+  unsigned npix;
+  int H, W;
+};
+__device__ __forceinline__ void decode_pix(unsigned pix, int H, int W, int& n, int& h, int& w) {
+  const unsigned t = pix / (unsigned)W;
+  w = (int)(pix - t * (unsigned)W);
+  n = (int)(t / (unsigned)H);
+  h = (int)(t - (unsigned)n * (unsigned)H);
+}
+#define FOR_EACH_PIXEL(pix, npix) \
+  for (unsigned pix = blockIdx.x * blockDim.y + threadIdx.y; pix < (npix); pix += gridDim.x * blockDim.y)
+#define FOR_EACH_VEC(v, cv) for (int v = threadIdx.x; v < (cv); v += blockDim.x)
+
+static inline dim3 pix_block(int cv) {
+  int vx = 1;
+  while (vx * 2 <= cv && vx < 32) vx *= 2;
+  return dim3(vx, kThreads / vx);
+}
+static inline int pix_grid(long long npix, dim3 block, int ctas_per_sm = 8) {
+  long long need = (npix + block.y - 1) / block.y;
+  long long cap = (long long)sm_count() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
 // ---- a4 space_to_depth ----------------------------------------------------------------------
 // reference: models/common.py:1457-1458.  One item = one 16-byte vector of the OUTPUT.
 __global__ void __launch_bounds__(kThreads) spd_kernel(const __nv_bfloat16* __restrict__ x,
-                                                       __nv_bfloat16* __restrict__ y, int N, int H, int W,
+                                                       __nv_bfloat16* __restrict__ y, unsigned npix, int H, int W,
                                                        int C, int ldx, int ldy) {
   const int Ho = H >> 1, Wo = W >> 1, cv = C >> 3;
-  const long long items = (long long)N * Ho * Wo * 4 * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
-       i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % cv);
-    long long t = i / cv;
-    int q = (int)(t & 3);  // q = dy + 2*dx
-    t >>= 2;
-    int wo = (int)(t % Wo);
-    t /= Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
-    int dy = q & 1, dx = q >> 1;
-    const __nv_bfloat16* src = x + (((long long)n * H + (2 * ho + dy)) * W + (2 * wo + dx)) * ldx + v * 8;
-    __nv_bfloat16* dst = y + (((long long)n * Ho + ho) * Wo + wo) * ldy + q * C + v * 8;
-    st_na16(dst, ld_nc16(src));
+  FOR_EACH_PIXEL(pix, npix) {  // output pixel
+    int n, ho, wo;
+    decode_pix(pix, Ho, Wo, n, ho, wo);
+    const __nv_bfloat16* src0 = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * ldx;
+    __nv_bfloat16* dst0 = y + (long long)pix * ldy;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // q = dy + 2*dx
+      const __nv_bfloat16* src = src0 + ((long long)(q & 1) * W + (q >> 1)) * ldx;
+      FOR_EACH_VEC(v, cv) st_na16(dst0 + q * C + v * 8, ld_nc16(src + v * 8));
+    }
   }
 }
 
@@ -56,140 +81,130 @@ struct CatArgs {
   float w[3];
 };
 __global__ void __launch_bounds__(kThreads) adconcat_kernel(CatArgs a, __nv_bfloat16* __restrict__ y, int n_in,
-                                                            int N, int H, int W, int ldy) {
-  const int cv0 = a.C[0] >> 3, cv1 = a.C[1] >> 3, cv2 = (n_in > 2 ? a.C[2] : 0) >> 3;
-  const int cvt = cv0 + cv1 + cv2;
-  const long long items = (long long)N * H * W * cvt;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
-       i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % cvt);
-    long long pix = i / cvt;
-    int w_ = (int)(pix % W);
-    long long t = pix / W;
-    int h_ = (int)(t % H);
-    int n = (int)(t / H);
-    int k = 0, vc = v;
-    if (vc >= cv0) {
-      vc -= cv0;
-      k = 1;
-      if (vc >= cv1) {
-        vc -= cv1;
-        k = 2;
+                                                            unsigned npix, int H, int W, int ldy) {
+  FOR_EACH_PIXEL(pix, npix) {
+    int n, h_, w_;
+    decode_pix(pix, H, W, n, h_, w_);
+    int coff = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < n_in) {
+        const int u = a.up[k];
+        const __nv_bfloat16* src =
+            a.x[k] + (((long long)n * (H >> u) + (h_ >> u)) * (W >> u) + (w_ >> u)) * a.ld[k];
+        __nv_bfloat16* dst = y + (long long)pix * ldy + coff;
+        const float wk = a.w[k];
+        const int cv = a.C[k] >> 3;
+        FOR_EACH_VEC(v, cv) {
+          float f[8];
+          unpack8(u ? ld16(src + v * 8) : ld_nc16(src + v * 8), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(wk, f[j]);
+          st_na16(dst + v * 8, pack8(f));
+        }
+        coff += a.C[k];
       }
     }
-    const int u = a.up[k];
-    const int Hi = H >> u, Wi = W >> u;
-    const __nv_bfloat16* src = a.x[k] + (((long long)n * Hi + (h_ >> u)) * Wi + (w_ >> u)) * a.ld[k] + vc * 8;
-    float f[8];
-    unpack8(u ? ld16(src) : ld_nc16(src), f);
-    const float wk = a.w[k];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(wk, f[j]);
-    st_na16(y + pix * ldy + v * 8, pack8(f));
   }
 }
 
 // ---- Adapt_Add2/3: y = silu(sum_i w_i x_i), models/common.py:1040-1061 -------------------------
 __global__ void __launch_bounds__(kThreads) adaptadd_kernel(CatArgs a, __nv_bfloat16* __restrict__ y, int n_in,
-                                                            long long npix, int C, int ldy) {
+                                                            unsigned npix, int C, int ldy) {
   const int cv = C >> 3;
-  const long long items = npix * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
-       i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % cv);
-    long long pix = i / cv;
-    float acc[8];
+  FOR_EACH_PIXEL(pix, npix) {
+    FOR_EACH_VEC(v, cv) {
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = 0; k < n_in; ++k) {
-      float f[8];
-      unpack8(ld_nc16(a.x[k] + pix * a.ld[k] + v * 8), f);
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int k = 0; k < n_in; ++k) {
+        float f[8];
+        unpack8(ld_nc16(a.x[k] + (long long)pix * a.ld[k] + v * 8), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += a.w[k] * f[j];
+        for (int j = 0; j < 8; ++j) acc[j] += a.w[k] * f[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] * sigmoid_acc(acc[j]);
+      st_na16(y + (long long)pix * ldy + v * 8, pack8(acc));
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = acc[j] * sigmoid_acc(acc[j]);
-    st_na16(y + pix * ldy + v * 8, pack8(acc));
   }
 }
 
 // ---- nn.Upsample(None, f, 'nearest') -----------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) upsample_kernel(const __nv_bfloat16* __restrict__ x,
-                                                            __nv_bfloat16* __restrict__ y, int N, int H, int W,
+                                                            __nv_bfloat16* __restrict__ y, unsigned npix, int H, int W,
                                                             int C, int ldx, int ldy, int f) {
   const int Ho = H * f, Wo = W * f, cv = C >> 3;
-  const long long items = (long long)N * Ho * Wo * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
-       i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % cv);
-    long long pix = i / cv;
-    int wo = (int)(pix % Wo);
-    long long t = pix / Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
-    const __nv_bfloat16* src = x + (((long long)n * H + ho / f) * W + wo / f) * ldx + v * 8;
-    st_na16(y + pix * ldy + v * 8, ld16(src));
+  FOR_EACH_PIXEL(pix, npix) {  // output pixel
+    int n, ho, wo;
+    decode_pix(pix, Ho, Wo, n, ho, wo);
+    const __nv_bfloat16* src = x + (((long long)n * H + ho / f) * W + wo / f) * ldx;
+    FOR_EACH_VEC(v, cv) st_na16(y + (long long)pix * ldy + v * 8, ld16(src + v * 8));
   }
 }
 
 // ---- a5 SCConv: AvgPool2d(r,r) and the calibration gate ------------------------------------------
 // reference: models/common.py:1281-1287 (k2 pooling), 1310-1314 (gate).
 __global__ void __launch_bounds__(kThreads) avgpool_kernel(const __nv_bfloat16* __restrict__ x,
-                                                           __nv_bfloat16* __restrict__ y, int N, int H, int W,
+                                                           __nv_bfloat16* __restrict__ y, unsigned npix, int H, int W,
                                                            int C, int ldx, int ldy, int r) {
   const int Ho = H / r, Wo = W / r, cv = C >> 3;
   const float inv = 1.0f / (float)(r * r);
-  const long long items = (long long)N * Ho * Wo * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
-       i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % cv);
-    long long pix = i / cv;
-    int wo = (int)(pix % Wo);
-    long long t = pix / Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
-    float acc[8];
+  FOR_EACH_PIXEL(pix, npix) {  // output pixel
+    int n, ho, wo;
+    decode_pix(pix, Ho, Wo, n, ho, wo);
+    const __nv_bfloat16* src0 = x + (((long long)n * H + ho * r) * W + (long long)wo * r) * ldx;
+    FOR_EACH_VEC(v, cv) {
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int dy = 0; dy < r; ++dy) {
-      const __nv_bfloat16* row = x + (((long long)n * H + ho * r + dy) * W + (long long)wo * r) * ldx + v * 8;
-      for (int dx = 0; dx < r; ++dx) {
-        float f[8];
-        unpack8(ld_nc16(row + (long long)dx * ldx), f);
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int dy = 0; dy < r; ++dy) {
+        const __nv_bfloat16* row = src0 + (long long)dy * W * ldx + v * 8;
+#pragma unroll 4
+        for (int dx = 0; dx < r; ++dx) {
+          float f[8];
+          unpack8(ld_nc16(row + (long long)dx * ldx), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] *= inv;
-    st16(y + pix * ldy + v * 8, pack8(acc));
+      for (int j = 0; j < 8; ++j) acc[j] *= inv;
+      st16(y + (long long)pix * ldy + v * 8, pack8(acc));
+    }
   }
+}
+
+__device__ __forceinline__ float tanh_apx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __global__ void __launch_bounds__(kThreads) scgate_kernel(const __nv_bfloat16* __restrict__ x,
                                                           const __nv_bfloat16* __restrict__ k3,
                                                           const __nv_bfloat16* __restrict__ k2,
-                                                          __nv_bfloat16* __restrict__ y, int N, int H, int W, int C,
+                                                          __nv_bfloat16* __restrict__ y, unsigned npix, int H, int W, int C,
                                                           int Hk, int Wk, int ldx, int ld3, int ld2, int ldy) {
   const int cv = C >> 3;
   const float sh = (float)Hk / (float)H, sw = (float)Wk / (float)W;
-  const long long items = (long long)N * H * W * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items;
-       i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % cv);
-    long long pix = i / cv;
-    int w_ = (int)(pix % W);
-    long long t = pix / W;
-    int h_ = (int)(t % H);
-    int n = (int)(t / H);
+  FOR_EACH_PIXEL(pix, npix) {
+    int n, h_, w_;
+    decode_pix(pix, H, W, n, h_, w_);
     const int hs = nearest_src(h_, Hk, H, sh), ws = nearest_src(w_, Wk, W, sw);
-    float fx[8], f3[8], f2[8];
-    unpack8(ld_nc16(x + pix * ldx + v * 8), fx);
-    unpack8(ld_nc16(k3 + pix * ld3 + v * 8), f3);
-    unpack8(ld16(k2 + (((long long)n * Hk + hs) * Wk + ws) * ld2 + v * 8), f2);
+    const __nv_bfloat16* k2p = k2 + (((long long)n * Hk + hs) * Wk + ws) * ld2;
+    FOR_EACH_VEC(v, cv) {
+      float fx[8], f3[8], f2[8];
+      const uint4 ux = ld_nc16(x + (long long)pix * ldx + v * 8);
+      const uint4 u3 = ld_nc16(k3 + (long long)pix * ld3 + v * 8);
+      const uint4 u2 = ld16(k2p + v * 8);
+      unpack8(ux, fx);
+      unpack8(u3, f3);
+      unpack8(u2, f2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f3[j] = f3[j] * sigmoid_fast(fx[j] + f2[j]);
-    st_na16(y + pix * ldy + v * 8, pack8(f3));
+      for (int j = 0; j < 8; ++j) f3[j] *= fmaf(0.5f, tanh_apx(0.5f * (fx[j] + f2[j])), 0.5f);  // sigmoid
+      st_na16(y + (long long)pix * ldy + v * 8, pack8(f3));
+    }
   }
 }
 
@@ -335,9 +350,11 @@ int dmay_spd(const dmay_spd_params* p, dmay_stream_t stream) {
   REQ(aligned16(p->x) && aligned16(p->y));
   if ((p->H | p->W) & 1) return DMAY_EUNSUPPORTED;
   if ((p->C | p->ldx | p->ldy) & 7) return DMAY_EUNSUPPORTED;
-  long long items = (long long)p->N * (p->H / 2) * (p->W / 2) * 4 * (p->C / 8);
-  spd_kernel<<<grid_for(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, p->N, p->H, p->W, p->C, p->ldx, p->ldy);
+  const long long npix = (long long)p->N * (p->H / 2) * (p->W / 2);
+  if (npix >= 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  const dim3 blk = pix_block(p->C / 8);
+  spd_kernel<<<pix_grid(npix, blk), blk, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, (unsigned)npix, p->H, p->W, p->C, p->ldx, p->ldy);
   return finish_launch();
 }
 
@@ -360,9 +377,14 @@ int dmay_adconcat(const dmay_adconcat_params* p, dmay_stream_t stream) {
   }
   REQ(aligned16(p->y));
   if (p->ldy & 7) return DMAY_EUNSUPPORTED;
-  long long items = (long long)p->N * p->H * p->W * (ctot / 8);
-  adconcat_kernel<<<grid_for(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      a, (__nv_bfloat16*)p->y, p->n_in, p->N, p->H, p->W, p->ldy);
+  const long long npix = (long long)p->N * p->H * p->W;
+  if (npix >= 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  int cmin = a.C[0];
+  for (int i = 1; i < p->n_in; ++i) cmin = a.C[i] < cmin ? a.C[i] : cmin;
+  (void)ctot;
+  const dim3 blk = pix_block(cmin / 8);
+  adconcat_kernel<<<pix_grid(npix, blk), blk, 0, (cudaStream_t)stream>>>(
+      a, (__nv_bfloat16*)p->y, p->n_in, (unsigned)npix, p->H, p->W, p->ldy);
   return finish_launch();
 }
 
@@ -378,9 +400,10 @@ int dmay_adaptadd(const dmay_adaptadd_params* p, dmay_stream_t stream) {
   a.up[0] = a.up[1] = a.up[2] = 0;
   a.w[0] = p->w0; a.w[1] = p->w1; a.w[2] = p->w2;
   REQ(aligned16(p->x0) && aligned16(p->x1) && aligned16(p->y) && (p->n_in < 3 || aligned16(p->x2)));
-  long long items = p->npix * (p->C / 8);
-  adaptadd_kernel<<<grid_for(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      a, (__nv_bfloat16*)p->y, p->n_in, p->npix, p->C, p->ldy);
+  if (p->npix >= 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  const dim3 blk = pix_block(p->C / 8);
+  adaptadd_kernel<<<pix_grid(p->npix, blk), blk, 0, (cudaStream_t)stream>>>(
+      a, (__nv_bfloat16*)p->y, p->n_in, (unsigned)p->npix, p->C, p->ldy);
   return finish_launch();
 }
 
@@ -388,9 +411,11 @@ int dmay_upsample_nearest(const dmay_upsample_params* p, dmay_stream_t stream) {
   REQ(p && p->x && p->y && p->N > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->factor >= 1);
   REQ(aligned16(p->x) && aligned16(p->y));
   if ((p->C | p->ldx | p->ldy) & 7) return DMAY_EUNSUPPORTED;
-  long long items = (long long)p->N * p->H * p->factor * p->W * p->factor * (p->C / 8);
-  upsample_kernel<<<grid_for(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, p->N, p->H, p->W, p->C, p->ldx, p->ldy, p->factor);
+  const long long npix = (long long)p->N * p->H * p->factor * p->W * p->factor;
+  if (npix >= 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  const dim3 blk = pix_block(p->C / 8);
+  upsample_kernel<<<pix_grid(npix, blk), blk, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, (unsigned)npix, p->H, p->W, p->C, p->ldx, p->ldy, p->factor);
   return finish_launch();
 }
 
@@ -399,9 +424,11 @@ int dmay_avgpool(const dmay_avgpool_params* p, dmay_stream_t stream) {
   REQ(aligned16(p->x) && aligned16(p->y));
   if ((p->C | p->ldx | p->ldy) & 7) return DMAY_EUNSUPPORTED;
   if (p->H / p->r < 1 || p->W / p->r < 1) return DMAY_EUNSUPPORTED;
-  long long items = (long long)p->N * (p->H / p->r) * (p->W / p->r) * (p->C / 8);
-  avgpool_kernel<<<grid_for(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, p->N, p->H, p->W, p->C, p->ldx, p->ldy, p->r);
+  const long long npix = (long long)p->N * (p->H / p->r) * (p->W / p->r);
+  if (npix >= 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  const dim3 blk = pix_block(p->C / 8);
+  avgpool_kernel<<<pix_grid(npix, blk), blk, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, (unsigned)npix, p->H, p->W, p->C, p->ldx, p->ldy, p->r);
   return finish_launch();
 }
 
@@ -409,10 +436,12 @@ int dmay_scconv_gate(const dmay_scgate_params* p, dmay_stream_t stream) {
   REQ(p && p->x && p->k3 && p->k2 && p->y && p->N > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->Hk > 0 && p->Wk > 0);
   REQ(aligned16(p->x) && aligned16(p->k3) && aligned16(p->k2) && aligned16(p->y));
   if ((p->C | p->ldx | p->ld3 | p->ld2 | p->ldy) & 7) return DMAY_EUNSUPPORTED;
-  long long items = (long long)p->N * p->H * p->W * (p->C / 8);
-  scgate_kernel<<<grid_for(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+  const long long npix = (long long)p->N * p->H * p->W;
+  if (npix >= 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  const dim3 blk = pix_block(p->C / 8);
+  scgate_kernel<<<pix_grid(npix, blk), blk, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)p->x, (const __nv_bfloat16*)p->k3, (const __nv_bfloat16*)p->k2, (__nv_bfloat16*)p->y,
-      p->N, p->H, p->W, p->C, p->Hk, p->Wk, p->ldx, p->ld3, p->ld2, p->ldy);
+      (unsigned)npix, p->H, p->W, p->C, p->Hk, p->Wk, p->ldx, p->ld3, p->ld2, p->ldy);
   return finish_launch();
 }
 

@@ -195,6 +195,9 @@ class Model(nn.Module):
                 else:
                     x = m(x)
             y.append(x if m.i in self.save else None)
+            tr = self.__dict__.get('_trace')
+            if tr is not None:  # test/debug hook: per-layer outputs (incl. layers that bypass nn.Module.__call__)
+                tr.append(x)
         return x
 
     @staticmethod

@@ -179,19 +179,22 @@ def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor |
          residual: torch.Tensor | None = None, gate: tuple | None = None, out_fp32: bool = False,
          block_n: int = 0, num_sms: int = 0) -> torch.Tensor:
     """y = act(scale * conv(x, w) + bias) (+ residual) | (* sigmoid(gate_x + up(gate_k)))."""
+    # uint8 images are normalised on the fly (x/255, the `img.float()/255` of val.py:199-202 folded into
+    # the layout kernel) — an extension: the reference only accepts float images.
+    mul = 1.0 / 255.0 if x.dtype == torch.uint8 else 1.0
     if pk.stem_spd:
         if x.shape[1] != pk.cin:
             raise DmayError(f"conv: expected {pk.cin} input channels, got {x.shape[1]}")
-        x = input_prep(x, spd=True, cpad=pk.cin_pad)
+        x = input_prep(x, spd=True, cpad=pk.cin_pad, mul=mul)
     elif x.shape[1] != pk.cin_pad or not (x.dtype == torch.bfloat16 and is_nhwc(x)):
         if x.shape[1] != pk.cin:
             raise DmayError(f"conv: expected {pk.cin} input channels, got {x.shape[1]}")
         if pk.cin != pk.cin_pad:
             if x.dtype == torch.bfloat16 and is_nhwc(x):
                 x = to_nchw(x, torch.bfloat16)
-            x = input_prep(x, spd=False, cpad=pk.cin_pad)
+            x = input_prep(x, spd=False, cpad=pk.cin_pad, mul=mul)
         else:
-            x = as_act(x)
+            x = as_act(x if x.dtype != torch.uint8 else x.float() / 255)
     n, _, h, w = x.shape
     ho = (h + 2 * pk.pad - pk.kh) // pk.stride + 1
     wo = (w + 2 * pk.pad - pk.kw) // pk.stride + 1
@@ -367,7 +370,8 @@ class CoordAttPack:
 
 
 def pack_coordatt(conv1, bn1, conv_h, conv_w, device) -> CoordAttPack:
-    """models/common.py:1168-1181 parameters -> fp32 device operands (BN folded to s1/t1; W_h/W_w transposed)."""
+    """models/common.py:1168-1181 parameters -> fp32 device operands (BN folded to s1/t1; all three weight
+    matrices transposed: w1 [C][Cm], whT/wwT [Cm][Cout])."""
     cm, c = conv1.weight.shape[:2]
     f = lambda t: t.detach().float().to(device).contiguous()
     inv = torch.rsqrt(bn1.running_var.detach().float() + bn1.eps)
@@ -375,7 +379,7 @@ def pack_coordatt(conv1, bn1, conv_h, conv_w, device) -> CoordAttPack:
     t1 = bn1.bias.detach().float() - bn1.running_mean.detach().float() * s1
     b1 = conv1.bias if conv1.bias is not None else torch.zeros(cm)
     zeros = lambda m: m.bias if m.bias is not None else torch.zeros(m.weight.shape[0])
-    return CoordAttPack(w1=f(conv1.weight.reshape(cm, c)), b1=f(b1), s1=f(s1), t1=f(t1),
+    return CoordAttPack(w1=f(conv1.weight.reshape(cm, c).t()), b1=f(b1), s1=f(s1), t1=f(t1),
                         whT=f(conv_h.weight.reshape(-1, cm).t()), bh=f(zeros(conv_h)),
                         wwT=f(conv_w.weight.reshape(-1, cm).t()), bw=f(zeros(conv_w)), c=c, cm=cm)
 

@@ -282,9 +282,10 @@ int dmay_scconv_gate(const dmay_scgate_params* p, dmay_stream_t stream);
 /* ---- a3: CoordAtt, models/common.py:1183-1207 -------------------------------------------
  * step 1 (pool):  pooled[n, h, c]   = mean_w x[n,h,w,c]        (h <  H)
  *                 pooled[n, H+w, c] = mean_h x[n,h,w,c]        (fp32, [N, H+W, C])
- * step 2 (mlp):   y = hardswish(s1 * (W1 . pooled + b1) + t1)  (W1 [Cm, C] fp32, conv1 bias b1,
- *                 BN folded into s1/t1);  gates[n,p,:] = sigmoid(Wh . y + bh) for p < H,
- *                 sigmoid(Ww . y + bw) for p >= H   (Wh/Ww [Cout, Cm] fp32), fp32 [N,H+W,Cout]
+ * step 2 (mlp):   y = hardswish(s1 * (W1 . pooled + b1) + t1)  (conv1 bias b1, BN folded into s1/t1);
+ *                 gates[n,p,:] = sigmoid(Wh . y + bh) for p < H, sigmoid(Ww . y + bw) for p >= H,
+ *                 fp32 [N,H+W,Cout].  Weight operands are passed TRANSPOSED, fp32:
+ *                 w1 = W1^T [C][Cm],  wh = Wh^T [Cm][Cout],  ww = Ww^T [Cm][Cout]  (Cout == C).
  * step 3 (apply): out = (x * a_w[n,w,c]) * a_h[n,h,c]  -> bf16
  * dmay_coordatt runs the three steps on the stream. */
 typedef struct dmay_coordatt_params {

@@ -12,13 +12,10 @@ pytestmark = pytest.mark.gpu
 
 def layer_outputs(m, x):
     """per-layer outputs of the kernel path (fp32 NCHW on CPU)."""
-    outs, hooks = [], []
-    for layer in m.model[:-1]:
-        hooks.append(layer.register_forward_hook(lambda mod, i, o: outs.append(o)))
+    m._trace = []
     with torch.no_grad():
         pred, raw = m(x)
-    for h in hooks:
-        h.remove()
+    outs, m._trace = m._trace[:-1], None
     from dma_yolo_b200.ops import Up
     outs = [(o.materialize() if isinstance(o, Up) else o).float().cpu() for o in outs]
     return pred, raw, outs
@@ -75,17 +72,24 @@ def test_model_end_to_end_nms_runs_and_is_consistent():
 
 
 def test_half_and_uint8_inputs_and_fuse():
+    """Input dtypes and model dtypes the callers use (val.py --half, detect.py) all reach the same kernels.
+    bf16-exact inputs make fp32 / fp16 / uint8 feeds bit-identical; .half() and .fuse() re-round the weights,
+    which a random-init net amplifies, so those are checked on the normalised error."""
     import dma_yolo_b200 as D
     from dma_yolo_b200.utils.calib import build_calibrated
     m = build_calibrated('yolov5s.yaml', seed=0).cuda().eval()
-    x = torch.rand(2, 3, 64, 64).cuda()
+    u8 = torch.randint(0, 256, (2, 3, 64, 64), dtype=torch.uint8)
+    x = (u8.float() / 255).bfloat16().float().cuda()
+    rel = lambda a, b: float((a - b).norm() / b.norm())
     with torch.no_grad():
         a = m(x)[0].dense().clone()
-        b = m(x.half())[0].dense().clone()
+        b = m(x.half())[0].dense().clone()          # bf16-exact values survive fp16
+        assert torch.equal(a, b)
+        u = m(u8.cuda())[0].dense().clone()         # uint8 is normalised by the prep kernel (x/255)
+        assert rel(u, a) < 0.05
         m.half()
         c = m(x.half())[0].dense().clone()
         m.float().fuse()
         e = m(x)[0].dense().clone()
-    assert_close(b, a, atol=0.5, rtol=5e-2, what='fp16 input')
-    assert_close(c, b, atol=0.5, rtol=5e-2, what='half model')
-    assert_close(e, a, atol=0.5, rtol=5e-2, what='fused model')
+    assert rel(c, a) < 0.15, rel(c, a)
+    assert rel(e, a) < 0.15, rel(e, a)

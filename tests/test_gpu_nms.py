@@ -115,10 +115,11 @@ def test_fused_decode_filter_equals_dense_path():
     det.stride = det.stride.cuda()
     xs = [torch.randn(3, 32, 20, 12).cuda(), torch.randn(3, 64, 10, 6).cuda(), torch.randn(3, 128, 5, 3).cuda()]
     with torch.no_grad():
+        kws = (dict(conf_thres=0.25, iou_thres=0.45, max_det=1000), dict(conf_thres=0.001, iou_thres=0.6, multi_label=True))
         pred, _ = det(xs)
-        for kw in (dict(conf_thres=0.25, iou_thres=0.45, max_det=1000), dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)):
-            fused = D.non_max_suppression(pred, **kw)
-            assert pred._dense is None, 'fused path must not materialise the dense prediction'
+        fused_all = [D.non_max_suppression(pred, **kw) for kw in kws]
+        assert pred._dense is None, 'fused path must not materialise the dense prediction'
+        for kw, fused in zip(kws, fused_all):
             dense = D.non_max_suppression(pred.dense().clone(), **kw)
             oracle = ON.non_max_suppression(pred.dense().cpu().numpy(), **kw)
             for f, dn, o in zip(fused, dense, oracle):

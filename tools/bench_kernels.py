@@ -136,7 +136,7 @@ def main():
         out = ops.empty_nhwc(B, cout, ho, ho, dev, torch.float32 if f32 else torch.bfloat16, c_alloc=ops.round_up(cout, 8))
         gflop = 2 * B * ho * ho * cout * cin * k * k / 1e9
         gb = (B * hi * hi * cin * 2 + B * ho * ho * cout * (4 if f32 else 2) + cout * cin * k * k * 2) / 1e9
-        ms = timeit(lambda: ops.conv(x, pk, 1, out=out, out_fp32=f32), reps=5, flush=flush)
+        ms = timeit(lambda: ops.conv(x, pk, 0 if f32 else 1, out=None if f32 else out, out_fp32=f32), reps=5, flush=flush)
         rec(f'conv {cin}->{cout} k{k}s{s} @{ho}', ms, gbytes=gb, gflop=gflop)
         del x, out
     # stem

@@ -1,0 +1,28 @@
+"""Run ONE kernel configuration a few times (for `ncu`): python tools/prof_one.py conv 128 128 3 1 80 [bs]"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from dma_yolo_b200 import ops  # noqa: E402
+
+kind = sys.argv[1]
+dev = 'cuda'
+if kind == 'conv':
+    cin, cout, k, s, ho = map(int, sys.argv[2:7])
+    B = int(sys.argv[7]) if len(sys.argv) > 7 else 64
+    x = ops.empty_nhwc(B, cin, ho * s, ho * s, dev).normal_()
+    pk = ops.pack_conv(torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5, stride=s, pad=k // 2, device=dev)
+    out = ops.empty_nhwc(B, cout, ho, ho, dev)
+    for _ in range(3):
+        ops.conv(x, pk, 1, out=out)
+elif kind == 'gate':
+    c, s = map(int, sys.argv[2:4])
+    B = 64
+    x, k3, k2, out = (ops.empty_nhwc(B, c, s, s, dev).normal_(), ops.empty_nhwc(B, c, s, s, dev).normal_(),
+                      ops.empty_nhwc(B, c, s // 4, s // 4, dev).normal_(), ops.empty_nhwc(B, c, s, s, dev))
+    for _ in range(3):
+        ops.scconv_gate(x, k3, k2, out=out)
+torch.cuda.synchronize()
+print('ok')
