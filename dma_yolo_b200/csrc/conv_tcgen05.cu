@@ -85,6 +85,22 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tma
       "l"(tmap), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+// B tile slice multicast to every CTA of the cluster (same smem offset, same mbarrier offset in each)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmap_prefetch(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -109,6 +125,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask` (stage release across the cluster)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -165,6 +187,8 @@ struct __align__(64) ConvArgs {
   int conv_stride, pad, Ho, Wo;
   int im2col;
   int block_n, acc_stride, tmem_cols, stages;
+  int subs, total_subs;      // sub-tiles (one tap x one CK-channel chunk) per pipeline stage / per tile
+  int cs;                    // cluster size: the B tile is loaded in `cs` row slices, each multicast to all CTAs
   int ldy, ldr, ldgx, ldgk, gHk, gWk;
   float g_sh, g_sw;
   int act, out_f32;
@@ -259,8 +283,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   float* s_bias = s_scale + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = a.num_m_tiles * a.num_n_tiles;
-  const int k_iters = a.taps * a.c_chunks;
+  // tile schedule: a cluster walks "super tiles" = cs consecutive m-tiles of one n-tile (so its CTAs share
+  // the B tile); n-tile fastest, so clusters running side by side share the activation rows in L2.
+  const int cs = a.cs;
+  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / cs, num_clusters = gridDim.x / cs;
+  const int m_groups = (a.num_m_tiles + cs - 1) / cs;
+  const int total_super = m_groups * a.num_n_tiles;
+  const int k_iters = (a.total_subs + a.subs - 1) / a.subs;
+  const uint16_t mc_mask = (uint16_t)((1u << cs) - 1u);
 
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&a.tmA);
@@ -269,7 +300,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < a.stages; ++i) {
       mbar_init(full_bar + i * 8, 1);
-      mbar_init(empty_bar + i * 8, 1);
+      mbar_init(empty_bar + i * 8, cs);   // every CTA of the cluster releases the stage (its B slice lands in all)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i * 8, 1);
@@ -280,6 +311,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anything multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -289,9 +321,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       const int HoWo = a.Ho * a.Wo;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / a.num_n_tiles, n_tile = tile % a.num_n_tiles;
-        const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;
+      const int b_rows = a.block_n / cs;                       // rows of the B tile this CTA fetches
+      const uint32_t b_slice = (uint32_t)(b_rows * a.CK * 2);
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
+        const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
+        const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;   // m0 >= M for a padding tile: loads zero-fill
         int n_img = 0, h0 = 0, w0 = 0;
         if (a.im2col) {
           n_img = m0 / HoWo;
@@ -300,22 +334,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           h0 = p * a.conv_stride - a.pad;
           w0 = q * a.conv_stride - a.pad;
         }
-        for (int tap = 0; tap < a.taps; ++tap) {
-          const int r = tap / a.kw, s = tap - r * a.kw;
-          for (int cc = 0; cc < a.c_chunks; ++cc) {
-            mbar_wait(empty_bar + stage * 8, phase ^ 1u);
-            const uint32_t fb = full_bar + stage * 8;
-            const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.a_bytes;
-            mbar_expect_tx(fb, a.a_bytes + a.b_bytes);
+        for (int it = 0; it < k_iters; ++it) {
+          const int g0 = it * a.subs;
+          const int nsub = min(a.subs, a.total_subs - g0);
+          mbar_wait(empty_bar + stage * 8, phase ^ 1u);
+          const uint32_t fb = full_bar + stage * 8;
+          const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.subs * a.a_bytes;
+          mbar_expect_tx(fb, (uint32_t)nsub * (a.a_bytes + a.b_bytes));
+          for (int j = 0; j < nsub; ++j) {
+            const int g = g0 + j;
+            const int tap = g / a.c_chunks, cc = g - tap * a.c_chunks;
+            const int r = tap / a.kw, s = tap - r * a.kw;
             if (a.im2col)
-              tma_load_im2col_4d(sa, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+              tma_load_im2col_4d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
             else
-              tma_load_2d(sa, &a.tmA, fb, cc * a.CK, m0);
-            tma_load_2d(sb, &a.tmB, fb, tap * a.Cin + cc * a.CK, n0);
-            if (++stage == a.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+              tma_load_2d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, m0);
+            if (cs > 1)
+              tma_load_2d_mc(sb + j * a.b_bytes + crank * b_slice, &a.tmB, fb, tap * a.Cin + cc * a.CK,
+                             n0 + (int)crank * b_rows, mc_mask);
+            else
+              tma_load_2d(sb + j * a.b_bytes, &a.tmB, fb, tap * a.Cin + cc * a.CK, n0);
+          }
+          if (++stage == a.stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -328,20 +370,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       int acc = 0;
       uint32_t acc_phase = 0;
       const int kk_n = a.CK / 16;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
         mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.acc_stride);
         for (int it = 0; it < k_iters; ++it) {
+          const int nsub = min(a.subs, a.total_subs - it * a.subs);
           mbar_wait(full_bar + stage * 8, phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.a_bytes;
-          const uint64_t da = make_smem_desc(sa, a.sbo_enc, a.layout_type);
-          const uint64_t db = make_smem_desc(sb, a.sbo_enc, a.layout_type);
+          const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.subs * a.a_bytes;
+          for (int j = 0; j < nsub; ++j) {
+            const uint64_t da = make_smem_desc(sa + j * a.a_bytes, a.sbo_enc, a.layout_type);
+            const uint64_t db = make_smem_desc(sb + j * a.b_bytes, a.sbo_enc, a.layout_type);
 #pragma unroll 1
-          for (int kk = 0; kk < kk_n; ++kk)  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
-            umma_bf16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), a.idesc, (uint32_t)((it | kk) != 0));
-          umma_commit(empty_bar + stage * 8);
+            for (int kk = 0; kk < kk_n; ++kk)  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
+              umma_bf16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), a.idesc, (uint32_t)((it | j | kk) != 0));
+          }
+          if (cs > 1) umma_commit_mc(empty_bar + stage * 8, mc_mask);
+          else umma_commit(empty_bar + stage * 8);
           if (++stage == a.stages) {
             stage = 0;
             phase ^= 1u;
@@ -362,8 +408,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t acc_phase = 0;
     int staged_n0 = -1;
     const int HoWo = a.Ho * a.Wo;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / a.num_n_tiles, n_tile = tile % a.num_n_tiles;
+    for (int st = cluster_id; st < total_super; st += num_clusters) {
+      const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
       const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;
       if (n0 != staged_n0) {  // uniform across the CTA
         epi_bar_sync();       // everyone is done reading the previous scale/bias
@@ -435,6 +481,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -517,6 +564,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   a.Wo = p->Wo;
   a.im2col = !(p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0);
   int bn = p->block_n > 0 ? p->block_n : (p->Cout_pad < 256 ? p->Cout_pad : 256);
+  if (p->block_n < -1) bn = -p->block_n;
   if ((bn & 15) || bn > 256 || bn < 16) return DMAY_EUNSUPPORTED;
   a.block_n = bn;
   a.acc_stride = pow2ceil(bn) < 32 ? 32 : pow2ceil(bn);
@@ -527,7 +575,22 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   a.Cout_pad = p->Cout_pad;
   a.a_bytes = (uint32_t)(BLOCK_M * a.CK * 2);
   a.b_bytes = (uint32_t)(bn * a.CK * 2);
-  a.stage_bytes = (a.a_bytes + a.b_bytes + 1023u) & ~1023u;
+  a.total_subs = a.taps * a.c_chunks;
+  // several sub-tiles per stage when they are small (one mbarrier round trip per stage, not per 16/32-channel tap)
+  int subs = (int)((56u * 1024u) / (a.a_bytes + a.b_bytes));
+  if (subs < 1) subs = 1;
+  if (subs > a.total_subs) subs = a.total_subs;
+  if (subs > 16) subs = 16;
+  a.subs = subs;
+  // B multicast over a 2-CTA cluster whenever there are at least two m-tiles and the slice keeps its alignment
+  const int sms_q = p->num_sms > 0 ? p->num_sms : sm_count();
+  const long long m_tiles_q = (M + BLOCK_M - 1) / BLOCK_M;
+  int cs = 2;
+  if (p->block_n < 0) cs = 1;                                   // block_n < 0: caller asks for the non-cluster path
+  if ((bn % (8 * cs)) || (((bn / cs) * a.CK * 2) % 1024 && a.CK == 64) || m_tiles_q < 2 || sms_q < 2) cs = 1;
+  if (a.CK != 64 && (((bn / cs) * a.CK * 2) % (a.CK == 32 ? 512 : 256))) cs = 1;
+  a.cs = cs;
+  a.stage_bytes = ((uint32_t)subs * (a.a_bytes + a.b_bytes) + 1023u) & ~1023u;
   const uint32_t budget = 227u * 1024u - 1024u - kTailBytes - 64u;
   int stages = (int)(budget / a.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -583,7 +646,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     const cuuint64_t ktot = (cuuint64_t)a.taps * p->Cin;
     cuuint64_t gdim[2] = {ktot, (cuuint64_t)p->Cout_pad};
     cuuint64_t gstr[1] = {ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)a.CK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)a.CK, (cuuint32_t)(bn / a.cs)};
     cuuint32_t estr[2] = {1, 1};
     r = g_encode_tiled(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w), gdim, gstr, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -593,8 +656,9 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
 
   const size_t smem = 1024 + (size_t)a.stages * a.stage_bytes + kTailBytes;
   const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
-  const long long tiles = (long long)a.num_m_tiles * a.num_n_tiles;
-  const int grid = (int)(tiles < sms ? tiles : sms);
+  const long long supers = (long long)((a.num_m_tiles + a.cs - 1) / a.cs) * a.num_n_tiles;
+  const long long max_clusters = sms / a.cs;
+  const int grid = (int)((supers < max_clusters ? supers : max_clusters) * a.cs);
   int mode;
   if (a.gate_x) mode = (!out_f32 && !a.residual) ? EPI_GATE : -1;
   else if (out_f32) mode = (a.act == DMAY_ACT_NONE && !a.residual) ? EPI_LINEAR_F32 : EPI_GENERIC;
@@ -611,7 +675,24 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
       if (e != cudaSuccess) return (int)e;                                                                          \
       attr_set = true;                                                                                              \
     }                                                                                                               \
-    conv_gemm_kernel<MODE><<<grid, kConvThreads, smem, stream>>>(a);                                                \
+    if (a.cs > 1) {                                                                                                 \
+      cudaLaunchConfig_t cfg = {};                                                                                  \
+      cfg.gridDim = dim3(grid);                                                                                     \
+      cfg.blockDim = dim3(kConvThreads);                                                                            \
+      cfg.dynamicSmemBytes = smem;                                                                                  \
+      cfg.stream = stream;                                                                                          \
+      cudaLaunchAttribute at[1];                                                                                    \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                                               \
+      at[0].val.clusterDim.x = a.cs;                                                                                \
+      at[0].val.clusterDim.y = 1;                                                                                   \
+      at[0].val.clusterDim.z = 1;                                                                                   \
+      cfg.attrs = at;                                                                                               \
+      cfg.numAttrs = 1;                                                                                             \
+      cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE>, a);                                          \
+      if (e != cudaSuccess) return (int)e;                                                                          \
+    } else {                                                                                                        \
+      conv_gemm_kernel<MODE><<<grid, kConvThreads, smem, stream>>>(a);                                              \
+    }                                                                                                               \
     break;                                                                                                          \
   }
   switch (mode) {

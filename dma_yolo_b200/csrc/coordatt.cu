@@ -104,55 +104,73 @@ __global__ void __launch_bounds__(256) ca_pool_kernel(const __nv_bfloat16* __res
   }
 }
 
-// ---- mlp.  grid = N * ceil((H+W)/PG); CTA handles PG consecutive positions of one image.
-// w1T: [C][Cm] fp32 (transposed: threads of a warp = consecutive hidden units j -> coalesced);
-// whT / wwT: [Cm][Cout] fp32 (consecutive threads = consecutive output channels -> coalesced).
+// ---- mlp.  grid = N * (ceil(H/PG) + ceil(W/PG)); a CTA handles PG consecutive positions of one image that
+// all lie in the H part or all in the W part (so it needs only one of Wh / Ww).
+// w1T: [C][Cm] fp32, whT / wwT: [Cm][Cout] fp32 (transposed: consecutive threads read consecutive floats).
+// Hidden layer: warp w owns the channel range [w*C/8, (w+1)*C/8) for every hidden unit (lane = j) and all PG
+// positions (register accumulators), so W1 is streamed ONCE per CTA with 8 independent loads in flight per
+// lane; partial sums are combined through shared memory.
 constexpr int PG = 8;
-__global__ void __launch_bounds__(256) ca_mlp_kernel(const float* __restrict__ pooled, float* __restrict__ gates,
-                                                     const float* __restrict__ w1T, const float* __restrict__ b1,
-                                                     const float* __restrict__ s1, const float* __restrict__ t1,
-                                                     const float* __restrict__ whT, const float* __restrict__ bh,
-                                                     const float* __restrict__ wwT, const float* __restrict__ bw,
-                                                     int H, int W, int C, int Cm, int Cout) {
+constexpr int kMlpWarps = 8;
+__global__ void __launch_bounds__(kMlpWarps * 32) ca_mlp_kernel(const float* __restrict__ pooled, float* __restrict__ gates,
+                                                                const float* __restrict__ w1T, const float* __restrict__ b1,
+                                                                const float* __restrict__ s1, const float* __restrict__ t1,
+                                                                const float* __restrict__ whT, const float* __restrict__ bh,
+                                                                const float* __restrict__ wwT, const float* __restrict__ bw,
+                                                                int H, int W, int C, int Cm, int Cout) {
   extern __shared__ float sm[];
-  float* sp = sm;            // [PG][C]
-  float* sy = sm + PG * C;   // [PG][Cm]
+  float* sp = sm;                         // [PG][C]
+  float* spart = sm + PG * C;             // [kMlpWarps][PG][Cm] partial hidden sums
+  float* sy = spart + kMlpWarps * PG * Cm;  // [PG][Cm]
   const int P = H + W;
-  const int pgroups = (P + PG - 1) / PG;
-  const int n = blockIdx.x / pgroups;
-  const int p0 = (blockIdx.x % pgroups) * PG;
-  const int np = min(PG, P - p0);
+  const int gh = (H + PG - 1) / PG, gw = (W + PG - 1) / PG;
+  const int n = blockIdx.x / (gh + gw);
+  const int g = blockIdx.x % (gh + gw);
+  const bool is_h = g < gh;
+  const int p0 = is_h ? g * PG : H + (g - gh) * PG;
+  const int np = min(PG, (is_h ? H : P) - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < PG * C; i += blockDim.x) {
     const int pp = i / C, c = i - pp * C;
     sp[i] = pp < np ? pooled[((long long)n * P + p0 + pp) * C + c] : 0.f;
   }
   __syncthreads();
-  // hidden: one thread per (position q, hidden unit j); 4 independent accumulators hide the load latency
-  for (int o = threadIdx.x; o < PG * Cm; o += blockDim.x) {
-    const int q = o / Cm, j = o - q * Cm;
-    const float* sq = sp + q * C;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int c = 0;
-    for (; c + 4 <= C; c += 4) {
-      a0 = fmaf(w1T[(long long)(c + 0) * Cm + j], sq[c + 0], a0);
-      a1 = fmaf(w1T[(long long)(c + 1) * Cm + j], sq[c + 1], a1);
-      a2 = fmaf(w1T[(long long)(c + 2) * Cm + j], sq[c + 2], a2);
-      a3 = fmaf(w1T[(long long)(c + 3) * Cm + j], sq[c + 3], a3);
+  const int cper = (C + kMlpWarps - 1) / kMlpWarps;
+  const int c0 = warp * cper, c1 = min(C, c0 + cper);
+  for (int j = lane; j < Cm; j += 32) {
+    float acc[PG];
+#pragma unroll
+    for (int q = 0; q < PG; ++q) acc[q] = 0.f;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) {
+      const float wv = w1T[(long long)c * Cm + j];
+#pragma unroll
+      for (int q = 0; q < PG; ++q) acc[q] = fmaf(wv, sp[q * C + c], acc[q]);
     }
-    for (; c < C; ++c) a0 = fmaf(w1T[(long long)c * Cm + j], sq[c], a0);
-    const float acc = (a0 + a1) + (a2 + a3);
-    sy[q * Cm + j] = hardswish(s1[j] * (acc + b1[j]) + t1[j]);
+#pragma unroll
+    for (int q = 0; q < PG; ++q) spart[(warp * PG + q) * Cm + j] = acc[q];
   }
   __syncthreads();
+  for (int o = threadIdx.x; o < PG * Cm; o += blockDim.x) {
+    const int j = o % Cm;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kMlpWarps; ++w) acc += spart[w * PG * Cm + o];
+    sy[o] = hardswish(s1[j] * (acc + b1[j]) + t1[j]);
+  }
+  __syncthreads();
+  const float* wT = is_h ? whT : wwT;
+  const float* bias = is_h ? bh : bw;
   for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
     float acc[PG];
-    const float bhc = bh[c], bwc = bw[c];
+    const float bc = bias[c];
 #pragma unroll
-    for (int q = 0; q < PG; ++q) acc[q] = (p0 + q < H) ? bhc : bwc;
+    for (int q = 0; q < PG; ++q) acc[q] = bc;
+#pragma unroll 8
     for (int j = 0; j < Cm; ++j) {
-      const float a = whT[(long long)j * Cout + c], b = wwT[(long long)j * Cout + c];
+      const float a = wT[(long long)j * Cout + c];
 #pragma unroll
-      for (int q = 0; q < PG; ++q) acc[q] = fmaf((p0 + q < H) ? a : b, sy[q * Cm + j], acc[q]);
+      for (int q = 0; q < PG; ++q) acc[q] = fmaf(a, sy[q * Cm + j], acc[q]);
     }
     for (int q = 0; q < np; ++q) gates[((long long)n * P + p0 + q) * Cout + c] = sigmoid_acc(acc[q]);
   }
@@ -224,15 +242,14 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
                                            bands);
   }
   // 2. mlp
-  const int P = p->H + p->W;
-  const int pgroups = (P + PG - 1) / PG;
-  const size_t smem = (size_t)PG * (p->C + p->Cm) * sizeof(float);
+  const int pgroups = (p->H + PG - 1) / PG + (p->W + PG - 1) / PG;
+  const size_t smem = ((size_t)PG * p->C + (size_t)(kMlpWarps + 1) * PG * p->Cm) * sizeof(float);
   if (smem > 200 * 1024) return DMAY_EUNSUPPORTED;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ca_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  ca_mlp_kernel<<<p->N * pgroups, 256, smem, s>>>((const float*)p->pooled, (float*)p->gates, (const float*)p->w1,
+  ca_mlp_kernel<<<p->N * pgroups, kMlpWarps * 32, smem, s>>>((const float*)p->pooled, (float*)p->gates, (const float*)p->w1,
                                                   (const float*)p->b1, (const float*)p->s1, (const float*)p->t1,
                                                   (const float*)p->wh, (const float*)p->bh, (const float*)p->ww,
                                                   (const float*)p->bw, p->H, p->W, p->C, p->Cm, p->C);

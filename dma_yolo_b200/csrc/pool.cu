@@ -19,16 +19,20 @@ __device__ __forceinline__ uint4 max16(const uint4& a, const uint4& b) {
   return r;
 }
 
-// smem: bufA[H*W*VL] + bufB[H*W*VL] uint4 (VL = CB/8 vectors per pixel)
-template <int STAGES>
+// smem: bufA[H*Wp*VL] + bufB[H*Wp*VL] uint4 (VL = CB/8 vectors per pixel, Wp = W|1: an odd row pitch keeps the
+// row-walking threads of a warp on different banks).
+// K5 = true: k == 5 with a rotating 5-element register window — one shared-memory read and one write per
+// element per pass (the straightforward form re-reads each element k times).
+template <int STAGES, bool K5>
 __global__ void __launch_bounds__(256) pool_plane_kernel(const __nv_bfloat16* __restrict__ x,
                                                          __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
                                                          __nv_bfloat16* __restrict__ y3, int H, int W, int C, int ldx,
                                                          int ldy, int k, int VL) {
   extern __shared__ uint4 smem[];
   const int HW = H * W;
+  const int Wp = W | 1;
   uint4* A = smem;
-  uint4* B = smem + (size_t)HW * VL;
+  uint4* B = smem + (size_t)H * Wp * VL;
   const int groups = (C / 8 + VL - 1) / VL;
   const int n = blockIdx.x / groups, g = blockIdx.x % groups;
   const int v0 = g * VL;                              // first channel-vector of this CTA
@@ -36,37 +40,71 @@ __global__ void __launch_bounds__(256) pool_plane_kernel(const __nv_bfloat16* __
   const int items = HW * vl;
   const int r = k >> 1;
   const long long pbase = (long long)n * HW;
+  const uint4 NEG = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // bf16 -inf x8
 
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    int v = i % vl, p = i / vl;
-    A[p * VL + v] = ld_nc16(x + (pbase + p) * ldx + (v0 + v) * 8);
+    const int p = i / vl, v = i - p * vl;
+    const int h_ = p / W, w_ = p - h_ * W;
+    A[(h_ * Wp + w_) * VL + v] = ld_nc16(x + (pbase + p) * ldx + (v0 + v) * 8);
   }
   __syncthreads();
   __nv_bfloat16* outs[3] = {y1, y2, y3};
 #pragma unroll
   for (int s = 0; s < STAGES; ++s) {
-    // row pass: B[h][w] = max_{|d|<=r} A[h][w+d]
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-      int v = i % vl, p = i / vl;
-      int w_ = p % W, h_ = p / W;
-      int lo = max(w_ - r, 0), hi = min(w_ + r, W - 1);
-      uint4 m = A[(h_ * W + lo) * VL + v];
-      for (int ww = lo + 1; ww <= hi; ++ww) m = max16(m, A[(h_ * W + ww) * VL + v]);
-      B[p * VL + v] = m;
+    if (K5) {
+      // row pass: thread = (row h, vector v) walks w with the window in registers
+      for (int i = threadIdx.x; i < H * vl; i += blockDim.x) {
+        const int h_ = i / vl, v = i - h_ * vl;
+        const uint4* in = A + (size_t)h_ * Wp * VL + v;
+        uint4* out = B + (size_t)h_ * Wp * VL + v;
+        uint4 a = NEG, b = NEG, c = in[0], d = W > 1 ? in[VL] : NEG, e;
+#pragma unroll 5
+        for (int w_ = 0; w_ < W; ++w_) {
+          e = w_ + 2 < W ? in[(w_ + 2) * VL] : NEG;
+          out[w_ * VL] = max16(max16(max16(a, b), max16(c, d)), e);
+          a = b; b = c; c = d; d = e;
+        }
+      }
+      __syncthreads();
+      // column pass: thread = (column w, vector v) walks h; writes the stage output and the next stage's input
+      for (int i = threadIdx.x; i < W * vl; i += blockDim.x) {
+        const int w_ = i / vl, v = i - w_ * vl;
+        const uint4* in = B + (size_t)w_ * VL + v;
+        uint4* nxt = A + (size_t)w_ * VL + v;
+        __nv_bfloat16* go = outs[s] + (pbase + w_) * ldy + (v0 + v) * 8;
+        const int pitch = Wp * VL;
+        uint4 a = NEG, b = NEG, c = in[0], d = H > 1 ? in[pitch] : NEG, e;
+#pragma unroll 5
+        for (int h_ = 0; h_ < H; ++h_) {
+          e = h_ + 2 < H ? in[(h_ + 2) * pitch] : NEG;
+          const uint4 m = max16(max16(max16(a, b), max16(c, d)), e);
+          st_na16(go + (long long)h_ * W * ldy, m);
+          if (s + 1 < STAGES) nxt[h_ * pitch] = m;
+          a = b; b = c; c = d; d = e;
+        }
+      }
+      __syncthreads();
+    } else {
+      for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int p = i / vl, v = i - p * vl;
+        const int h_ = p / W, w_ = p - h_ * W;
+        const int lo = max(w_ - r, 0), hi = min(w_ + r, W - 1);
+        uint4 m = A[(h_ * Wp + lo) * VL + v];
+        for (int ww = lo + 1; ww <= hi; ++ww) m = max16(m, A[(h_ * Wp + ww) * VL + v]);
+        B[(h_ * Wp + w_) * VL + v] = m;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int p = i / vl, v = i - p * vl;
+        const int h_ = p / W, w_ = p - h_ * W;
+        const int lo = max(h_ - r, 0), hi = min(h_ + r, H - 1);
+        uint4 m = B[(lo * Wp + w_) * VL + v];
+        for (int hh = lo + 1; hh <= hi; ++hh) m = max16(m, B[(hh * Wp + w_) * VL + v]);
+        st_na16(outs[s] + (pbase + p) * ldy + (v0 + v) * 8, m);
+        if (s + 1 < STAGES) A[(h_ * Wp + w_) * VL + v] = m;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    // column pass: A[h][w] = max_{|d|<=r} B[h+d][w]; also the stage output
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-      int v = i % vl, p = i / vl;
-      int w_ = p % W, h_ = p / W;
-      int lo = max(h_ - r, 0), hi = min(h_ + r, H - 1);
-      uint4 m = B[(lo * W + w_) * VL + v];
-      for (int hh = lo + 1; hh <= hi; ++hh) m = max16(m, B[(hh * W + w_) * VL + v]);
-      st_na16(outs[s] + (pbase + p) * ldy + (v0 + v) * 8, m);
-      if (s + 1 < STAGES) A[p * VL + v] = m;  // each thread overwrites only the element it owns; A is
-                                              // not read in this pass, so no hazard before the barrier
-    }
-    __syncthreads();
   }
 }
 
@@ -120,12 +158,12 @@ static int launch_pool(const void* x, void* y1, void* y2, void* y3, int N, int H
   int VL = 0;
   for (int cand : {8, 4, 2, 1}) {
     if (cand > cvec && cand != 1) continue;
-    if (HW * cand * 16 * 2 <= 100 * 1024) { VL = cand; break; }
+    if ((long long)H * (W | 1) * cand * 16 * 2 <= 100 * 1024) { VL = cand; break; }
   }
   if (VL == 0)
     for (int cand : {8, 4, 2, 1}) {
       if (cand > cvec && cand != 1) continue;
-      if (HW * cand * 16 * 2 <= 200 * 1024) { VL = cand; break; }
+      if ((long long)H * (W | 1) * cand * 16 * 2 <= 200 * 1024) { VL = cand; break; }
     }
   if (VL == 0) {
     long long items = (long long)N * HW * cvec;
@@ -134,22 +172,27 @@ static int launch_pool(const void* x, void* y1, void* y2, void* y3, int N, int H
                                                             ldy, k, stages);
     return finish_launch();
   }
-  const size_t smem = (size_t)HW * VL * 16 * 2;
+  const size_t smem = (size_t)H * (W | 1) * VL * 16 * 2;
   const int groups = (cvec + VL - 1) / VL;
   const long long grid = (long long)N * groups;
   if (grid > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
-  cudaError_t e;
+  const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
+  __nv_bfloat16 *o1 = (__nv_bfloat16*)y1, *o2 = (__nv_bfloat16*)y2, *o3 = (__nv_bfloat16*)y3;
+#define DMAY_POOL_LAUNCH(ST, K5)                                                                                  \
+  do {                                                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(pool_plane_kernel<ST, K5>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         (int)smem);                                                              \
+    if (e != cudaSuccess) return (int)e;                                                                          \
+    pool_plane_kernel<ST, K5><<<(int)grid, 256, smem, s>>>(xi, o1, o2, o3, H, W, C, ldx, ldy, k, VL);             \
+  } while (0)
   if (stages == 3) {
-    e = cudaFuncSetAttribute(pool_plane_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    pool_plane_kernel<3><<<(int)grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y1, (__nv_bfloat16*)y2,
-                                                      (__nv_bfloat16*)y3, H, W, C, ldx, ldy, k, VL);
+    if (k == 5) DMAY_POOL_LAUNCH(3, true);
+    else DMAY_POOL_LAUNCH(3, false);
   } else {
-    e = cudaFuncSetAttribute(pool_plane_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    pool_plane_kernel<1><<<(int)grid, 256, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y1, nullptr, nullptr, H,
-                                                      W, C, ldx, ldy, k, VL);
+    if (k == 5) DMAY_POOL_LAUNCH(1, true);
+    else DMAY_POOL_LAUNCH(1, false);
   }
+#undef DMAY_POOL_LAUNCH
   return finish_launch();
 }
 
