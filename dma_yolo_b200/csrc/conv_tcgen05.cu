@@ -564,7 +564,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   a.Wo = p->Wo;
   a.im2col = !(p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0);
   int bn = p->block_n > 0 ? p->block_n : (p->Cout_pad < 256 ? p->Cout_pad : 256);
-  if (p->block_n < -1) bn = -p->block_n;
+
   if ((bn & 15) || bn > 256 || bn < 16) return DMAY_EUNSUPPORTED;
   a.block_n = bn;
   a.acc_stride = pow2ceil(bn) < 32 ? 32 : pow2ceil(bn);
@@ -585,8 +585,10 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   // B multicast over a 2-CTA cluster whenever there are at least two m-tiles and the slice keeps its alignment
   const int sms_q = p->num_sms > 0 ? p->num_sms : sm_count();
   const long long m_tiles_q = (M + BLOCK_M - 1) / BLOCK_M;
-  int cs = 2;
-  if (p->block_n < 0) cs = 1;                                   // block_n < 0: caller asks for the non-cluster path
+  // Measured on B200 (profiles/r01_notes.md): the 2-CTA multicast is bit-correct but 20-30 % SLOWER than
+  // independent CTAs (cluster lock-step stalls; L2 already de-duplicates concurrent requests for the same
+  // weight tile), so it is opt-in: block_n == -2 requests it.
+  int cs = (p->block_n == -2) ? 2 : 1;
   if ((bn % (8 * cs)) || (((bn / cs) * a.CK * 2) % 1024 && a.CK == 64) || m_tiles_q < 2 || sms_q < 2) cs = 1;
   if (a.CK != 64 && (((bn / cs) * a.CK * 2) % (a.CK == 32 ? 512 : 256))) cs = 1;
   a.cs = cs;
