@@ -13,7 +13,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 HEADER = PKG.parent / "include" / "dmayolo.h"
-SO = PKG / "libdmayolo.so"
+SO = Path(__import__("os").environ.get("DMAY_SO", PKG / "libdmayolo.so"))  # DMAY_SO: A/B a second build
 
 _CTYPES = {
     "const void*": ctypes.c_void_p,

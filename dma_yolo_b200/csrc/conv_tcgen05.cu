@@ -55,9 +55,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a lost arrival (bad descriptor, wrong byte count) traps after ~2 s instead of
-// hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// hanging the GPU.  The slow path is out of line to keep the role loops small.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -66,6 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -202,6 +206,21 @@ struct __align__(64) ConvArgs {
 //   full[8], empty[8], tmem_full[2], tmem_empty[2] mbarriers, tmem base ptr, scale[256], bias[256]
 constexpr uint32_t kTailBytes = (2 * kMaxStages + 4) * 8 + 16 + 2 * 256 * 4;
 
+// one elected lane of a converged warp (the warp stays converged, so operands live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_enc, uint32_t layout_type) {
   // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout[61,64)
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)sbo_enc << 32) | ((uint64_t)1 << 46) |
@@ -316,35 +335,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int HoWo = a.Ho * a.Wo;
-      const int b_rows = a.block_n / cs;                       // rows of the B tile this CTA fetches
-      const uint32_t b_slice = (uint32_t)(b_rows * a.CK * 2);
-      for (int st = cluster_id; st < total_super; st += num_clusters) {
-        const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
-        const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;   // m0 >= M for a padding tile: loads zero-fill
-        int n_img = 0, h0 = 0, w0 = 0;
-        if (a.im2col) {
-          n_img = m0 / HoWo;
-          const int rem = m0 - n_img * HoWo;
-          const int p = rem / a.Wo, q = rem - p * a.Wo;
-          h0 = p * a.conv_stride - a.pad;
-          w0 = q * a.conv_stride - a.pad;
-        }
-        for (int it = 0; it < k_iters; ++it) {
-          const int g0 = it * a.subs;
-          const int nsub = min(a.subs, a.total_subs - g0);
-          mbar_wait(empty_bar + stage * 8, phase ^ 1u);
-          const uint32_t fb = full_bar + stage * 8;
-          const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.subs * a.a_bytes;
-          mbar_expect_tx(fb, (uint32_t)nsub * (a.a_bytes + a.b_bytes));
-          for (int j = 0; j < nsub; ++j) {
-            const int g = g0 + j;
-            const int tap = g / a.c_chunks, cc = g - tap * a.c_chunks;
-            const int r = tap / a.kw, s = tap - r * a.kw;
+    // ===== TMA producer: the whole warp walks the schedule (uniform), one elected lane issues =====
+    int stage = 0;
+    uint32_t phase = 0;
+    const int HoWo = a.Ho * a.Wo;
+    const int b_rows = a.block_n / cs;                       // rows of the B tile this CTA fetches
+    const uint32_t b_slice = (uint32_t)(b_rows * a.CK * 2);
+#pragma unroll 1
+    for (int st = cluster_id; st < total_super; st += num_clusters) {
+      const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
+      const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;   // m0 >= M for a padding tile: loads zero-fill
+      int n_img = 0, h0 = 0, w0 = 0;
+      if (a.im2col) {
+        n_img = m0 / HoWo;
+        const int rem = m0 - n_img * HoWo;
+        const int p = rem / a.Wo, q = rem - p * a.Wo;
+        h0 = p * a.conv_stride - a.pad;
+        w0 = q * a.conv_stride - a.pad;
+      }
+      int tap = 0, cc = 0, r = 0, s = 0;   // running (tap, channel chunk) of the next sub-tile: no divisions in the loop
+#pragma unroll 1
+      for (int it = 0; it < k_iters; ++it) {
+        const int nsub = min(a.subs, a.total_subs - it * a.subs);
+        mbar_wait(empty_bar + stage * 8, phase ^ 1u);
+        const uint32_t fb = full_bar + stage * 8;
+        const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.subs * a.a_bytes;
+        const bool leader = elect_one();
+        if (leader) mbar_expect_tx(fb, (uint32_t)nsub * (a.a_bytes + a.b_bytes));
+#pragma unroll 1
+        for (int j = 0; j < nsub; ++j) {
+          if (leader) {
             if (a.im2col)
               tma_load_im2col_4d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
             else
@@ -355,48 +375,70 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             else
               tma_load_2d(sb + j * a.b_bytes, &a.tmB, fb, tap * a.Cin + cc * a.CK, n0);
           }
-          if (++stage == a.stages) {
-            stage = 0;
-            phase ^= 1u;
+          if (++cc == a.c_chunks) {
+            cc = 0;
+            ++tap;
+            if (++s == a.kw) {
+              s = 0;
+              ++r;
+            }
           }
+        }
+        __syncwarp();
+        if (++stage == a.stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const int kk_n = a.CK / 16;
-      for (int st = cluster_id; st < total_super; st += num_clusters) {
-        mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.acc_stride);
-        for (int it = 0; it < k_iters; ++it) {
-          const int nsub = min(a.subs, a.total_subs - it * a.subs);
-          mbar_wait(full_bar + stage * 8, phase);
-          tc_fence_after();
-          const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.subs * a.a_bytes;
-          for (int j = 0; j < nsub; ++j) {
-            const uint64_t da = make_smem_desc(sa + j * a.a_bytes, a.sbo_enc, a.layout_type);
-            const uint64_t db = make_smem_desc(sb + j * a.b_bytes, a.sbo_enc, a.layout_type);
+    // ===== MMA issuer: converged warp, elect.sync around the tcgen05 instructions =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int kk_n = a.CK / 16;
+    // descriptor halves: lo = start>>4 | LBO(1)<<16 ; hi = SBO | version 1 (bit 46) | layout (bits 61..63)
+    const uint32_t desc_hi = a.sbo_enc | (1u << 14) | (a.layout_type << 29);
+    const uint32_t a_step = a.a_bytes >> 4, b_step = a.b_bytes >> 4;
 #pragma unroll 1
-            for (int kk = 0; kk < kk_n; ++kk)  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
-              umma_bf16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), a.idesc, (uint32_t)((it | j | kk) != 0));
+    for (int st = cluster_id; st < total_super; st += num_clusters) {
+      mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.acc_stride);
+      uint32_t accum = 0;
+#pragma unroll 1
+      for (int it = 0; it < k_iters; ++it) {
+        const int nsub = min(a.subs, a.total_subs - it * a.subs);
+        mbar_wait(full_bar + stage * 8, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.subs * a.a_bytes;
+        if (elect_one()) {
+          uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll 1
+          for (int j = 0; j < nsub; ++j) {
+#pragma unroll 4
+            for (int kk = 0; kk < kk_n; ++kk) {  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
+              umma_bf16(tmem_d, pack64(a_lo + kk * 2, desc_hi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+              accum = 1;
+            }
+            a_lo += a_step;
+            b_lo += b_step;
           }
           if (cs > 1) umma_commit_mc(empty_bar + stage * 8, mc_mask);
           else umma_commit(empty_bar + stage * 8);
-          if (++stage == a.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
         }
-        umma_commit(tfull_bar + acc * 8);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        accum = 1;
+        __syncwarp();
+        if (++stage == a.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
+      if (elect_one()) umma_commit(tfull_bar + acc * 8);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else if (warp >= 4) {
     // ===== epilogue: warp pair (w, w+4) shares TMEM lane quadrant w%4 and interleaves 32-column chunks =====
@@ -408,6 +450,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t acc_phase = 0;
     int staged_n0 = -1;
     const int HoWo = a.Ho * a.Wo;
+#pragma unroll 1
     for (int st = cluster_id; st < total_super; st += num_clusters) {
       const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
       const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;
@@ -433,6 +476,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * a.acc_stride) + ((uint32_t)(quad * 32) << 16);
       bool waited = false;
+#pragma unroll 1
       for (int c0 = half * 32; c0 < a.block_n; c0 += 64) {
         const int width = a.block_n - c0 >= 32 ? 32 : 16;
         const int col0 = n0 + c0;
