@@ -81,6 +81,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tmap, uint32_t bar, int c, int w, int h, int n,
                                                    uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -193,6 +199,15 @@ struct __align__(64) ConvArgs {
   int block_n, acc_stride, tmem_cols, stages;
   int subs, total_subs;      // sub-tiles (one tap x one CK-channel chunk) per pipeline stage / per tile
   int cs;                    // cluster size: the B tile is loaded in `cs` row slices, each multicast to all CTAs
+  // halo mode (3x3 stride-1 pad-1): an output tile is a 16x8 pixel patch; its 18 x pitch input patch is loaded
+  // ONCE per channel chunk and the 9 taps read shifted windows of it (descriptor start = +(r*pitch+s) rows,
+  // SBO = one patch row) instead of 9 im2col loads of the same pixels from L2.
+  int halo, halo_pitch, tiles_x, tiles_y, n_abuf;
+  uint32_t a_halo_bytes, a_halo_tx, halo_sbo_enc;
+  // weights-resident variant of halo mode: the whole [block_n x 9*Cin] weight set (<= ~96 KB) is loaded into
+  // smem once per CTA, so the steady state streams input patches only (deep patch ring, no B pipeline)
+  int b_resident;
+  uint32_t bres_bytes;
   int ldy, ldr, ldgx, ldgk, gHk, gWk;
   float g_sh, g_sw;
   int act, out_f32;
@@ -203,8 +218,12 @@ struct __align__(64) ConvArgs {
 
 // smem carve-up (after manual 1024-byte alignment):
 //   [stages][A tile | B tile]   stage_bytes each
-//   full[8], empty[8], tmem_full[2], tmem_empty[2] mbarriers, tmem base ptr, scale[256], bias[256]
-constexpr uint32_t kTailBytes = (2 * kMaxStages + 4) * 8 + 16 + 2 * 256 * 4;
+//   full[8], empty[8], tmem_full[2], tmem_empty[2], afull[4], aempty[4] mbarriers, tmem base ptr, scale[256], bias[256]
+//   (halo mode: [n_abuf halo buffers] precede the stages, which then hold B tiles only)
+constexpr int kMaxABuf = 8;
+constexpr int kHaloTH = 16, kHaloTW = 8;
+constexpr uint32_t kNumBars = 2 * kMaxStages + 4 + 2 * kMaxABuf;
+constexpr uint32_t kTailBytes = kNumBars * 8 + 16 + 2 * 256 * 4;
 
 // one elected lane of a converged warp (the warp stays converged, so operands live in uniform registers)
 __device__ __forceinline__ bool elect_one() {
@@ -292,13 +311,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t tail = base + a.stages * a.stage_bytes;
-  uint8_t* tail_ptr = base_ptr + (size_t)a.stages * a.stage_bytes;
+  const uint32_t bres0 = base;                                           // resident weights (b_resident only)
+  const uint32_t abuf0 = base + a.bres_bytes;                            // halo ring (halo mode only)
+  const uint32_t stage0 = abuf0 + (a.halo ? a.n_abuf * a.a_halo_bytes : 0u);
+  const uint32_t data_bytes = (stage0 - base) + a.stages * a.stage_bytes;
+  const uint32_t tail = base + data_bytes;
+  uint8_t* tail_ptr = base_ptr + data_bytes;
   const uint32_t full_bar = tail, empty_bar = tail + kMaxStages * 8;
   const uint32_t tfull_bar = tail + 2 * kMaxStages * 8, tempty_bar = tfull_bar + 16;
-  const uint32_t tmem_slot = tempty_bar + 16;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_ptr + (2 * kMaxStages + 4) * 8);
-  float* s_scale = reinterpret_cast<float*>(tail_ptr + (2 * kMaxStages + 4) * 8 + 16);
+  const uint32_t afull_bar = tempty_bar + 16, aempty_bar = afull_bar + kMaxABuf * 8;
+  const uint32_t tmem_slot = tail + kNumBars * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_ptr + kNumBars * 8);
+  float* s_scale = reinterpret_cast<float*>(tail_ptr + kNumBars * 8 + 16);
   float* s_bias = s_scale + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -325,6 +349,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_init(tfull_bar + i * 8, 1);
       mbar_init(tempty_bar + i * 8, kEpiThreads);
     }
+    for (int i = 0; i < kMaxABuf; ++i) {
+      mbar_init(afull_bar + i * 8, 1);
+      mbar_init(aempty_bar + i * 8, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
@@ -336,9 +364,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 
   if (warp == 0) {
     // ===== TMA producer: the whole warp walks the schedule (uniform), one elected lane issues =====
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, ab = 0;
+    uint32_t phase = 0, aphase = 0;
     const int HoWo = a.Ho * a.Wo;
+    if (a.b_resident) {
+      // weights once (barrier full[0]), then one input patch per (tile, channel chunk)
+      if (elect_one()) {
+        mbar_expect_tx(full_bar, (uint32_t)a.total_subs * a.b_bytes);
+        int g = 0;
+#pragma unroll 1
+        for (int cc = 0; cc < a.c_chunks; ++cc)
+#pragma unroll 1
+          for (int tap = 0; tap < a.taps; ++tap, ++g)
+            tma_load_2d(bres0 + g * a.b_bytes, &a.tmB, full_bar, tap * a.Cin + cc * a.CK, 0);
+      }
+      __syncwarp();
+      const int per_img = a.tiles_x * a.tiles_y;
+#pragma unroll 1
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
+        const int m_tile = st;
+        const int n_img = m_tile / per_img;
+        const int rem = m_tile - n_img * per_img;
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+#pragma unroll 1
+        for (int cc = 0; cc < a.c_chunks; ++cc) {
+          mbar_wait(aempty_bar + ab * 8, aphase ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(afull_bar + ab * 8, a.a_halo_tx);
+            tma_load_4d(abuf0 + ab * a.a_halo_bytes, &a.tmA, afull_bar + ab * 8, cc * a.CK, tx * kHaloTW - 1,
+                        ty * kHaloTH - 1, n_img);
+          }
+          __syncwarp();
+          if (++ab == a.n_abuf) {
+            ab = 0;
+            aphase ^= 1u;
+          }
+        }
+      }
+    } else {
     const int b_rows = a.block_n / cs;                       // rows of the B tile this CTA fetches
     const uint32_t b_slice = (uint32_t)(b_rows * a.CK * 2);
 #pragma unroll 1
@@ -346,26 +409,47 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
       const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;   // m0 >= M for a padding tile: loads zero-fill
       int n_img = 0, h0 = 0, w0 = 0;
-      if (a.im2col) {
+      if (a.halo) {
+        const int per_img = a.tiles_x * a.tiles_y;
+        n_img = m_tile / per_img;
+        const int rem = m_tile - n_img * per_img;
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        h0 = ty * kHaloTH - 1;
+        w0 = tx * kHaloTW - 1;
+      } else if (a.im2col) {
         n_img = m0 / HoWo;
         const int rem = m0 - n_img * HoWo;
         const int p = rem / a.Wo, q = rem - p * a.Wo;
         h0 = p * a.conv_stride - a.pad;
         w0 = q * a.conv_stride - a.pad;
       }
-      int tap = 0, cc = 0, r = 0, s = 0;   // running (tap, channel chunk) of the next sub-tile: no divisions in the loop
+      // running (tap, channel chunk) of the next sub-tile: no divisions in the loop.
+      // im2col order: tap outer, chunk inner.  halo order: chunk outer, tap inner (one patch serves 9 taps).
+      int tap = 0, cc = 0, r = 0, s = 0;
 #pragma unroll 1
       for (int it = 0; it < k_iters; ++it) {
         const int nsub = min(a.subs, a.total_subs - it * a.subs);
+        const bool leader = elect_one();
+        if (a.halo && tap == 0) {   // first tap of a channel chunk: fetch the input patch once
+          mbar_wait(aempty_bar + ab * 8, aphase ^ 1u);
+          if (leader) {
+            mbar_expect_tx(afull_bar + ab * 8, a.a_halo_tx);
+            tma_load_4d(abuf0 + ab * a.a_halo_bytes, &a.tmA, afull_bar + ab * 8, cc * a.CK, w0, h0, n_img);
+          }
+          if (++ab == a.n_abuf) {
+            ab = 0;
+            aphase ^= 1u;
+          }
+        }
         mbar_wait(empty_bar + stage * 8, phase ^ 1u);
         const uint32_t fb = full_bar + stage * 8;
-        const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.subs * a.a_bytes;
-        const bool leader = elect_one();
-        if (leader) mbar_expect_tx(fb, (uint32_t)nsub * (a.a_bytes + a.b_bytes));
+        const uint32_t sa = stage0 + stage * a.stage_bytes, sb = sa + (a.halo ? 0u : a.subs * a.a_bytes);
+        if (leader) mbar_expect_tx(fb, (uint32_t)nsub * ((a.halo ? 0u : a.a_bytes) + a.b_bytes));
 #pragma unroll 1
         for (int j = 0; j < nsub; ++j) {
           if (leader) {
-            if (a.im2col)
+            if (a.halo) {
+            } else if (a.im2col)
               tma_load_im2col_4d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
             else
               tma_load_2d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, m0);
@@ -375,7 +459,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             else
               tma_load_2d(sb + j * a.b_bytes, &a.tmB, fb, tap * a.Cin + cc * a.CK, n0);
           }
-          if (++cc == a.c_chunks) {
+          if (a.halo) {
+            if (++tap == a.taps) {
+              tap = 0;
+              ++cc;
+            }
+          } else if (++cc == a.c_chunks) {
             cc = 0;
             ++tap;
             if (++s == a.kw) {
@@ -391,44 +480,127 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         }
       }
     }
+    }  // !b_resident
   } else if (warp == 1) {
     // ===== MMA issuer: converged warp, elect.sync around the tcgen05 instructions =====
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, ab = 0;
+    uint32_t phase = 0, aphase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int kk_n = a.CK / 16;
     // descriptor halves: lo = start>>4 | LBO(1)<<16 ; hi = SBO | version 1 (bit 46) | layout (bits 61..63)
     const uint32_t desc_hi = a.sbo_enc | (1u << 14) | (a.layout_type << 29);
+    const uint32_t desc_hi_halo = a.halo_sbo_enc | (1u << 14) | (a.layout_type << 29);   // SBO = one patch row
+    const uint32_t row_bytes = (uint32_t)a.CK * 2u;
     const uint32_t a_step = a.a_bytes >> 4, b_step = a.b_bytes >> 4;
+    if (a.b_resident) {
+      mbar_wait(full_bar, 0);   // resident weights have landed
+#pragma unroll 1
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
+        mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.acc_stride);
+        uint32_t accum = 0;
+        uint32_t b_lo = ((bres0 >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < a.c_chunks; ++cc) {
+          mbar_wait(afull_bar + ab * 8, aphase);
+          tc_fence_after();
+          const uint32_t a_patch = abuf0 + ab * a.a_halo_bytes;
+          if (elect_one()) {
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r)
+#pragma unroll 1
+              for (int s2 = 0; s2 < 3; ++s2) {
+                const uint32_t start = a_patch + (uint32_t)(r * a.halo_pitch + s2) * row_bytes;
+                const uint32_t hlo = ((start >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll 4
+                for (int kk = 0; kk < kk_n; ++kk) {
+                  umma_bf16(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                  accum = 1;
+                }
+                b_lo += b_step;
+              }
+            umma_commit(aempty_bar + ab * 8);
+          } else {
+            b_lo += 9u * b_step;   // keep the (uniform) running descriptor in step on the non-elected lanes
+          }
+          accum = 1;
+          __syncwarp();
+          if (++ab == a.n_abuf) {
+            ab = 0;
+            aphase ^= 1u;
+          }
+        }
+        if (elect_one()) umma_commit(tfull_bar + acc * 8);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    } else {
 #pragma unroll 1
     for (int st = cluster_id; st < total_super; st += num_clusters) {
       mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * a.acc_stride);
       uint32_t accum = 0;
+      int tap = 0;                       // halo mode: tap of the next sub-tile (chunk outer, tap inner)
+      uint32_t a_patch = 0;
 #pragma unroll 1
       for (int it = 0; it < k_iters; ++it) {
         const int nsub = min(a.subs, a.total_subs - it * a.subs);
+        if (a.halo && tap == 0) {
+          mbar_wait(afull_bar + ab * 8, aphase);
+          a_patch = abuf0 + ab * a.a_halo_bytes;
+        }
         mbar_wait(full_bar + stage * 8, phase);
         tc_fence_after();
-        const uint32_t sa = base + stage * a.stage_bytes, sb = sa + a.subs * a.a_bytes;
+        const uint32_t sa = stage0 + stage * a.stage_bytes, sb = sa + (a.halo ? 0u : a.subs * a.a_bytes);
+        const bool last_of_chunk = a.halo && (tap + nsub == a.taps);
         if (elect_one()) {
           uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
+          if (a.halo) {
 #pragma unroll 1
-          for (int j = 0; j < nsub; ++j) {
+            for (int j = 0; j < nsub; ++j) {
+              const int t = tap + j;
+              const int r = t / 3, s = t - 3 * r;
+              const uint32_t start = a_patch + (uint32_t)(r * a.halo_pitch + s) * row_bytes;   // shifted window
+              const uint32_t hlo = ((start >> 4) & 0x3FFFu) | (1u << 16);
+              const uint32_t hhi = desc_hi_halo;   // base-offset field stays 0: UMMA swizzles on absolute smem address bits
 #pragma unroll 4
-            for (int kk = 0; kk < kk_n; ++kk) {  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
-              umma_bf16(tmem_d, pack64(a_lo + kk * 2, desc_hi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
-              accum = 1;
+              for (int kk = 0; kk < kk_n; ++kk) {
+                umma_bf16(tmem_d, pack64(hlo + kk * 2, hhi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                accum = 1;
+              }
+              b_lo += b_step;
             }
-            a_lo += a_step;
-            b_lo += b_step;
+          } else {
+#pragma unroll 1
+            for (int j = 0; j < nsub; ++j) {
+#pragma unroll 4
+              for (int kk = 0; kk < kk_n; ++kk) {  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
+                umma_bf16(tmem_d, pack64(a_lo + kk * 2, desc_hi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                accum = 1;
+              }
+              a_lo += a_step;
+              b_lo += b_step;
+            }
           }
           if (cs > 1) umma_commit_mc(empty_bar + stage * 8, mc_mask);
           else umma_commit(empty_bar + stage * 8);
+          if (last_of_chunk) umma_commit(aempty_bar + ab * 8);   // all 9 taps of this patch have been issued
         }
         accum = 1;
+        if (a.halo) {
+          tap += nsub;
+          if (tap == a.taps) {
+            tap = 0;
+            if (++ab == a.n_abuf) {
+              ab = 0;
+              aphase ^= 1u;
+            }
+          }
+        }
         __syncwarp();
         if (++stage == a.stages) {
           stage = 0;
@@ -440,6 +612,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    }  // !b_resident
   } else if (warp >= 4) {
     // ===== epilogue: warp pair (w, w+4) shares TMEM lane quadrant w%4 and interleaves 32-column chunks =====
     const int quad = warp & 3;
@@ -464,13 +637,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         epi_bar_sync();
         staged_n0 = n0;
       }
-      const long long row = (long long)m0 + row_in_tile;
-      const bool valid = row < a.M;
+      long long row = (long long)m0 + row_in_tile;
+      bool valid = row < a.M;
+      int hp = 0, hq = 0, hn = 0;
+      if (a.halo) {   // 16x8 pixel patch: row i of the tile is pixel (ty*16 + i/8, tx*8 + i%8)
+        const int per_img = a.tiles_x * a.tiles_y;
+        hn = m_tile / per_img;
+        const int rem = m_tile - hn * per_img;
+        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        hp = ty * kHaloTH + (row_in_tile >> 3);
+        hq = tx * kHaloTW + (row_in_tile & 7);
+        valid = m_tile < a.num_m_tiles && hp < a.Ho && hq < a.Wo;
+        row = ((long long)hn * a.Ho + hp) * a.Wo + hq;
+      }
       const __nv_bfloat16* gk_row = nullptr;
       if (MODE == EPI_GATE && valid) {
-        const int n_img = (int)(row / HoWo);
-        const int rem = (int)(row - (long long)n_img * HoWo);
-        const int p = rem / a.Wo, q = rem - p * a.Wo;
+        int n_img, p, q;
+        if (a.halo) {
+          n_img = hn; p = hp; q = hq;
+        } else {
+          n_img = (int)(row / HoWo);
+          const int rem = (int)(row - (long long)n_img * HoWo);
+          p = rem / a.Wo;
+          q = rem - p * a.Wo;
+        }
         const int hs = nearest_src(p, a.gHk, a.Ho, a.g_sh), ws = nearest_src(q, a.gWk, a.Wo, a.g_sw);
         gk_row = a.gate_k + (((long long)n_img * a.gHk + hs) * a.gWk + ws) * a.ldgk;
       }
@@ -636,11 +826,51 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   if ((bn % (8 * cs)) || (((bn / cs) * a.CK * 2) % 1024 && a.CK == 64) || m_tiles_q < 2 || sms_q < 2) cs = 1;
   if (a.CK != 64 && (((bn / cs) * a.CK * 2) % (a.CK == 32 ? 512 : 256))) cs = 1;
   a.cs = cs;
-  a.stage_bytes = ((uint32_t)subs * (a.a_bytes + a.b_bytes) + 1023u) & ~1023u;
-  const uint32_t budget = 227u * 1024u - 1024u - kTailBytes - 64u;
+  // ---- halo mode decision: 3x3 / stride 1 / pad 1 on maps that 16x8 patches tile well, enough tiles to fill the chip
+  const int tiles_x = (p->Wo + kHaloTW - 1) / kHaloTW, tiles_y = (p->Ho + kHaloTH - 1) / kHaloTH;
+  const double patch_eff = (double)p->Ho * p->Wo / ((double)tiles_x * kHaloTW * tiles_y * kHaloTH);
+  bool halo = p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !(p->flags & 1) && cs == 1;
+  if (halo && !(p->flags & 2)) {
+    // worth it where the conv is L2->SM bound: few channels per tile (C <= 128) on maps the patches tile >= 90 %
+    halo = patch_eff >= 0.9 && p->Cin <= 128 && (long long)p->N * tiles_x * tiles_y >= 2LL * sms_q;
+  }
+  uint32_t halo_bytes_total = 0;
+  if (halo) {
+    a.halo = 1;
+    a.halo_pitch = kHaloTW + 2;
+    a.tiles_x = tiles_x;
+    a.tiles_y = tiles_y;
+    a.num_m_tiles = p->N * tiles_x * tiles_y;
+    a.a_halo_tx = (uint32_t)(a.halo_pitch * (kHaloTH + 2) * a.CK * 2);
+    a.a_halo_bytes = (a.a_halo_tx + 1023u) & ~1023u;
+    a.halo_sbo_enc = (uint32_t)(a.halo_pitch * a.CK * 2) >> 4;
+    const uint32_t smem_avail = 227u * 1024u - 1024u - kTailBytes - 64u;
+    const uint32_t w_bytes = (uint32_t)a.total_subs * a.b_bytes;           // all taps x chunks of this n-tile
+    if (a.num_n_tiles == 1 && w_bytes <= 100u * 1024u && !(p->flags & 4)) {
+      a.b_resident = 1;
+      a.bres_bytes = (w_bytes + 1023u) & ~1023u;
+      int nb = (int)((smem_avail - a.bres_bytes) / a.a_halo_bytes);
+      a.n_abuf = nb > kMaxABuf ? kMaxABuf : nb;
+      if (a.n_abuf < 2) return DMAY_EUNSUPPORTED;
+      subs = 1;
+      a.subs = 1;
+      a.stage_bytes = 1024u;   // no B pipeline
+    } else {
+      a.n_abuf = 4;
+      // stages hold B tiles only; sub-tiles per stage must divide the 9 taps (a stage never straddles a chunk)
+      subs = (9u * a.b_bytes <= 48u * 1024u) ? 9 : ((3u * a.b_bytes <= 48u * 1024u) ? 3 : 1);
+      a.subs = subs;
+      a.stage_bytes = ((uint32_t)subs * a.b_bytes + 1023u) & ~1023u;
+    }
+    halo_bytes_total = a.bres_bytes + (uint32_t)a.n_abuf * a.a_halo_bytes;
+  } else {
+    a.stage_bytes = ((uint32_t)subs * (a.a_bytes + a.b_bytes) + 1023u) & ~1023u;
+  }
+  const uint32_t budget = 227u * 1024u - 1024u - kTailBytes - 64u - halo_bytes_total;
   int stages = (int)(budget / a.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return DMAY_EUNSUPPORTED;
+  if (a.b_resident) stages = 1;
+  else if (stages < 2) return DMAY_EUNSUPPORTED;
   a.stages = stages;
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
   // both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -664,7 +894,16 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
 
   // ---- tensor maps ----
   CUresult r;
-  if (a.im2col) {
+  if (a.halo) {
+    cuuint64_t gdim[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+    cuuint64_t gstr[3] = {(cuuint64_t)p->ldx * 2, (cuuint64_t)p->W * p->ldx * 2, (cuuint64_t)p->H * p->W * p->ldx * 2};
+    cuuint32_t box[4] = {(cuuint32_t)a.CK, (cuuint32_t)a.halo_pitch, (cuuint32_t)(kHaloTH + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = g_encode_tiled(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DMAY_EDRIVER;
+  } else if (a.im2col) {
     cuuint64_t gdim[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
     cuuint64_t gstr[3] = {(cuuint64_t)p->ldx * 2, (cuuint64_t)p->W * p->ldx * 2, (cuuint64_t)p->H * p->W * p->ldx * 2};
     int lower[2] = {-p->pad, -p->pad};
@@ -700,7 +939,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return DMAY_EDRIVER;
   }
 
-  const size_t smem = 1024 + (size_t)a.stages * a.stage_bytes + kTailBytes;
+  const size_t smem = 1024 + (size_t)halo_bytes_total + (size_t)a.stages * a.stage_bytes + kTailBytes;
   const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
   const long long supers = (long long)((a.num_m_tiles + a.cs - 1) / a.cs) * a.num_n_tiles;
   const long long max_clusters = sms / a.cs;

@@ -175,9 +175,12 @@ def pack_conv(weight: torch.Tensor, bn=None, conv_bias=None, stride=1, pad=0, de
                     kh=kh, kw=kw, stride=stride, pad=pad, stem_spd=stem)
 
 
+CONV_FLAGS = int(__import__('os').environ.get('DMAY_CONV_FLAGS', '0'))   # default tuning flags (see include/dmayolo.h)
+
+
 def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor | None = None,
          residual: torch.Tensor | None = None, gate: tuple | None = None, out_fp32: bool = False,
-         block_n: int = 0, num_sms: int = 0) -> torch.Tensor:
+         block_n: int = 0, num_sms: int = 0, flags: int | None = None) -> torch.Tensor:
     """y = act(scale * conv(x, w) + bias) (+ residual) | (* sigmoid(gate_x + up(gate_k)))."""
     # uint8 images are normalised on the fly (x/255, the `img.float()/255` of val.py:199-202 folded into
     # the layout kernel) — an extension: the reference only accepts float images.
@@ -210,7 +213,7 @@ def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor |
     f = dict(x=x.data_ptr(), w=pk.w.data_ptr(), scale=pk.scale.data_ptr(), bias=pk.bias.data_ptr(), y=out.data_ptr(),
              N=n, H=h, W=w, Cin=pk.cin_pad, ldx=ld_of(x), Cout=cstore, Cout_pad=pk.cout_pad, kh=pk.kh, kw=pk.kw,
              stride=pk.stride, pad=pk.pad, Ho=ho, Wo=wo, ldy=ld_of(out), act=act,
-             out_dtype=_DT[odt], block_n=block_n, num_sms=num_sms)
+             out_dtype=_DT[odt], block_n=block_n, num_sms=num_sms, flags=CONV_FLAGS if flags is None else flags)
     if residual is not None:
         residual = as_act(residual)
         if tuple(residual.shape) != (n, pk.cout, ho, wo):

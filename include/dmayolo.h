@@ -63,7 +63,11 @@ const char* dmay_strerror(int code);
  *   m = (n*Ho + p)*Wo + q.
  * w is packed [Cout_pad][kh][kw][Cin] bf16 (Cin multiple of 16, Cout_pad multiple of 16).
  * mode gate (gate_x != NULL): y = (scale*acc+bias) * sigmoid(gate_x[m,co] + gate_k[n, hs, ws, co])
- *   with nearest index hs=min(floor(p*gate_sh),gHk-1) — SCConv.forward models/common.py:1308-1316. */
+ *   with nearest index hs=min(floor(p*gate_sh),gHk-1) — SCConv.forward models/common.py:1308-1316.
+ * block_n: 0 = auto, >0 = force the N tile, -2 = 2-CTA cluster multicast of the weight tile (experiment).
+ * flags (tuning / A-B switches, 0 = auto): bit0 = never use the halo path (3x3 s1 p1 input patch loaded once
+ *   per channel chunk, taps read shifted windows), bit1 = force it where legal, bit2 = never keep the weight
+ *   set resident in shared memory in halo mode. */
 typedef struct dmay_conv_params {
   const void* x;
   const void* w;
@@ -95,6 +99,7 @@ typedef struct dmay_conv_params {
   int out_dtype;
   int block_n;
   int num_sms;
+  int flags;
 } dmay_conv_params;
 int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream);
 
