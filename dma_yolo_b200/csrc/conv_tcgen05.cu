@@ -223,7 +223,8 @@ struct __align__(64) ConvArgs {
 constexpr int kMaxABuf = 8;
 constexpr int kHaloTH = 16, kHaloTW = 8;
 constexpr uint32_t kNumBars = 2 * kMaxStages + 4 + 2 * kMaxABuf;
-constexpr uint32_t kTailBytes = kNumBars * 8 + 16 + 2 * 256 * 4;
+constexpr uint32_t kEpiStageOff = kNumBars * 8 + 16 + 2 * 256 * 4;   // 8 warps x 2 KB transpose stage
+constexpr uint32_t kTailBytes = kEpiStageOff + kEpiWarps * 2048;
 
 // one elected lane of a converged warp (the warp stays converged, so operands live in uniform registers)
 __device__ __forceinline__ bool elect_one() {
@@ -259,6 +260,34 @@ __device__ __forceinline__ float silu_t(float x) {
 __device__ __forceinline__ float sigmoid_t(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// bf16 modes: one 8-column group of one output row -> packed bf16x8 (stored later, coalesced, via the warp's
+// shared-memory transpose stage).  aux0 / aux1 = residual (or gate_x) / gate_k values of the same 8 columns.
+template <int MODE>
+__device__ __forceinline__ uint4 epi_compute8(const uint32_t* r, const float* sc, const float* bi, const uint4& aux0,
+                                              const uint4& aux1) {
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(r[j]), sc[j], bi[j]);
+  if (MODE == EPI_SILU || MODE == EPI_SILU_RES) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = silu_t(f[j]);
+  }
+  if (MODE == EPI_SILU_RES) {
+    float rs[8];
+    unpack8(aux0, rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += rs[j];
+  }
+  if (MODE == EPI_GATE) {
+    float gx[8], gk[8];
+    unpack8(aux0, gx);
+    unpack8(aux1, gk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= sigmoid_t(gx[j] + gk[j]);
+  }
+  return pack8(f);
+}
 
 // One 8-column group of one output row: registers r[0..7] (fp32 accumulators) -> global.
 template <int MODE>
@@ -614,7 +643,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     }  // !b_resident
   } else if (warp >= 4) {
-    // ===== epilogue: warp pair (w, w+4) shares TMEM lane quadrant w%4 and interleaves 32-column chunks =====
+    // ===== epilogue: warp pair (w, w+4) shares TMEM lane quadrant w%4 and interleaves 32-column chunks.
+    // The warp's work is a flat sequence of (tile, chunk) items; the residual / gate operands of item i+1 are
+    // fetched before item i is processed, so their latency hides behind the accumulator wait and the math of
+    // item i (the epilogue, not the MMA, is the critical path of the small-channel layers).
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;  // 0 or 1
     const int et = threadIdx.x - 128;  // 0..kEpiThreads-1
@@ -623,22 +655,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t acc_phase = 0;
     int staged_n0 = -1;
     const int HoWo = a.Ho * a.Wo;
-#pragma unroll 1
-    for (int st = cluster_id; st < total_super; st += num_clusters) {
+    const int cpw = (a.block_n - half * 32 + 63) / 64;                      // chunks of a tile owned by this warp
+    const int my_tiles = cluster_id < total_super ? (total_super - cluster_id + num_clusters - 1) / num_clusters : 0;
+    const int items = my_tiles * (cpw > 0 ? cpw : 1);                       // cpw == 0: one "empty" item per tile
+
+    // bf16 modes go through a per-warp 2 KB shared-memory transpose so that every global load / store
+    // instruction of the warp covers 8 rows x 64 contiguous bytes (8 lines) instead of 32 rows x 16 bytes
+    // (32 lines): with thread == row the LSU wavefront count, not HBM, bounded the 64-channel layers.
+    constexpr bool kStaged = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_LINEAR || MODE == EPI_GATE);
+    uint4* stg = reinterpret_cast<uint4*>(tail_ptr + kEpiStageOff) + (warp - 4) * 128;
+    auto sidx = [](int r, int j) { return r * 4 + (j ^ ((r >> 1) & 3)); };   // 64-byte rows, XOR swizzle: conflict-free
+    const int lr = lane >> 2, lc = lane & 3;                                  // coalesced mapping: 8 rows x 4 chunks
+
+    struct Item {
+      long long row;   // -1: row not stored (beyond M / outside the image)
+      const __nv_bfloat16* gk_row;
+      int n0, c0, width;
+      bool first, last;
+    };
+    auto make_item = [&](int idx, Item& it) {
+      const int per = cpw > 0 ? cpw : 1;
+      const int ti = idx / per, ch = idx - ti * per;
+      const int st = cluster_id + ti * num_clusters;
       const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
-      const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;
-      if (n0 != staged_n0) {  // uniform across the CTA
-        epi_bar_sync();       // everyone is done reading the previous scale/bias
-        for (int i = et; i < a.block_n; i += kEpiThreads) {
-          const bool in = n0 + i < a.Cout_pad;
-          s_scale[i] = in ? a.scale[n0 + i] : 0.f;
-          s_bias[i] = in ? a.bias[n0 + i] : 0.f;
-        }
-        epi_bar_sync();
-        staged_n0 = n0;
-      }
-      long long row = (long long)m0 + row_in_tile;
-      bool valid = row < a.M;
+      it.n0 = n_tile * a.block_n;
+      it.c0 = half * 32 + ch * 64;
+      it.width = cpw > 0 ? (a.block_n - it.c0 >= 32 ? 32 : 16) : 0;
+      it.first = ch == 0;
+      it.last = ch == per - 1;
+      it.row = (long long)m_tile * BLOCK_M + row_in_tile;
+      bool valid = it.row < a.M;
       int hp = 0, hq = 0, hn = 0;
       if (a.halo) {   // 16x8 pixel patch: row i of the tile is pixel (ty*16 + i/8, tx*8 + i%8)
         const int per_img = a.tiles_x * a.tiles_y;
@@ -648,68 +694,129 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         hp = ty * kHaloTH + (row_in_tile >> 3);
         hq = tx * kHaloTW + (row_in_tile & 7);
         valid = m_tile < a.num_m_tiles && hp < a.Ho && hq < a.Wo;
-        row = ((long long)hn * a.Ho + hp) * a.Wo + hq;
+        it.row = ((long long)hn * a.Ho + hp) * a.Wo + hq;
       }
-      const __nv_bfloat16* gk_row = nullptr;
+      it.gk_row = nullptr;
       if (MODE == EPI_GATE && valid) {
         int n_img, p, q;
         if (a.halo) {
           n_img = hn; p = hp; q = hq;
         } else {
-          n_img = (int)(row / HoWo);
-          const int rem = (int)(row - (long long)n_img * HoWo);
+          n_img = (int)(it.row / HoWo);
+          const int rem = (int)(it.row - (long long)n_img * HoWo);
           p = rem / a.Wo;
           q = rem - p * a.Wo;
         }
         const int hs = nearest_src(p, a.gHk, a.Ho, a.g_sh), ws = nearest_src(q, a.gWk, a.Wo, a.g_sw);
-        gk_row = a.gate_k + (((long long)n_img * a.gHk + hs) * a.gWk + ws) * a.ldgk;
+        it.gk_row = a.gate_k + (((long long)n_img * a.gHk + hs) * a.gWk + ws) * a.ldgk;
       }
-      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * a.acc_stride) + ((uint32_t)(quad * 32) << 16);
-      bool waited = false;
+      if (!valid) it.row = -1;
+    };
+    // x0: residual / gate_x in the COALESCED mapping (lane -> row k*8+lr, chunk lc); x1: gate_k in the row mapping
+    auto prefetch = [&](const Item& it, uint4* x0, uint4* x1) {
+      if (MODE == EPI_SILU_RES || MODE == EPI_GATE) {
+        const __nv_bfloat16* src = MODE == EPI_SILU_RES ? a.residual : a.gate_x;
+        const int ld = MODE == EPI_SILU_RES ? a.ldr : a.ldgx;
+        const int col = it.n0 + it.c0 + lc * 8;
+        const bool col_on = lc * 8 < it.width && col + 8 <= a.n_store;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long long rowR = __shfl_sync(0xffffffffu, it.row, k * 8 + lr);
+          x0[k] = (col_on && rowR >= 0) ? ld_nc16(src + rowR * ld + col) : make_uint4(0, 0, 0, 0);
+        }
+        if (MODE == EPI_GATE) {
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            const int c = it.n0 + it.c0 + v8 * 8;
+            x1[v8] = (it.row >= 0 && v8 * 8 < it.width && c + 8 <= a.n_store) ? ld16(it.gk_row + c) : make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+    };
+
+    Item cur, nxt;
+    uint4 ca0[4], ca1[4], na0[4], na1[4];
+    if (items > 0) {
+      make_item(0, cur);
+      prefetch(cur, ca0, ca1);
+    }
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < a.block_n; c0 += 64) {
-        const int width = a.block_n - c0 >= 32 ? 32 : 16;
-        const int col0 = n0 + c0;
-        // operands that do not depend on the accumulator are fetched before waiting for it
-        uint4 aux0[4], aux1[4];
-        if (MODE == EPI_SILU_RES || MODE == EPI_GATE) {
-#pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            const int col = col0 + v8 * 8;
-            const bool on = valid && v8 * 8 < width && col + 8 <= a.n_store;
-            if (MODE == EPI_SILU_RES) aux0[v8] = on ? ld_nc16(a.residual + row * a.ldr + col) : make_uint4(0, 0, 0, 0);
-            if (MODE == EPI_GATE) {
-              aux0[v8] = on ? ld_nc16(a.gate_x + row * a.ldgx + col) : make_uint4(0, 0, 0, 0);
-              aux1[v8] = on ? ld16(gk_row + col) : make_uint4(0, 0, 0, 0);
-            }
-          }
-        }
-        if (!waited) {
-          mbar_wait(tfull_bar + acc * 8, acc_phase);
-          tc_fence_after();
-          waited = true;
-        }
-        uint32_t r[32];
-        if (width == 32) tmem_ld32(taddr0 + c0, r);
-        else tmem_ld16(taddr0 + c0, r);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            const int col = col0 + v8 * 8;
-            if (v8 * 8 < width && col + 8 <= a.n_store)
-              epi_store8<MODE>(a, r + v8 * 8, s_scale + c0 + v8 * 8, s_bias + c0 + v8 * 8, row, col, aux0[v8], aux1[v8]);
-          }
-        }
+    for (int idx = 0; idx < items; ++idx) {
+      if (idx + 1 < items) {
+        make_item(idx + 1, nxt);
+        prefetch(nxt, na0, na1);
       }
-      if (!waited) {  // this warp had no chunk (block_n <= 32 and half == 1): still consume the phase
+      if (cur.first) {
+        if (cur.n0 != staged_n0) {  // uniform across the CTA
+          epi_bar_sync();           // everyone is done reading the previous scale/bias
+          for (int i = et; i < a.block_n; i += kEpiThreads) {
+            const bool in = cur.n0 + i < a.Cout_pad;
+            s_scale[i] = in ? a.scale[cur.n0 + i] : 0.f;
+            s_bias[i] = in ? a.bias[cur.n0 + i] : 0.f;
+          }
+          epi_bar_sync();
+          staged_n0 = cur.n0;
+        }
         mbar_wait(tfull_bar + acc * 8, acc_phase);
         tc_fence_after();
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar + acc * 8);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (cur.width > 0) {
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * a.acc_stride) + ((uint32_t)(quad * 32) << 16) + cur.c0;
+        uint32_t r[32];
+        if (cur.width == 32) tmem_ld32(taddr, r);
+        else tmem_ld16(taddr, r);
+        if (kStaged) {
+          uint4 own[4];
+          if (MODE == EPI_SILU_RES || MODE == EPI_GATE) {   // coalesced -> row layout
+#pragma unroll
+            for (int k = 0; k < 4; ++k) stg[sidx(k * 8 + lr, lc)] = ca0[k];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) own[j] = stg[sidx(lane, j)];
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          uint4 outv[4];
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8)
+            outv[v8] = epi_compute8<MODE>(r + v8 * 8, s_scale + cur.c0 + v8 * 8, s_bias + cur.c0 + v8 * 8, own[v8], ca1[v8]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) stg[sidx(lane, j)] = outv[j];
+          __syncwarp();
+          const int col = cur.n0 + cur.c0 + lc * 8;
+          const bool col_on = lc * 8 < cur.width && col + 8 <= a.n_store;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const long long rowR = __shfl_sync(0xffffffffu, cur.row, k * 8 + lr);
+            const uint4 v = stg[sidx(k * 8 + lr, lc)];
+            if (col_on && rowR >= 0) st16(reinterpret_cast<__nv_bfloat16*>(a.y) + rowR * a.ldy + col, v);
+          }
+          __syncwarp();
+        } else {
+          tmem_ld_wait();
+          if (cur.row >= 0) {
+#pragma unroll
+            for (int v8 = 0; v8 < 4; ++v8) {
+              const int col = cur.n0 + cur.c0 + v8 * 8;
+              if (v8 * 8 < cur.width && col + 8 <= a.n_store)
+                epi_store8<MODE>(a, r + v8 * 8, s_scale + cur.c0 + v8 * 8, s_bias + cur.c0 + v8 * 8, cur.row, col, ca0[v8],
+                                 ca1[v8]);
+            }
+          }
+        }
+      }
+      if (cur.last) {
+        tc_fence_before();
+        mbar_arrive(tempty_bar + acc * 8);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      cur = nxt;
+#pragma unroll
+      for (int v8 = 0; v8 < 4; ++v8) {
+        ca0[v8] = na0[v8];
+        ca1[v8] = na1[v8];
+      }
     }
   }
 

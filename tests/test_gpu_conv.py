@@ -115,3 +115,60 @@ def test_conv_rejects_bad_arguments():
     pk = ops.pack_conv(torch.randn(64, 64, 1, 1), device='cuda')
     with pytest.raises(D.DmayError):
         ops.conv(torch.randn(1, 32, 4, 4).cuda(), pk)
+
+
+# ---- kernel path variants that auto-selection only engages at full-size layers: force them at test sizes ----
+def run_flags(n, cin, h, w, cout, flags=0, block_n=0, residual=False, gate=False, seed=0):
+    from dma_yolo_b200 import ops
+    from oracle import blocks as O
+    g = torch.Generator().manual_seed(seed)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = bf(torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5)
+    pk = ops.pack_conv(wt, stride=1, pad=1, device='cuda')
+    ref = F.conv2d(x, wt, None, 1, 1)
+    xa = ops.as_act(x.cuda())
+    kw = {}
+    if gate:
+        k2 = bf(torch.randn(n, cout, max(h // 4, 1), max(w // 4, 1), generator=g))
+        ref = O.scconv_gate(x, ref, k2)
+        kw['gate'] = (xa, ops.as_act(k2.cuda()))
+        act = 0
+    else:
+        ref = ref * torch.sigmoid(ref)
+        act = 1
+    if residual:
+        res = bf(torch.randn(ref.shape, generator=g))
+        ref = ref + res
+        kw['residual'] = ops.as_act(res.cuda())
+    y = ops.conv(xa, pk, act, flags=flags, block_n=block_n, **kw)
+    torch.cuda.synchronize()
+    return back(y), ref
+
+
+HALO_SHAPES = [(2, 64, 32, 16, 64), (1, 128, 48, 40, 128), (2, 64, 20, 20, 64), (1, 16, 32, 32, 32), (1, 32, 16, 24, 64),
+               (3, 256, 16, 8, 256), (1, 64, 19, 23, 64), (2, 128, 33, 9, 48)]
+
+
+@pytest.mark.parametrize('shape', HALO_SHAPES, ids=[str(s) for s in HALO_SHAPES])
+@pytest.mark.parametrize('flags', [2, 2 | 4], ids=['halo-resident-if-fits', 'halo-streamed-weights'])
+def test_conv_halo_paths(shape, flags):
+    """3x3 s1 p1 through the halo path (input patch loaded once, taps = shifted UMMA windows), incl. maps the
+    16x8 patches do not tile (19x23, 33x9) and every swizzle width (Cin 16 / 32 / 64+)."""
+    y, ref = run_flags(*shape, flags=flags)
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'halo {shape} flags={flags}')
+
+
+@pytest.mark.parametrize('kw', [dict(residual=True), dict(gate=True)], ids=['residual', 'gate'])
+@pytest.mark.parametrize('flags', [1, 2], ids=['im2col', 'halo'])
+def test_conv_epilogue_variants_on_both_paths(kw, flags):
+    y, ref = run_flags(2, 64, 24, 16, 64, flags=flags, seed=9, **kw)
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'{kw} flags={flags}')
+    y, ref = run_flags(1, 128, 19, 23, 128, flags=flags, seed=10, **kw)     # M tail + non-tiling map
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'{kw} flags={flags} odd')
+
+
+def test_conv_cluster_multicast_path():
+    """block_n = -2: weight tile fetched in two halves and multicast across a 2-CTA cluster (opt-in experiment)."""
+    for shape in [(2, 64, 32, 16, 64), (1, 256, 24, 24, 256), (1, 128, 17, 13, 128)]:
+        y, ref = run_flags(*shape, flags=1, block_n=-2)
+        assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'cluster {shape}')
