@@ -416,14 +416,25 @@ class DetectLevel:
     ld: int
 
 
-def _level_meta(levels, na, device):
+def _level_meta_host(levels, na):
     words, row0 = [], 0
     for lv in levels:
         flat = [float(v) for wh in lv.anchors_px for v in wh] + [0.0] * (10 - 2 * na)
         words.append(struct.pack("<5if10f", row0, lv.ny, lv.nx, lv.ld, na, float(lv.stride), *flat))
         row0 += na * lv.ny * lv.nx
-    buf = torch.frombuffer(bytearray(b"".join(words)), dtype=torch.uint8).to(device)
+    return b"".join(words), row0
+
+
+def _level_meta(levels, na, device):
+    raw, row0 = _level_meta_host(levels, na)
+    buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
     return buf, row0
+
+
+# candidate-buffer capacity of the fused filter, remembered per (device, batch, rows, nc, multi_label): the
+# kernel counts every candidate but only writes those below `capacity`, so an undersized guess costs one re-run.
+_FUSED_CAP: dict = {}
+FUSED_FILTER = __import__('os').environ.get('DMAY_FUSED_FILTER', '1') != '0'
 
 
 def detect_decode(levels, na: int, no: int) -> torch.Tensor:
@@ -449,6 +460,8 @@ def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, 
     if levels is not None:
         dev = levels[0].logits.device
         n = levels[0].logits.shape[0]
+        if FUSED_FILTER:
+            return _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
         meta, rows = _level_meta(levels, na, dev)
         src = dict(levels=len(levels), lv_meta=meta.data_ptr())
         for i, lv in enumerate(levels):
@@ -473,14 +486,9 @@ def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, 
     common = dict(blk_counts=blk_counts.data_ptr(), blk_offsets=blk_offsets.data_ptr(), img_counts=img_counts.data_ptr(),
                   img_offsets=img_offsets.data_ptr(), N=n, R=rows, nc=nc, multi_label=int(multi_label),
                   rows_per_block=rpb, conf_thres=float(conf_thres), **src)
-    if classes is not None:
-        cm = torch.zeros(nc, dtype=torch.uint8)
-        for c in classes:
-            if 0 <= int(c) < nc:
-                cm[int(c)] = 1
-        cm = cm.to(dev)
+    cm = _class_mask(classes, nc, dev)
+    if cm is not None:
         common["class_mask"] = cm.data_ptr()
-        keep_alive += (cm,)
     call("dmay_nms_filter", s, phase=0, **common)
     total = int(img_offsets[n].item())  # the one sizing sync of the batch
     out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
@@ -490,17 +498,79 @@ def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, 
     keys = torch.empty(total, device=dev, dtype=torch.int64)
     cand = torch.empty((total, 6), device=dev, dtype=torch.float32)
     call("dmay_nms_filter", s, phase=1, keys=keys.data_ptr(), cand=cand.data_ptr(), capacity=total, **common)
-    img_bits = max(1, (n - 1).bit_length())
-    ws_bytes = int(_lib.lib().dmay_nms_sort_ws(total, img_bits))
-    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-    keys_out = torch.empty_like(keys)
-    idx = torch.empty(total, device=dev, dtype=torch.int32)
-    call("dmay_nms_sort", s, keys_in=keys.data_ptr(), keys_out=keys_out.data_ptr(), idx_out=idx.data_ptr(),
-         ws=ws.data_ptr(), ws_bytes=ws_bytes, n=total, img_bits=img_bits)
+    _keys_out, idx = _sort_candidates(keys, total, n, dev, s)
     call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=img_counts.data_ptr(),
          img_offsets=img_offsets.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
          max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
-    del keep_alive
+    del keep_alive, cm
+    return out, out_counts
+
+
+def _class_mask(classes, nc, dev):
+    if classes is None:
+        return None
+    cm = torch.zeros(nc, dtype=torch.uint8)
+    for c in classes:
+        if 0 <= int(c) < nc:
+            cm[int(c)] = 1
+    return cm.to(dev)
+
+
+def _sort_candidates(keys, total, n, dev, s):
+    """Stable radix sort of the (image, ~score) keys; payload = candidate index."""
+    img_bits = max(1, (n - 1).bit_length())
+    ws_bytes = int(_lib.lib().dmay_nms_sort_ws(total, img_bits))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    keys_out = torch.empty(total, device=dev, dtype=torch.int64)
+    idx = torch.empty(total, device=dev, dtype=torch.int32)
+    call("dmay_nms_sort", s, keys_in=keys.data_ptr(), keys_out=keys_out.data_ptr(), idx_out=idx.data_ptr(),
+         ws=ws.data_ptr(), ws_bytes=ws_bytes, n=total, img_bits=img_bits)
+    return keys_out, idx
+
+
+def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
+    """Detect-logits source: single-pass fused decode+filter (unordered compaction) -> sort -> tie fix -> greedy."""
+    import ctypes
+    dev = levels[0].logits.device
+    n = levels[0].logits.shape[0]
+    s = torch.cuda.current_stream(dev).cuda_stream
+    multi_label = bool(multi_label) and nc > 1
+    raw, rows = _level_meta_host(levels, na)
+    meta_host = ctypes.create_string_buffer(raw, len(raw))
+    cm = _class_mask(classes, nc, dev)
+    key = (dev.index, n, rows, nc, multi_label, float(conf_thres))
+    capacity = _FUSED_CAP.get(key, n * rows * (2 if multi_label else 1) // 2 + 4096)
+    out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
+    out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
+    img_offsets = torch.empty(n + 1, device=dev, dtype=torch.int64)
+    while True:
+        counters = torch.zeros(2 + n, device=dev, dtype=torch.int32)   # [0:2] = u64 total, [2:] = per-image counts
+        keys = torch.empty(capacity, device=dev, dtype=torch.int64)
+        cand = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
+        ordv = torch.empty(capacity, device=dev, dtype=torch.int32)
+        f = dict(lv_meta_host=ctypes.addressof(meta_host), total=counters.data_ptr(), img_counts=counters.data_ptr() + 8,
+                 img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(), cand=cand.data_ptr(), ord=ordv.data_ptr(),
+                 N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
+                 conf_thres=float(conf_thres))
+        for i, lv in enumerate(levels):
+            f[f"lv_logits{i}"] = lv.logits.data_ptr()
+        if cm is not None:
+            f["class_mask"] = cm.data_ptr()
+        call("dmay_nms_filter_fused", s, **f)
+        total = int(img_offsets[n].item())   # the one sizing sync of the batch
+        if total <= capacity:
+            break
+        capacity = total + total // 8 + 4096   # undersized guess: every candidate was counted, repeat once
+    _FUSED_CAP[key] = max(total + total // 4 + 4096, _FUSED_CAP.get(key, 0) // 2)
+    if total == 0:
+        return out, out_counts
+    keys_out, idx = _sort_candidates(keys, total, n, dev, s)
+    idx2 = torch.empty(total, device=dev, dtype=torch.int32)
+    call("dmay_nms_tiefix", s, keys_sorted=keys_out.data_ptr(), idx_in=idx.data_ptr(), ord=ordv.data_ptr(),
+         idx_out=idx2.data_ptr(), n=total)
+    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx2.data_ptr(), img_counts=counters.data_ptr() + 8,
+         img_offsets=img_offsets.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
+         max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
     return out, out_counts
 
 

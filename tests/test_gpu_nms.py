@@ -126,3 +126,49 @@ def test_fused_decode_filter_equals_dense_path():
                 assert torch.equal(f, dn)
                 assert np.array_equal(dn.cpu().numpy(), o)
             assert sum(len(f) for f in fused) > 0
+
+
+def _quantised_levels(N, nc, shapes, seed, step):
+    """Detect logits on a coarse grid of values: confidences collide massively, so equal sort keys are the rule."""
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    na, no = 3, 5 + nc
+    ld = ops.round_up(na * no, 8)
+    levels = []
+    for (ny, nx), stride in zip(shapes, (8., 16., 32.)):
+        lg = (torch.randn(N, ny, nx, ld, generator=g) * 2.0 / step).round() * step
+        anchors = [(stride * (1 + a), stride * (2 + a)) for a in range(na)]
+        levels.append(ops.DetectLevel(logits=lg.cuda().contiguous(), stride=stride, anchors_px=anchors, ny=ny, nx=nx, ld=ld))
+    return levels, na, no
+
+
+@pytest.mark.parametrize('kw', [dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300),
+                                dict(conf_thres=0.25, iou_thres=0.45, max_det=1000),
+                                dict(conf_thres=0.05, iou_thres=0.5, multi_label=True, classes=[1, 4, 6], max_det=100),
+                                dict(conf_thres=0.05, iou_thres=0.5, agnostic=True, max_det=50)])
+def test_fused_filter_ties_match_ordered_path(kw):
+    """Single-pass fused filter compacts in arbitrary order; the tie fix must reproduce the order-preserving
+    path bit for bit even when thousands of candidates share a score (ragged tiles: 13x7, 5x3 pixels)."""
+    from dma_yolo_b200 import ops
+    levels, na, no = _quantised_levels(3, 7, [(20, 12), (13, 7), (5, 3)], seed=5, step=0.5)
+    fo, fc = ops.nms_batched(None, kw['conf_thres'], kw['iou_thres'], levels=levels, na=na, nc=no - 5,
+                             **{k: v for k, v in kw.items() if k not in ('conf_thres', 'iou_thres')})
+    dense = ops.detect_decode(levels, na, no)
+    do, dc = ops.nms_batched(dense, kw['conf_thres'], kw['iou_thres'],
+                             **{k: v for k, v in kw.items() if k not in ('conf_thres', 'iou_thres')})
+    assert torch.equal(fc, dc)
+    assert int(fc.sum()) > 0
+    assert torch.equal(fo, do)
+    ref = ON.non_max_suppression(dense.cpu().numpy(), **kw)
+    for i, r in enumerate(ref):
+        assert np.array_equal(fo[i, :int(fc[i])].cpu().numpy(), r)
+
+
+def test_fused_filter_capacity_overflow_reruns():
+    from dma_yolo_b200 import ops
+    levels, na, no = _quantised_levels(2, 7, [(20, 12), (13, 7), (5, 3)], seed=9, step=0.25)
+    a = ops.nms_batched(None, 0.001, 0.6, levels=levels, na=na, nc=no - 5, multi_label=True)
+    for k in list(ops._FUSED_CAP):
+        ops._FUSED_CAP[k] = 64          # far too small: the kernel counts everything, the wrapper repeats
+    b = ops.nms_batched(None, 0.001, 0.6, levels=levels, na=na, nc=no - 5, multi_label=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

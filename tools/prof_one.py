@@ -24,5 +24,21 @@ elif kind == 'gate':
                       ops.empty_nhwc(B, c, s // 4, s // 4, dev).normal_(), ops.empty_nhwc(B, c, s, s, dev))
     for _ in range(3):
         ops.scconv_gate(x, k3, k2, out=out)
+elif kind == 'model':
+    # whole hot path (forward + fused decode/filter + NMS) once warm, once profiled-range: for `ncu -k regex:...`
+    import dma_yolo_b200 as D
+    from dma_yolo_b200.utils.calib import build_calibrated
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    m = build_calibrated('ablation-ca-scconv-sppfcspc-bifpn.yaml', seed=0).to(dev).eval()
+    x = torch.rand(B, 3, 640, 640, generator=torch.Generator().manual_seed(1)).to(dev)
+    with torch.no_grad():
+        for it in range(2):
+            if it == 1:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.start()
+            pred, _ = m(x)
+            D.non_max_suppression(pred, 0.001, 0.6, multi_label=True, max_det=300)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 torch.cuda.synchronize()
 print('ok')
