@@ -95,6 +95,8 @@ def lib():
                 argtypes.append(ctypes.POINTER(STRUCTS[sname]))
             elif a.startswith("dmay_stream_t"):
                 argtypes.append(ctypes.c_void_p)
+            elif a.startswith("const void*") or a.startswith("void*"):
+                argtypes.append(ctypes.c_void_p)
             elif a.startswith("long long"):
                 argtypes.append(ctypes.c_longlong)
             elif a.startswith("int"):

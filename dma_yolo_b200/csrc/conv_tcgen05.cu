@@ -214,6 +214,10 @@ struct __align__(64) ConvArgs {
   uint32_t a_bytes, b_bytes, stage_bytes;
   uint32_t idesc;
   uint32_t sbo_enc, layout_type;
+  // magic-number division (q = umulhi(n, mul) >> shr, mul == 0 <=> divisor 1) for the per-tile / per-item index
+  // decompositions: the generic integer division is ~25 instructions + 2 XU ops each, and the epilogue of the
+  // small-channel layers is issue- and XU-bound
+  uint32_t fd_nn[2], fd_pi[2], fd_tx[2], fd_hw[2], fd_wo[2];
 };
 
 // smem carve-up (after manual 1024-byte alignment):
@@ -245,6 +249,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
   // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout[61,64)
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)sbo_enc << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)layout_type << 61);
+}
+
+__device__ __forceinline__ int fdiv(int n, const uint32_t (&fd)[2]) {
+  return fd[0] ? (int)(__umulhi((uint32_t)n, fd[0]) >> fd[1]) : n;
 }
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -412,9 +420,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll 1
       for (int st = cluster_id; st < total_super; st += num_clusters) {
         const int m_tile = st;
-        const int n_img = m_tile / per_img;
+        const int n_img = fdiv(m_tile, a.fd_pi);
         const int rem = m_tile - n_img * per_img;
-        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int ty = fdiv(rem, a.fd_tx), tx = rem - ty * a.tiles_x;
 #pragma unroll 1
         for (int cc = 0; cc < a.c_chunks; ++cc) {
           mbar_wait(aempty_bar + ab * 8, aphase ^ 1u);
@@ -435,20 +443,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const uint32_t b_slice = (uint32_t)(b_rows * a.CK * 2);
 #pragma unroll 1
     for (int st = cluster_id; st < total_super; st += num_clusters) {
-      const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
+      const int sq = fdiv(st, a.fd_nn);
+      const int n_tile = st - sq * a.num_n_tiles, m_tile = sq * cs + (int)crank;
       const int m0 = m_tile * BLOCK_M, n0 = n_tile * a.block_n;   // m0 >= M for a padding tile: loads zero-fill
       int n_img = 0, h0 = 0, w0 = 0;
       if (a.halo) {
         const int per_img = a.tiles_x * a.tiles_y;
-        n_img = m_tile / per_img;
+        n_img = fdiv(m_tile, a.fd_pi);
         const int rem = m_tile - n_img * per_img;
-        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int ty = fdiv(rem, a.fd_tx), tx = rem - ty * a.tiles_x;
         h0 = ty * kHaloTH - 1;
         w0 = tx * kHaloTW - 1;
       } else if (a.im2col) {
-        n_img = m0 / HoWo;
+        n_img = fdiv(m0, a.fd_hw);
         const int rem = m0 - n_img * HoWo;
-        const int p = rem / a.Wo, q = rem - p * a.Wo;
+        const int p = fdiv(rem, a.fd_wo), q = rem - p * a.Wo;
         h0 = p * a.conv_stride - a.pad;
         w0 = q * a.conv_stride - a.pad;
       }
@@ -673,11 +682,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       int n0, c0, width;
       bool first, last;
     };
-    auto make_item = [&](int idx, Item& it) {
-      const int per = cpw > 0 ? cpw : 1;
-      const int ti = idx / per, ch = idx - ti * per;
+    // (tile, chunk) of the next item to build: advanced incrementally, no division by `per`
+    int mk_ti = 0, mk_ch = 0;
+    const int per = cpw > 0 ? cpw : 1;
+    auto make_item = [&](Item& it) {
+      const int ti = mk_ti, ch = mk_ch;
+      if (++mk_ch == per) {
+        mk_ch = 0;
+        ++mk_ti;
+      }
       const int st = cluster_id + ti * num_clusters;
-      const int n_tile = st % a.num_n_tiles, m_tile = (st / a.num_n_tiles) * cs + (int)crank;
+      const int sq = fdiv(st, a.fd_nn);
+      const int n_tile = st - sq * a.num_n_tiles, m_tile = sq * cs + (int)crank;
       it.n0 = n_tile * a.block_n;
       it.c0 = half * 32 + ch * 64;
       it.width = cpw > 0 ? (a.block_n - it.c0 >= 32 ? 32 : 16) : 0;
@@ -688,9 +704,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       int hp = 0, hq = 0, hn = 0;
       if (a.halo) {   // 16x8 pixel patch: row i of the tile is pixel (ty*16 + i/8, tx*8 + i%8)
         const int per_img = a.tiles_x * a.tiles_y;
-        hn = m_tile / per_img;
+        hn = fdiv(m_tile, a.fd_pi);
         const int rem = m_tile - hn * per_img;
-        const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+        const int ty = fdiv(rem, a.fd_tx), tx = rem - ty * a.tiles_x;
         hp = ty * kHaloTH + (row_in_tile >> 3);
         hq = tx * kHaloTW + (row_in_tile & 7);
         valid = m_tile < a.num_m_tiles && hp < a.Ho && hq < a.Wo;
@@ -702,9 +718,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         if (a.halo) {
           n_img = hn; p = hp; q = hq;
         } else {
-          n_img = (int)(it.row / HoWo);
-          const int rem = (int)(it.row - (long long)n_img * HoWo);
-          p = rem / a.Wo;
+          n_img = fdiv((int)it.row, a.fd_hw);
+          const int rem = (int)it.row - n_img * HoWo;
+          p = fdiv(rem, a.fd_wo);
           q = rem - p * a.Wo;
         }
         const int hs = nearest_src(p, a.gHk, a.Ho, a.g_sh), ws = nearest_src(q, a.gWk, a.Wo, a.g_sw);
@@ -737,13 +753,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     Item cur, nxt;
     uint4 ca0[4], ca1[4], na0[4], na1[4];
     if (items > 0) {
-      make_item(0, cur);
+      make_item(cur);
       prefetch(cur, ca0, ca1);
     }
 #pragma unroll 1
     for (int idx = 0; idx < items; ++idx) {
       if (idx + 1 < items) {
-        make_item(idx + 1, nxt);
+        make_item(nxt);
         prefetch(nxt, na0, na1);
       }
       if (cur.first) {
@@ -855,6 +871,19 @@ static bool load_driver_fns() {
   g_encode_tiled = (EncodeTiledFn)f1;
   g_encode_im2col = (EncodeIm2colFn)f2;
   return true;
+}
+
+static void find_divisor(uint32_t (&fd)[2], int d) {   // q = umulhi(n, mul) >> shr for 0 <= n < 2^31 (CUTLASS FastDivmod)
+  if (d <= 1) {
+    fd[0] = 0;
+    fd[1] = 0;
+    return;
+  }
+  int lg = 0;
+  while ((1ll << lg) < d) ++lg;
+  const int p = 31 + lg;
+  fd[0] = (uint32_t)(((1ull << p) + (unsigned)d - 1) / (unsigned)d);
+  fd[1] = (uint32_t)(p - 32);
 }
 
 static int pow2ceil(int v) {
@@ -998,6 +1027,11 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   a.g_sw = p->gWk > 0 ? (float)p->gWk / (float)p->Wo : 0.f;
   a.act = p->act;
   a.out_f32 = out_f32 ? 1 : 0;
+  find_divisor(a.fd_nn, a.num_n_tiles);
+  find_divisor(a.fd_pi, a.halo ? a.tiles_x * a.tiles_y : 1);
+  find_divisor(a.fd_tx, a.halo ? a.tiles_x : 1);
+  find_divisor(a.fd_hw, p->Ho * p->Wo);
+  find_divisor(a.fd_wo, p->Wo);
 
   // ---- tensor maps ----
   CUresult r;

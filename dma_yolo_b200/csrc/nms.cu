@@ -261,70 +261,115 @@ __global__ void __launch_bounds__(kFilterThreads) filter_write_kernel(
 }
 
 // ---- fused single-pass filter (Detect logits source) ---------------------------------------------------
-// One CTA = one tile of P consecutive pixels of one (image, level): the tile's logits ([P][ld] fp32, one
-// contiguous block of memory) are staged in shared memory with 128-bit coalesced loads, so HBM is read
-// exactly ONCE.  Phase 1: a warp per (pixel, anchor) row decodes the box, turns the class logits into
-// confidences IN PLACE (failed classes marked -1) and counts; the CTA scans its <=160 row counts and
-// reserves a range with ONE atomicAdd on the batch counter (plus one on the image counter).  Phase 2
-// writes the candidates of the tile into that range.  Candidate order in memory is therefore arbitrary
-// between CTAs; `ord` = row*nc+cls records the reference order (utils/general.py:684-688: rows
-// ascending, classes ascending within a row) and tiefix_kernel applies it among equal sort keys, which
-// is the only place a stable sort consults the input order.
+// One CTA = one tile of P consecutive pixels of ONE anchor of one (image, level), taken in the reference row
+// order (image, level, anchor, y, x — models/yolo.py:101-103), so "tile order" == "candidate order".  The
+// tile's 5+nc logits per pixel are staged in shared memory (each logit is read from HBM once; a pixel's 1 KB
+// is shared by the na tiles of its anchors), a warp per row decodes the box and turns the class logits into
+// confidences in place, and the CTA's candidates are placed by a decoupled look-back scan over the tiles
+// (status word = flag | count; tile ids come from an atomic ticket so every predecessor is already running).
+// Result: order-preserving compaction of the whole batch in ONE pass, no count/scan/write re-reads.
 constexpr int kFuseThreads = 256;
 constexpr int kFuseWarps = kFuseThreads / 32;
-constexpr int kFuseMaxRows = 160;            // P * na <= 32 * 5
-constexpr int kFuseTileFloats = 8192;        // 32 KB of logits per tile
+constexpr int kFuseP = 64;                   // rows (pixels of one anchor) per tile
 
 struct FuseArgs {
   const float* logits[5];
   LevelMeta meta[5];
-  int tile0[6];        // first tile index of each level (+ total)
-  int tiles_per_img[5];
-  int P[5];
-  int levels, nc, multi_label;
+  int tile0[6];        // first tile (within an image) of each level, [levels] = tiles per image
+  int tpa[5];          // tiles per anchor plane
+  int levels, nc, multi_label, N;
   float thr;
   long long capacity;
 };
 
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// exclusive prefix of `count` over all tiles before `tile` (called by one full warp)
+__device__ __forceinline__ long long tile_lookback(unsigned long long* status, int tile, int count, int lane) {
+  constexpr unsigned long long kAgg = 1ull << 62, kIncl = 2ull << 62, kVal = (1ull << 62) - 1;
+  if (tile == 0) {
+    if (lane == 0) st_status(status, kIncl | (unsigned long long)count);
+    return 0;
+  }
+  if (lane == 0) st_status(status + tile, kAgg | (unsigned long long)count);
+  long long excl = 0;
+  int j = tile - 1;
+  while (true) {
+    const int idx = j - lane;
+    const unsigned long long w = idx >= 0 ? ld_status(status + idx) : kIncl;   // before tile 0: inclusive prefix 0
+    const unsigned f = (unsigned)(w >> 62);
+    const unsigned incl = __ballot_sync(0xffffffffu, f == 2u), notready = __ballot_sync(0xffffffffu, f == 0u);
+    if (incl) {
+      const int first = __ffs(incl) - 1;                       // nearest predecessor with an inclusive prefix
+      const unsigned need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+      if (notready & need) continue;                           // somebody closer is not published yet: poll again
+      long long v = lane <= first ? (long long)(w & kVal) : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      excl += v;
+      break;
+    }
+    if (notready) continue;
+    long long v = (long long)(w & kVal);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    excl += v;
+    j -= 32;
+  }
+  if (lane == 0) st_status(status + tile, kIncl | (unsigned long long)(excl + count));
+  return excl;
+}
+
 __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid_constant__ FuseArgs fa,
                                                                     const unsigned char* __restrict__ class_mask,
-                                                                    unsigned long long* __restrict__ total,
-                                                                    int* __restrict__ img_counts,
+                                                                    unsigned* __restrict__ ticket,
+                                                                    unsigned long long* __restrict__ status,
+                                                                    long long* __restrict__ img_offsets,
                                                                     unsigned long long* __restrict__ keys,
-                                                                    float* __restrict__ cand, unsigned* __restrict__ ord) {
-  extern __shared__ __align__(16) float tile[];     // [P][ld]
-  __shared__ int row_cnt[kFuseMaxRows];
+                                                                    float* __restrict__ cand) {
+  extern __shared__ float tile[];     // [P][no]
+  __shared__ int row_cnt[kFuseP];
   __shared__ long long base_s;
+  __shared__ int tile_s;
+  if (threadIdx.x == 0) tile_s = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile_id = tile_s;
+  const int tiles_img = fa.tile0[fa.levels];
+  const int img = tile_id / tiles_img;
+  int t = tile_id - img * tiles_img;
   int l = 0;
-  while (l + 1 < fa.levels && (int)blockIdx.x >= fa.tile0[l + 1]) ++l;
+  while (l + 1 < fa.levels && t >= fa.tile0[l + 1]) ++l;
+  t -= fa.tile0[l];
   const LevelMeta& m = fa.meta[l];
-  const int t = blockIdx.x - fa.tile0[l];
-  const int img = t / fa.tiles_per_img[l], ti = t - img * fa.tiles_per_img[l];
+  const int a = t / fa.tpa[l], ti = t - a * fa.tpa[l];
   const int npix = m.ny * m.nx;
-  const int P = fa.P[l];
-  const int p0 = ti * P;
-  const int np = min(P, npix - p0);
-  const int nc = fa.nc, no = 5 + nc, na = m.na, ld = m.ld;
+  const int p0 = ti * kFuseP;
+  const int np = min(kFuseP, npix - p0);
+  const int nc = fa.nc, no = 5 + nc, ld = m.ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float thr = fa.thr;
+  const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * no;
 
-  // ---- stage the tile: np*ld contiguous floats (ld % 4 == 0, base 16-byte aligned) ----
-  {
-    const float4* src = reinterpret_cast<const float4*>(fa.logits[l] + ((long long)img * npix + p0) * ld);
-    float4* dst = reinterpret_cast<float4*>(tile);
-    const int n4 = np * ld / 4;
-    for (int i = threadIdx.x; i < n4; i += kFuseThreads) {
-      const uint4 v = ld_nc16(src + i);
-      dst[i] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
-    }
+  // ---- stage + phase 1 (the warp that loads a row also processes it: only warp-level sync needed) ----
+  // (rows start on 4-byte boundaries only — a*no floats into the pixel — hence 4-byte cp.async: every lane's copy is
+  // in flight at once, no register staging)
+  for (int row = warp; row < np; row += kFuseWarps) {
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(tile + row * no);
+    const float* g = gsrc + (long long)row * ld;
+    for (int c = lane; c < no; c += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + c * 4), "l"(g + c) : "memory");
   }
-  __syncthreads();
-
-  // ---- phase 1: decode + confidences in place + per-row counts ----
-  const int nrows = np * na;
-  for (int row = warp; row < nrows; row += kFuseWarps) {
-    const int p = row / na, a = row - p * na;
-    float* s = tile + p * ld + a * no;
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
+  for (int row = warp; row < np; row += kFuseWarps) {
+    float* s = tile + row * no;
     const float hv = lane < 5 ? sigmoid_dec(s[lane]) : 0.f;
     const float sx = __shfl_sync(0xffffffffu, hv, 0), sy = __shfl_sync(0xffffffffu, hv, 1);
     const float sw = __shfl_sync(0xffffffffu, hv, 2), sh = __shfl_sync(0xffffffffu, hv, 3);
@@ -374,7 +419,7 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
         cnt = keep ? 1 : 0;
       }
       if (cnt > 0 && lane == 0) {
-        const int pix = p0 + p;
+        const int pix = p0 + row;
         const int gy = pix / m.nx, gx = pix - gy * m.nx;
         // models/yolo.py:91-97 operation order, then xywh2xyxy (utils/general.py:539-546)
         const float x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), m.stride);
@@ -392,47 +437,42 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
     if (lane == 0) row_cnt[row] = cnt;
   }
   __syncthreads();
-  // ---- exclusive scan of the row counts (warp 0), one reservation per CTA ----
+  // ---- exclusive scan of the row counts, then this tile's place among all tiles (warp 0) ----
   if (warp == 0) {
     int carry = 0;
-    for (int b0 = 0; b0 < nrows; b0 += 32) {
+    for (int b0 = 0; b0 < np; b0 += 32) {
       const int i = b0 + lane;
-      const int v = i < nrows ? row_cnt[i] : 0;
+      const int v = i < np ? row_cnt[i] : 0;
       int inc = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int u = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += u;
       }
-      if (i < nrows) row_cnt[i] = (v > 0) ? (carry + inc - v) : -1;   // offset, or -1 = empty row
+      if (i < np) row_cnt[i] = (v > 0) ? (carry + inc - v) : -1;   // offset, or -1 = empty row
       carry += __shfl_sync(0xffffffffu, inc, 31);
     }
+    const long long excl = tile_lookback(status, tile_id, carry, lane);
     if (lane == 0) {
-      long long b = 0;
-      if (carry > 0) {
-        b = (long long)atomicAdd(total, (unsigned long long)carry);
-        atomicAdd(img_counts + img, carry);
-      }
-      base_s = b;
+      base_s = excl;
+      if (tile_id == img * tiles_img) img_offsets[img] = excl;                          // first tile of an image
+      if (tile_id == fa.N * tiles_img - 1) img_offsets[fa.N] = excl + carry;            // last tile: batch total
     }
   }
   __syncthreads();
   // ---- phase 2: write ----
   const long long base = base_s;
-  for (int row = warp; row < nrows; row += kFuseWarps) {
+  for (int row = warp; row < np; row += kFuseWarps) {
     const int off = row_cnt[row];
     if (off < 0) continue;
-    const int p = row / na, a = row - p * na;
-    const float* s = tile + p * ld + a * no;
-    const int pix = p0 + p;
-    const unsigned row_g = (unsigned)(m.row0 + a * npix + pix);
+    const float* s = tile + row * no;
     const float x1 = s[0], y1 = s[1], x2 = s[2], y2 = s[3];
     long long g0 = base + off;
     if (fa.multi_label) {
       for (int c0 = 0; c0 < nc; c0 += 32) {
         const int c = c0 + lane;
         const float conf = c < nc ? s[5 + c] : -1.f;
-        const bool pass = conf > 0.f || (conf == 0.f && thr < 0.f);   // marked failures are -1; thr >= 0 in practice
+        const bool pass = conf > thr;                           // failed classes were overwritten with -1
         const unsigned bal = __ballot_sync(0xffffffffu, pass);
         if (pass) {
           const long long g = g0 + __popc(bal & ((1u << lane) - 1u));
@@ -440,7 +480,6 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
             float* cd = cand + g * 6;
             cd[0] = x1; cd[1] = y1; cd[2] = x2; cd[3] = y2; cd[4] = conf; cd[5] = (float)c;
             keys[g] = ((unsigned long long)(unsigned)img << 32) | (unsigned long long)(~__float_as_uint(conf));
-            ord[g] = row_g * (unsigned)nc + (unsigned)c;
           }
         }
         g0 += __popc(bal);
@@ -449,33 +488,13 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
       float* cd = cand + g0 * 6;
       cd[0] = x1; cd[1] = y1; cd[2] = x2; cd[3] = y2; cd[4] = s[4]; cd[5] = s[5];
       keys[g0] = ((unsigned long long)(unsigned)img << 32) | (unsigned long long)(~__float_as_uint(s[4]));
-      ord[g0] = row_g;
     }
   }
 }
 
-// Restores the reference candidate order inside every run of equal (image, score) keys: element i of a run
-// [s, e) moves to s + rank(ord[idx[i]]).  Runs are 1 long almost everywhere (one compare with each neighbour).
-__global__ void __launch_bounds__(256) tiefix_kernel(const unsigned long long* __restrict__ keys,
-                                                     const unsigned* __restrict__ idx_in,
-                                                     const unsigned* __restrict__ ord, unsigned* __restrict__ idx_out,
-                                                     long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long k = keys[i];
-    const unsigned me = idx_in[i];
-    const bool left = i > 0 && keys[i - 1] == k, right = i + 1 < n && keys[i + 1] == k;
-    if (!left && !right) {
-      idx_out[i] = me;
-      continue;
-    }
-    long long s = i, e = i + 1;
-    while (s > 0 && keys[s - 1] == k) --s;
-    while (e < n && keys[e] == k) ++e;
-    const unsigned mo = ord[me];
-    long long rank = 0;
-    for (long long j = s; j < e; ++j) rank += ord[idx_in[j]] < mo ? 1 : 0;
-    idx_out[s + rank] = me;
-  }
+__global__ void img_counts_kernel(const long long* __restrict__ img_offsets, int* __restrict__ img_counts, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) img_counts[i] = (int)(img_offsets[i + 1] - img_offsets[i]);
 }
 
 __global__ void iota_kernel(unsigned* __restrict__ idx, long long n) {
@@ -696,58 +715,68 @@ int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream) {
   return finish_launch();
 }
 
+static long long fused_tiles_per_image(const LevelMeta* hm, int levels, FuseArgs* fa) {
+  long long tiles = 0;
+  for (int l = 0; l < levels; ++l) {
+    const int npix = hm[l].ny * hm[l].nx;
+    const int tpa = (npix + kFuseP - 1) / kFuseP;
+    if (fa) {
+      fa->tpa[l] = tpa;
+      fa->tile0[l] = (int)tiles;
+    }
+    tiles += (long long)hm[l].na * tpa;
+  }
+  if (fa) fa->tile0[levels] = (int)tiles;
+  return tiles;
+}
+
+long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N) {
+  if (!lv_meta_host || levels <= 0 || levels > 5 || N <= 0) return DMAY_EINVAL;
+  return 16 + 8 * N * fused_tiles_per_image((const LevelMeta*)lv_meta_host, levels, nullptr);
+}
+
 int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t stream) {
   if (!p || p->N <= 0 || p->nc <= 0 || p->levels <= 0 || p->levels > 5) return DMAY_EINVAL;
-  if (!p->lv_meta_host || !p->lv_logits0 || !p->total || !p->img_counts || !p->img_offsets) return DMAY_EINVAL;
-  if (!p->keys || !p->cand || !p->ord || p->capacity <= 0) return DMAY_EINVAL;
+  if (!p->lv_meta_host || !p->lv_logits0 || !p->ws || !p->img_counts || !p->img_offsets) return DMAY_EINVAL;
+  if (!p->keys || !p->cand || p->capacity <= 0) return DMAY_EINVAL;
   FuseArgs fa;
   memset(&fa, 0, sizeof(fa));
   const void* lg[5] = {p->lv_logits0, p->lv_logits1, p->lv_logits2, p->lv_logits3, p->lv_logits4};
   const LevelMeta* hm = (const LevelMeta*)p->lv_meta_host;
-  long long tiles = 0, rows = 0;
-  size_t smem = 0;
+  long long rows = 0;
   for (int l = 0; l < p->levels; ++l) {
     const LevelMeta& m = hm[l];
-    if (!lg[l] || !aligned16(lg[l])) return DMAY_EINVAL;
+    if (!lg[l] || (reinterpret_cast<uintptr_t>(lg[l]) & 3u)) return DMAY_EINVAL;
     if (m.na <= 0 || m.na > 5 || m.ny <= 0 || m.nx <= 0) return DMAY_EINVAL;
-    if (m.ld < m.na * (5 + p->nc) || (m.ld & 3) || m.ld > kFuseTileFloats) return DMAY_EUNSUPPORTED;
+    if (m.ld < m.na * (5 + p->nc)) return DMAY_EUNSUPPORTED;
     if (m.row0 != rows) return DMAY_EINVAL;
     fa.logits[l] = (const float*)lg[l];
     fa.meta[l] = m;
-    int P = kFuseTileFloats / m.ld;
-    if (P > 32) P = 32;
-    fa.P[l] = P;
-    const int npix = m.ny * m.nx;
-    fa.tiles_per_img[l] = (npix + P - 1) / P;
-    fa.tile0[l] = (int)tiles;
-    tiles += (long long)p->N * fa.tiles_per_img[l];
-    rows += (long long)m.na * npix;
-    const size_t need = (size_t)P * m.ld * sizeof(float);
-    if (need > smem) smem = need;
+    rows += (long long)m.na * m.ny * m.nx;
   }
+  const long long tiles = (long long)p->N * fused_tiles_per_image(hm, p->levels, &fa);
   if (tiles > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
-  if (rows * (p->multi_label ? p->nc : 1) > 0xffffffffLL) return DMAY_EUNSUPPORTED;   // `ord` is 32-bit
-  fa.tile0[p->levels] = (int)tiles;
+  if (p->ws_bytes < 16 + 8 * tiles) return DMAY_ETOOBIG;
+  const size_t smem = (size_t)kFuseP * (5 + p->nc) * sizeof(float);
+  if (smem > 200 * 1024) return DMAY_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(filter_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
   fa.levels = p->levels;
   fa.nc = p->nc;
   fa.multi_label = p->multi_label;
+  fa.N = p->N;
   fa.thr = p->conf_thres;
   fa.capacity = p->capacity;
   cudaStream_t s = (cudaStream_t)stream;
-  filter_fused_kernel<<<(int)tiles, kFuseThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask,
-                                                           (unsigned long long*)p->total, (int*)p->img_counts,
-                                                           (unsigned long long*)p->keys, (float*)p->cand,
-                                                           (unsigned*)p->ord);
-  img_scan_kernel<<<1, 32, 0, s>>>((const int*)p->img_counts, (long long*)p->img_offsets, p->N);
+  unsigned* ticket = (unsigned*)p->ws;
+  unsigned long long* status = (unsigned long long*)((char*)p->ws + 16);
+  filter_fused_kernel<<<(int)tiles, kFuseThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
+                                                           (long long*)p->img_offsets, (unsigned long long*)p->keys,
+                                                           (float*)p->cand);
+  img_counts_kernel<<<(p->N + 255) / 256, 256, 0, s>>>((const long long*)p->img_offsets, (int*)p->img_counts, p->N);
   return finish_launch(2);
-}
-
-int dmay_nms_tiefix(const dmay_tiefix_params* p, dmay_stream_t stream) {
-  if (!p || !p->keys_sorted || !p->idx_in || !p->ord || !p->idx_out || p->n <= 0) return DMAY_EINVAL;
-  tiefix_kernel<<<grid_for(p->n, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const unsigned long long*)p->keys_sorted, (const unsigned*)p->idx_in, (const unsigned*)p->ord,
-      (unsigned*)p->idx_out, p->n);
-  return finish_launch();
 }
 
 static size_t cub_ws_bytes(long long n, int end_bit) {

@@ -529,7 +529,7 @@ def _sort_candidates(keys, total, n, dev, s):
 
 
 def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
-    """Detect-logits source: single-pass fused decode+filter (unordered compaction) -> sort -> tie fix -> greedy."""
+    """Detect-logits source: single-pass fused decode + filter + order-preserving compaction -> sort -> greedy."""
     import ctypes
     dev = levels[0].logits.device
     n = levels[0].logits.shape[0]
@@ -537,20 +537,23 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     multi_label = bool(multi_label) and nc > 1
     raw, rows = _level_meta_host(levels, na)
     meta_host = ctypes.create_string_buffer(raw, len(raw))
+    ws_bytes = int(_lib.lib().dmay_nms_filter_fused_ws(ctypes.addressof(meta_host), len(levels), n))
+    if ws_bytes < 0:
+        raise DmayError(f"dmay_nms_filter_fused_ws failed: {ws_bytes}")
     cm = _class_mask(classes, nc, dev)
     key = (dev.index, n, rows, nc, multi_label, float(conf_thres))
     capacity = _FUSED_CAP.get(key, n * rows * (2 if multi_label else 1) // 2 + 4096)
     out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
     out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
+    img_counts = torch.empty(n, device=dev, dtype=torch.int32)
     img_offsets = torch.empty(n + 1, device=dev, dtype=torch.int64)
     while True:
-        counters = torch.zeros(2 + n, device=dev, dtype=torch.int32)   # [0:2] = u64 total, [2:] = per-image counts
+        ws = torch.zeros(ws_bytes // 8 + 1, device=dev, dtype=torch.int64)   # ticket + tile status words (zeroed)
         keys = torch.empty(capacity, device=dev, dtype=torch.int64)
         cand = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
-        ordv = torch.empty(capacity, device=dev, dtype=torch.int32)
-        f = dict(lv_meta_host=ctypes.addressof(meta_host), total=counters.data_ptr(), img_counts=counters.data_ptr() + 8,
-                 img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(), cand=cand.data_ptr(), ord=ordv.data_ptr(),
-                 N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
+        f = dict(lv_meta_host=ctypes.addressof(meta_host), ws=ws.data_ptr(), ws_bytes=ws.numel() * 8,
+                 img_counts=img_counts.data_ptr(), img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(),
+                 cand=cand.data_ptr(), N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
                  conf_thres=float(conf_thres))
         for i, lv in enumerate(levels):
             f[f"lv_logits{i}"] = lv.logits.data_ptr()
@@ -564,11 +567,8 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     _FUSED_CAP[key] = max(total + total // 4 + 4096, _FUSED_CAP.get(key, 0) // 2)
     if total == 0:
         return out, out_counts
-    keys_out, idx = _sort_candidates(keys, total, n, dev, s)
-    idx2 = torch.empty(total, device=dev, dtype=torch.int32)
-    call("dmay_nms_tiefix", s, keys_sorted=keys_out.data_ptr(), idx_in=idx.data_ptr(), ord=ordv.data_ptr(),
-         idx_out=idx2.data_ptr(), n=total)
-    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx2.data_ptr(), img_counts=counters.data_ptr() + 8,
+    _keys_out, idx = _sort_candidates(keys, total, n, dev, s)
+    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=img_counts.data_ptr(),
          img_offsets=img_offsets.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
          max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
     return out, out_counts

@@ -385,14 +385,14 @@ typedef struct dmay_filter_params {
 } dmay_filter_params;
 int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream);
 
-/* Single-pass fused variant (Detect logits source only): decode + confidence filter with ONE read of
- * the logits.  Candidates are compacted in arbitrary order (one range reservation per CTA);
- *   total[0]      (u64, zeroed by the caller)  <- number of candidates of the batch
- *   img_counts[N] (i32, zeroed by the caller)  <- per image; img_offsets[N+1] (i64) is their scan
- *   ord[g]        (u32) = row*nc + cls (multi_label) or row: the candidate's position in the reference
- *                 order (utils/general.py:684-688), consumed by dmay_nms_tiefix after the sort.
- * Candidates beyond `capacity` are counted but not written: the caller compares total with capacity
- * and repeats the call with larger buffers.  lv_meta_host: HOST array of `levels` x 16 words
+/* Single-pass fused variant (Detect logits source only): decode + confidence filter + ORDER-PRESERVING
+ * compaction of the whole batch with ONE read of the logits.  A CTA owns 64 consecutive pixels of one
+ * anchor plane, in the reference row order (image, level, anchor, y, x); its candidates are placed by a
+ * decoupled look-back scan over the tiles.  Outputs as dmay_nms_filter (keys, cand in reference order),
+ * plus img_offsets[N+1] (i64; [N] = total candidates of the batch) and img_counts[N] (i32).
+ * ws: caller-ZEROED workspace of dmay_nms_filter_fused_ws() bytes (ticket + one status word per tile).
+ * Candidates beyond `capacity` are counted but not written: the caller compares img_offsets[N] with
+ * capacity and repeats the call with larger buffers.  lv_meta_host: HOST array of `levels` x 16 words
  * {row0, ny, nx, ld, na, stride(f32), anchor_px[10](f32)}. */
 typedef struct dmay_filter_fused_params {
   const void* lv_logits0;
@@ -402,12 +402,12 @@ typedef struct dmay_filter_fused_params {
   const void* lv_logits4;
   const void* lv_meta_host;
   const void* class_mask;
-  void* total;
+  void* ws;
   void* img_counts;
   void* img_offsets;
   void* keys;
   void* cand;
-  void* ord;
+  long long ws_bytes;
   int N;
   int nc;
   int levels;
@@ -415,18 +415,8 @@ typedef struct dmay_filter_fused_params {
   long long capacity;
   float conf_thres;
 } dmay_filter_fused_params;
+long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N);
 int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t stream);
-
-/* after dmay_nms_sort: inside every run of equal keys, order the payload by ord[] ascending (the order a
- * stable sort of reference-ordered candidates would have produced).  idx_out may not alias idx_in. */
-typedef struct dmay_tiefix_params {
-  const void* keys_sorted;
-  const void* idx_in;
-  const void* ord;
-  void* idx_out;
-  long long n;
-} dmay_tiefix_params;
-int dmay_nms_tiefix(const dmay_tiefix_params* p, dmay_stream_t stream);
 
 /* stable sort of candidate keys (payload = candidate index).  CUB radix sort over the
  * (img, ~score) composite key: equal scores keep ascending candidate index like

@@ -147,8 +147,9 @@ def _quantised_levels(N, nc, shapes, seed, step):
                                 dict(conf_thres=0.05, iou_thres=0.5, multi_label=True, classes=[1, 4, 6], max_det=100),
                                 dict(conf_thres=0.05, iou_thres=0.5, agnostic=True, max_det=50)])
 def test_fused_filter_ties_match_ordered_path(kw):
-    """Single-pass fused filter compacts in arbitrary order; the tie fix must reproduce the order-preserving
-    path bit for bit even when thousands of candidates share a score (ragged tiles: 13x7, 5x3 pixels)."""
+    """Single-pass fused filter (tile look-back compaction) must reproduce the count/scan/write path bit for bit,
+    also when thousands of candidates share a score — the stable sort then exposes any ordering slip
+    (ragged tiles: 13x7, 5x3 pixels)."""
     from dma_yolo_b200 import ops
     levels, na, no = _quantised_levels(3, 7, [(20, 12), (13, 7), (5, 3)], seed=5, step=0.5)
     fo, fc = ops.nms_batched(None, kw['conf_thres'], kw['iou_thres'], levels=levels, na=na, nc=no - 5,
