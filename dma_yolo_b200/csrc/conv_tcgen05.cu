@@ -163,14 +163,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// TMA tile stores (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int BLOCK_M = 128;
 constexpr int kMaxStages = 8;
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kConvThreads = 128 + kEpiThreads;    // warps 0-3: TMA / MMA / TMEM alloc / spare
+constexpr int kEpiWarps = 16;                      // up to four warps per TMEM lane quadrant (8 or 16 per launch)
+constexpr int kConvThreads = 128 + kEpiWarps * 32; // warps 0-3: TMA / MMA / TMEM alloc / spare
 
 // epilogue flavours (compile-time: keeps the hot loop branch-free and small enough for the I-cache)
 enum EpiMode : int {
@@ -185,6 +200,11 @@ enum EpiMode : int {
 struct __align__(64) ConvArgs {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmY;   // bf16 output tile store: box = 32 channels x 32 rows (halo mode: 32 ch x 8 x 4 pixels)
+  CUtensorMap tmR;   // residual / gate_x tile load, same geometry
+  int opnd_stage;    // 1: the epilogue stages a residual / gate_x tile per item
+  int sb_floats;     // staged scale / bias entries (columns covered by all n-tiles, <= kMaxCout)
+  int epi_warps;     // 8 or 16 (blockDim = 128 + 32 * epi_warps): 16 where the epilogue, not the MMA, paces the tile
   const float* scale;
   const float* bias;
   const __nv_bfloat16* residual;
@@ -226,9 +246,15 @@ struct __align__(64) ConvArgs {
 //   (halo mode: [n_abuf halo buffers] precede the stages, which then hold B tiles only)
 constexpr int kMaxABuf = 8;
 constexpr int kHaloTH = 16, kHaloTW = 8;
-constexpr uint32_t kNumBars = 2 * kMaxStages + 4 + 2 * kMaxABuf;
-constexpr uint32_t kEpiStageOff = kNumBars * 8 + 16 + 2 * 256 * 4;   // 8 warps x 2 KB transpose stage
-constexpr uint32_t kTailBytes = kEpiStageOff + kEpiWarps * 2048;
+constexpr uint32_t kNumBars = 2 * kMaxStages + 4 + 2 * kMaxABuf + kEpiWarps;   // + one operand barrier per epilogue warp
+constexpr int kMaxCout = 2048;                                                 // scale/bias staged once per CTA
+// tail (1024-aligned, after the pipeline stages):
+//   [kEpiWarps x 2 KB] output staging (thread == row writes 4 x 16 B, 64-byte-swizzled, a TMA store drains it)
+//   [kEpiWarps x 2 KB] operand staging (residual / gate_x tile of the warp's NEXT item, TMA-loaded) — only when used
+//   barriers, TMEM base slot, scale[kMaxCout], bias[kMaxCout]
+__host__ __device__ constexpr uint32_t tail_bytes(int epi_warps, bool operand_stage, uint32_t sb_floats) {
+  return (uint32_t)epi_warps * 2048u * (operand_stage ? 2u : 1u) + kNumBars * 8 + 16 + 2 * sb_floats * 4;
+}
 
 // one elected lane of a converged warp (the warp stays converged, so operands live in uniform registers)
 __device__ __forceinline__ bool elect_one() {
@@ -266,8 +292,6 @@ __device__ __forceinline__ float silu_t(float x) {
   return fmaf(h, tanh_approx(h), h);
 }
 __device__ __forceinline__ float sigmoid_t(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 // bf16 modes: one 8-column group of one output row -> packed bf16x8 (stored later, coalesced, via the warp's
 // shared-memory transpose stage).  aux0 / aux1 = residual (or gate_x) / gate_k values of the same 8 columns.
@@ -352,15 +376,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t abuf0 = base + a.bres_bytes;                            // halo ring (halo mode only)
   const uint32_t stage0 = abuf0 + (a.halo ? a.n_abuf * a.a_halo_bytes : 0u);
   const uint32_t data_bytes = (stage0 - base) + a.stages * a.stage_bytes;
-  const uint32_t tail = base + data_bytes;
+  const uint32_t tail = base + data_bytes;                               // 1024-aligned (all data regions are)
   uint8_t* tail_ptr = base_ptr + data_bytes;
-  const uint32_t full_bar = tail, empty_bar = tail + kMaxStages * 8;
-  const uint32_t tfull_bar = tail + 2 * kMaxStages * 8, tempty_bar = tfull_bar + 16;
+  const uint32_t epi_stage_bytes = (uint32_t)a.epi_warps * 2048u;
+  const uint32_t bars_off = epi_stage_bytes * (a.opnd_stage ? 2u : 1u);
+  const uint32_t full_bar = tail + bars_off, empty_bar = full_bar + kMaxStages * 8;
+  const uint32_t tfull_bar = full_bar + 2 * kMaxStages * 8, tempty_bar = tfull_bar + 16;
   const uint32_t afull_bar = tempty_bar + 16, aempty_bar = afull_bar + kMaxABuf * 8;
-  const uint32_t tmem_slot = tail + kNumBars * 8;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_ptr + kNumBars * 8);
-  float* s_scale = reinterpret_cast<float*>(tail_ptr + kNumBars * 8 + 16);
-  float* s_bias = s_scale + 256;
+  const uint32_t opnd_bar = aempty_bar + kMaxABuf * 8;                   // [kEpiWarps]
+  const uint32_t tmem_slot = full_bar + kNumBars * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_ptr + bars_off + kNumBars * 8);
+  float* s_scale = reinterpret_cast<float*>(tail_ptr + bars_off + kNumBars * 8 + 16);
+  float* s_bias = s_scale + a.sb_floats;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile schedule: a cluster walks "super tiles" = cs consecutive m-tiles of one n-tile (so its CTAs share
@@ -376,6 +403,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&a.tmA);
     tmap_prefetch(&a.tmB);
+    tmap_prefetch(&a.tmY);
+    if (a.opnd_stage) tmap_prefetch(&a.tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < a.stages; ++i) {
@@ -384,13 +413,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i * 8, 1);
-      mbar_init(tempty_bar + i * 8, kEpiThreads);
+      mbar_init(tempty_bar + i * 8, (uint32_t)a.epi_warps * 32u);
     }
     for (int i = 0; i < kMaxABuf; ++i) {
       mbar_init(afull_bar + i * 8, 1);
       mbar_init(aempty_bar + i * 8, 1);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(opnd_bar + i * 8, 1);
     fence_barrier_init();
+  }
+  // folded-BN scale / bias of every output channel, staged once (Cout_pad <= kMaxCout, checked on the host)
+  for (int i = threadIdx.x; i < a.sb_floats; i += blockDim.x) {
+    const bool in = i < a.Cout_pad;
+    s_scale[i] = in ? a.scale[i] : 0.f;
+    s_bias[i] = in ? a.bias[i] : 0.f;
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   tc_fence_before();
@@ -652,34 +688,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     }  // !b_resident
   } else if (warp >= 4) {
-    // ===== epilogue: warp pair (w, w+4) shares TMEM lane quadrant w%4 and interleaves 32-column chunks.
-    // The warp's work is a flat sequence of (tile, chunk) items; the residual / gate operands of item i+1 are
-    // fetched before item i is processed, so their latency hides behind the accumulator wait and the math of
-    // item i (the epilogue, not the MMA, is the critical path of the small-channel layers).
+    // ===== epilogue: 16 warps; warp w reads TMEM lane quadrant w%4 (hardware rule) and owns the 32-column chunks
+    // c0 = sub*32 + k*128 (sub = (w-4)/4) of every tile of this CTA, as a flat sequence of (tile, chunk) items.
+    // Four epilogue warps per scheduler instead of two: the per-item instruction stream is a chain of short
+    // dependencies (TMEM load -> FMA -> MUFU -> pack -> smem), so throughput comes from warps, not from ILP.
+    //   output  : thread == row packs 32 bf16 into the warp's 2 KB staging tile (64-byte swizzle) and ONE TMA
+    //             store drains it — bounds (M tail, image border in halo mode, Cout) are clipped by the tensor map.
+    //   operand : the residual / gate_x tile of the warp's NEXT item is TMA-loaded into a second 2 KB tile while
+    //             the current item is processed (no registers held across items).
+    const int ew = warp - 4;
     const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;  // 0 or 1
-    const int et = threadIdx.x - 128;  // 0..kEpiThreads-1
+    const int sub = ew >> 2;
     const int row_in_tile = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int staged_n0 = -1;
     const int HoWo = a.Ho * a.Wo;
-    const int cpw = (a.block_n - half * 32 + 63) / 64;                      // chunks of a tile owned by this warp
+    const int cstride = a.epi_warps * 8;                                               // columns between a warp's chunks
+    const int cpw = a.block_n > sub * 32 ? (a.block_n - sub * 32 + cstride - 1) / cstride : 0;   // chunks per tile of this warp
     const int my_tiles = cluster_id < total_super ? (total_super - cluster_id + num_clusters - 1) / num_clusters : 0;
-    const int items = my_tiles * (cpw > 0 ? cpw : 1);                       // cpw == 0: one "empty" item per tile
+    const int items = my_tiles * (cpw > 0 ? cpw : 1);                                  // cpw == 0: one "empty" item per tile
 
-    // bf16 modes go through a per-warp 2 KB shared-memory transpose so that every global load / store
-    // instruction of the warp covers 8 rows x 64 contiguous bytes (8 lines) instead of 32 rows x 16 bytes
-    // (32 lines): with thread == row the LSU wavefront count, not HBM, bounded the 64-channel layers.
     constexpr bool kStaged = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_LINEAR || MODE == EPI_GATE);
-    uint4* stg = reinterpret_cast<uint4*>(tail_ptr + kEpiStageOff) + (warp - 4) * 128;
-    auto sidx = [](int r, int j) { return r * 4 + (j ^ ((r >> 1) & 3)); };   // 64-byte rows, XOR swizzle: conflict-free
-    const int lr = lane >> 2, lc = lane & 3;                                  // coalesced mapping: 8 rows x 4 chunks
+    constexpr bool kOpnd = (MODE == EPI_SILU_RES || MODE == EPI_GATE);
+    const uint32_t out_stage = tail + (uint32_t)ew * 2048u;
+    uint4* out_ptr = reinterpret_cast<uint4*>(tail_ptr + ew * 2048);
+    const uint32_t op_stage = tail + epi_stage_bytes + (uint32_t)ew * 2048u;
+    const uint4* op_ptr = reinterpret_cast<const uint4*>(tail_ptr + epi_stage_bytes + ew * 2048);
+    const uint32_t my_opnd_bar = opnd_bar + (uint32_t)ew * 8u;
+    uint32_t opnd_phase = 0;
+    auto sidx = [](int r, int j) { return r * 4 + (j ^ ((r >> 1) & 3)); };   // 64-byte rows, TMA SWIZZLE_64B pattern
 
     struct Item {
-      long long row;   // -1: row not stored (beyond M / outside the image)
+      int row;         // this thread's output row (pixel index), -1: not stored (beyond M / outside the image)
       const __nv_bfloat16* gk_row;
       int n0, c0, width;
+      int t1, t2, t3;  // TMA coordinates of the warp's 32-row box: 2-D {col, t1}; halo {col, t1 = w, t2 = h, t3 = n}
       bool first, last;
     };
     // (tile, chunk) of the next item to build: advanced incrementally, no division by `per`
@@ -695,12 +738,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int sq = fdiv(st, a.fd_nn);
       const int n_tile = st - sq * a.num_n_tiles, m_tile = sq * cs + (int)crank;
       it.n0 = n_tile * a.block_n;
-      it.c0 = half * 32 + ch * 64;
+      it.c0 = sub * 32 + ch * cstride;
       it.width = cpw > 0 ? (a.block_n - it.c0 >= 32 ? 32 : 16) : 0;
       it.first = ch == 0;
       it.last = ch == per - 1;
-      it.row = (long long)m_tile * BLOCK_M + row_in_tile;
-      bool valid = it.row < a.M;
+      const long long row64 = (long long)m_tile * BLOCK_M + row_in_tile;
+      it.row = (int)row64;
+      bool valid = row64 < a.M;
+      it.t1 = m_tile * BLOCK_M + quad * 32;
+      it.t2 = it.t3 = 0;
       int hp = 0, hq = 0, hn = 0;
       if (a.halo) {   // 16x8 pixel patch: row i of the tile is pixel (ty*16 + i/8, tx*8 + i%8)
         const int per_img = a.tiles_x * a.tiles_y;
@@ -710,7 +756,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         hp = ty * kHaloTH + (row_in_tile >> 3);
         hq = tx * kHaloTW + (row_in_tile & 7);
         valid = m_tile < a.num_m_tiles && hp < a.Ho && hq < a.Wo;
-        it.row = ((long long)hn * a.Ho + hp) * a.Wo + hq;
+        it.row = (hn * a.Ho + hp) * a.Wo + hq;
+        it.t1 = tx * kHaloTW;
+        it.t2 = ty * kHaloTH + quad * 4;
+        it.t3 = hn;
       }
       it.gk_row = nullptr;
       if (MODE == EPI_GATE && valid) {
@@ -718,8 +767,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         if (a.halo) {
           n_img = hn; p = hp; q = hq;
         } else {
-          n_img = fdiv((int)it.row, a.fd_hw);
-          const int rem = (int)it.row - n_img * HoWo;
+          n_img = fdiv(it.row, a.fd_hw);
+          const int rem = it.row - n_img * HoWo;
           p = fdiv(rem, a.fd_wo);
           q = rem - p * a.Wo;
         }
@@ -728,95 +777,73 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       if (!valid) it.row = -1;
     };
-    // x0: residual / gate_x in the COALESCED mapping (lane -> row k*8+lr, chunk lc); x1: gate_k in the row mapping
-    auto prefetch = [&](const Item& it, uint4* x0, uint4* x1) {
-      if (MODE == EPI_SILU_RES || MODE == EPI_GATE) {
-        const __nv_bfloat16* src = MODE == EPI_SILU_RES ? a.residual : a.gate_x;
-        const int ld = MODE == EPI_SILU_RES ? a.ldr : a.ldgx;
-        const int col = it.n0 + it.c0 + lc * 8;
-        const bool col_on = lc * 8 < it.width && col + 8 <= a.n_store;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const long long rowR = __shfl_sync(0xffffffffu, it.row, k * 8 + lr);
-          x0[k] = (col_on && rowR >= 0) ? ld_nc16(src + rowR * ld + col) : make_uint4(0, 0, 0, 0);
-        }
-        if (MODE == EPI_GATE) {
-#pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            const int c = it.n0 + it.c0 + v8 * 8;
-            x1[v8] = (it.row >= 0 && v8 * 8 < it.width && c + 8 <= a.n_store) ? ld16(it.gk_row + c) : make_uint4(0, 0, 0, 0);
-          }
-        }
+    // residual / gate_x tile of `it` -> the warp's operand staging tile (lane 0 issues; 2048 bytes always land:
+    // out-of-bounds elements are zero-filled)
+    auto issue_opnd = [&](const Item& it) {
+      if (lane == 0) {
+        mbar_expect_tx(my_opnd_bar, 2048u);
+        if (a.halo) tma_load_4d(op_stage, &a.tmR, my_opnd_bar, it.n0 + it.c0, it.t1, it.t2, it.t3);
+        else tma_load_2d(op_stage, &a.tmR, my_opnd_bar, it.n0 + it.c0, it.t1);
       }
     };
 
     Item cur, nxt;
-    uint4 ca0[4], ca1[4], na0[4], na1[4];
     if (items > 0) {
       make_item(cur);
-      prefetch(cur, ca0, ca1);
+      if (kOpnd && cpw > 0) issue_opnd(cur);
     }
 #pragma unroll 1
     for (int idx = 0; idx < items; ++idx) {
-      if (idx + 1 < items) {
-        make_item(nxt);
-        prefetch(nxt, na0, na1);
-      }
+      const bool has_next = idx + 1 < items;
+      if (has_next) make_item(nxt);
       if (cur.first) {
-        if (cur.n0 != staged_n0) {  // uniform across the CTA
-          epi_bar_sync();           // everyone is done reading the previous scale/bias
-          for (int i = et; i < a.block_n; i += kEpiThreads) {
-            const bool in = cur.n0 + i < a.Cout_pad;
-            s_scale[i] = in ? a.scale[cur.n0 + i] : 0.f;
-            s_bias[i] = in ? a.bias[cur.n0 + i] : 0.f;
-          }
-          epi_bar_sync();
-          staged_n0 = cur.n0;
-        }
         mbar_wait(tfull_bar + acc * 8, acc_phase);
         tc_fence_after();
       }
       if (cur.width > 0) {
         const uint32_t taddr = tmem_base + (uint32_t)(acc * a.acc_stride) + ((uint32_t)(quad * 32) << 16) + cur.c0;
+        const float* sc = s_scale + cur.n0 + cur.c0;
+        const float* bi = s_bias + cur.n0 + cur.c0;
         uint32_t r[32];
         if (cur.width == 32) tmem_ld32(taddr, r);
         else tmem_ld16(taddr, r);
         if (kStaged) {
           uint4 own[4];
-          if (MODE == EPI_SILU_RES || MODE == EPI_GATE) {   // coalesced -> row layout
+          if (kOpnd) {
+            mbar_wait(my_opnd_bar, opnd_phase);
+            opnd_phase ^= 1u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) stg[sidx(k * 8 + lr, lc)] = ca0[k];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) own[j] = stg[sidx(lane, j)];
-            __syncwarp();
+            for (int j = 0; j < 4; ++j) own[j] = op_ptr[sidx(lane, j)];
           }
           tmem_ld_wait();
-          uint4 outv[4];
-#pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8)
-            outv[v8] = epi_compute8<MODE>(r + v8 * 8, s_scale + cur.c0 + v8 * 8, s_bias + cur.c0 + v8 * 8, own[v8], ca1[v8]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) stg[sidx(lane, j)] = outv[j];
+          if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the staging tile
           __syncwarp();
-          const int col = cur.n0 + cur.c0 + lc * 8;
-          const bool col_on = lc * 8 < cur.width && col + 8 <= a.n_store;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const long long rowR = __shfl_sync(0xffffffffu, cur.row, k * 8 + lr);
-            const uint4 v = stg[sidx(k * 8 + lr, lc)];
-            if (col_on && rowR >= 0) st16(reinterpret_cast<__nv_bfloat16*>(a.y) + rowR * a.ldy + col, v);
+          for (int v8 = 0; v8 < 4; ++v8) {
+            uint4 gk = make_uint4(0, 0, 0, 0);
+            if (MODE == EPI_GATE) {
+              const int c = cur.n0 + cur.c0 + v8 * 8;
+              if (cur.row >= 0 && v8 * 8 < cur.width && c + 8 <= a.n_store) gk = ld16(cur.gk_row + c);
+            }
+            out_ptr[sidx(lane, v8)] = epi_compute8<MODE>(r + v8 * 8, sc + v8 * 8, bi + v8 * 8, own[v8], gk);
           }
-          __syncwarp();
+          fence_proxy_async();
+          __syncwarp();   // every lane's staging writes are done, and its operand row has been consumed (own[] fed the math)
+          if (lane == 0) {
+            if (a.halo) tma_store_4d(&a.tmY, out_stage, cur.n0 + cur.c0, cur.t1, cur.t2, cur.t3);
+            else tma_store_2d(&a.tmY, out_stage, cur.n0 + cur.c0, cur.t1);
+            tma_store_commit();
+          }
+          if (kOpnd && has_next) issue_opnd(nxt);   // refill the operand tile for the next item
         } else {
           tmem_ld_wait();
           if (cur.row >= 0) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int v8 = 0; v8 < 4; ++v8) {
               const int col = cur.n0 + cur.c0 + v8 * 8;
               if (v8 * 8 < cur.width && col + 8 <= a.n_store)
-                epi_store8<MODE>(a, r + v8 * 8, s_scale + cur.c0 + v8 * 8, s_bias + cur.c0 + v8 * 8, cur.row, col, ca0[v8],
-                                 ca1[v8]);
+                epi_store8<MODE>(a, r + v8 * 8, sc + v8 * 8, bi + v8 * 8, (long long)cur.row, col, z, z);
             }
           }
         }
@@ -828,12 +855,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         if (acc == 0) acc_phase ^= 1u;
       }
       cur = nxt;
-#pragma unroll
-      for (int v8 = 0; v8 < 4; ++v8) {
-        ca0[v8] = na0[v8];
-        ca1[v8] = na1[v8];
-      }
     }
+    if (kStaged && lane == 0) tma_store_wait_all();   // staging tiles stay valid until every store has read them
   }
 
   tc_fence_before();
@@ -899,7 +922,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     return DMAY_EINVAL;
   if (!aligned16(p->x) || !aligned16(p->w) || !aligned16(p->y)) return DMAY_EINVAL;
   if (p->Cin & 15) return DMAY_EUNSUPPORTED;
-  if (p->Cout_pad < p->Cout || (p->Cout_pad & 15)) return DMAY_EUNSUPPORTED;
+  if (p->Cout_pad < p->Cout || (p->Cout_pad & 15) || p->Cout_pad > kMaxCout) return DMAY_EUNSUPPORTED;
   if (p->ldx < p->Cin || (p->ldx & 7) || (p->ldy & 3)) return DMAY_EUNSUPPORTED;
   const bool out_f32 = p->out_dtype == DMAY_DT_F32;
   if (p->out_dtype != DMAY_DT_F32 && p->out_dtype != DMAY_DT_BF16) return DMAY_EUNSUPPORTED;
@@ -934,6 +957,24 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   a.Wo = p->Wo;
   a.im2col = !(p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0);
   int bn = p->block_n > 0 ? p->block_n : (p->Cout_pad < 256 ? p->Cout_pad : 256);
+  int mode;
+  if (p->gate_x) mode = (!out_f32 && !p->residual) ? EPI_GATE : -1;
+  else if (out_f32) mode = (p->act == DMAY_ACT_NONE && !p->residual) ? EPI_LINEAR_F32 : EPI_GENERIC;
+  else if (p->act == DMAY_ACT_SILU) mode = p->residual ? EPI_SILU_RES : EPI_SILU;
+  else if (p->act == DMAY_ACT_NONE && !p->residual) mode = EPI_LINEAR;
+  else mode = EPI_GENERIC;
+  if (mode < 0) return DMAY_EUNSUPPORTED;
+  const bool staged = mode == EPI_SILU || mode == EPI_SILU_RES || mode == EPI_LINEAR || mode == EPI_GATE;
+  a.opnd_stage = (mode == EPI_SILU_RES || mode == EPI_GATE) ? 1 : 0;
+  a.sb_floats = ((p->Cout_pad + bn - 1) / bn) * bn;
+  if (a.sb_floats > kMaxCout) return DMAY_EUNSUPPORTED;
+  // epilogue warps, measured (profiles/r1_conv_notes.md): 16 warps win only where a tile's MMA is a few hundred
+  // clocks (1x1 convs with K <= 256: +10..30 %); from K = 576 up 8 warps are as fast or faster, and their smaller
+  // staging area leaves one more pipeline stage
+  a.epi_warps = ((long long)p->kh * p->kw * p->Cin <= 384) ? 16 : 8;
+  if (p->flags & 8) a.epi_warps = 8;
+  if (p->flags & 16) a.epi_warps = 16;
+  const uint32_t kTailBytes = tail_bytes(a.epi_warps, a.opnd_stage != 0, (uint32_t)a.sb_floats);
 
   if ((bn & 15) || bn > 256 || bn < 16) return DMAY_EUNSUPPORTED;
   a.block_n = bn;
@@ -992,11 +1033,25 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
       a.subs = 1;
       a.stage_bytes = 1024u;   // no B pipeline
     } else {
-      a.n_abuf = 4;
-      // stages hold B tiles only; sub-tiles per stage must divide the 9 taps (a stage never straddles a chunk)
-      subs = (9u * a.b_bytes <= 48u * 1024u) ? 9 : ((3u * a.b_bytes <= 48u * 1024u) ? 3 : 1);
+      // stages hold B tiles only; sub-tiles per stage must divide the 9 taps (a stage never straddles a chunk).
+      // Patch ring of 4 (3, 2 when shared memory is short) and the widest stage that still leaves >= 3 stages.
+      // Measured: one mbarrier round trip per tap (subs = 1) costs 40 % on the 128-channel layers, so the widest
+      // stage wins even when only two stages and a shorter patch ring fit.
+      bool ok = false;
+      for (int sb : {9, 3, 1}) {
+        const uint32_t stg = ((uint32_t)sb * a.b_bytes + 1023u) & ~1023u;
+        if (stg > 48u * 1024u && sb > 1) continue;
+        for (int nab = 4; nab >= 2 && !ok; --nab)
+          if ((uint64_t)nab * a.a_halo_bytes + 2ull * stg <= smem_avail) {
+            a.n_abuf = nab;
+            subs = sb;
+            a.stage_bytes = stg;
+            ok = true;
+          }
+        if (ok) break;
+      }
+      if (!ok) return DMAY_EUNSUPPORTED;
       a.subs = subs;
-      a.stage_bytes = ((uint32_t)subs * a.b_bytes + 1023u) & ~1023u;
     }
     halo_bytes_total = a.bres_bytes + (uint32_t)a.n_abuf * a.a_halo_bytes;
   } else {
@@ -1080,18 +1135,45 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return DMAY_EDRIVER;
   }
 
+  if (staged) {
+    // output tile store / operand tile load: 32 channels x 32 rows (halo: 32 ch x 8 x 4 pixels), 64-byte swizzle.
+    // The maps are clipped to [Cout] channels, so a slab neighbour is never touched, and to M rows / the image.
+    auto encode_epi = [&](CUtensorMap* tm, const void* basep, int ld) -> bool {
+      CUresult rr;
+      if (a.halo) {
+        cuuint64_t gdim[4] = {(cuuint64_t)p->Cout, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)p->N};
+        cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)p->Wo * ld * 2, (cuuint64_t)p->Ho * p->Wo * ld * 2};
+        cuuint32_t box[4] = {32, (cuuint32_t)kHaloTW, 4, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        rr = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(basep), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else {
+        cuuint64_t gdim[2] = {(cuuint64_t)p->Cout, (cuuint64_t)M};
+        cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t estr[2] = {1, 1};
+        rr = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(basep), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      return rr == CUDA_SUCCESS;
+    };
+    if (!encode_epi(&a.tmY, p->y, p->ldy)) return DMAY_EDRIVER;
+    if (a.opnd_stage) {
+      const void* src = mode == EPI_SILU_RES ? p->residual : p->gate_x;
+      const int ld = mode == EPI_SILU_RES ? p->ldr : p->ldgx;
+      if (!encode_epi(&a.tmR, src, ld)) return DMAY_EDRIVER;
+    }
+  } else {
+    a.tmY = a.tmB;   // never used by the direct-store modes; keeps the descriptor prefetch well-defined
+  }
+
   const size_t smem = 1024 + (size_t)halo_bytes_total + (size_t)a.stages * a.stage_bytes + kTailBytes;
   const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
   const long long supers = (long long)((a.num_m_tiles + a.cs - 1) / a.cs) * a.num_n_tiles;
   const long long max_clusters = sms / a.cs;
   const int grid = (int)((supers < max_clusters ? supers : max_clusters) * a.cs);
-  int mode;
-  if (a.gate_x) mode = (!out_f32 && !a.residual) ? EPI_GATE : -1;
-  else if (out_f32) mode = (a.act == DMAY_ACT_NONE && !a.residual) ? EPI_LINEAR_F32 : EPI_GENERIC;
-  else if (a.act == DMAY_ACT_SILU) mode = a.residual ? EPI_SILU_RES : EPI_SILU;
-  else if (a.act == DMAY_ACT_NONE && !a.residual) mode = EPI_LINEAR;
-  else mode = EPI_GENERIC;
-  if (mode < 0) return DMAY_EUNSUPPORTED;
 #define DMAY_LAUNCH_MODE(MODE)                                                                                     \
   case MODE: {                                                                                                      \
     static bool attr_set = false;                                                                                   \
@@ -1104,7 +1186,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     if (a.cs > 1) {                                                                                                 \
       cudaLaunchConfig_t cfg = {};                                                                                  \
       cfg.gridDim = dim3(grid);                                                                                     \
-      cfg.blockDim = dim3(kConvThreads);                                                                            \
+      cfg.blockDim = dim3(128 + 32 * a.epi_warps);                                                                            \
       cfg.dynamicSmemBytes = smem;                                                                                  \
       cfg.stream = stream;                                                                                          \
       cudaLaunchAttribute at[1];                                                                                    \
@@ -1117,7 +1199,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
       cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE>, a);                                          \
       if (e != cudaSuccess) return (int)e;                                                                          \
     } else {                                                                                                        \
-      conv_gemm_kernel<MODE><<<grid, kConvThreads, smem, stream>>>(a);                                              \
+      conv_gemm_kernel<MODE><<<grid, 128 + 32 * a.epi_warps, smem, stream>>>(a);                                              \
     }                                                                                                               \
     break;                                                                                                          \
   }

@@ -238,7 +238,7 @@ def _run_chain(mods, t, final_out):
     return t
 
 
-class C3(nn.Module):
+class C3(_PackMixin, nn.Module):
     """CSP Bottleneck with 3 convolutions — models/common.py:159-182."""
 
     def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
@@ -254,6 +254,29 @@ class C3(nn.Module):
             return self.forward_b200(x)
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
 
+    def _merged_cv12(self, device):
+        """cv1 and cv2 read the same x with the same geometry: ONE GEMM with their weights stacked along Cout
+        writes both halves of the concat slab (x is read once, one launch less).  None when they differ."""
+        a, b = self.cv1, self.cv2
+        if not (type(a) is Conv and type(b) is Conv and _conv_supported(a.conv) and _conv_supported(b.conv)):
+            return None
+        ca, cb = a.conv, b.conv
+        code = _act_code(a.act)
+        if (code is None or code != _act_code(b.act) or ca.weight.shape != cb.weight.shape or ca.stride != cb.stride
+                or ca.padding != cb.padding or ca.out_channels % 16 or (getattr(a, 'bn', None) is None) != (getattr(b, 'bn', None) is None)):
+            return None
+        pa = get_conv_pack(a, 'conv', ca, getattr(a, 'bn', None), device)
+        pb = get_conv_pack(b, 'conv', cb, getattr(b, 'bn', None), device)
+        cache = self.__dict__.setdefault('_b200_packs', {})
+        pk = cache.get('cv12')
+        if pk is None or pk.key != (pa.key, pb.key):
+            pk = ops.ConvPack(w=torch.cat((pa.w, pb.w), 0).contiguous(), scale=torch.cat((pa.scale, pb.scale)).contiguous(),
+                              bias=torch.cat((pa.bias, pb.bias)).contiguous(), cin=pa.cin, cin_pad=pa.cin_pad,
+                              cout=pa.cout + pb.cout, cout_pad=pa.cout_pad + pb.cout_pad, kh=pa.kh, kw=pa.kw,
+                              stride=pa.stride, pad=pa.pad, key=(pa.key, pb.key))
+            cache['cv12'] = pk
+        return pk, code
+
     def forward_b200(self, x, out=None):
         # cv1 -> bottlenecks write the first half of the concat slab, cv2 the second half: no torch.cat
         x = ops.as_act(x)
@@ -261,6 +284,12 @@ class C3(nn.Module):
         c_ = self.cv1.conv.out_channels
         slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
         first = slab[:, :c_]
+        merged = self._merged_cv12(x.device) if isinstance(self.m, nn.Sequential) else None
+        if merged is not None:
+            ops.conv(x, merged[0], merged[1], out=slab)          # [cv1(x) | cv2(x)] in one launch
+            if len(self.m) > 0:
+                _run_chain(self.m, first, first)                 # the last block overwrites cv1(x) in place
+            return self.cv3.forward_b200(slab, out=out)
         if isinstance(self.m, nn.Sequential) and len(self.m) > 0:
             _run_chain(self.m, self.cv1.forward_b200(x), first)
         elif isinstance(self.m, nn.Sequential):

@@ -9,7 +9,7 @@ flag = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 B, dev = 64, 'cuda'
 flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 convs = [(64, 64, 3, 1, 320), (64, 64, 3, 1, 160), (64, 64, 1, 1, 160), (128, 128, 3, 1, 160), (128, 128, 3, 1, 80), (128, 128, 1, 1, 80),
-         (256, 256, 3, 1, 80), (256, 256, 3, 1, 40), (256, 256, 1, 1, 40), (512, 512, 3, 1, 40), (512, 512, 3, 1, 20),
+         (256, 256, 3, 1, 80), (256, 256, 3, 1, 40), (256, 256, 1, 1, 40), (256, 256, 1, 1, 80), (512, 512, 1, 1, 40), (512, 512, 1, 1, 20), (1024, 256, 1, 1, 40), (128, 256, 1, 1, 80), (512, 512, 3, 1, 40), (512, 512, 3, 1, 20),
          (1024, 1024, 3, 1, 20), (4096, 1024, 1, 1, 20), (1024, 1024, 1, 1, 20)]
 for cin, cout, k, s, ho in convs:
     x = ops.empty_nhwc(B, cin, ho * s, ho * s, dev).normal_()
