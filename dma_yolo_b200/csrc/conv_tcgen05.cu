@@ -205,6 +205,8 @@ struct __align__(64) ConvArgs {
   int opnd_stage;    // 1: the epilogue stages a residual / gate_x tile per item
   int sb_floats;     // staged scale / bias entries (columns covered by all n-tiles, <= kMaxCout)
   int epi_warps;     // 8 or 16 (blockDim = 128 + 32 * epi_warps): 16 where the epilogue, not the MMA, paces the tile
+  int epi_groups;    // 2: narrow tiles (block_n <= 64) — the 16 warps form two groups that take alternate tiles (one TMEM
+                     //    accumulator buffer each), because 8 warps already cover the 64 columns
   const float* scale;
   const float* bias;
   const __nv_bfloat16* residual;
@@ -217,6 +219,7 @@ struct __align__(64) ConvArgs {
   int conv_stride, pad, Ho, Wo;
   int im2col;
   int block_n, acc_stride, tmem_cols, stages;
+  int nacc;          // accumulator buffers in TMEM (2..8): the MMA of tile j+nacc waits for the epilogue's TMEM loads of tile j
   int subs, total_subs;      // sub-tiles (one tap x one CK-channel chunk) per pipeline stage / per tile
   int cs;                    // cluster size: the B tile is loaded in `cs` row slices, each multicast to all CTAs
   // halo mode (3x3 stride-1 pad-1): an output tile is a 16x8 pixel patch; its 18 x pitch input patch is loaded
@@ -246,7 +249,8 @@ struct __align__(64) ConvArgs {
 //   (halo mode: [n_abuf halo buffers] precede the stages, which then hold B tiles only)
 constexpr int kMaxABuf = 8;
 constexpr int kHaloTH = 16, kHaloTW = 8;
-constexpr uint32_t kNumBars = 2 * kMaxStages + 4 + 2 * kMaxABuf + kEpiWarps;   // + one operand barrier per epilogue warp
+constexpr int kMaxAcc = 8;                                                     // TMEM accumulator ring (512 columns / block_n)
+constexpr uint32_t kNumBars = 2 * kMaxStages + 2 * kMaxAcc + 2 * kMaxABuf + kEpiWarps;   // + one operand barrier per epilogue warp
 constexpr int kMaxCout = 2048;                                                 // scale/bias staged once per CTA
 // tail (1024-aligned, after the pipeline stages):
 //   [kEpiWarps x 2 KB] output staging (thread == row writes 4 x 16 B, 64-byte-swizzled, a TMA store drains it)
@@ -381,8 +385,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t epi_stage_bytes = (uint32_t)a.epi_warps * 2048u;
   const uint32_t bars_off = epi_stage_bytes * (a.opnd_stage ? 2u : 1u);
   const uint32_t full_bar = tail + bars_off, empty_bar = full_bar + kMaxStages * 8;
-  const uint32_t tfull_bar = full_bar + 2 * kMaxStages * 8, tempty_bar = tfull_bar + 16;
-  const uint32_t afull_bar = tempty_bar + 16, aempty_bar = afull_bar + kMaxABuf * 8;
+  const uint32_t tfull_bar = full_bar + 2 * kMaxStages * 8, tempty_bar = tfull_bar + kMaxAcc * 8;
+  const uint32_t afull_bar = tempty_bar + kMaxAcc * 8, aempty_bar = afull_bar + kMaxABuf * 8;
   const uint32_t opnd_bar = aempty_bar + kMaxABuf * 8;                   // [kEpiWarps]
   const uint32_t tmem_slot = full_bar + kNumBars * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_ptr + bars_off + kNumBars * 8);
@@ -411,9 +415,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       mbar_init(full_bar + i * 8, 1);
       mbar_init(empty_bar + i * 8, cs);   // every CTA of the cluster releases the stage (its B slice lands in all)
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(tfull_bar + i * 8, 1);
-      mbar_init(tempty_bar + i * 8, (uint32_t)a.epi_warps * 32u);
+      mbar_init(tempty_bar + i * 8, (uint32_t)(a.epi_warps / a.epi_groups) * 32u);
     }
     for (int i = 0; i < kMaxABuf; ++i) {
       mbar_init(afull_bar + i * 8, 1);
@@ -608,8 +612,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         }
         if (elect_one()) umma_commit(tfull_bar + acc * 8);
         __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == a.nacc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     } else {
 #pragma unroll 1
@@ -683,8 +689,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       if (elect_one()) umma_commit(tfull_bar + acc * 8);
       __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == a.nacc) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
     }  // !b_resident
   } else if (warp >= 4) {
@@ -698,14 +706,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     //             the current item is processed (no registers held across items).
     const int ew = warp - 4;
     const int quad = warp & 3;
-    const int sub = ew >> 2;
+    const int grp = a.epi_groups == 2 ? (ew >> 3) : 0;          // tile parity this warp serves (two-group mode)
+    const int wpg = a.epi_warps / a.epi_groups;                 // warps per group
+    const int sub = (ew >> 2) & (wpg / 4 - 1);
     const int row_in_tile = quad * 32 + lane;
-    int acc = 0;
+    int acc = grp;                                              // ring slot of this warp's next tile (tile j -> j % nacc)
     uint32_t acc_phase = 0;
     const int HoWo = a.Ho * a.Wo;
-    const int cstride = a.epi_warps * 8;                                               // columns between a warp's chunks
+    const int cstride = wpg * 8;                                                       // columns between a warp's chunks
     const int cpw = a.block_n > sub * 32 ? (a.block_n - sub * 32 + cstride - 1) / cstride : 0;   // chunks per tile of this warp
-    const int my_tiles = cluster_id < total_super ? (total_super - cluster_id + num_clusters - 1) / num_clusters : 0;
+    const int cta_tiles = cluster_id < total_super ? (total_super - cluster_id + num_clusters - 1) / num_clusters : 0;
+    const int my_tiles = a.epi_groups == 2 ? (cta_tiles + 1 - grp) / 2 : cta_tiles;
     const int items = my_tiles * (cpw > 0 ? cpw : 1);                                  // cpw == 0: one "empty" item per tile
 
     constexpr bool kStaged = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_LINEAR || MODE == EPI_GATE);
@@ -734,7 +745,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         mk_ch = 0;
         ++mk_ti;
       }
-      const int st = cluster_id + ti * num_clusters;
+      const int st = cluster_id + (a.epi_groups == 2 ? 2 * ti + grp : ti) * num_clusters;
       const int sq = fdiv(st, a.fd_nn);
       const int n_tile = st - sq * a.num_n_tiles, m_tile = sq * cs + (int)crank;
       it.n0 = n_tile * a.block_n;
@@ -816,6 +827,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             for (int j = 0; j < 4; ++j) own[j] = op_ptr[sidx(lane, j)];
           }
           tmem_ld_wait();
+          if (cur.last) {   // the accumulators are in registers: hand the TMEM buffer back before the math and the store
+            tc_fence_before();
+            mbar_arrive(tempty_bar + acc * 8);
+          }
           if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the staging tile
           __syncwarp();
 #pragma unroll
@@ -837,6 +852,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if (kOpnd && has_next) issue_opnd(nxt);   // refill the operand tile for the next item
         } else {
           tmem_ld_wait();
+          if (cur.last) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar + acc * 8);
+          }
           if (cur.row >= 0) {
             const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -848,11 +867,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
         }
       }
-      if (cur.last) {
+      if (cur.last && cur.width == 0) {   // a warp without columns in this tile still takes part in the hand-back
         tc_fence_before();
         mbar_arrive(tempty_bar + acc * 8);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (cur.last) {
+        acc += a.epi_groups;        // next tile of this warp (nacc is even, so a group keeps its slot parity)
+        if (acc >= a.nacc) {
+          acc -= a.nacc;
+          acc_phase ^= 1u;
+        }
       }
       cur = nxt;
     }
@@ -972,14 +996,19 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   // clocks (1x1 convs with K <= 256: +10..30 %); from K = 576 up 8 warps are as fast or faster, and their smaller
   // staging area leaves one more pipeline stage
   a.epi_warps = ((long long)p->kh * p->kw * p->Cin <= 384) ? 16 : 8;
+  if (bn <= 64 && !(p->flags & 32)) a.epi_warps = 16;   // narrow tiles: two groups of 8 warps on alternate tiles
   if (p->flags & 8) a.epi_warps = 8;
   if (p->flags & 16) a.epi_warps = 16;
+  a.epi_groups = (a.epi_warps == 16 && bn <= 64 && !(p->flags & 32)) ? 2 : 1;
   const uint32_t kTailBytes = tail_bytes(a.epi_warps, a.opnd_stage != 0, (uint32_t)a.sb_floats);
 
   if ((bn & 15) || bn > 256 || bn < 16) return DMAY_EUNSUPPORTED;
   a.block_n = bn;
   a.acc_stride = pow2ceil(bn) < 32 ? 32 : pow2ceil(bn);
-  a.tmem_cols = 2 * a.acc_stride;
+  a.nacc = 512 / a.acc_stride;
+  if (a.nacc > kMaxAcc) a.nacc = kMaxAcc;
+  if (p->flags & 64) a.nacc = 2;
+  a.tmem_cols = a.nacc * a.acc_stride;
   a.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
   a.num_n_tiles = (p->Cout_pad + bn - 1) / bn;
   a.n_store = p->Cout;

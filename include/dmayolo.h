@@ -67,7 +67,9 @@ const char* dmay_strerror(int code);
  * block_n: 0 = auto, >0 = force the N tile, -2 = 2-CTA cluster multicast of the weight tile (experiment).
  * flags (tuning / A-B switches, 0 = auto): bit0 = never use the halo path (3x3 s1 p1 input patch loaded once
  *   per channel chunk, taps read shifted windows), bit1 = force it where legal, bit2 = never keep the weight
- *   set resident in shared memory in halo mode, bit3 / bit4 = force 8 / 16 epilogue warps. */
+ *   set resident in shared memory in halo mode, bit3 / bit4 = force 8 / 16 epilogue warps,
+ *   bit5 = never split the epilogue warps into two alternate-tile groups (narrow tiles),
+ *   bit6 = two TMEM accumulator buffers instead of 512 / block_n. */
 typedef struct dmay_conv_params {
   const void* x;
   const void* w;
