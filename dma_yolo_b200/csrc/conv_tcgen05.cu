@@ -438,6 +438,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anything multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, folded-BN constants) ran
+  // while the previous kernel of the stream was still draining; activations are only touched after this point.
+  // The next kernel may start its own preamble as soon as every CTA of this grid has passed here (or exited).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer: the whole warp walks the schedule (uniform), one elected lane issues =====
@@ -1212,24 +1217,29 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
       if (e != cudaSuccess) return (int)e;                                                                          \
       attr_set = true;                                                                                              \
     }                                                                                                               \
-    if (a.cs > 1) {                                                                                                 \
-      cudaLaunchConfig_t cfg = {};                                                                                  \
-      cfg.gridDim = dim3(grid);                                                                                     \
-      cfg.blockDim = dim3(128 + 32 * a.epi_warps);                                                                            \
-      cfg.dynamicSmemBytes = smem;                                                                                  \
-      cfg.stream = stream;                                                                                          \
-      cudaLaunchAttribute at[1];                                                                                    \
-      at[0].id = cudaLaunchAttributeClusterDimension;                                                               \
-      at[0].val.clusterDim.x = a.cs;                                                                                \
-      at[0].val.clusterDim.y = 1;                                                                                   \
-      at[0].val.clusterDim.z = 1;                                                                                   \
-      cfg.attrs = at;                                                                                               \
-      cfg.numAttrs = 1;                                                                                             \
-      cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE>, a);                                          \
-      if (e != cudaSuccess) return (int)e;                                                                          \
-    } else {                                                                                                        \
-      conv_gemm_kernel<MODE><<<grid, 128 + 32 * a.epi_warps, smem, stream>>>(a);                                              \
+    cudaLaunchConfig_t cfg = {};                                                                                    \
+    cfg.gridDim = dim3(grid);                                                                                       \
+    cfg.blockDim = dim3(128 + 32 * a.epi_warps);                                                                    \
+    cfg.dynamicSmemBytes = smem;                                                                                    \
+    cfg.stream = stream;                                                                                            \
+    cudaLaunchAttribute at[2];                                                                                      \
+    int nat = 0;                                                                                                    \
+    if (!(p->flags & 128)) {                                                                                        \
+      at[nat].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                              \
+      at[nat].val.programmaticStreamSerializationAllowed = 1;                                                       \
+      ++nat;                                                                                                        \
     }                                                                                                               \
+    if (a.cs > 1) {                                                                                                 \
+      at[nat].id = cudaLaunchAttributeClusterDimension;                                                             \
+      at[nat].val.clusterDim.x = a.cs;                                                                              \
+      at[nat].val.clusterDim.y = 1;                                                                                 \
+      at[nat].val.clusterDim.z = 1;                                                                                 \
+      ++nat;                                                                                                        \
+    }                                                                                                               \
+    cfg.attrs = at;                                                                                                 \
+    cfg.numAttrs = nat;                                                                                             \
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE>, a);                                            \
+    if (e != cudaSuccess) return (int)e;                                                                            \
     break;                                                                                                          \
   }
   switch (mode) {

@@ -69,7 +69,8 @@ const char* dmay_strerror(int code);
  *   per channel chunk, taps read shifted windows), bit1 = force it where legal, bit2 = never keep the weight
  *   set resident in shared memory in halo mode, bit3 / bit4 = force 8 / 16 epilogue warps,
  *   bit5 = never split the epilogue warps into two alternate-tile groups (narrow tiles),
- *   bit6 = two TMEM accumulator buffers instead of 512 / block_n. */
+ *   bit6 = two TMEM accumulator buffers instead of 512 / block_n,
+ *   bit7 = launch without programmatic dependent launch (the kernel's preamble then waits for the previous kernel). */
 typedef struct dmay_conv_params {
   const void* x;
   const void* w;
