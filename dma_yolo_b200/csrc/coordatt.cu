@@ -200,23 +200,228 @@ __global__ void __launch_bounds__(256) ca_apply_kernel(const __nv_bfloat16* __re
   }
 }
 
+// ---- fast path (plane of 64 channels fits in shared memory): TWO launches ---------------------------------
+// K1  ca_pool_hidden_kernel : CTA = (image, 64-channel group).  Stages its H x W x 64 plane (one coalesced read of x),
+//     reduces it to the pooled row / column means, multiplies them with its 64-row slice of W1 (partial hidden
+//     layer, [H+W][Cm] per CTA) and writes the partial.  The LAST CTA of an image to arrive (atomic ticket) sums
+//     the image's partials and applies bias + folded BN + hardswish: y[n][H+W][Cm].  No spin-waiting.
+// K2  ca_gate_apply_kernel  : CTA = (image, 64-channel group).  Computes the sigmoid gates of its 64 channels from
+//     y (shared memory, 10 KB), then streams its plane once more (L2-resident at cfg-2: 52 MB) and writes
+//     out = (x * a_w) * a_h.  Gates / pooled means go to global memory only when the caller asks for them.
+constexpr int kCaVL = 8;   // 16-byte channel vectors per CTA (64 channels)
+
+__global__ void __launch_bounds__(256) ca_pool_hidden_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             float* __restrict__ pooled_out, float* __restrict__ partial,
+                                                             float* __restrict__ yhid, unsigned* __restrict__ counters,
+                                                             const float* __restrict__ w1T, const float* __restrict__ b1,
+                                                             const float* __restrict__ s1, const float* __restrict__ t1,
+                                                             int H, int W, int C, int Cm, int ldx, int G) {
+  extern __shared__ uint4 plane[];                    // [H*W][kCaVL]
+  const int HW = H * W, P = H + W;
+  float* pooled_s = reinterpret_cast<float*>(plane + (size_t)HW * kCaVL);   // [P][64]
+  __shared__ unsigned ticket_s;
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int cvec = C >> 3;
+  const int v0 = g * kCaVL;
+  const int vl = min(kCaVL, cvec - v0);
+  const __nv_bfloat16* xb = x + (long long)n * HW * ldx + v0 * 8;
+  // four independent 16-byte loads in flight per thread (a load -> store loop left one: ~12 KB in flight per SM)
+  for (int i0 = threadIdx.x; i0 < HW * kCaVL; i0 += 4 * blockDim.x) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int p = i >> 3, v = i & 7;
+      r[u] = (i < HW * kCaVL && v < vl) ? ld16(xb + (long long)p * ldx + v * 8) : make_uint4(0, 0, 0, 0);   // default caching: K2 re-reads x from L2
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < HW * kCaVL) plane[i] = r[u];
+    }
+  }
+  __syncthreads();
+  const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+  for (int i = threadIdx.x; i < P * kCaVL; i += blockDim.x) {
+    const int p = i >> 3, v = i & 7;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int start, step, cnt;
+    float inv;
+    if (p < H) { start = p * W; step = 1; cnt = W; inv = invW; }
+    else { start = p - H; step = W; cnt = H; inv = invH; }
+#pragma unroll 4
+    for (int k = 0; k < cnt; ++k) {
+      float f[8];
+      unpack8(plane[(start + k * step) * kCaVL + v], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] *= inv;
+      pooled_s[p * 64 + v * 8 + j] = acc[j];
+    }
+    if (pooled_out != nullptr && v < vl) {
+      float4* o = reinterpret_cast<float4*>(pooled_out + ((long long)n * P + p) * C + (v0 + v) * 8);
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+  __syncthreads();
+  // partial hidden layer of this channel group: [P][Cm]; thread -> (position p, hidden unit j).  The group's 64-row
+  // slice of W1 is staged in shared memory: strided L2 loads inside the dot product were latency-bound.
+  const int nch = vl * 8;
+  float* w1s = pooled_s + P * 64;                               // [nch][Cm]
+  for (int i = threadIdx.x; i < nch * Cm; i += blockDim.x) w1s[i] = w1T[(long long)(v0 * 8) * Cm + i];
+  __syncthreads();
+  float* part = partial + (long long)(n * G + g) * P * Cm;
+  for (int o = threadIdx.x; o < P * Cm; o += blockDim.x) {
+    const int p = o / Cm, j = o - p * Cm;
+    const float* pr = pooled_s + p * 64;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < nch; ++c) acc = fmaf(w1s[c * Cm + j], pr[c], acc);
+    part[o] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket_s = atomicAdd(counters + n, 1u);
+  __syncthreads();
+  if (ticket_s == (unsigned)(G - 1)) {   // every other group of this image has published its partial
+    __threadfence();
+    const float* pn = partial + (long long)n * G * P * Cm;
+    for (int o = threadIdx.x; o < P * Cm; o += blockDim.x) {
+      const int j = o % Cm;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int gg = 0; gg < G; ++gg) acc += __ldcg(pn + (long long)gg * P * Cm + o);
+      yhid[(long long)n * P * Cm + o] = hardswish(s1[j] * (acc + b1[j]) + t1[j]);
+    }
+    if (threadIdx.x == 0) counters[n] = 0u;   // ready for the next launch
+  }
+}
+
+__global__ void __launch_bounds__(256) ca_gate_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ yhid,
+                                                            __nv_bfloat16* __restrict__ out, float* __restrict__ gates_out,
+                                                            const float* __restrict__ whT, const float* __restrict__ bh,
+                                                            const float* __restrict__ wwT, const float* __restrict__ bw,
+                                                            int H, int W, int C, int Cm, int ldx, int ldy, int G) {
+  extern __shared__ float sm[];
+  const int HW = H * W, P = H + W;
+  float* ys = sm;                 // [P][Cm]
+  float* gs = sm + P * Cm;        // [P][64]
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int cvec = C >> 3;
+  const int v0 = g * kCaVL;
+  const int vl = min(kCaVL, cvec - v0);
+  const int nch = vl * 8;
+  float* whs = gs + P * 64;       // [Cm][64]
+  float* wws = whs + Cm * 64;     // [Cm][64]
+  for (int i = threadIdx.x; i < P * Cm; i += blockDim.x) ys[i] = yhid[(long long)n * P * Cm + i];
+  for (int i = threadIdx.x; i < Cm * 64; i += blockDim.x) {
+    const int j = i >> 6, c = i & 63;
+    const bool in = c < nch;
+    whs[i] = in ? whT[(long long)j * C + v0 * 8 + c] : 0.f;
+    wws[i] = in ? wwT[(long long)j * C + v0 * 8 + c] : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < P * 64; o += blockDim.x) {
+    const int p = o >> 6, c = o & 63;
+    float gate = 0.f;
+    if (c < nch) {
+      const bool is_h = p < H;
+      const float* wT = (is_h ? whs : wws) + c;
+      float acc = (is_h ? bh : bw)[v0 * 8 + c];
+      const float* yr = ys + p * Cm;
+#pragma unroll 8
+      for (int j = 0; j < Cm; ++j) acc = fmaf(wT[j * 64], yr[j], acc);
+      gate = sigmoid_acc(acc);
+      if (gates_out != nullptr) gates_out[((long long)n * P + p) * C + v0 * 8 + c] = gate;
+    }
+    gs[o] = gate;
+  }
+  __syncthreads();
+  const __nv_bfloat16* xb = x + (long long)n * HW * ldx + v0 * 8;
+  __nv_bfloat16* ob = out + (long long)n * HW * ldy + v0 * 8;
+  for (int i0 = threadIdx.x; i0 < HW * kCaVL; i0 += 4 * blockDim.x) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int p = i >> 3, v = i & 7;
+      r[u] = (i < HW * kCaVL && v < vl) ? ld_nc16(xb + (long long)p * ldx + v * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int p = i >> 3, v = i & 7;
+      if (i >= HW * kCaVL || v >= vl) continue;
+      const int h_ = p / W, w_ = p - h_ * W;
+      float f[8];
+      unpack8(r[u], f);
+      const float4* gh = reinterpret_cast<const float4*>(gs + h_ * 64 + v * 8);
+      const float4* gw = reinterpret_cast<const float4*>(gs + (H + w_) * 64 + v * 8);
+      const float4 h0 = gh[0], h1 = gh[1], w0 = gw[0], w1 = gw[1];
+      f[0] = (f[0] * w0.x) * h0.x; f[1] = (f[1] * w0.y) * h0.y; f[2] = (f[2] * w0.z) * h0.z; f[3] = (f[3] * w0.w) * h0.w;
+      f[4] = (f[4] * w1.x) * h1.x; f[5] = (f[5] * w1.y) * h1.y; f[6] = (f[6] * w1.z) * h1.z; f[7] = (f[7] * w1.w) * h1.w;
+      st_na16(ob + (long long)p * ldy + v * 8, pack8(f));
+    }
+  }
+}
+
 }  // namespace dmay
 
 using namespace dmay;
 
+extern "C" long long dmay_coordatt_ws(int N, int H, int W, int C, int Cm) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cm <= 0) return DMAY_EINVAL;
+  const long long G = (C / 8 + kCaVL - 1) / kCaVL, P = H + W;
+  return ((long long)N * G * P * Cm + (long long)N * P * Cm) * 4 + (long long)N * 4;
+}
+
 extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream) {
-  if (!p || !p->x || !p->y || !p->pooled || !p->gates || !p->w1 || !p->b1 || !p->s1 || !p->t1 || !p->wh || !p->bh ||
-      !p->ww || !p->bw)
+  if (!p || !p->x || !p->y || !p->w1 || !p->b1 || !p->s1 || !p->t1 || !p->wh || !p->bh || !p->ww || !p->bw)
     return DMAY_EINVAL;
   if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->C <= 0 || p->Cm <= 0) return DMAY_EINVAL;
   if ((p->C | p->ldx | p->ldy) & 7) return DMAY_EUNSUPPORTED;
-  if (!aligned16(p->x) || !aligned16(p->y) || !aligned16(p->pooled) || !aligned16(p->gates)) return DMAY_EINVAL;
+  if (!aligned16(p->x) || !aligned16(p->y) || (p->pooled && !aligned16(p->pooled)) || (p->gates && !aligned16(p->gates)))
+    return DMAY_EINVAL;
   const long long npix = (long long)p->N * p->H * p->W;
   if (npix >= 0x7fffffffLL) return DMAY_EUNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int cvec = p->C / 8;
   const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
   const long long HW = (long long)p->H * p->W;
+  // fast path: two launches (see ca_pool_hidden_kernel); needs the partial / y / ticket workspace
+  {
+    const int G = (cvec + kCaVL - 1) / kCaVL, P = p->H + p->W;
+    const size_t smem1 = (size_t)HW * kCaVL * 16 + (size_t)P * 64 * 4 + (size_t)64 * p->Cm * 4;
+    const size_t smem2 = ((size_t)P * p->Cm + (size_t)P * 64 + 2 * (size_t)p->Cm * 64) * 4;
+    const long long need = ((long long)p->N * G * P * p->Cm + (long long)p->N * P * p->Cm) * 4 + (long long)p->N * 4;
+    if (p->ws != nullptr && p->ws_bytes >= need && smem1 <= 100 * 1024 && smem2 <= 100 * 1024 && aligned16(p->ws)) {
+      float* partial = (float*)p->ws;
+      float* yhid = partial + (long long)p->N * G * P * p->Cm;
+      unsigned* counters = (unsigned*)(yhid + (long long)p->N * P * p->Cm);   // zero on first use, self-resetting
+      if (smem1 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ca_pool_hidden_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) return (int)e;
+      }
+      if (smem2 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ca_gate_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return (int)e;
+      }
+      ca_pool_hidden_kernel<<<p->N * G, 256, smem1, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, partial, yhid, counters,
+                                                        (const float*)p->w1, (const float*)p->b1, (const float*)p->s1,
+                                                        (const float*)p->t1, p->H, p->W, p->C, p->Cm, p->ldx, G);
+      ca_gate_apply_kernel<<<p->N * G, 256, smem2, s>>>((const __nv_bfloat16*)p->x, yhid, (__nv_bfloat16*)p->y, (float*)p->gates,
+                                                       (const float*)p->wh, (const float*)p->bh, (const float*)p->ww,
+                                                       (const float*)p->bw, p->H, p->W, p->C, p->Cm, p->ldx, p->ldy, G);
+      return finish_launch(2);
+    }
+  }
+  if (!p->pooled || !p->gates) return DMAY_EINVAL;   // the three-launch path needs both workspaces
   // 1. pool
   int VL = 0;
   for (int cand : {8, 4, 2, 1}) {

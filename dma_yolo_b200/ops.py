@@ -387,6 +387,9 @@ def pack_coordatt(conv1, bn1, conv_h, conv_w, device) -> CoordAttPack:
                         wwT=f(conv_w.weight.reshape(-1, cm).t()), bw=f(zeros(conv_w)), c=c, cm=cm)
 
 
+_CA_WS: dict = {}   # (device, N, H, W, C, Cm) -> zero-initialised workspace (arrival tickets reset themselves)
+
+
 def coordatt(x: torch.Tensor, pk: CoordAttPack, out=None, return_gates=False):
     x = as_act(x)
     n, c, h, w = x.shape
@@ -394,12 +397,22 @@ def coordatt(x: torch.Tensor, pk: CoordAttPack, out=None, return_gates=False):
         raise DmayError("coordatt: channel mismatch (needs c2 == c1)")
     if out is None:
         out = empty_nhwc(n, c, h, w, x.device)
-    pooled = torch.empty((n, h + w, c), device=x.device, dtype=torch.float32)
-    gates = torch.empty((n, h + w, c), device=x.device, dtype=torch.float32)
-    call("dmay_coordatt", _stream(x), x=x.data_ptr(), y=out.data_ptr(), pooled=pooled.data_ptr(), gates=gates.data_ptr(),
-         w1=pk.w1.data_ptr(), b1=pk.b1.data_ptr(), s1=pk.s1.data_ptr(), t1=pk.t1.data_ptr(), wh=pk.whT.data_ptr(),
-         bh=pk.bh.data_ptr(), ww=pk.wwT.data_ptr(), bw=pk.bw.data_ptr(), N=n, H=h, W=w, C=c, Cm=pk.cm, ldx=ld_of(x),
-         ldy=ld_of(out), num_sms=0)
+    key = (x.device.index, n, h, w, c, pk.cm, torch.cuda.current_stream(x.device).cuda_stream)
+    ws = _CA_WS.get(key)
+    if ws is None:
+        nbytes = int(_lib.lib().dmay_coordatt_ws(n, h, w, c, pk.cm))
+        ws = _CA_WS[key] = torch.zeros((nbytes + 15) // 16 * 4, device=x.device, dtype=torch.int32)
+    f = dict(x=x.data_ptr(), y=out.data_ptr(), w1=pk.w1.data_ptr(), b1=pk.b1.data_ptr(), s1=pk.s1.data_ptr(),
+             t1=pk.t1.data_ptr(), wh=pk.whT.data_ptr(), bh=pk.bh.data_ptr(), ww=pk.wwT.data_ptr(), bw=pk.bw.data_ptr(),
+             N=n, H=h, W=w, C=c, Cm=pk.cm, ldx=ld_of(x), ldy=ld_of(out), num_sms=0, ws=ws.data_ptr(), ws_bytes=ws.numel() * 4)
+    pooled = gates = None
+    plane_fits = (h * w * 128 + (h + w) * 256 + 256 * pk.cm <= 100 * 1024
+                  and ((h + w) * (pk.cm + 64) + 128 * pk.cm) * 4 <= 100 * 1024)   # mirrors the fast-path test in coordatt.cu
+    if return_gates or not plane_fits:   # the three-launch path (large planes) needs both; tests ask for them
+        pooled = torch.empty((n, h + w, c), device=x.device, dtype=torch.float32)
+        gates = torch.empty((n, h + w, c), device=x.device, dtype=torch.float32)
+        f.update(pooled=pooled.data_ptr(), gates=gates.data_ptr())
+    call("dmay_coordatt", _stream(x), **f)
     return (out, pooled, gates) if return_gates else out
 
 

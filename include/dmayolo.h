@@ -295,7 +295,12 @@ int dmay_scconv_gate(const dmay_scgate_params* p, dmay_stream_t stream);
  *                 fp32 [N,H+W,Cout].  Weight operands are passed TRANSPOSED, fp32:
  *                 w1 = W1^T [C][Cm],  wh = Wh^T [Cm][Cout],  ww = Ww^T [Cm][Cout]  (Cout == C).
  * step 3 (apply): out = (x * a_w[n,w,c]) * a_h[n,h,c]  -> bf16
- * dmay_coordatt runs the three steps on the stream. */
+ * dmay_coordatt runs the three steps on the stream.
+ * Fast path (two launches; taken when `ws` is given and a 64-channel plane fits in shared memory): pool + partial
+ * hidden layer per (image, 64-channel group) with the image's last CTA finishing y, then gates + apply per group.
+ * ws: workspace of dmay_coordatt_ws() bytes, ZERO-initialised before its first use (it holds per-image arrival
+ * tickets that the kernel resets itself; one workspace per stream).  pooled / gates may then be NULL (they are
+ * only written when given). */
 typedef struct dmay_coordatt_params {
   const void* x;
   void* y;
@@ -317,7 +322,10 @@ typedef struct dmay_coordatt_params {
   int ldx;
   int ldy;
   int num_sms;
+  void* ws;
+  long long ws_bytes;
 } dmay_coordatt_params;
+long long dmay_coordatt_ws(int N, int H, int W, int C, int Cm);
 int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream);
 
 /* ---- a8: Detect grid/anchor decode, models/yolo.py:81-101 -------------------------------

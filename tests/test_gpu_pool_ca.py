@@ -73,3 +73,21 @@ def test_coordatt_stages_vs_oracle(shape):
     with torch.no_grad():
         ref = m(x)
     assert_close(back(y), ref, atol=1e-2, rtol=1e-2, what='coordatt out')
+
+
+def test_coordatt_fast_path_is_repeatable_without_side_outputs():
+    """Two-launch path (pool + partial hidden layer with a last-CTA reduction, then gates + apply): the arrival
+    tickets reset themselves, so repeated calls on one workspace agree bit for bit and match the 3-stage result."""
+    from dma_yolo_b200 import ops
+    from dma_yolo_b200.models import common as C
+    torch.manual_seed(3)
+    m = C.CoorAttention(256, 256).eval()
+    x = ops.as_act(bf(torch.randn(3, 256, 20, 12)).cuda())
+    pk = ops.pack_coordatt(m.conv1, m.bn1, m.conv_h, m.conv_w, 'cuda')
+    y1 = ops.coordatt(x, pk).clone()
+    y2 = ops.coordatt(x, pk).clone()
+    y3, _, _ = ops.coordatt(x, pk, return_gates=True)
+    assert torch.equal(y1, y2) and torch.equal(y1, y3)
+    with torch.no_grad():
+        ref = m(back(x))
+    assert_close(back(y1), ref, atol=1e-2, rtol=1e-2, what='coordatt fast path')
