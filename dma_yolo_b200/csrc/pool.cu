@@ -136,7 +136,7 @@ __device__ __forceinline__ void window5(uint4 (&a)[kRegD + 4]) {
 }
 
 template <int STAGES>
-__global__ void __launch_bounds__(kRegD* kRegVL) pool_reg_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(kRegD* kRegVL, 3) pool_reg_kernel(const __nv_bfloat16* __restrict__ x,
                                                                  __nv_bfloat16* __restrict__ y1,
                                                                  __nv_bfloat16* __restrict__ y2,
                                                                  __nv_bfloat16* __restrict__ y3, int H, int W, int C,
@@ -272,10 +272,12 @@ static int launch_pool(const void* x, void* y1, void* y2, void* y3, int N, int H
     if (stages == 3) {
       cudaError_t e = cudaFuncSetAttribute(pool_reg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
+      cudaFuncSetAttribute(pool_reg_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       pool_reg_kernel<3><<<(int)grid, kRegD * kRegVL, smem, s>>>(xi, o1, o2, o3, H, W, C, ldx, ldy);
     } else {
       cudaError_t e = cudaFuncSetAttribute(pool_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
+      cudaFuncSetAttribute(pool_reg_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       pool_reg_kernel<1><<<(int)grid, kRegD * kRegVL, smem, s>>>(xi, o1, o2, o3, H, W, C, ldx, ldy);
     }
     return finish_launch();

@@ -407,7 +407,7 @@ def coordatt(x: torch.Tensor, pk: CoordAttPack, out=None, return_gates=False):
              N=n, H=h, W=w, C=c, Cm=pk.cm, ldx=ld_of(x), ldy=ld_of(out), num_sms=0, ws=ws.data_ptr(), ws_bytes=ws.numel() * 4)
     pooled = gates = None
     plane_fits = (h * w * 128 + (h + w) * 256 + 256 * pk.cm <= 100 * 1024
-                  and ((h + w) * (pk.cm + 64) + 128 * pk.cm) * 4 <= 100 * 1024)   # mirrors the fast-path test in coordatt.cu
+                  and ((h + w) * (pk.cm + 64) + 128 * pk.cm) * 4 <= 100 * 1024 and pk.cm <= 256)   # mirrors coordatt.cu
     if return_gates or not plane_fits:   # the three-launch path (large planes) needs both; tests ask for them
         pooled = torch.empty((n, h + w, c), device=x.device, dtype=torch.float32)
         gates = torch.empty((n, h + w, c), device=x.device, dtype=torch.float32)

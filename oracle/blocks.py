@@ -7,10 +7,33 @@ re-derivation of `Model._forward_once` that shares no code with `dma_yolo_b200`.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 
 import torch
 import torch.nn.functional as F
+
+# bf16-storage emulation.  The reference in fp32 is the default oracle.  Under `bf16_storage()` every tensor that the
+# B200 path STORES as bf16 between two fused kernels is rounded to bf16 here as well (and only there: inside a fused
+# kernel — conv accumulator -> BN -> SiLU -> residual / gate — everything stays fp32, exactly one rounding at the
+# end).  This is the oracle for the "within 1e-2 in bf16" tolerance: it removes the storage rounding, which
+# compounds over 25 layers of an untrained net, from the comparison and leaves only arithmetic differences
+# (accumulation order, tanh.approx SiLU).
+_BF16 = False
+
+
+@contextlib.contextmanager
+def bf16_storage(on=True):
+    global _BF16
+    old, _BF16 = _BF16, on
+    try:
+        yield
+    finally:
+        _BF16 = old
+
+
+def q(t):
+    return t.bfloat16().float() if _BF16 else t
 
 
 def _bn(x, sd, p, eps):
@@ -22,7 +45,7 @@ def silu(x):
     return x * torch.sigmoid(x)
 
 
-def conv_bn_act(x, sd, p, k=1, s=1, pad=None, act=True, eps=1e-3):
+def conv_bn_act(x, sd, p, k=1, s=1, pad=None, act=True, eps=1e-3, raw=False):
     """Conv.forward — models/common.py:50-77: act(bn(conv(x))), conv bias=False, pad=k//2.
     After Model.fuse() (models/yolo.py:315-323) the module has a biased conv and no bn."""
     pad = k // 2 if pad is None else pad
@@ -30,14 +53,16 @@ def conv_bn_act(x, sd, p, k=1, s=1, pad=None, act=True, eps=1e-3):
         y = _bn(F.conv2d(x, sd[p + 'conv.weight'], None, s, pad), sd, p + 'bn.', eps)
     else:
         y = F.conv2d(x, sd[p + 'conv.weight'], sd.get(p + 'conv.bias'), s, pad)
-    return silu(y) if act else y
+    y = silu(y) if act else y
+    return y if raw else q(y)
 
 
 def bottleneck(x, sd, p, shortcut=True, eps=1e-3):
     """Bottleneck.forward — models/common.py:119-137 (e=1.0 inside C3): x + cv2(cv1(x))."""
-    y = conv_bn_act(conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps), sd, p + 'cv2.', 3, eps=eps)
     c1, c2 = sd[p + 'cv1.conv.weight'].shape[1], sd[p + 'cv2.conv.weight'].shape[0]
-    return x + y if (shortcut and c1 == c2) else y
+    add = shortcut and c1 == c2
+    y = conv_bn_act(conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps), sd, p + 'cv2.', 3, eps=eps, raw=add)
+    return q(x + y) if add else y      # the residual add lives in cv2's epilogue: one rounding after the sum
 
 
 def c3(x, sd, p, n=1, shortcut=True, eps=1e-3):
@@ -58,7 +83,7 @@ def coordatt(x, sd, p, eps=1e-3):
     yh, yw = torch.split(y, [h, w], dim=2)
     a_h = torch.sigmoid(F.conv2d(yh, sd[p + 'conv_h.weight'], sd[p + 'conv_h.bias']))                      # [n,c,h,1]
     a_w = torch.sigmoid(F.conv2d(yw.permute(0, 1, 3, 2), sd[p + 'conv_w.weight'], sd[p + 'conv_w.bias']))  # [n,c,1,w]
-    return x * a_w * a_h
+    return q(x * a_w * a_h)
 
 
 def space_to_depth(x):
@@ -85,22 +110,22 @@ def scconv_gate(x, k3o, k2o):
 
 def scconv(x, sd, p, stride, pooling_r=4, eps=1e-3):
     """SCConv.forward — models/common.py:1279-1316 (no activation anywhere inside)."""
-    k2o = _bn(F.conv2d(F.avg_pool2d(x, pooling_r, pooling_r), sd[p + 'k2.1.weight'], None, 1, 1), sd, p + 'k2.2.', eps)
-    k3o = _bn(F.conv2d(x, sd[p + 'k3.0.weight'], None, 1, 1), sd, p + 'k3.1.', eps)
-    g = scconv_gate(x, k3o, k2o)
-    return _bn(F.conv2d(g, sd[p + 'k4.0.weight'], None, stride, 1), sd, p + 'k4.1.', eps)
+    k2o = q(_bn(F.conv2d(q(F.avg_pool2d(x, pooling_r, pooling_r)), sd[p + 'k2.1.weight'], None, 1, 1), sd, p + 'k2.2.', eps))
+    k3o = _bn(F.conv2d(x, sd[p + 'k3.0.weight'], None, 1, 1), sd, p + 'k3.1.', eps)   # stays fp32: the gate is k3's epilogue
+    g = q(scconv_gate(x, k3o, k2o))
+    return q(_bn(F.conv2d(g, sd[p + 'k4.0.weight'], None, stride, 1), sd, p + 'k4.1.', eps))
 
 
 def adconcat(xs, w, epsilon=1e-4):
     """AdConcat2/3.forward — models/common.py:1003-1008,1021-1026."""
     weight = w / (torch.sum(w, dim=0) + epsilon)
-    return torch.cat([weight[i] * x for i, x in enumerate(xs)], 1)
+    return torch.cat([q(weight[i] * x) for i, x in enumerate(xs)], 1)
 
 
 def adapt_add2(xs, w, epsilon=1e-4):
     """Adapt_Add2.forward — models/common.py:1040-1045."""
     weight = w / (torch.sum(w, dim=0) + epsilon)
-    return silu(weight[0] * xs[0] + weight[1] * xs[1])
+    return q(silu(weight[0] * xs[0] + weight[1] * xs[1]))
 
 
 def adapt_add3(xs, sd, p, epsilon=1e-4):
@@ -108,7 +133,7 @@ def adapt_add3(xs, sd, p, epsilon=1e-4):
     w = sd[p + 'w']
     weight = w / (torch.sum(w, dim=0) + epsilon)
     cv = lambda t: F.conv2d(t, sd[p + 'conv.weight'], sd[p + 'conv.bias'])
-    return silu(weight[0] * cv(xs[0]) + weight[1] * cv(xs[1]) + weight[2] * xs[2])
+    return q(silu(weight[0] * cv(xs[0]) + weight[1] * cv(xs[1]) + weight[2] * xs[2]))
 
 
 def maxpool_cascade(x, k=5):
@@ -177,6 +202,7 @@ def forward_model(cfg: dict, sd: dict, x: torch.Tensor, strides, eps=1e-3):
     `sd` = state_dict of the model (keys `model.{i}....`).  Returns (pred, raw_list, per-layer outputs)."""
     gd, nc = cfg['depth_multiple'], cfg['nc']
     ys, outs = [], []
+    x = q(x)
     for i, (f, n, m, args) in enumerate(cfg['backbone'] + cfg['head']):
         p = f'model.{i}.'
         if f != -1:

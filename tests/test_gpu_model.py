@@ -93,3 +93,61 @@ def test_half_and_uint8_inputs_and_fuse():
         e = m(x)[0].dense().clone()
     assert rel(c, a) < 0.15, rel(c, a)
     assert rel(e, a) < 0.15, rel(e, a)
+
+
+@pytest.mark.parametrize('cfg', ['yolov5s', 'ablation-ca-scconv-sppfcspc-bifpn'])
+def test_model_vs_bf16_storage_oracle(cfg):
+    """The parity test proper for the bf16 path (north_star tolerance: 1e-2 in bf16).  Both sides hold IDENTICAL
+    weights (conv weights rounded to bf16 once) and the oracle rounds to bf16 exactly where the kernel path stores
+    bf16 (oracle.blocks.bf16_storage).  Every layer of the model is run on the kernel path with the ORACLE's
+    tensors as its inputs (teacher forcing), so each comparison is "same inputs, same weights": what is left is
+    arithmetic (accumulation order, tanh.approx SiLU, a one-ulp flip now and then).  A free-running chain is
+    printed for information only: an untrained net amplifies one-ulp flips ~1.3x per layer (oracle-vs-oracle shows
+    the same growth for fp32-vs-bf16 storage), which says nothing about any single kernel.
+    Tolerance per layer: max|err| <= 1e-2 * max(1, max|ref|) (1e-2 absolute for O(1) activations; the calibrated
+    random-init head reaches |activations| ~ 5e3 at this input size, where one bf16 ulp is 16-32) and relative L2
+    <= 1e-2; decoded boxes within 1e-2 of the image size, confidences within 1e-2 absolute."""
+    from dma_yolo_b200.models import yolo as Y
+    from dma_yolo_b200.ops import Up
+    from dma_yolo_b200.utils.calib import build_calibrated
+    m = build_calibrated(cfg + '.yaml', seed=0)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 4:
+                p.copy_(p.bfloat16().float())
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    strides = m.stride.tolist()
+    S = 128
+    x = torch.rand(2, 3, S, S, generator=torch.Generator().manual_seed(11)).bfloat16().float()
+    cfgd = yaml.safe_load(open(Y.CFG_DIR / (cfg + '.yaml')))
+    with torch.no_grad(), O.bf16_storage():
+        ref_pred, _, ref_layers = O.forward_model(cfgd, sd, x, strides)
+    m = m.cuda().eval()
+    worst, rl2 = [], []
+    with torch.no_grad():
+        for i, mod in enumerate(m.model):
+            f = mod.f
+            if isinstance(f, int):
+                xin = (x if i == 0 else ref_layers[i - 1]).cuda() if f == -1 else ref_layers[f].cuda()
+            else:
+                xin = [(ref_layers[i - 1] if j == -1 else ref_layers[j]).cuda() for j in f]
+            y = mod(xin)
+            if i == len(m.model) - 1:
+                dense = y[0].dense().float().cpu()
+                box_err = float(((dense[..., :4] - ref_pred[..., :4]).abs() / S).max())
+                conf_err = float((dense[..., 4:] - ref_pred[..., 4:]).abs().max())
+                break
+            y = (y.materialize() if isinstance(y, Up) else y).float().cpu()
+            r = ref_layers[i]
+            assert y.shape == r.shape, (i, y.shape, r.shape)
+            worst.append(float((y - r).abs().max() / max(1.0, float(r.abs().max()))))
+            rl2.append(float((y - r).norm() / (r.norm() + 1e-12)))
+    print('teacher-forced per-layer max|err|/max(1,max|ref|):', ' '.join(f'{v:.4f}' for v in worst))
+    print('teacher-forced per-layer rel L2:', ' '.join(f'{v:.4f}' for v in rl2))
+    print(f'decoded prediction: max box error {box_err:.5f} of the image size, max confidence error {conf_err:.5f}')
+    assert max(worst) <= 1e-2, worst
+    assert max(rl2) <= 1e-2, rl2
+    assert box_err < 1e-2 and conf_err < 1e-2, (box_err, conf_err)
+    # information: the free-running chain
+    _, _, outs = layer_outputs(m, x.cuda())
+    print('free-running chain, per-layer rel L2:', ' '.join(f'{float((o - r).norm() / (r.norm() + 1e-12)):.4f}' for o, r in zip(outs, ref_layers)))

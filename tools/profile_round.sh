@@ -25,7 +25,7 @@ $NCU --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.
 
 # full captures: memory-bound kernels of the warm step
 $NCU --profile-from-start off --set full -c 24 \
-    -k regex:'filter_|ca_|coordatt|pool_plane|adconcat|avgpool|nms_greedy|prep_kernel|tiefix' \
+    -k regex:'filter_|ca_|coordatt|pool_|adconcat|avgpool|nms_greedy|prep_kernel|img_' \
     -o $OUT/prof_membound -f python tools/prof_one.py model > $OUT/ncu_membound.log 2>&1
 
 # full captures: representative conv shapes (isolated, third launch)
@@ -36,6 +36,7 @@ prof_conv() {  # name cin cout k s ho
 }
 prof_conv c256k3_40 256 256 3 1 40
 prof_conv c64k3_160 64 64 3 1 160
+prof_conv c128k3_80 128 128 3 1 80
 prof_conv c256k1_40 256 256 1 1 40
 prof_conv c1024k3_20 1024 1024 3 1 20
 ls -la $OUT > $OUT/ls.txt
