@@ -124,3 +124,43 @@ def test_nms_oracle_vs_torchvision_random():
             want = torchvision.ops.nms(b, scores, thr).numpy()
             got = ON.nms_reference(b.numpy(), scores.numpy(), thr)
             assert np.array_equal(got, want), (trial, thr)
+
+
+def test_metrics_oracle_and_host_port_match_the_executed_reference():
+    """mAP arithmetic (val.process_batch + utils.metrics.ap_per_class): the numpy oracle AND the product's host-side
+    mirror (dma_yolo_b200.val / utils.metrics) against outputs of the executed reference (tests/golden/metrics.npz)."""
+    import numpy as np
+    import torch
+    from dma_yolo_b200 import val as PV
+    from dma_yolo_b200.utils import metrics as PM
+    from dma_yolo_b200.utils.general import xywh2xyxy
+    from oracle import metrics as OM
+    from pathlib import Path
+    d = np.load(Path(__file__).resolve().parent / 'golden' / 'metrics.npz')
+    n_img, S = int(d['n_img']), int(d['S'])
+    dets = [d[f'det_{i}'] for i in range(n_img)]
+    labs = [d[f'lab_{i}'] for i in range(n_img)]
+    iouv = np.linspace(0.5, 0.95, 10).astype(np.float32)
+    stats_o, stats_p = [], []
+    for i in range(n_img):
+        if f'correct_{i}' not in d.files:
+            continue
+        half = labs[i][:, 3:5] * S / 2
+        lab = np.concatenate([labs[i][:, 0:1], labs[i][:, 1:3] * S - half, labs[i][:, 1:3] * S + half], 1).astype(np.float32)
+        if len(labs[i]):
+            co = OM.process_batch(dets[i], lab, iouv)
+            lt = torch.from_numpy(labs[i])
+            cp = PV.process_batch(torch.from_numpy(dets[i]), torch.cat((lt[:, 0:1], xywh2xyxy(lt[:, 1:5] * S)), 1),
+                                  torch.linspace(0.5, 0.95, 10)).numpy()
+            assert np.array_equal(co, d[f'correct_{i}']), i
+            assert np.array_equal(cp, d[f'correct_{i}']), i
+    mp, mr, m50, m = OM.evaluate(dets, labs, (S, S))
+    assert np.allclose([mp, mr, m50, m], d['summary'], atol=1e-9), ([mp, mr, m50, m], d['summary'])
+    # product port of ap_per_class on the reference's own `correct` matrices
+    tp = np.concatenate([d[f'correct_{i}'] for i in range(n_img) if f'correct_{i}' in d.files], 0)
+    conf = np.concatenate([dets[i][:, 4] for i in range(n_img) if f'correct_{i}' in d.files], 0)
+    pcls = np.concatenate([dets[i][:, 5] for i in range(n_img) if f'correct_{i}' in d.files], 0)
+    tcls = np.concatenate([labs[i][:, 0] for i in range(n_img) if (len(dets[i]) or len(labs[i]))], 0)
+    p, r, ap, f1, cls = PM.ap_per_class(tp, conf, pcls, tcls)
+    assert np.allclose(ap, d['ap'], atol=1e-9) and np.allclose(p, d['p'], atol=1e-9) and np.allclose(r, d['r'], atol=1e-9)
+    assert np.array_equal(cls, d['ap_class'])
