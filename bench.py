@@ -307,6 +307,19 @@ def main():
         launches = int(lt.item())
 
     pk = peaks()
+    # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches
+    # of ONE step, from the committed ncu launch list of this workload (profiles/<tag>_launches.json, written by
+    # tools/summarize_profiles.py; ncu cannot run inside this timed process)
+    traffic, traffic_src = None, None
+    try:
+        prof = sorted((ROOT / 'profiles').glob('*_launches.json'))[-1]
+        pj = json.load(open(prof))
+        convs = [v for k, v in pj.items() if 'conv_gemm' in k]
+        if convs and B == BS:
+            traffic = float(sum(v['rd'] + v['wr'] for v in convs))
+            traffic_src = f'{prof.name}: {sum(v["n"] for v in convs)} conv launches of one step (ncu, cold cache)'
+    except Exception:
+        pass
     value = world * B * args.steps / (ms / 1e3)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
@@ -323,7 +336,8 @@ def main():
         gpu_launches=launches, clocks=clk,
         roofline=dict(kernel='conv_gemm_kernel (tcgen05 implicit GEMM, all Conv+BN+SiLU layers)', bound='tensor',
                       achieved=round(achieved, 1) if achieved else None, peak=peak_tf, unit='TFLOP/s',
-                      frac=round(achieved / peak_tf, 3) if achieved else None, traffic=None,
+                      frac=round(achieved / peak_tf, 3) if achieved else None, traffic=traffic, traffic_unit='bytes per step (all conv launches)',
+                      traffic_source=traffic_src,
                       launches_per_step=n_conv // max(args.steps, 1), share_of_step=round(min(conv_ms / ms, 1.0), 3),
                       measured_over=f'{args.steps} further steps of the same workload right after the timed region, one CUDA-event pair per launch',
                       peak_source=f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",

@@ -1030,7 +1030,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   // B multicast over a 2-CTA cluster whenever there are at least two m-tiles and the slice keeps its alignment
   const int sms_q = p->num_sms > 0 ? p->num_sms : sm_count();
   const long long m_tiles_q = (M + BLOCK_M - 1) / BLOCK_M;
-  // Measured on B200 (profiles/r01_notes.md): the 2-CTA multicast is bit-correct but 20-30 % SLOWER than
+  // Measured on B200 (profiles/r1_conv_notes.md): the 2-CTA multicast is bit-correct but 20-30 % SLOWER than
   // independent CTAs (cluster lock-step stalls; L2 already de-duplicates concurrent requests for the same
   // weight tile), so it is opt-in: block_n == -2 requests it.
   int cs = (p->block_n == -2) ? 2 : 1;
