@@ -142,6 +142,49 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: one 256-row MMA across the two SMs of a TPC --------------------------------
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> the pair's even CTA
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// TMA loads issued by either CTA of the pair; the transaction bytes are credited to the EVEN CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c, int w, int h, int n,
+                                                        uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(tmap), "r"(bar & kPeerMask), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+// epilogue hand-back: arrive on the even CTA's barrier (local for the even CTA, remote for its peer)
+__device__ __forceinline__ void mbar_arrive_pair(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -222,6 +265,8 @@ struct __align__(64) ConvArgs {
   int nacc;          // accumulator buffers in TMEM (2..8): the MMA of tile j+nacc waits for the epilogue's TMEM loads of tile j
   int subs, total_subs;      // sub-tiles (one tap x one CK-channel chunk) per pipeline stage / per tile
   int cs;                    // cluster size: the B tile is loaded in `cs` row slices, each multicast to all CTAs
+  int pair;                  // 1: cta_group::2 — the 2 CTAs of a cluster form one 256 x block_n tile (each loads its own 128
+                             //    rows of A and HALF of the weight tile; the even CTA issues the MMAs for both)
   // halo mode (3x3 stride-1 pad-1): an output tile is a 16x8 pixel patch; its 18 x pitch input patch is loaded
   // ONCE per channel chunk and the 9 taps read shifted windows of it (descriptor start = +(r*pitch+s) rows,
   // SBO = one patch row) instead of 9 im2col loads of the same pixels from L2.
@@ -370,7 +415,9 @@ __device__ __forceinline__ void epi_store8(const ConvArgs& a, const uint32_t* r,
   }
 }
 
-template <int MODE>
+// PAIR is a template parameter (not a runtime flag): a kernel image that contains cta_group::2 instructions can only be
+// launched as a cluster (error 912 otherwise), so the single-CTA and the CTA-pair tile shapes are separate images.
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -413,11 +460,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < a.stages; ++i) {
       mbar_init(full_bar + i * 8, 1);
-      mbar_init(empty_bar + i * 8, cs);   // every CTA of the cluster releases the stage (its B slice lands in all)
+      mbar_init(empty_bar + i * 8, PAIR ? 1 : cs);   // multicast mode: every CTA of the cluster releases the stage
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(tfull_bar + i * 8, 1);
-      mbar_init(tempty_bar + i * 8, (uint32_t)(a.epi_warps / a.epi_groups) * 32u);
+      mbar_init(tempty_bar + i * 8, (uint32_t)(a.epi_warps / a.epi_groups) * 32u * (PAIR ? 2u : 1u));
     }
     for (int i = 0; i < kMaxABuf; ++i) {
       mbar_init(afull_bar + i * 8, 1);
@@ -432,7 +479,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     s_scale[i] = in ? a.scale[i] : 0.f;
     s_bias[i] = in ? a.bias[i] : 0.f;
   }
-  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc2(tmem_slot, (uint32_t)a.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
   if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anything multicasts into them
@@ -527,16 +577,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         mbar_wait(empty_bar + stage * 8, phase ^ 1u);
         const uint32_t fb = full_bar + stage * 8;
         const uint32_t sa = stage0 + stage * a.stage_bytes, sb = sa + (a.halo ? 0u : a.subs * a.a_bytes);
-        if (leader) mbar_expect_tx(fb, (uint32_t)nsub * ((a.halo ? 0u : a.a_bytes) + a.b_bytes));
+        if (PAIR) {
+          // the even CTA's barrier collects the bytes of both CTAs (its own expect may come after the peer's first
+          // complete_tx of the phase: the transaction count is signed)
+          if (leader && crank == 0) mbar_expect_tx(fb, 2u * (uint32_t)nsub * (a.a_bytes + a.b_bytes));
+        } else if (leader) {
+          mbar_expect_tx(fb, (uint32_t)nsub * ((a.halo ? 0u : a.a_bytes) + a.b_bytes));
+        }
 #pragma unroll 1
         for (int j = 0; j < nsub; ++j) {
           if (leader) {
-            if (a.halo) {
+            if (PAIR) {
+              if (a.im2col)
+                tma_load_im2col_4d_pair(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+              else
+                tma_load_2d_pair(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, m0);
+              tma_load_2d_pair(sb + j * a.b_bytes, &a.tmB, fb, tap * a.Cin + cc * a.CK, n0 + (int)crank * (a.block_n / 2));
+            } else if (a.halo) {
             } else if (a.im2col)
               tma_load_im2col_4d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
             else
               tma_load_2d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, m0);
-            if (cs > 1)
+            if (PAIR) {
+            } else if (cs > 1)
               tma_load_2d_mc(sb + j * a.b_bytes + crank * b_slice, &a.tmB, fb, tap * a.Cin + cc * a.CK,
                              n0 + (int)crank * b_rows, mc_mask);
             else
@@ -622,6 +685,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           acc_phase ^= 1u;
         }
       }
+    } else if (PAIR && crank != 0) {
+      // CTA pair: the even CTA issues every MMA (they read both CTAs' shared memory and write both CTAs' TMEM)
     } else {
 #pragma unroll 1
     for (int st = cluster_id; st < total_super; st += num_clusters) {
@@ -664,14 +729,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             for (int j = 0; j < nsub; ++j) {
 #pragma unroll 4
               for (int kk = 0; kk < kk_n; ++kk) {  // advance 16 elements = 32 bytes (>>4 = 2) inside the swizzle atom
-                umma_bf16(tmem_d, pack64(a_lo + kk * 2, desc_hi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                if (PAIR) umma_bf16_2(tmem_d, pack64(a_lo + kk * 2, desc_hi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                else umma_bf16(tmem_d, pack64(a_lo + kk * 2, desc_hi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
                 accum = 1;
               }
               a_lo += a_step;
               b_lo += b_step;
             }
           }
-          if (cs > 1) umma_commit_mc(empty_bar + stage * 8, mc_mask);
+          if (PAIR) umma_commit_2(empty_bar + stage * 8);
+          else if (cs > 1) umma_commit_mc(empty_bar + stage * 8, mc_mask);
           else umma_commit(empty_bar + stage * 8);
           if (last_of_chunk) umma_commit(aempty_bar + ab * 8);   // all 9 taps of this patch have been issued
         }
@@ -692,7 +759,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           phase ^= 1u;
         }
       }
-      if (elect_one()) umma_commit(tfull_bar + acc * 8);
+      if (elect_one()) {
+        if (PAIR) umma_commit_2(tfull_bar + acc * 8);
+        else umma_commit(tfull_bar + acc * 8);
+      }
       __syncwarp();
       if (++acc == a.nacc) {
         acc = 0;
@@ -834,7 +904,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           tmem_ld_wait();
           if (cur.last) {   // the accumulators are in registers: hand the TMEM buffer back before the math and the store
             tc_fence_before();
-            mbar_arrive(tempty_bar + acc * 8);
+            if (PAIR) mbar_arrive_pair(tempty_bar + acc * 8);
+            else mbar_arrive(tempty_bar + acc * 8);
           }
           if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the staging tile
           __syncwarp();
@@ -859,7 +930,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           tmem_ld_wait();
           if (cur.last) {
             tc_fence_before();
-            mbar_arrive(tempty_bar + acc * 8);
+            if (PAIR) mbar_arrive_pair(tempty_bar + acc * 8);
+            else mbar_arrive(tempty_bar + acc * 8);
           }
           if (cur.row >= 0) {
             const uint4 z = make_uint4(0, 0, 0, 0);
@@ -874,7 +946,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       if (cur.last && cur.width == 0) {   // a warp without columns in this tile still takes part in the hand-back
         tc_fence_before();
-        mbar_arrive(tempty_bar + acc * 8);
+        if (PAIR) mbar_arrive_pair(tempty_bar + acc * 8);
+        else mbar_arrive(tempty_bar + acc * 8);
       }
       if (cur.last) {
         acc += a.epi_groups;        // next tile of this warp (nacc is even, so a group keeps its slot parity)
@@ -893,7 +966,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   if (cs > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)a.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -1018,8 +1092,23 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   a.num_n_tiles = (p->Cout_pad + bn - 1) / bn;
   a.n_store = p->Cout;
   a.Cout_pad = p->Cout_pad;
+  // ---- CTA-pair mode (cta_group::2): 256 x block_n tiles, each CTA of a 2-CTA cluster loads its own 128 rows of A and
+  // HALF of the weight tile.  For the deep-K layers a 128 x 256 tile is L2->SM bound (85 flop per byte fetched,
+  // profiles/r1_conv_notes.md section 1); the pair fetches (128 + 128) x K per CTA for the same flops: 128 flop/B.
+  const int sms_q = p->num_sms > 0 ? p->num_sms : sm_count();
+  const long long m_tiles_q = (M + BLOCK_M - 1) / BLOCK_M;
+  {
+    const int tx_ = (p->Wo + kHaloTW - 1) / kHaloTW, ty_ = (p->Ho + kHaloTH - 1) / kHaloTH;
+    const double eff_ = (double)p->Ho * p->Wo / ((double)tx_ * kHaloTW * ty_ * kHaloTH);
+    const bool halo_auto = p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !(p->flags & 1) &&
+                           ((p->flags & 2) || (eff_ >= 0.9 && p->Cin <= 128 && (long long)p->N * tx_ * ty_ >= 2LL * sms_q));
+    const bool legal = !halo_auto && p->block_n != -2 && a.CK == 64 && bn >= 128 && (bn % 32) == 0 && m_tiles_q >= 2 &&
+                       sms_q >= 2 && mode != EPI_GENERIC;
+    const bool want = (long long)a.taps * p->Cin >= 1024 && bn == 256 && m_tiles_q >= sms_q;
+    a.pair = legal && ((p->flags & 256) || (want && !(p->flags & 512))) ? 1 : 0;
+  }
   a.a_bytes = (uint32_t)(BLOCK_M * a.CK * 2);
-  a.b_bytes = (uint32_t)(bn * a.CK * 2);
+  a.b_bytes = (uint32_t)((a.pair ? bn / 2 : bn) * a.CK * 2);
   a.total_subs = a.taps * a.c_chunks;
   // several sub-tiles per stage when they are small (one mbarrier round trip per stage, not per 16/32-channel tap)
   int subs = (int)((56u * 1024u) / (a.a_bytes + a.b_bytes));
@@ -1028,14 +1117,13 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   if (subs > 16) subs = 16;
   a.subs = subs;
   // B multicast over a 2-CTA cluster whenever there are at least two m-tiles and the slice keeps its alignment
-  const int sms_q = p->num_sms > 0 ? p->num_sms : sm_count();
-  const long long m_tiles_q = (M + BLOCK_M - 1) / BLOCK_M;
   // Measured on B200 (profiles/r1_conv_notes.md): the 2-CTA multicast is bit-correct but 20-30 % SLOWER than
   // independent CTAs (cluster lock-step stalls; L2 already de-duplicates concurrent requests for the same
   // weight tile), so it is opt-in: block_n == -2 requests it.
   int cs = (p->block_n == -2) ? 2 : 1;
   if ((bn % (8 * cs)) || (((bn / cs) * a.CK * 2) % 1024 && a.CK == 64) || m_tiles_q < 2 || sms_q < 2) cs = 1;
   if (a.CK != 64 && (((bn / cs) * a.CK * 2) % (a.CK == 32 ? 512 : 256))) cs = 1;
+  if (a.pair) cs = 2;
   a.cs = cs;
   // ---- halo mode decision: 3x3 / stride 1 / pad 1 on maps that 16x8 patches tile well, enough tiles to fill the chip
   const int tiles_x = (p->Wo + kHaloTW - 1) / kHaloTW, tiles_y = (p->Ho + kHaloTH - 1) / kHaloTH;
@@ -1099,7 +1187,8 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   a.stages = stages;
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),
   // both K-major, N>>3 at [17,23), M>>4 at [24,29)
-  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) |
+            ((uint32_t)((a.pair ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
   a.scale = (const float*)p->scale;
   a.bias = (const float*)p->bias;
   a.residual = (const __nv_bfloat16*)p->residual;
@@ -1212,8 +1301,10 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   case MODE: {                                                                                                      \
     static bool attr_set = false;                                                                                   \
     if (!attr_set) {                                                                                                \
-      cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            227 * 1024);                                                            \
+      if (e != cudaSuccess) return (int)e;                                                                          \
+      e = cudaFuncSetAttribute(conv_gemm_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       if (e != cudaSuccess) return (int)e;                                                                          \
       attr_set = true;                                                                                              \
     }                                                                                                               \
@@ -1238,7 +1329,8 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     }                                                                                                               \
     cfg.attrs = at;                                                                                                 \
     cfg.numAttrs = nat;                                                                                             \
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE>, a);                                            \
+    cudaError_t e = a.pair ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE, true>, a)                              \
+                           : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE, false>, a);                            \
     if (e != cudaSuccess) return (int)e;                                                                            \
     break;                                                                                                          \
   }

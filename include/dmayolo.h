@@ -70,7 +70,9 @@ const char* dmay_strerror(int code);
  *   set resident in shared memory in halo mode, bit3 / bit4 = force 8 / 16 epilogue warps,
  *   bit5 = never split the epilogue warps into two alternate-tile groups (narrow tiles),
  *   bit6 = two TMEM accumulator buffers instead of 512 / block_n,
- *   bit7 = launch without programmatic dependent launch (the kernel's preamble then waits for the previous kernel). */
+ *   bit7 = launch without programmatic dependent launch (the kernel's preamble then waits for the previous kernel),
+ *   bit8 / bit9 = force / forbid the CTA-pair mode (cta_group::2: a 2-CTA cluster computes one 256 x block_n tile,
+ *   each CTA loading its own 128 rows of A and half of the weight tile). */
 typedef struct dmay_conv_params {
   const void* x;
   const void* w;

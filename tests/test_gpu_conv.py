@@ -172,3 +172,34 @@ def test_conv_cluster_multicast_path():
     for shape in [(2, 64, 32, 16, 64), (1, 256, 24, 24, 256), (1, 128, 17, 13, 128)]:
         y, ref = run_flags(*shape, flags=1, block_n=-2)
         assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'cluster {shape}')
+
+
+PAIR_SHAPES = [(2, 256, 24, 24, 256), (1, 128, 17, 13, 256), (3, 64, 16, 8, 512), (1, 256, 20, 20, 128), (1, 512, 9, 7, 384)]
+
+
+@pytest.mark.parametrize('shape', PAIR_SHAPES, ids=[str(s) for s in PAIR_SHAPES])
+@pytest.mark.parametrize('kw', [dict(), dict(residual=True), dict(gate=True)], ids=['plain', 'residual', 'gate'])
+def test_conv_cta_pair_mode(shape, kw):
+    """flags bit8: cta_group::2 — a 2-CTA cluster computes one 256 x block_n tile (each CTA loads its own 128 rows
+    of A and half of the weight tile, the even CTA issues the MMAs into both CTAs' TMEM).  Odd tile counts (a
+    padding m-tile), M tails, two n-tiles, block_n 128 / 256 and 128-wide last tiles, with every epilogue."""
+    if kw.get('gate') and shape[1] != shape[4]:
+        pytest.skip('the SCConv gate multiplies by x: needs Cin == Cout')
+    y, ref = run_flags(*shape, flags=256 | 1, seed=3, **kw)
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'pair {shape} {kw}')
+
+
+def test_conv_cta_pair_mode_1x1_and_strided():
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    for (n, cin, h, w, cout, k, s) in [(2, 1024, 20, 20, 256, 1, 1), (1, 256, 23, 19, 512, 3, 2), (4, 512, 10, 10, 1024, 1, 1)]:
+        x = bf(torch.randn(n, cin, h, w, generator=g))
+        wt = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+        pk = ops.pack_conv(wt, stride=s, pad=k // 2, device='cuda')
+        ref = F.conv2d(x, wt, None, s, k // 2)
+        ref = ref * torch.sigmoid(ref)
+        y = ops.conv(ops.as_act(x.cuda()), pk, 1, flags=256)
+        y0 = ops.conv(ops.as_act(x.cuda()), pk, 1, flags=512)
+        torch.cuda.synchronize()
+        assert_close(back(y), ref, atol=1e-2, rtol=1e-2, what=f'pair {(n, cin, h, w, cout, k, s)}')
+        assert_close(back(y), back(y0), atol=1e-2, rtol=1e-2, what='pair vs single-CTA tiles')
