@@ -271,11 +271,9 @@ def main():
                 done[i & 1].record(cur)
                 dets = D.non_max_suppression(pred, **NMS_KW)    # public API: list of (n,6) tensors (syncs on counts)
             if world > 1:
-                from dma_yolo_b200.dist import pad_detections
-                p, c = pad_detections(dets, max_det, dev)
-                all_gather_detections(p, c)
-            for j, d in enumerate(dets):                        # D2H of the step's result
-                out_host[j, :d.shape[0]].copy_(d, non_blocking=True)
+                all_gather_detections(dets.padded, dets.counts)
+            out_host.copy_(dets.padded, non_blocking=True)      # D2H of the step's result: the batch buffer the list
+            cnt_host.copy_(dets.counts, non_blocking=True)      # elements are views of, and the per-image counts
             return dets
 
         for ev in done:

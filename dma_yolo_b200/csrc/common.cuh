@@ -79,6 +79,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case DMAY_ACT_SILU: return silu_fast(x);
     case DMAY_ACT_HARDSWISH: return hardswish(x);
     case DMAY_ACT_SIGMOID: return sigmoid_fast(x);
+    case DMAY_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
     default: return x;
   }
 }

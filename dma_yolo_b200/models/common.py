@@ -603,6 +603,265 @@ class C3CA(C3):
         self.m = nn.Sequential(*(CABottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)))
 
 
+# ---- 8f-1: Swin transformer block inside C3 (C3STR) ---------------------------------------------------------------
+class Mlp(nn.Module):
+    """MLP as used in Vision Transformer — models/common.py:97-117."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.drop1 = nn.Dropout(drop)
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop2 = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop2(self.fc2(self.drop1(self.act(self.fc1(x)))))
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample — models/common.py:386-413 (identity in eval)."""
+
+    def __init__(self, drop_prob=None):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if not self.drop_prob or not self.training:
+            return x
+        keep = 1 - self.drop_prob
+        rnd = keep + torch.rand((x.shape[0],) + (1,) * (x.ndim - 1), dtype=x.dtype, device=x.device)
+        return x.div(keep) * rnd.floor_()
+
+
+def window_partition(x, window_size: int):
+    """(B, H, W, C) -> (num_windows*B, ws, ws, C) — models/common.py:415-428."""
+    B, H, W, C = x.shape
+    x = x.view(B, H // window_size, window_size, W // window_size, window_size, C)
+    return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, window_size, window_size, C)
+
+
+def window_reverse(windows, window_size: int, H: int, W: int):
+    """models/common.py:430-446."""
+    B = int(windows.shape[0] / (H * W / window_size / window_size))
+    x = windows.view(B, H // window_size, W // window_size, window_size, window_size, -1)
+    return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(B, H, W, -1)
+
+
+class WindowAttention(nn.Module):
+    """Window based multi-head self attention with relative position bias — models/common.py:448-515."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        self.dim = dim
+        self.window_size = window_size
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim ** -0.5
+        self.relative_position_bias_table = nn.Parameter(
+            torch.zeros((2 * window_size[0] - 1) * (2 * window_size[1] - 1), num_heads))
+        coords = torch.stack(torch.meshgrid([torch.arange(window_size[0]), torch.arange(window_size[1])], indexing='ij'))
+        cf = torch.flatten(coords, 1)
+        rel = (cf[:, :, None] - cf[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += window_size[0] - 1
+        rel[:, :, 1] += window_size[1] - 1
+        rel[:, :, 0] *= 2 * window_size[1] - 1
+        self.register_buffer('relative_position_index', rel.sum(-1))
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.softmax = nn.Softmax(dim=-1)
+
+    def rel_bias(self):
+        """[heads, N, N] relative position bias (gathered table)."""
+        n = self.window_size[0] * self.window_size[1]
+        return self.relative_position_bias_table[self.relative_position_index.view(-1)].view(n, n, -1).permute(2, 0, 1).contiguous()
+
+    def forward(self, x, mask=None):
+        B_, N, C = x.shape
+        qkv = self.qkv(x).reshape(B_, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv.unbind(0)
+        attn = (q * self.scale) @ k.transpose(-2, -1)
+        attn = attn + self.rel_bias().unsqueeze(0)
+        if mask is not None:
+            nW = mask.shape[0]
+            attn = attn.view(B_ // nW, nW, self.num_heads, N, N) + mask.unsqueeze(1).unsqueeze(0)
+            attn = attn.view(-1, self.num_heads, N, N)
+        attn = self.attn_drop(self.softmax(attn))
+        x = (attn @ v).transpose(1, 2).reshape(B_, N, C)
+        return self.proj_drop(self.proj(x))
+
+
+def _linear_pack(owner, slot, lin: nn.Linear, device):
+    """A Linear as a 1x1 convolution for the implicit-GEMM kernel (cached like the conv packs)."""
+    key = (str(device),) + _ver(lin.weight, lin.bias)
+    cache = owner.__dict__.setdefault('_b200_packs', {})
+    pk = cache.get(slot)
+    if pk is None or pk.key != key:
+        pk = ops.pack_conv(lin.weight.view(lin.out_features, lin.in_features, 1, 1), conv_bias=lin.bias, device=device)
+        pk.key = key
+        cache[slot] = pk
+    return pk
+
+
+class SwinTransformerLayer(_PackMixin, nn.Module):
+    """models/common.py:517-634.  Note the reference reads its NCHW input as (b, c, w, h): windows, shift mask and
+    relative positions live in the TRANSPOSED spatial frame; the kernel path reproduces that by index arithmetic."""
+
+    def __init__(self, c, num_heads, window_size=7, shift_size=0, mlp_ratio=4, qkv_bias=False, drop=0., attn_drop=0.,
+                 drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        if num_heads > 10:
+            drop_path = 0.1
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        self.norm1 = norm_layer(c)
+        self.attn = WindowAttention(c, window_size=(window_size, window_size), num_heads=num_heads, qkv_bias=qkv_bias,
+                                    attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.norm2 = norm_layer(c)
+        self.mlp = Mlp(in_features=c, hidden_features=int(c * mlp_ratio), act_layer=act_layer, drop=drop)
+
+    def create_mask(self, x, H, W):
+        """models/common.py:567-591, including its quirk: the first h-slice is the TUPLE (0, -ws), i.e. the two rows
+        0 and Hp-ws, not a range."""
+        ws, ss = self.window_size, self.shift_size
+        Hp = int(math.ceil(H / ws)) * ws
+        Wp = int(math.ceil(W / ws)) * ws
+        img_mask = torch.zeros((1, Hp, Wp, 1), device=x.device)
+        h_slices = ((0, -ws), slice(-ws, -ss), slice(-ss, None))
+        w_slices = (slice(0, -ws), slice(-ws, -ss), slice(-ss, None))
+        cnt = 0
+        for h in h_slices:
+            for w in w_slices:
+                img_mask[:, h, w, :] = cnt
+                cnt += 1
+        mw = window_partition(img_mask, ws).view(-1, ws * ws)
+        am = mw.unsqueeze(1) - mw.unsqueeze(2)
+        return am.masked_fill(am != 0, -100.0).masked_fill(am == 0, 0.0)
+
+    def forward(self, x):
+        if kernel_path(self, x) and self._kernel_ok():
+            return self.forward_b200(x)
+        b, c, w, h = x.shape
+        x = x.permute(0, 3, 2, 1).contiguous()
+        attn_mask = self.create_mask(x, h, w)
+        shortcut = x
+        x = self.norm1(x)
+        ws = self.window_size
+        pad_r = (ws - w % ws) % ws
+        pad_b = (ws - h % ws) % ws
+        x = F.pad(x, (0, 0, 0, pad_r, 0, pad_b))
+        _, hp, wp, _ = x.shape
+        if self.shift_size > 0:
+            shifted = torch.roll(x, shifts=(-self.shift_size, -self.shift_size), dims=(1, 2))
+        else:
+            shifted, attn_mask = x, None
+        xw = window_partition(shifted, ws).view(-1, ws * ws, c)
+        aw = self.attn(xw, mask=attn_mask).view(-1, ws, ws, c)
+        shifted = window_reverse(aw, ws, hp, wp)
+        x = torch.roll(shifted, shifts=(self.shift_size, self.shift_size), dims=(1, 2)) if self.shift_size > 0 else shifted
+        if pad_r > 0 or pad_b > 0:
+            x = x[:, :h, :w, :].contiguous()
+        x = shortcut + self.drop_path(x)
+        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x.permute(0, 3, 2, 1).contiguous()
+
+    def _kernel_ok(self):
+        a = self.attn
+        return (self.window_size == 8 and a.dim == a.num_heads * 32 and a.qkv.bias is None
+                and isinstance(self.norm1, nn.LayerNorm) and isinstance(self.mlp.act, nn.GELU)
+                and getattr(self.mlp.act, 'approximate', 'none') == 'none')
+
+    def _aux(self, dev, H, W):
+        """fp32 device operands derived from the parameters: LN affine, gathered relative bias, shift mask per (H, W)."""
+        a = self.attn
+        key = (str(dev),) + _ver(self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
+                                 a.relative_position_bias_table)
+        cache = self.__dict__.setdefault('_b200_packs', {})
+        aux = cache.get('aux')
+        if aux is None or aux['key'] != key:
+            f = lambda t: t.detach().float().to(dev).contiguous()
+            aux = dict(key=key, g1=f(self.norm1.weight), b1=f(self.norm1.bias), g2=f(self.norm2.weight), b2=f(self.norm2.bias),
+                       rel=f(a.rel_bias()), masks={})
+            cache['aux'] = aux
+        mask = None
+        if self.shift_size > 0:
+            mask = aux['masks'].get((H, W))
+            if mask is None:
+                # the reference calls create_mask(x, h, w) with h = x.shape[3], w = x.shape[2] of the NCHW input
+                mask = aux['masks'][(H, W)] = self.create_mask(torch.zeros(1), W, H).float().to(dev).contiguous()
+        return aux, mask
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        n, c, H, W = x.shape
+        dev = x.device
+        aux, mask = self._aux(dev, H, W)
+        a = self.attn
+        y = ops.layernorm(x, aux['g1'], aux['b1'], self.norm1.eps)
+        qkv = ops.conv(y, _linear_pack(self, 'qkv', a.qkv, dev), ACT_NONE)
+        att = ops.window_attention(qkv, aux['rel'], mask, a.num_heads, self.shift_size, a.scale)
+        x1 = ops.conv(att, _linear_pack(self, 'proj', a.proj, dev), ACT_NONE, residual=x)
+        y2 = ops.layernorm(x1, aux['g2'], aux['b2'], self.norm2.eps)
+        hdn = ops.conv(y2, _linear_pack(self, 'fc1', self.mlp.fc1, dev), ops.ACT_GELU)
+        return ops.conv(hdn, _linear_pack(self, 'fc2', self.mlp.fc2, dev), ACT_NONE, residual=x1, out=out)
+
+
+class SwinTransformerBlock(nn.Module):
+    """models/common.py:636-654."""
+
+    def __init__(self, c1, c2, num_heads, num_layers, window_size=8):
+        super().__init__()
+        self.conv = None
+        if c1 != c2:
+            self.conv = Conv(c1, c2)
+        self.window_size = window_size
+        self.shift_size = window_size // 2
+        self.tr = nn.Sequential(*(SwinTransformerLayer(c2, num_heads=num_heads, window_size=window_size,
+                                                       shift_size=0 if (i % 2 == 0) else self.shift_size)
+                                  for i in range(num_layers)))
+
+    def forward(self, x):
+        if self.conv is not None:
+            x = self.conv(x)
+        return self.tr(x)
+
+    def forward_b200(self, x, out=None):
+        if self.conv is not None:
+            x = self.conv.forward_b200(x)
+        return _run_chain(self.tr, x, out)
+
+
+class C3STR(C3):
+    """C3 module with SwinTransformerBlock() — models/common.py:191-196."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__(c1, c2, n, shortcut, g, e)
+        c_ = int(c2 * e)
+        self.m = SwinTransformerBlock(c_, c_, c_ // 32, n)
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        n, _, h, w = x.shape
+        c_ = self.cv1.conv.out_channels
+        slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
+        merged = self._merged_cv12(x.device)
+        if merged is not None:
+            ops.conv(x, merged[0], merged[1], out=slab)
+            t = slab[:, :c_]
+        else:
+            t = self.cv1.forward_b200(x)
+            self.cv2.forward_b200(x, out=slab[:, c_:])
+        self.m.forward_b200(t, out=slab[:, :c_])      # the last Swin layer writes the first half of the concat slab
+        return self.cv3.forward_b200(slab, out=out)
+
+
 class SPPCSPC(nn.Module):
     """CSP SPP — models/common.py:1237-1255."""
 

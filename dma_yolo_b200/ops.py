@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import CONSTS, DmayError, call
 
-ACT_NONE, ACT_SILU, ACT_HSWISH, ACT_SIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_HSWISH, ACT_SIGMOID, ACT_GELU = 0, 1, 2, 3, 4
 _DT = {torch.bfloat16: CONSTS["DMAY_DT_BF16"], torch.float32: CONSTS["DMAY_DT_F32"],
        torch.float16: CONSTS["DMAY_DT_F16"], torch.uint8: CONSTS["DMAY_DT_U8"]}
 
@@ -414,6 +414,34 @@ def coordatt(x: torch.Tensor, pk: CoordAttPack, out=None, return_gates=False):
         f.update(pooled=pooled.data_ptr(), gates=gates.data_ptr())
     call("dmay_coordatt", _stream(x), **f)
     return (out, pooled, gates) if return_gates else out
+
+
+# --------------------------------------------------------------------------------------------
+# 8f-1 Swin pieces (C3STR): LayerNorm over channels, window attention
+# --------------------------------------------------------------------------------------------
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out=None) -> torch.Tensor:
+    """nn.LayerNorm(C) applied to the channel vector of every pixel of an NHWC activation."""
+    x = as_act(x)
+    n, c, h, w = x.shape
+    if out is None:
+        out = empty_nhwc(n, c, h, w, x.device)
+    call("dmay_layernorm", _stream(x), x=x.data_ptr(), y=out.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+         npix=n * h * w, C=c, ldx=ld_of(x), ldy=ld_of(out), eps=float(eps))
+    return out
+
+
+def window_attention(qkv: torch.Tensor, rel_bias: torch.Tensor, mask, heads: int, shift: int, scale: float, out=None):
+    """W-MSA / SW-MSA on the qkv tensor [N, 3C, H, W] (NHWC) -> [N, C, H, W]; padding, shift and window (un)partition are
+    index arithmetic inside the kernel (models/common.py:483-515, 603-627)."""
+    qkv = as_act(qkv)
+    n, c3, h, w = qkv.shape
+    c = c3 // 3
+    if out is None:
+        out = empty_nhwc(n, c, h, w, qkv.device)
+    call("dmay_window_attention", _stream(qkv), qkv=qkv.data_ptr(), out=out.data_ptr(), rel_bias=rel_bias.data_ptr(),
+         mask=mask.data_ptr() if mask is not None else 0, N=n, H=h, W=w, C=c, heads=heads, window=8, shift=int(shift),
+         ldq=ld_of(qkv), ldo=ld_of(out), scale=float(scale))
+    return out
 
 
 # --------------------------------------------------------------------------------------------

@@ -165,4 +165,13 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
         dense = prediction.dense() if isinstance(prediction, LazyPred) else prediction
         out, cnt = ops.nms_batched(dense, conf_thres, iou_thres, **kw)
     counts = cnt.tolist()  # one D2H of N ints: the list-of-tensors return type needs the sizes
-    return [out[i, :c] for i, c in enumerate(counts)]
+    dets = Detections(out[i, :c] for i, c in enumerate(counts))
+    dets.padded, dets.counts = out, cnt
+    return dets
+
+
+class Detections(list):
+    """The reference's return type (a list of (n,6) tensors) plus the batch buffers its elements are views of:
+    `padded` [N, max_det, 6] fp32 and `counts` [N] int32 on the device — one D2H / one all_gather moves the batch."""
+    padded = None
+    counts = None

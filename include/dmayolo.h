@@ -39,6 +39,7 @@ extern "C" {
 #define DMAY_ACT_SILU 1
 #define DMAY_ACT_HARDSWISH 2
 #define DMAY_ACT_SIGMOID 3
+#define DMAY_ACT_GELU 4      /* exact (erf) GELU, nn.GELU default */
 
 #define DMAY_DT_BF16 0
 #define DMAY_DT_F32 1
@@ -466,6 +467,48 @@ typedef struct dmay_nms_params {
   double iou_thres;
 } dmay_nms_params;
 int dmay_nms_greedy(const dmay_nms_params* p, dmay_stream_t stream);
+
+/* ---- 8f-1: SwinTransformerLayer pieces (models/common.py:452-634; C3STR in cfg-3) ----------------------------
+ * The four Linear layers run as 1x1 convolutions on dmay_conv_bn_act (act = DMAY_ACT_GELU for mlp.fc1).
+ * dmay_layernorm: nn.LayerNorm over the C channels of every pixel (biased variance), bf16 in / out, fp32 affine. */
+typedef struct dmay_layernorm_params {
+  const void* x;
+  void* y;
+  const void* gamma;
+  const void* beta;
+  long long npix;
+  int C;
+  int ldx;
+  int ldy;
+  float eps;
+} dmay_layernorm_params;
+int dmay_layernorm(const dmay_layernorm_params* p, dmay_stream_t stream);
+
+/* dmay_window_attention: WindowAttention.forward (models/common.py:483-515) together with the layer's padding, cyclic
+ * shift, window_partition / window_reverse and crop (models/common.py:603-627) as index arithmetic.
+ *   qkv  [N, H, W, ldq] bf16, channel = which*C + head*32 + d (output of the qkv Linear, no bias)
+ *   out  [N, H, W, ldo] bf16, channel = head*32 + d           (input of the proj Linear)
+ *   rel_bias [heads][64][64] fp32: relative_position_bias_table gathered through relative_position_index
+ *   mask [nW][64][64] fp32 (0 / -100) for shifted layers, NULL otherwise; nW ordered as the reference's
+ *        window_partition of its (h, w) = (our W, our H) frame
+ * window must be 8 and C == heads * 32 (what C3STR builds: SwinTransformerBlock(c_, c_, c_//32, n)). */
+typedef struct dmay_winattn_params {
+  const void* qkv;
+  void* out;
+  const void* rel_bias;
+  const void* mask;
+  int N;
+  int H;
+  int W;
+  int C;
+  int heads;
+  int window;
+  int shift;
+  int ldq;
+  int ldo;
+  float scale;
+} dmay_winattn_params;
+int dmay_window_attention(const dmay_winattn_params* p, dmay_stream_t stream);
 
 /* ---- measurement helpers ---------------------------------------------------------------
  * plain vectorised copy (roofline calibration inside bench.py) and L2 flush (memset-like

@@ -223,6 +223,10 @@ def forward_model(cfg: dict, sd: dict, x: torch.Tensor, strides, eps=1e-3):
                 x = conv_bn_act(xin, sd, p, k, s, pad, eps=eps)
         elif m == 'C3':
             x = c3(xin, sd, p, n, a[1] if len(a) > 1 else True, eps)
+        elif m == 'C3STR':
+            x = c3str(xin, sd, p, n, eps)
+        elif m == 'C3CA':
+            x = c3ca(xin, sd, p, n, a[1] if len(a) > 1 else True, eps)
         elif m == 'SCConv':
             x = scconv(xin, sd, p, a[1], eps=eps)
         elif m in ('CA', 'CoorAttention'):
@@ -256,3 +260,85 @@ def forward_model(cfg: dict, sd: dict, x: torch.Tensor, strides, eps=1e-3):
         ys.append(x)
         outs.append(x)
     return x, None, outs
+
+
+# ---- 8f-1: Swin transformer layer / C3STR (models/common.py:448-654, 191-196) -------------------------------------
+def swin_shift_labels(Rp, Sp, ws, ss):
+    """Region labels of SwinTransformerLayer.create_mask (models/common.py:567-591) on the padded (rows, cols) grid.
+    The reference's first row selector is the TUPLE (0, -ws): it labels the two rows 0 and Rp-ws, not a range; later
+    assignments overwrite earlier ones."""
+    lab = torch.zeros(Rp, Sp)
+    row_sets = ([0, Rp - ws], list(range(Rp - ws, Rp - ss)), list(range(Rp - ss, Rp)))
+    col_sets = (list(range(0, Sp - ws)), list(range(Sp - ws, Sp - ss)), list(range(Sp - ss, Sp)))
+    cnt = 0
+    for rows in row_sets:
+        for cols in col_sets:
+            for r in rows:
+                for c in cols:
+                    lab[r, c] = cnt
+            cnt += 1
+    return lab
+
+
+def swin_layer(x, sd, p, heads, ws=8, shift=0, eps=1e-5):
+    """SwinTransformerLayer.forward (models/common.py:593-634) with explicit index arithmetic.  x is NCHW; the
+    reference reads it as (b, c, w, h) and works on the transposed map (b, h, w, c)."""
+    b, c, D2, D3 = x.shape
+    hd = c // heads
+    t = x.permute(0, 3, 2, 1)                                    # rows R = D3, cols S = D2
+    R, S = D3, D2
+    Rp, Sp = -(-R // ws) * ws, -(-S // ws) * ws
+    y = q(F.layer_norm(t, (c,), sd[p + 'norm1.weight'], sd[p + 'norm1.bias'], eps))
+    yp = torch.zeros(b, Rp, Sp, c)
+    yp[:, :R, :S] = y                                            # zero padding AFTER the norm
+    qkv = q(yp @ sd[p + 'attn.qkv.weight'].t())                  # no bias: padded tokens give q = k = v = 0
+    table, index = sd[p + 'attn.relative_position_bias_table'], sd[p + 'attn.relative_position_index']
+    n_tok = ws * ws
+    bias = table[index.reshape(-1).long()].reshape(n_tok, n_tok, heads).permute(2, 0, 1)   # [heads, N, N]
+    lab = swin_shift_labels(Rp, Sp, ws, shift) if shift > 0 else None
+    out = torch.zeros(b, Rp, Sp, c)
+    scale = hd ** -0.5
+    ri = torch.arange(ws).repeat_interleave(ws)
+    si = torch.arange(ws).repeat(ws)
+    for wr in range(Rp // ws):
+        for wc in range(Sp // ws):
+            rows = (wr * ws + ri + shift) % Rp                   # roll(-shift): shifted[i] = x[(i + shift) % n]
+            cols = (wc * ws + si + shift) % Sp
+            tok = qkv[:, rows, cols]                             # [b, N, 3c]
+            qq, kk, vv = tok.reshape(b, n_tok, 3, heads, hd).permute(2, 0, 3, 1, 4)
+            a = (qq * scale) @ kk.transpose(-2, -1) + bias[None]
+            if lab is not None:
+                l = lab[wr * ws + ri, wc * ws + si]              # labels are defined on the SHIFTED grid
+                a = a + torch.where(l[None, :] != l[:, None], torch.tensor(-100.0), torch.tensor(0.0))[None, None]
+            o = torch.softmax(a, -1) @ vv                        # [b, heads, N, hd]
+            out[:, rows, cols] = o.permute(0, 2, 1, 3).reshape(b, n_tok, c)
+    att = q(out[:, :R, :S])
+    x1 = q(t + att @ sd[p + 'attn.proj.weight'].t() + sd[p + 'attn.proj.bias'])
+    y2 = q(F.layer_norm(x1, (c,), sd[p + 'norm2.weight'], sd[p + 'norm2.bias'], eps))
+    hdn = q(F.gelu(y2 @ sd[p + 'mlp.fc1.weight'].t() + sd[p + 'mlp.fc1.bias']))
+    x2 = q(x1 + hdn @ sd[p + 'mlp.fc2.weight'].t() + sd[p + 'mlp.fc2.bias'])
+    return x2.permute(0, 3, 2, 1).contiguous()
+
+
+def c3str(x, sd, p, n=1, eps=1e-3, ws=8):
+    """C3STR.forward — models/common.py:191-196 on top of C3 (159-182): cv3(cat(swin(cv1 x), cv2 x))."""
+    y = conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps)
+    heads = y.shape[1] // 32
+    for i in range(n):
+        y = swin_layer(y, sd, f'{p}m.tr.{i}.', heads, ws, 0 if i % 2 == 0 else ws // 2)
+    return conv_bn_act(torch.cat((y, conv_bn_act(x, sd, p + 'cv2.', 1, eps=eps)), 1), sd, p + 'cv3.', 1, eps=eps)
+
+
+def ca_bottleneck(x, sd, p, shortcut=True, eps=1e-3):
+    """CABottleneck.forward — models/common.py:1209-1227 (e=1.0 inside C3CA): x + ca(cv2(cv1(x)))."""
+    y = coordatt(conv_bn_act(conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps), sd, p + 'cv2.', 3, eps=eps), sd, p + 'ca.', eps)
+    c1, c2 = sd[p + 'cv1.conv.weight'].shape[1], sd[p + 'cv2.conv.weight'].shape[0]
+    return q(x + y) if (shortcut and c1 == c2) else y
+
+
+def c3ca(x, sd, p, n=1, shortcut=True, eps=1e-3):
+    """C3CA.forward — models/common.py:1229-1235 on top of C3 (159-182)."""
+    y = conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps)
+    for i in range(n):
+        y = ca_bottleneck(y, sd, f'{p}m.{i}.', shortcut, eps)
+    return conv_bn_act(torch.cat((y, conv_bn_act(x, sd, p + 'cv2.', 1, eps=eps)), 1), sd, p + 'cv3.', 1, eps=eps)

@@ -23,6 +23,11 @@ CTORS = {
     'adconcat2': lambda: C.AdConcat2(), 'adconcat3': lambda: C.AdConcat3(), 'adapt_add2': lambda: C.Adapt_Add2(),
     'adapt_add3': lambda: C.Adapt_Add3(16, 16, 32), 'sppf_20': lambda: C.SPPF(32, 32, 5),
     'sppfcspc_12x9': lambda: C.SPPFCSPC(32, 32), 'spp': lambda: C.SPP(32, 32), 'sppcspc': lambda: C.SPPCSPC(32, 32),
+    'swin_layer_16x24': lambda: C.SwinTransformerLayer(64, num_heads=2, window_size=8, shift_size=0),
+    'swin_layer_shift_16x24': lambda: C.SwinTransformerLayer(64, num_heads=2, window_size=8, shift_size=4),
+    'swin_layer_shift_13x10': lambda: C.SwinTransformerLayer(64, num_heads=2, window_size=8, shift_size=4),
+    'swin_layer_13x10': lambda: C.SwinTransformerLayer(32, num_heads=1, window_size=8, shift_size=0),
+    'c3str_n2_20x12': lambda: C.C3STR(64, 128, 2, False),
 }
 
 
