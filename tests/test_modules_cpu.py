@@ -100,7 +100,7 @@ def test_fuse_only_top_level_convs():
 
 
 def test_unknown_module_is_reported():
-    cfg = dict(nc=2, depth_multiple=1, width_multiple=1, anchors=3, backbone=[[-1, 1, 'C3STR', [64]]],
+    cfg = dict(nc=2, depth_multiple=1, width_multiple=1, anchors=3, backbone=[[-1, 1, 'C3HB', [64]]],
                head=[[[0], 1, 'Detect', ['nc', 'anchors']]])
     with pytest.raises(NotImplementedError):
         D.Model(cfg)
