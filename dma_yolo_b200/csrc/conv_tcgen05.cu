@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     int stage = 0, ab = 0;
     uint32_t phase = 0, aphase = 0;
     const int HoWo = a.Ho * a.Wo;
-    if (a.b_resident) {
+    if (a.b_resident == 1) {
       // weights once (barrier full[0]), then one input patch per (tile, channel chunk)
       if (elect_one()) {
         mbar_expect_tx(full_bar, (uint32_t)a.total_subs * a.b_bytes);
@@ -536,6 +536,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     } else {
     const int b_rows = a.block_n / cs;                       // rows of the B tile this CTA fetches
     const uint32_t b_slice = (uint32_t)(b_rows * a.CK * 2);
+    if (a.b_resident == 2) {
+      // plain (non-halo) weights-resident mode: the whole [block_n x K] weight set is fetched ONCE per CTA (single
+      // n-tile, <= ~130 KB), the pipeline then streams activation tiles only.  For the shallow-K 1x1 layers the weight
+      // tile was 2/3 of the L2 -> SM traffic of every tile.
+      if (elect_one()) {
+        mbar_expect_tx(afull_bar, (uint32_t)a.total_subs * a.b_bytes);
+#pragma unroll 1
+        for (int g = 0; g < a.total_subs; ++g) tma_load_2d(bres0 + g * a.b_bytes, &a.tmB, afull_bar, g * a.CK, 0);
+      }
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int st = cluster_id; st < total_super; st += num_clusters) {
       const int sq = fdiv(st, a.fd_nn);
@@ -582,7 +593,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           // complete_tx of the phase: the transaction count is signed)
           if (leader && crank == 0) mbar_expect_tx(fb, 2u * (uint32_t)nsub * (a.a_bytes + a.b_bytes));
         } else if (leader) {
-          mbar_expect_tx(fb, (uint32_t)nsub * ((a.halo ? 0u : a.a_bytes) + a.b_bytes));
+          mbar_expect_tx(fb, (uint32_t)nsub * ((a.halo ? 0u : a.a_bytes) + (a.b_resident == 2 ? 0u : a.b_bytes)));
         }
 #pragma unroll 1
         for (int j = 0; j < nsub; ++j) {
@@ -598,7 +609,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               tma_load_im2col_4d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
             else
               tma_load_2d(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, m0);
-            if (PAIR) {
+            if (PAIR || a.b_resident == 2) {
             } else if (cs > 1)
               tma_load_2d_mc(sb + j * a.b_bytes + crank * b_slice, &a.tmB, fb, tap * a.Cin + cc * a.CK,
                              n0 + (int)crank * b_rows, mc_mask);
@@ -639,7 +650,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const uint32_t desc_hi_halo = a.halo_sbo_enc | (1u << 14) | (a.layout_type << 29);   // SBO = one patch row
     const uint32_t row_bytes = (uint32_t)a.CK * 2u;
     const uint32_t a_step = a.a_bytes >> 4, b_step = a.b_bytes >> 4;
-    if (a.b_resident) {
+    if (a.b_resident == 1) {
       mbar_wait(full_bar, 0);   // resident weights have landed
 #pragma unroll 1
       for (int st = cluster_id; st < total_super; st += num_clusters) {
@@ -688,6 +699,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     } else if (PAIR && crank != 0) {
       // CTA pair: the even CTA issues every MMA (they read both CTAs' shared memory and write both CTAs' TMEM)
     } else {
+    if (a.b_resident == 2) mbar_wait(afull_bar, 0);   // resident weights have landed
 #pragma unroll 1
     for (int st = cluster_id; st < total_super; st += num_clusters) {
       mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
@@ -709,6 +721,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const bool last_of_chunk = a.halo && (tap + nsub == a.taps);
         if (elect_one()) {
           uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (1u << 16), b_lo = ((sb >> 4) & 0x3FFFu) | (1u << 16);
+          if (a.b_resident == 2) b_lo = (((bres0 + (uint32_t)(it * a.subs) * a.b_bytes) >> 4) & 0x3FFFu) | (1u << 16);
           if (a.halo) {
 #pragma unroll 1
             for (int j = 0; j < nsub; ++j) {
@@ -1177,12 +1190,29 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     }
     halo_bytes_total = a.bres_bytes + (uint32_t)a.n_abuf * a.a_halo_bytes;
   } else {
-    a.stage_bytes = ((uint32_t)subs * (a.a_bytes + a.b_bytes) + 1023u) & ~1023u;
+    const uint32_t w_bytes = (uint32_t)a.total_subs * a.b_bytes;
+    const uint32_t avail = 227u * 1024u - 1024u - kTailBytes - 64u;
+    if (!a.pair && a.cs == 1 && a.num_n_tiles == 1 && w_bytes <= 132u * 1024u && !(p->flags & 1024) &&
+        (p->flags & 2048) && avail >   // opt-in: measured no faster than streaming (profiles/r1_conv_notes.md section 4)
+        ((w_bytes + 1023u) & ~1023u) + 2u * a.a_bytes) {
+      a.b_resident = 2;
+      a.bres_bytes = (w_bytes + 1023u) & ~1023u;
+      const uint32_t left = avail - a.bres_bytes;
+      subs = (int)(left / 3u / a.a_bytes);            // aim for >= 3 stages
+      if (subs < 1) subs = 1;
+      if (subs > a.total_subs) subs = a.total_subs;
+      if (subs > 4) subs = 4;
+      a.subs = subs;
+      a.stage_bytes = ((uint32_t)subs * a.a_bytes + 1023u) & ~1023u;
+      halo_bytes_total = a.bres_bytes;
+    } else {
+      a.stage_bytes = ((uint32_t)subs * (a.a_bytes + a.b_bytes) + 1023u) & ~1023u;
+    }
   }
   const uint32_t budget = 227u * 1024u - 1024u - kTailBytes - 64u - halo_bytes_total;
   int stages = (int)(budget / a.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (a.b_resident) stages = 1;
+  if (a.b_resident == 1) stages = 1;
   else if (stages < 2) return DMAY_EUNSUPPORTED;
   a.stages = stages;
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13),

@@ -73,7 +73,8 @@ const char* dmay_strerror(int code);
  *   bit6 = two TMEM accumulator buffers instead of 512 / block_n,
  *   bit7 = launch without programmatic dependent launch (the kernel's preamble then waits for the previous kernel),
  *   bit8 / bit9 = force / forbid the CTA-pair mode (cta_group::2: a 2-CTA cluster computes one 256 x block_n tile,
- *   each CTA loading its own 128 rows of A and half of the weight tile). */
+ *   each CTA loading its own 128 rows of A and half of the weight tile), bit10 / bit11 = never / always (where legal) keep
+ *   the weights resident in shared memory on the plain (non-halo) path. */
 typedef struct dmay_conv_params {
   const void* x;
   const void* w;

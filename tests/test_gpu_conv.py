@@ -203,3 +203,22 @@ def test_conv_cta_pair_mode_1x1_and_strided():
         torch.cuda.synchronize()
         assert_close(back(y), ref, atol=1e-2, rtol=1e-2, what=f'pair {(n, cin, h, w, cout, k, s)}')
         assert_close(back(y), back(y0), atol=1e-2, rtol=1e-2, what='pair vs single-CTA tiles')
+
+
+def test_conv_weights_resident_plain_path():
+    """flags bit11: the whole weight set stays in shared memory on the plain (1x1 / im2col) path and only activation
+    tiles are streamed (auto-selected for shallow-K layers with many tiles); checked against the streamed-weights path."""
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    for (n, cin, h, w, cout, k, s) in [(2, 256, 24, 20, 256, 1, 1), (3, 128, 17, 13, 128, 1, 1), (2, 64, 16, 16, 128, 3, 2),
+                                       (1, 64, 9, 7, 48, 1, 1), (2, 32, 12, 12, 64, 3, 1)]:
+        x = bf(torch.randn(n, cin, h, w, generator=g))
+        wt = bf(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+        pk = ops.pack_conv(wt, stride=s, pad=k // 2, device='cuda')
+        ref = F.conv2d(x, wt, None, s, k // 2)
+        ref = ref * torch.sigmoid(ref)
+        y = ops.conv(ops.as_act(x.cuda()), pk, 1, flags=2048 | 1)
+        y0 = ops.conv(ops.as_act(x.cuda()), pk, 1, flags=1024 | 1)
+        torch.cuda.synchronize()
+        assert_close(back(y), ref, atol=1e-2, rtol=1e-2, what=f'resident {(n, cin, h, w, cout, k, s)}')
+        assert torch.equal(back(y), back(y0)), 'resident and streamed weights must give identical results'
