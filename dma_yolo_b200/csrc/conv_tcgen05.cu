@@ -172,6 +172,12 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap,
       "l"(tmap), "r"(bar & kPeerMask), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c, int w, int h, int n,
                                                         uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -577,8 +583,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         if (a.halo && tap == 0) {   // first tap of a channel chunk: fetch the input patch once
           mbar_wait(aempty_bar + ab * 8, aphase ^ 1u);
           if (leader) {
-            mbar_expect_tx(afull_bar + ab * 8, a.a_halo_tx);
-            tma_load_4d(abuf0 + ab * a.a_halo_bytes, &a.tmA, afull_bar + ab * 8, cc * a.CK, w0, h0, n_img);
+            if (PAIR) {   // both CTAs' patches are credited to the even CTA's barrier
+              if (crank == 0) mbar_expect_tx(afull_bar + ab * 8, 2u * a.a_halo_tx);
+              tma_load_4d_pair(abuf0 + ab * a.a_halo_bytes, &a.tmA, afull_bar + ab * 8, cc * a.CK, w0, h0, n_img);
+            } else {
+              mbar_expect_tx(afull_bar + ab * 8, a.a_halo_tx);
+              tma_load_4d(abuf0 + ab * a.a_halo_bytes, &a.tmA, afull_bar + ab * 8, cc * a.CK, w0, h0, n_img);
+            }
           }
           if (++ab == a.n_abuf) {
             ab = 0;
@@ -591,7 +602,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         if (PAIR) {
           // the even CTA's barrier collects the bytes of both CTAs (its own expect may come after the peer's first
           // complete_tx of the phase: the transaction count is signed)
-          if (leader && crank == 0) mbar_expect_tx(fb, 2u * (uint32_t)nsub * (a.a_bytes + a.b_bytes));
+          if (leader && crank == 0) mbar_expect_tx(fb, 2u * (uint32_t)nsub * ((a.halo ? 0u : a.a_bytes) + a.b_bytes));
         } else if (leader) {
           mbar_expect_tx(fb, (uint32_t)nsub * ((a.halo ? 0u : a.a_bytes) + (a.b_resident == 2 ? 0u : a.b_bytes)));
         }
@@ -599,7 +610,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         for (int j = 0; j < nsub; ++j) {
           if (leader) {
             if (PAIR) {
-              if (a.im2col)
+              if (a.halo) {
+              } else if (a.im2col)
                 tma_load_im2col_4d_pair(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
               else
                 tma_load_2d_pair(sa + j * a.a_bytes, &a.tmA, fb, cc * a.CK, m0);
@@ -732,7 +744,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               const uint32_t hhi = desc_hi_halo;   // base-offset field stays 0: UMMA swizzles on absolute smem address bits
 #pragma unroll 4
               for (int kk = 0; kk < kk_n; ++kk) {
-                umma_bf16(tmem_d, pack64(hlo + kk * 2, hhi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                if (PAIR) umma_bf16_2(tmem_d, pack64(hlo + kk * 2, hhi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                else umma_bf16(tmem_d, pack64(hlo + kk * 2, hhi), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
                 accum = 1;
               }
               b_lo += b_step;
@@ -753,7 +766,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if (PAIR) umma_commit_2(empty_bar + stage * 8);
           else if (cs > 1) umma_commit_mc(empty_bar + stage * 8, mc_mask);
           else umma_commit(empty_bar + stage * 8);
-          if (last_of_chunk) umma_commit(aempty_bar + ab * 8);   // all 9 taps of this patch have been issued
+          if (last_of_chunk) {   // all 9 taps of this patch have been issued
+            if (PAIR) umma_commit_2(aempty_bar + ab * 8);
+            else umma_commit(aempty_bar + ab * 8);
+          }
         }
         accum = 1;
         if (a.halo) {
@@ -1115,9 +1131,10 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     const double eff_ = (double)p->Ho * p->Wo / ((double)tx_ * kHaloTW * ty_ * kHaloTH);
     const bool halo_auto = p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !(p->flags & 1) &&
                            ((p->flags & 2) || (eff_ >= 0.9 && p->Cin <= 128 && (long long)p->N * tx_ * ty_ >= 2LL * sms_q));
-    const bool legal = !halo_auto && p->block_n != -2 && a.CK == 64 && bn >= 128 && (bn % 32) == 0 && m_tiles_q >= 2 &&
-                       sms_q >= 2 && mode != EPI_GENERIC;
-    const bool want = (long long)a.taps * p->Cin >= 1024 && bn == 256 && m_tiles_q >= sms_q;
+    const bool legal = p->block_n != -2 && a.CK == 64 && bn >= 128 && (bn % 32) == 0 && m_tiles_q >= 2 && sms_q >= 2 &&
+                       mode != EPI_GENERIC;
+    // halo + pair (128-channel 3x3 layers): per CTA one input patch + HALF of the 9-tap weight set per chunk
+    const bool want = (long long)a.taps * p->Cin >= 1024 && (bn == 256 || (halo_auto && bn >= 128)) && m_tiles_q >= sms_q;
     a.pair = legal && ((p->flags & 256) || (want && !(p->flags & 512))) ? 1 : 0;
   }
   a.a_bytes = (uint32_t)(BLOCK_M * a.CK * 2);
@@ -1141,7 +1158,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   // ---- halo mode decision: 3x3 / stride 1 / pad 1 on maps that 16x8 patches tile well, enough tiles to fill the chip
   const int tiles_x = (p->Wo + kHaloTW - 1) / kHaloTW, tiles_y = (p->Ho + kHaloTH - 1) / kHaloTH;
   const double patch_eff = (double)p->Ho * p->Wo / ((double)tiles_x * kHaloTW * tiles_y * kHaloTH);
-  bool halo = p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !(p->flags & 1) && cs == 1;
+  bool halo = p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !(p->flags & 1) && (cs == 1 || a.pair);
   if (halo && !(p->flags & 2)) {
     // worth it where the conv is L2->SM bound: few channels per tile (C <= 128) on maps the patches tile >= 90 %
     halo = patch_eff >= 0.9 && p->Cin <= 128 && (long long)p->N * tiles_x * tiles_y >= 2LL * sms_q;
@@ -1158,7 +1175,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     a.halo_sbo_enc = (uint32_t)(a.halo_pitch * a.CK * 2) >> 4;
     const uint32_t smem_avail = 227u * 1024u - 1024u - kTailBytes - 64u;
     const uint32_t w_bytes = (uint32_t)a.total_subs * a.b_bytes;           // all taps x chunks of this n-tile
-    if (a.num_n_tiles == 1 && w_bytes <= 100u * 1024u && !(p->flags & 4)) {
+    if (a.num_n_tiles == 1 && w_bytes <= 100u * 1024u && !(p->flags & 4) && !a.pair) {
       a.b_resident = 1;
       a.bres_bytes = (w_bytes + 1023u) & ~1023u;
       int nb = (int)((smem_avail - a.bres_bytes) / a.a_halo_bytes);

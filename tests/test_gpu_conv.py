@@ -222,3 +222,15 @@ def test_conv_weights_resident_plain_path():
         torch.cuda.synchronize()
         assert_close(back(y), ref, atol=1e-2, rtol=1e-2, what=f'resident {(n, cin, h, w, cout, k, s)}')
         assert torch.equal(back(y), back(y0)), 'resident and streamed weights must give identical results'
+
+
+@pytest.mark.parametrize('shape', [(2, 128, 32, 24, 128), (1, 128, 19, 23, 256), (3, 64, 16, 8, 128), (1, 256, 17, 9, 128)],
+                         ids=str)
+@pytest.mark.parametrize('kw', [dict(), dict(residual=True), dict(gate=True)], ids=['plain', 'residual', 'gate'])
+def test_conv_cta_pair_with_halo(shape, kw):
+    """flags bit8 | bit1: CTA-pair tiles on the halo path — each CTA of the pair loads its own 18x10 input patch and half
+    of the 9-tap weight set; the even CTA's MMAs read both CTAs' patches through shifted-window descriptors."""
+    if kw.get('gate') and shape[1] != shape[4]:
+        pytest.skip('the SCConv gate multiplies by x: needs Cin == Cout')
+    y, ref = run_flags(*shape, flags=256 | 2, seed=4, **kw)
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'pair+halo {shape} {kw}')
