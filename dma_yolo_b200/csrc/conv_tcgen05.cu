@@ -244,6 +244,8 @@ enum EpiMode : int {
   EPI_GATE = 3,        // bf16( (s*acc + b) * sigmoid(gate_x + up(gate_k)) )
   EPI_LINEAR_F32 = 4,  // fp32( s*acc + b )                       (Detect head logits)
   EPI_GENERIC = 5,     // runtime activation / optional residual / either dtype (rare layers)
+  EPI_LINEAR_RES = 6,  // bf16( s*acc + b + residual )              (Swin proj / fc2: Linear + shortcut)
+  EPI_GELU = 7,        // bf16( gelu(s*acc + b) )                   (Swin mlp.fc1, exact erf GELU)
 };
 
 struct __align__(64) ConvArgs {
@@ -360,7 +362,11 @@ __device__ __forceinline__ uint4 epi_compute8(const uint32_t* r, const float* sc
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = silu_t(f[j]);
   }
-  if (MODE == EPI_SILU_RES) {
+  if (MODE == EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+  }
+  if (MODE == EPI_SILU_RES || MODE == EPI_LINEAR_RES) {
     float rs[8];
     unpack8(aux0, rs);
 #pragma unroll
@@ -823,8 +829,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int my_tiles = a.epi_groups == 2 ? (cta_tiles + 1 - grp) / 2 : cta_tiles;
     const int items = my_tiles * (cpw > 0 ? cpw : 1);                                  // cpw == 0: one "empty" item per tile
 
-    constexpr bool kStaged = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_LINEAR || MODE == EPI_GATE);
-    constexpr bool kOpnd = (MODE == EPI_SILU_RES || MODE == EPI_GATE);
+    constexpr bool kStaged = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_LINEAR || MODE == EPI_GATE ||
+                              MODE == EPI_LINEAR_RES || MODE == EPI_GELU);
+    constexpr bool kOpnd = (MODE == EPI_SILU_RES || MODE == EPI_GATE || MODE == EPI_LINEAR_RES);
     const uint32_t out_stage = tail + (uint32_t)ew * 2048u;
     uint4* out_ptr = reinterpret_cast<uint4*>(tail_ptr + ew * 2048);
     const uint32_t op_stage = tail + epi_stage_bytes + (uint32_t)ew * 2048u;
@@ -1093,11 +1100,13 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   if (p->gate_x) mode = (!out_f32 && !p->residual) ? EPI_GATE : -1;
   else if (out_f32) mode = (p->act == DMAY_ACT_NONE && !p->residual) ? EPI_LINEAR_F32 : EPI_GENERIC;
   else if (p->act == DMAY_ACT_SILU) mode = p->residual ? EPI_SILU_RES : EPI_SILU;
-  else if (p->act == DMAY_ACT_NONE && !p->residual) mode = EPI_LINEAR;
+  else if (p->act == DMAY_ACT_NONE) mode = p->residual ? EPI_LINEAR_RES : EPI_LINEAR;
+  else if (p->act == DMAY_ACT_GELU && !p->residual) mode = EPI_GELU;
   else mode = EPI_GENERIC;
   if (mode < 0) return DMAY_EUNSUPPORTED;
-  const bool staged = mode == EPI_SILU || mode == EPI_SILU_RES || mode == EPI_LINEAR || mode == EPI_GATE;
-  a.opnd_stage = (mode == EPI_SILU_RES || mode == EPI_GATE) ? 1 : 0;
+  const bool staged = mode == EPI_SILU || mode == EPI_SILU_RES || mode == EPI_LINEAR || mode == EPI_GATE ||
+                      mode == EPI_LINEAR_RES || mode == EPI_GELU;
+  a.opnd_stage = (mode == EPI_SILU_RES || mode == EPI_GATE || mode == EPI_LINEAR_RES) ? 1 : 0;
   a.sb_floats = ((p->Cout_pad + bn - 1) / bn) * bn;
   if (a.sb_floats > kMaxCout) return DMAY_EUNSUPPORTED;
   // epilogue warps, measured (profiles/r1_conv_notes.md): 16 warps win only where a tile's MMA is a few hundred
@@ -1331,8 +1340,8 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     };
     if (!encode_epi(&a.tmY, p->y, p->ldy)) return DMAY_EDRIVER;
     if (a.opnd_stage) {
-      const void* src = mode == EPI_SILU_RES ? p->residual : p->gate_x;
-      const int ld = mode == EPI_SILU_RES ? p->ldr : p->ldgx;
+      const void* src = mode == EPI_GATE ? p->gate_x : p->residual;
+      const int ld = mode == EPI_GATE ? p->ldgx : p->ldr;
       if (!encode_epi(&a.tmR, src, ld)) return DMAY_EDRIVER;
     }
   } else {
@@ -1388,6 +1397,8 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     DMAY_LAUNCH_MODE(EPI_GATE)
     DMAY_LAUNCH_MODE(EPI_LINEAR_F32)
     DMAY_LAUNCH_MODE(EPI_GENERIC)
+    DMAY_LAUNCH_MODE(EPI_LINEAR_RES)
+    DMAY_LAUNCH_MODE(EPI_GELU)
   }
 #undef DMAY_LAUNCH_MODE
   return finish_launch();

@@ -162,6 +162,170 @@ __global__ void __launch_bounds__(kTok) window_attention_kernel(const __nv_bfloa
   }
 }
 
+// ---- window attention on mma.sync (bf16 m16n8k16, fp32 accumulate): one warp per (image, window, head) ----------
+// A 64-token x 32-dim head is far below a tcgen05 tile (and there are tens of thousands of them), so this uses the
+// warp-level tensor path: S = (Q K^T) per 16-query block in registers, softmax on the fragments (rows live in lane
+// quads), P re-used as the A operand of P V straight from the accumulator registers (no shared-memory round trip).
+// The scalar kernel above stays as the reference implementation (tests compare the two).
+constexpr int kAttnWarps = 3;   // 3 x 15 KB of staged q, k, v stays under the 48 KB static limit
+constexpr int kPitch = 40;   // bf16 per staged row (80 bytes): ldmatrix rows fall on distinct bank groups
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kAttnWarps * 32) window_attention_mma_kernel(
+    const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const float* __restrict__ rel_bias,
+    const float* __restrict__ mask, int H, int W, int C, int heads, int ldq, int ldo, int shift, int nWr, int nWc,
+    float scale, long long items) {
+  __shared__ __align__(16) __nv_bfloat16 sm[kAttnWarps][3][kTok][kPitch];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * kAttnWarps + warp;
+  if (item >= items) return;                       // whole warp leaves together; no block-level sync below
+  long long b = item;
+  const int head = (int)(b % heads);
+  b /= heads;
+  const int wc = (int)(b % nWc);
+  b /= nWc;
+  const int wr = (int)(b % nWr);
+  const int n = (int)(b / nWr);
+  const int R = W, S = H, Rp = nWr * kWs, Sp = nWc * kWs;
+  // ---- stage q, k, v of the 64 tokens: lane handles tokens lane and lane + 32 ----
+  long long pixs[2];
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int t = lane + 32 * h2;
+    int r = wr * kWs + (t >> 3) + shift, s_ = wc * kWs + (t & 7) + shift;
+    if (r >= Rp) r -= Rp;
+    if (s_ >= Sp) s_ -= Sp;
+    const bool real = r < R && s_ < S;
+    pixs[h2] = real ? ((long long)n * H + s_) * W + r : -1;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (real) v = ld16(qkv + pixs[h2] * ldq + m * C + head * kHd + k * 8);
+        *reinterpret_cast<uint4*>(&sm[warp][m][t][k * 8]) = v;
+      }
+    }
+  }
+  __syncwarp();
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(&sm[warp][0][0][0]);
+  const uint32_t k_base = (uint32_t)__cvta_generic_to_shared(&sm[warp][1][0][0]);
+  const uint32_t v_base = (uint32_t)__cvta_generic_to_shared(&sm[warp][2][0][0]);
+  const float* bias_h = rel_bias + (long long)head * kTok * kTok;
+  const float* mask_w = mask != nullptr ? mask + ((long long)wr * nWc + wc) * kTok * kTok : nullptr;
+#pragma unroll 1
+  for (int mt = 0; mt < 4; ++mt) {
+    // Q fragments of this 16-row block, both k-steps
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kof = ks * 16 + (lane >> 4) * 8;
+      ldsm_x4(q_base + (uint32_t)(row * kPitch + kof) * 2u, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+    float sacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+    }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {       // pairs of key tiles (16 keys)
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t b0, b1, b2, b3;
+        const int krow = np * 16 + (lane & 7) + (lane >> 4) * 8, kof = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(k_base + (uint32_t)(krow * kPitch + kof) * 2u, b0, b1, b2, b3);
+        mma_bf16(sacc[2 * np], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+        mma_bf16(sacc[2 * np + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+      }
+    }
+    // scale + relative position bias (+ shift mask), row-wise softmax (rows g and g+8 of the block)
+    const int i0 = mt * 16 + g, i1 = i0 + 8;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int j = nt * 8 + tq * 2;
+      float2 bb0 = *reinterpret_cast<const float2*>(bias_h + i0 * kTok + j);
+      float2 bb1 = *reinterpret_cast<const float2*>(bias_h + i1 * kTok + j);
+      if (mask_w != nullptr) {
+        const float2 m0 = *reinterpret_cast<const float2*>(mask_w + i0 * kTok + j);
+        const float2 m1 = *reinterpret_cast<const float2*>(mask_w + i1 * kTok + j);
+        bb0.x += m0.x; bb0.y += m0.y; bb1.x += m1.x; bb1.y += m1.y;
+      }
+      sacc[nt][0] = fmaf(sacc[nt][0], scale, bb0.x);
+      sacc[nt][1] = fmaf(sacc[nt][1], scale, bb0.y);
+      sacc[nt][2] = fmaf(sacc[nt][2], scale, bb1.x);
+      sacc[nt][3] = fmaf(sacc[nt][3], scale, bb1.y);
+      mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sacc[nt][0] = __expf(sacc[nt][0] - mx0); sacc[nt][1] = __expf(sacc[nt][1] - mx0);
+      sacc[nt][2] = __expf(sacc[nt][2] - mx1); sacc[nt][3] = __expf(sacc[nt][3] - mx1);
+      d0 += sacc[nt][0] + sacc[nt][1];
+      d1 += sacc[nt][2] + sacc[nt][3];
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    const float inv0 = 1.0f / d0, inv1 = 1.0f / d1;
+    // O = P V: P from the accumulator registers (bf16), V through transposed ldmatrix
+    float oacc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[nt][e] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {       // 16 keys per step
+      const uint32_t a0 = pack_bf2(sacc[2 * kk][0] * inv0, sacc[2 * kk][1] * inv0);
+      const uint32_t a1 = pack_bf2(sacc[2 * kk][2] * inv1, sacc[2 * kk][3] * inv1);
+      const uint32_t a2 = pack_bf2(sacc[2 * kk + 1][0] * inv0, sacc[2 * kk + 1][1] * inv0);
+      const uint32_t a3 = pack_bf2(sacc[2 * kk + 1][2] * inv1, sacc[2 * kk + 1][3] * inv1);
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) {     // pairs of 8-dim tiles
+        uint32_t b0, b1, b2, b3;
+        const int vrow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dof = dp * 16 + (lane >> 4) * 8;
+        ldsm_x4_t(v_base + (uint32_t)(vrow * kPitch + dof) * 2u, b0, b1, b2, b3);
+        mma_bf16(oacc[2 * dp], a0, a1, a2, a3, b0, b1);
+        mma_bf16(oacc[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    // rows i0 / i1 of the window -> pixels; lanes of a quad cover 8 consecutive dims of one 8-dim tile
+    const long long p0 = __shfl_sync(0xffffffffu, pixs[i0 >> 5], i0 & 31);
+    const long long p1 = __shfl_sync(0xffffffffu, pixs[i1 >> 5], i1 & 31);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int d = head * kHd + nt * 8 + tq * 2;
+      if (p0 >= 0) *reinterpret_cast<uint32_t*>(out + p0 * ldo + d) = pack_bf2(oacc[nt][0], oacc[nt][1]);
+      if (p1 >= 0) *reinterpret_cast<uint32_t*>(out + p1 * ldo + d) = pack_bf2(oacc[nt][2], oacc[nt][3]);
+    }
+  }
+}
+
 }  // namespace dmay
 
 using namespace dmay;
@@ -199,9 +363,16 @@ int dmay_window_attention(const dmay_winattn_params* p, dmay_stream_t stream) {
   const int nWr = (p->W + kWs - 1) / kWs, nWc = (p->H + kWs - 1) / kWs;       // transposed frame: rows = x, columns = y
   const long long grid = (long long)p->N * nWr * nWc * p->heads;
   if (grid > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
-  window_attention_kernel<<<(int)grid, kTok, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)p->qkv, (__nv_bfloat16*)p->out, (const float*)p->rel_bias, (const float*)p->mask, p->H, p->W,
-      p->C, p->heads, p->ldq, p->ldo, p->shift, nWr, nWc, p->scale);
+  if (p->variant == 1) {   // scalar fp32 reference kernel
+    window_attention_kernel<<<(int)grid, kTok, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)p->qkv, (__nv_bfloat16*)p->out, (const float*)p->rel_bias, (const float*)p->mask, p->H, p->W,
+        p->C, p->heads, p->ldq, p->ldo, p->shift, nWr, nWc, p->scale);
+  } else {
+    const long long blocks = (grid + kAttnWarps - 1) / kAttnWarps;
+    window_attention_mma_kernel<<<(int)blocks, kAttnWarps * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)p->qkv, (__nv_bfloat16*)p->out, (const float*)p->rel_bias, (const float*)p->mask, p->H, p->W,
+        p->C, p->heads, p->ldq, p->ldo, p->shift, nWr, nWc, p->scale, grid);
+  }
   return finish_launch();
 }
 

@@ -430,7 +430,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def window_attention(qkv: torch.Tensor, rel_bias: torch.Tensor, mask, heads: int, shift: int, scale: float, out=None):
+def window_attention(qkv: torch.Tensor, rel_bias: torch.Tensor, mask, heads: int, shift: int, scale: float, out=None,
+                     variant: int = 0):
     """W-MSA / SW-MSA on the qkv tensor [N, 3C, H, W] (NHWC) -> [N, C, H, W]; padding, shift and window (un)partition are
     index arithmetic inside the kernel (models/common.py:483-515, 603-627)."""
     qkv = as_act(qkv)
@@ -440,7 +441,7 @@ def window_attention(qkv: torch.Tensor, rel_bias: torch.Tensor, mask, heads: int
         out = empty_nhwc(n, c, h, w, qkv.device)
     call("dmay_window_attention", _stream(qkv), qkv=qkv.data_ptr(), out=out.data_ptr(), rel_bias=rel_bias.data_ptr(),
          mask=mask.data_ptr() if mask is not None else 0, N=n, H=h, W=w, C=c, heads=heads, window=8, shift=int(shift),
-         ldq=ld_of(qkv), ldo=ld_of(out), scale=float(scale))
+         ldq=ld_of(qkv), ldo=ld_of(out), scale=float(scale), variant=int(variant))
     return out
 
 

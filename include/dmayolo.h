@@ -492,7 +492,9 @@ int dmay_layernorm(const dmay_layernorm_params* p, dmay_stream_t stream);
  *   rel_bias [heads][64][64] fp32: relative_position_bias_table gathered through relative_position_index
  *   mask [nW][64][64] fp32 (0 / -100) for shifted layers, NULL otherwise; nW ordered as the reference's
  *        window_partition of its (h, w) = (our W, our H) frame
- * window must be 8 and C == heads * 32 (what C3STR builds: SwinTransformerBlock(c_, c_, c_//32, n)). */
+ * window must be 8 and C == heads * 32 (what C3STR builds: SwinTransformerBlock(c_, c_, c_//32, n)).
+ * variant 0: one warp per (image, window, head) on mma.sync bf16 tensor instructions (default);
+ * variant 1: scalar fp32 kernel, one thread per query token (kept as the in-library cross-check). */
 typedef struct dmay_winattn_params {
   const void* qkv;
   void* out;
@@ -508,6 +510,7 @@ typedef struct dmay_winattn_params {
   int ldq;
   int ldo;
   float scale;
+  int variant;
 } dmay_winattn_params;
 int dmay_window_attention(const dmay_winattn_params* p, dmay_stream_t stream);
 

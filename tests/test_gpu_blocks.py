@@ -75,3 +75,24 @@ def test_detect_head_lazy_and_dense():
         y[..., 2:4] = (y[..., 2:4] * 2) ** 2 * ag
         z.append(y.reshape(bs, -1, no))
     assert_close(dense, torch.cat(z, 1), atol=1e-5, rtol=1e-4, what='decode of identical logits')
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 16, 24, 0), (2, 64, 16, 24, 4), (1, 128, 13, 10, 4), (3, 32, 8, 8, 0), (1, 256, 20, 36, 4)],
+                         ids=str)
+def test_window_attention_mma_vs_scalar_kernel(shape):
+    """The mma.sync window-attention kernel against the scalar fp32 kernel of the same library on identical qkv
+    (both against the oracle through the Swin block fixtures): padding, shift, mask and the transposed frame."""
+    from dma_yolo_b200 import ops
+    from dma_yolo_b200.models import common as C
+    n, c, h, w, shift = shape
+    torch.manual_seed(c + h + shift)
+    layer = C.SwinTransformerLayer(c, num_heads=c // 32, window_size=8, shift_size=shift).eval()
+    with torch.no_grad():
+        layer.attn.relative_position_bias_table.normal_(0, 0.5)
+    qkv = ops.as_act(torch.randn(n, 3 * c, h, w).bfloat16().float().cuda())
+    rel = layer.attn.rel_bias().float().cuda().contiguous()
+    mask = layer.create_mask(torch.zeros(1), w, h).float().cuda().contiguous() if shift else None
+    a = ops.window_attention(qkv, rel, mask, c // 32, shift, layer.attn.scale, variant=0)
+    b = ops.window_attention(qkv, rel, mask, c // 32, shift, layer.attn.scale, variant=1)
+    torch.cuda.synchronize()
+    assert_close(a.float().cpu(), b.float().cpu(), atol=2e-2, rtol=2e-2, what=f'attention mma vs scalar {shape}')

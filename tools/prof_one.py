@@ -29,8 +29,10 @@ elif kind == 'model':
     import dma_yolo_b200 as D
     from dma_yolo_b200.utils.calib import build_calibrated
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    m = build_calibrated('ablation-ca-scconv-sppfcspc-bifpn.yaml', seed=0).to(dev).eval()
-    x = torch.rand(B, 3, 640, 640, generator=torch.Generator().manual_seed(1)).to(dev)
+    cfg = sys.argv[3] if len(sys.argv) > 3 else 'ablation-ca-scconv-sppfcspc-bifpn.yaml'
+    S = int(sys.argv[4]) if len(sys.argv) > 4 else 640
+    m = build_calibrated(cfg, seed=0).to(dev).eval()
+    x = torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(1)).to(dev)
     with torch.no_grad():
         for it in range(2):
             if it == 1:
