@@ -246,6 +246,7 @@ enum EpiMode : int {
   EPI_GENERIC = 5,     // runtime activation / optional residual / either dtype (rare layers)
   EPI_LINEAR_RES = 6,  // bf16( s*acc + b + residual )              (Swin proj / fc2: Linear + shortcut)
   EPI_GELU = 7,        // bf16( gelu(s*acc + b) )                   (Swin mlp.fc1, exact erf GELU)
+  EPI_LINEAR_MUL = 8,  // bf16( (s*acc + b) * operand )             (GnConv gating: pws_i(x) * dw_{i+1})
 };
 
 struct __align__(64) ConvArgs {
@@ -371,6 +372,12 @@ __device__ __forceinline__ uint4 epi_compute8(const uint32_t* r, const float* sc
     unpack8(aux0, rs);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] += rs[j];
+  }
+  if (MODE == EPI_LINEAR_MUL) {
+    float rs[8];
+    unpack8(aux0, rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= rs[j];
   }
   if (MODE == EPI_GATE) {
     float gx[8], gk[8];
@@ -830,8 +837,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int items = my_tiles * (cpw > 0 ? cpw : 1);                                  // cpw == 0: one "empty" item per tile
 
     constexpr bool kStaged = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_LINEAR || MODE == EPI_GATE ||
-                              MODE == EPI_LINEAR_RES || MODE == EPI_GELU);
-    constexpr bool kOpnd = (MODE == EPI_SILU_RES || MODE == EPI_GATE || MODE == EPI_LINEAR_RES);
+                              MODE == EPI_LINEAR_RES || MODE == EPI_GELU || MODE == EPI_LINEAR_MUL);
+    constexpr bool kOpnd = (MODE == EPI_SILU_RES || MODE == EPI_GATE || MODE == EPI_LINEAR_RES || MODE == EPI_LINEAR_MUL);
     const uint32_t out_stage = tail + (uint32_t)ew * 2048u;
     uint4* out_ptr = reinterpret_cast<uint4*>(tail_ptr + ew * 2048);
     const uint32_t op_stage = tail + epi_stage_bytes + (uint32_t)ew * 2048u;
@@ -1100,13 +1107,14 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   if (p->gate_x) mode = (!out_f32 && !p->residual) ? EPI_GATE : -1;
   else if (out_f32) mode = (p->act == DMAY_ACT_NONE && !p->residual) ? EPI_LINEAR_F32 : EPI_GENERIC;
   else if (p->act == DMAY_ACT_SILU) mode = p->residual ? EPI_SILU_RES : EPI_SILU;
+  else if (p->res_op == 1) mode = (p->act == DMAY_ACT_NONE && p->residual) ? EPI_LINEAR_MUL : -1;
   else if (p->act == DMAY_ACT_NONE) mode = p->residual ? EPI_LINEAR_RES : EPI_LINEAR;
   else if (p->act == DMAY_ACT_GELU && !p->residual) mode = EPI_GELU;
   else mode = EPI_GENERIC;
   if (mode < 0) return DMAY_EUNSUPPORTED;
   const bool staged = mode == EPI_SILU || mode == EPI_SILU_RES || mode == EPI_LINEAR || mode == EPI_GATE ||
-                      mode == EPI_LINEAR_RES || mode == EPI_GELU;
-  a.opnd_stage = (mode == EPI_SILU_RES || mode == EPI_GATE || mode == EPI_LINEAR_RES) ? 1 : 0;
+                      mode == EPI_LINEAR_RES || mode == EPI_GELU || mode == EPI_LINEAR_MUL;
+  a.opnd_stage = (mode == EPI_SILU_RES || mode == EPI_GATE || mode == EPI_LINEAR_RES || mode == EPI_LINEAR_MUL) ? 1 : 0;
   a.sb_floats = ((p->Cout_pad + bn - 1) / bn) * bn;
   if (a.sb_floats > kMaxCout) return DMAY_EUNSUPPORTED;
   // epilogue warps, measured (profiles/r1_conv_notes.md): 16 warps win only where a tile's MMA is a few hundred
@@ -1399,6 +1407,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     DMAY_LAUNCH_MODE(EPI_GENERIC)
     DMAY_LAUNCH_MODE(EPI_LINEAR_RES)
     DMAY_LAUNCH_MODE(EPI_GELU)
+    DMAY_LAUNCH_MODE(EPI_LINEAR_MUL)
   }
 #undef DMAY_LAUNCH_MODE
   return finish_launch();

@@ -862,6 +862,197 @@ class C3STR(C3):
         return self.cv3.forward_b200(slab, out=out)
 
 
+# ---- 8f-2: HorNet block inside C3 (C3HB) ------------------------------------------------------------------------------
+class LayerNorm(nn.Module):
+    """LayerNorm with channels_last (default) or channels_first data format — models/common.py:1385-1409."""
+
+    def __init__(self, normalized_shape, eps=1e-6, data_format='channels_last'):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.bias = nn.Parameter(torch.zeros(normalized_shape))
+        self.eps = eps
+        self.data_format = data_format
+        if self.data_format not in ['channels_last', 'channels_first']:
+            raise NotImplementedError
+        self.normalized_shape = (normalized_shape,)
+
+    def forward(self, x):
+        if self.data_format == 'channels_last':
+            return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+        u = x.mean(1, keepdim=True)
+        s = (x - u).pow(2).mean(1, keepdim=True)
+        x = (x - u) / torch.sqrt(s + self.eps)
+        return self.weight[:, None, None] * x + self.bias[:, None, None]
+
+
+def get_dwconv(dim, kernel, bias):
+    """models/common.py:1348-1349."""
+    return nn.Conv2d(dim, dim, kernel_size=kernel, padding=(kernel - 1) // 2, bias=bias, groups=dim)
+
+
+class GnConv(_PackMixin, nn.Module):
+    """Recursive gated convolution — models/common.py:1318-1346."""
+
+    def __init__(self, c1, c2, ksize=1, stride=1, order=5, gflayer=None, h=14, w=8, s=1.0):
+        super().__init__()
+        self.order = order
+        self.dims = [c1 // 2 ** i for i in range(order)]
+        self.dims.reverse()
+        self.proj_in = nn.Conv2d(c1, 2 * c1, 1)
+        if gflayer is None:
+            self.dwconv = get_dwconv(sum(self.dims), 7, True)
+        else:
+            self.dwconv = gflayer(sum(self.dims), h=h, w=w)
+        self.proj_out = Conv(c1, c2, ksize, stride)
+        self.pws = nn.ModuleList([nn.Conv2d(self.dims[i], self.dims[i + 1], 1) for i in range(order - 1)])
+        self.scale = s
+
+    def forward(self, x, mask=None, dummy=False):
+        if kernel_path(self, x) and self._kernel_ok():
+            return self.forward_b200(x)
+        fused_x = self.proj_in(x)
+        pwa, abc = torch.split(fused_x, (self.dims[0], sum(self.dims)), dim=1)
+        dw_list = torch.split(self.dwconv(abc) * self.scale, self.dims, dim=1)
+        x = pwa * dw_list[0]
+        for i in range(self.order - 1):
+            x = self.pws[i](x) * dw_list[i + 1]
+        return self.proj_out(x)
+
+    def _kernel_ok(self):
+        dw = self.dwconv
+        return (isinstance(dw, nn.Conv2d) and dw.kernel_size == (7, 7) and dw.groups == dw.in_channels and dw.padding == (3, 3)
+                and dw.stride == (1, 1) and self.dims[0] % 2 == 0 and all(d % 8 == 0 for d in self.dims[1:])
+                and self.proj_in.in_channels % 16 == 0)
+
+    def _conv1x1_pack(self, slot, conv, dev):
+        key = (str(dev),) + _ver(conv.weight, conv.bias)
+        cache = self.__dict__.setdefault('_b200_packs', {})
+        pk = cache.get(slot)
+        if pk is None or pk.key != key:
+            pk = ops.pack_conv(conv.weight, conv_bias=conv.bias, device=dev)
+            pk.key = key
+            cache[slot] = pk
+        return pk
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        dev = x.device
+        dims = self.dims
+        fused = ops.conv(x, self._conv1x1_pack('proj_in', self.proj_in, dev), ACT_NONE)          # [pwa | abc]
+        # depth-wise 7x7 over abc; segment i (gating order i) lands at an 8-channel-aligned offset
+        seg_start = [sum(dims[:i]) for i in range(len(dims))]
+        seg_out, o = [], 0
+        for d in dims:
+            seg_out.append(o)
+            o += ops.round_up(d, 8)
+        cache = self.__dict__.setdefault('_b200_packs', {})
+        kdw = (str(dev),) + _ver(self.dwconv.weight, self.dwconv.bias)
+        dwp = cache.get('dw')
+        if dwp is None or dwp[0] != kdw:
+            w49 = self.dwconv.weight.detach().float().reshape(sum(dims), 49).t().contiguous().to(dev)
+            dwp = cache['dw'] = (kdw, w49, self.dwconv.bias.detach().float().to(dev).contiguous())
+        dw = ops.dwconv7(fused, dims[0], dwp[1], dwp[2], self.scale, seg_start, seg_out, o)
+        # recursive gating: x0 = pwa * dw0, x_{i+1} = pws_i(x_i) * dw_{i+1} (the product is the GEMM's epilogue)
+        t = ops.mul_channels(fused[:, :dims[0]], dw[:, :dims[0]], dims[0], ops.round_up(dims[0], 16))
+        n, _, h, w = x.shape
+        for i in range(self.order - 1):
+            d1 = dims[i + 1]
+            buf = torch.zeros((n, h, w, ops.round_up(d1, 16)), device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2) \
+                if d1 % 16 else ops.empty_nhwc(n, d1, h, w, dev)
+            ops.conv(t, self._conv1x1_pack(f'pws{i}', self.pws[i], dev), ACT_NONE, out=buf[:, :d1],
+                     residual=dw[:, seg_out[i + 1]:seg_out[i + 1] + d1], res_mul=True)
+            t = buf
+        return self.proj_out.forward_b200(t[:, :dims[-1]] if t.shape[1] != dims[-1] else t, out=out)
+
+
+class HorBlock(_PackMixin, nn.Module):
+    """HorNet block — models/common.py:1351-1383."""
+
+    def __init__(self, dim, drop_path=0., layer_scale_init_value=1e-6, gnconv=GnConv):
+        super().__init__()
+        self.norm1 = LayerNorm(dim, eps=1e-6, data_format='channels_first')
+        self.gnconv = GnConv(dim, dim)
+        self.norm2 = LayerNorm(dim, eps=1e-6)
+        self.pwconv1 = nn.Linear(dim, 4 * dim)
+        self.act = nn.GELU()
+        self.pwconv2 = nn.Linear(4 * dim, dim)
+        self.gamma1 = nn.Parameter(layer_scale_init_value * torch.ones(dim), requires_grad=True) \
+            if layer_scale_init_value > 0 else None
+        self.gamma2 = nn.Parameter(layer_scale_init_value * torch.ones(dim), requires_grad=True) \
+            if layer_scale_init_value > 0 else None
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+
+    def forward(self, x):
+        if kernel_path(self, x) and self.gnconv._kernel_ok() and x.shape[1] % 8 == 0:
+            return self.forward_b200(x)
+        B, C, H, W = x.shape
+        gamma1 = self.gamma1.view(C, 1, 1) if self.gamma1 is not None else 1
+        x = x + self.drop_path(gamma1 * self.gnconv(self.norm1(x)))
+        inp = x
+        x = self.pwconv2(self.act(self.pwconv1(self.norm2(x.permute(0, 2, 3, 1)))))
+        if self.gamma2 is not None:
+            x = self.gamma2 * x
+        return inp + self.drop_path(x.permute(0, 3, 1, 2))
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        n, c, h, w = x.shape
+        dev = x.device
+        key = (str(dev),) + _ver(self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias, self.gamma1, self.gamma2,
+                                 self.pwconv2.weight, self.pwconv2.bias)
+        cache = self.__dict__.setdefault('_b200_packs', {})
+        aux = cache.get('aux')
+        if aux is None or aux['key'] != key:
+            f = lambda t: t.detach().float().to(dev).contiguous()
+            g2 = (self.gamma2.detach().float() if self.gamma2 is not None else torch.ones(c)).to(dev)
+            fc2 = ops.pack_conv(self.pwconv2.weight.view(c, 4 * c, 1, 1), conv_bias=self.pwconv2.bias, device=dev)
+            fc2.scale = (fc2.scale[:c] * g2).contiguous()          # gamma2 * (W h + b): layer scale folded into the GEMM's
+            fc2.bias = (fc2.bias[:c] * g2).contiguous()            # per-channel scale / bias (c % 16 == 0: no padding rows)
+            aux = dict(key=key, g1=f(self.norm1.weight), b1=f(self.norm1.bias), g2=f(self.norm2.weight), b2=f(self.norm2.bias),
+                       gamma1=f(self.gamma1) if self.gamma1 is not None else torch.ones(c, device=dev), fc2=fc2)
+            cache['aux'] = aux
+        y = ops.layernorm(x, aux['g1'], aux['b1'], self.norm1.eps)
+        g = self.gnconv.forward_b200(y)
+        x1 = ops.axpy_channels(x, g, aux['gamma1'])
+        y2 = ops.layernorm(x1, aux['g2'], aux['b2'], self.norm2.eps)
+        hdn = ops.conv(y2, _linear_pack(self, 'fc1', self.pwconv1, dev), ops.ACT_GELU)
+        return ops.conv(hdn, aux['fc2'], ACT_NONE, residual=x1, out=out)
+
+
+class C3HB(_PackMixin, nn.Module):
+    """CSP bottleneck with HorBlocks — models/common.py:1412-1426."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(HorBlock(c_) for _ in range(n)))
+
+    def forward(self, x):
+        if kernel_path(self, x):
+            return self.forward_b200(x)
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
+
+    _merged_cv12 = C3._merged_cv12
+
+    def forward_b200(self, x, out=None):
+        x = ops.as_act(x)
+        n, _, h, w = x.shape
+        c_ = self.cv1.conv.out_channels
+        slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
+        merged = self._merged_cv12(x.device)
+        if merged is not None:
+            ops.conv(x, merged[0], merged[1], out=slab)
+            t = slab[:, :c_]
+        else:
+            t = self.cv1.forward_b200(x)
+            self.cv2.forward_b200(x, out=slab[:, c_:])
+        _run_chain(self.m, t, slab[:, :c_])
+        return self.cv3.forward_b200(slab, out=out)
+
+
 class SPPCSPC(nn.Module):
     """CSP SPP — models/common.py:1237-1255."""
 

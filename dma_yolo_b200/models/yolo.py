@@ -20,7 +20,7 @@ from ..utils.general import LOGGER, check_version, make_divisible
 from ..utils.torch_utils import copy_attr, fuse_conv_and_bn, initialize_weights, model_info, scale_img, time_sync
 from . import common as _common
 from .common import *  # noqa: F401,F403  (module names are looked up by parse_model)
-from .common import (CA, SM, AdConcat2, AdConcat3, Adapt_Add2, Adapt_Add3, Bottleneck, BottleneckCSP, C3, C3CA, C3STR,
+from .common import (CA, SM, AdConcat2, AdConcat3, Adapt_Add2, Adapt_Add3, Bottleneck, BottleneckCSP, C3, C3CA, C3HB, C3STR,
                      CABottleneck, Concat, Contract, CoorAttention, DWConv, Expand, Focus, SCConv, SPP, SPPCSPC, SPPF,
                      SPPFCSPC, _materialize, _PackMixin, get_conv_pack, kernel_path, space_to_depth)
 from .cspcm import Conv  # shadows common.Conv exactly like `from models.cspcm import *` (models/yolo.py:24)
@@ -296,8 +296,8 @@ def parse_model(d, ch):
     na = (len(anchors[0]) // 2) if isinstance(anchors, list) else anchors
     no = na * (nc + 5)
     scaled = [Conv, _common.Conv, Bottleneck, SPP, SPPF, DWConv, Focus, BottleneckCSP, C3, nn.ConvTranspose2d,
-              CoorAttention, CABottleneck, C3CA, C3STR, SPPCSPC, SPPFCSPC, SCConv]
-    repeated = [BottleneckCSP, C3, C3CA, C3STR]
+              CoorAttention, CABottleneck, C3CA, C3STR, C3HB, SPPCSPC, SPPFCSPC, SCConv]
+    repeated = [BottleneckCSP, C3, C3CA, C3STR, C3HB]
     layers, save, c2 = [], [], ch[-1]
     for i, (f, n, m, args) in enumerate(d['backbone'] + d['head']):
         if isinstance(m, str):

@@ -180,7 +180,7 @@ CONV_FLAGS = int(__import__('os').environ.get('DMAY_CONV_FLAGS', '0'))   # defau
 
 def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor | None = None,
          residual: torch.Tensor | None = None, gate: tuple | None = None, out_fp32: bool = False,
-         block_n: int = 0, num_sms: int = 0, flags: int | None = None) -> torch.Tensor:
+         block_n: int = 0, num_sms: int = 0, flags: int | None = None, res_mul: bool = False) -> torch.Tensor:
     """y = act(scale * conv(x, w) + bias) (+ residual) | (* sigmoid(gate_x + up(gate_k)))."""
     # uint8 images are normalised on the fly (x/255, the `img.float()/255` of val.py:199-202 folded into
     # the layout kernel) — an extension: the reference only accepts float images.
@@ -218,7 +218,7 @@ def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor |
         residual = as_act(residual)
         if tuple(residual.shape) != (n, pk.cout, ho, wo):
             raise DmayError("conv: residual shape mismatch")
-        f.update(residual=residual.data_ptr(), ldr=ld_of(residual))
+        f.update(residual=residual.data_ptr(), ldr=ld_of(residual), res_op=int(res_mul))
     if gate is not None:
         gx, gk = gate
         gx, gk = as_act(gx), as_act(gk)
@@ -614,6 +614,47 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
          img_offsets=img_offsets.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
          max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
     return out, out_counts
+
+
+# --------------------------------------------------------------------------------------------
+# 8f-2 HorBlock / GnConv pieces (C3HB)
+# --------------------------------------------------------------------------------------------
+def dwconv7(x: torch.Tensor, c_off: int, w49: torch.Tensor, bias: torch.Tensor, scale: float, seg_start, seg_out, c_out: int):
+    """7x7 depth-wise conv over channels [c_off, c_off + Cd) of the NHWC tensor x; segment i of the result lands at channel
+    seg_out[i] of a [N, c_out, H, W] tensor (zero-initialised when the segments leave gaps)."""
+    x = as_act(x)
+    n, _, h, w = x.shape
+    cd = w49.shape[1]
+    dense = c_out == cd
+    y = empty_nhwc(n, c_out, h, w, x.device) if dense else torch.zeros((n, h, w, c_out), device=x.device,
+                                                                       dtype=torch.bfloat16).permute(0, 3, 1, 2)
+    f = dict(x=x.data_ptr() + 2 * c_off, w=w49.data_ptr(), bias=bias.data_ptr(), y=y.data_ptr(), N=n, H=h, W=w, Cd=cd,
+             ldx=ld_of(x), ldy=ld_of(y), scale=float(scale), n_seg=len(seg_start))
+    for i, (a, b) in enumerate(zip(seg_start, seg_out)):
+        f[f"seg_start{i}"] = int(a)
+        f[f"seg_out{i}"] = int(b)
+    call("dmay_dwconv7", _stream(x), **f)
+    return y
+
+
+def mul_channels(a: torch.Tensor, b: torch.Tensor, d: int, c_alloc: int):
+    """[N, d] product of the first d channels of two NHWC tensors, in a zero-padded [N, c_alloc, H, W] tensor."""
+    n, _, h, w = a.shape
+    y = torch.zeros((n, h, w, c_alloc), device=a.device, dtype=torch.bfloat16).permute(0, 3, 1, 2)
+    call("dmay_mul_channels", _stream(a), a=a.data_ptr(), b=b.data_ptr(), y=y.data_ptr(), npix=n * h * w, d=d, lda=ld_of(a),
+         ldb=ld_of(b), ldy=c_alloc)
+    return y
+
+
+def axpy_channels(x: torch.Tensor, g: torch.Tensor, gamma: torch.Tensor, out=None):
+    """x + gamma[c] * g."""
+    x, g = as_act(x), as_act(g)
+    n, c, h, w = x.shape
+    if out is None:
+        out = empty_nhwc(n, c, h, w, x.device)
+    call("dmay_axpy_channels", _stream(x), x=x.data_ptr(), g=g.data_ptr(), gamma=gamma.data_ptr(), y=out.data_ptr(),
+         npix=n * h * w, C=c, ldx=ld_of(x), ldg=ld_of(g), ldy=ld_of(out))
+    return out
 
 
 def device_copy(dst: torch.Tensor, src: torch.Tensor):

@@ -65,6 +65,8 @@ const char* dmay_strerror(int code);
  * w is packed [Cout_pad][kh][kw][Cin] bf16 (Cin multiple of 16, Cout_pad multiple of 16).
  * mode gate (gate_x != NULL): y = (scale*acc+bias) * sigmoid(gate_x[m,co] + gate_k[n, hs, ws, co])
  *   with nearest index hs=min(floor(p*gate_sh),gHk-1) — SCConv.forward models/common.py:1308-1316.
+ * res_op: 0 = the residual operand is added after the activation (Bottleneck); 1 = act must be NONE and the result is
+ *   MULTIPLIED by the residual operand: y = (scale*acc + bias) * residual  (GnConv recursive gating, common.py:1344).
  * block_n: 0 = auto, >0 = force the N tile, -2 = 2-CTA cluster multicast of the weight tile (experiment).
  * flags (tuning / A-B switches, 0 = auto): bit0 = never use the halo path (3x3 s1 p1 input patch loaded once
  *   per channel chunk, taps read shifted windows), bit1 = force it where legal, bit2 = never keep the weight
@@ -107,6 +109,7 @@ typedef struct dmay_conv_params {
   int block_n;
   int num_sms;
   int flags;
+  int res_op;
 } dmay_conv_params;
 int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream);
 
@@ -513,6 +516,64 @@ typedef struct dmay_winattn_params {
   int variant;
 } dmay_winattn_params;
 int dmay_window_attention(const dmay_winattn_params* p, dmay_stream_t stream);
+
+/* ---- 8f-2: HorBlock / GnConv pieces (models/common.py:1318-1426; C3HB in spdconv.yaml) ----------------------------
+ * GEMM parts (proj_in, pws chain with the gating product as epilogue — dmay_conv_params.res_op = 1 —, proj_out, MLP) run
+ * on dmay_conv_bn_act.  dmay_dwconv7: 7x7 depth-wise conv (pad 3) + bias, times `scale`, over Cd channels starting at
+ * `x` (the caller passes the base already offset to the first `abc` channel); w is tap-major [49][Cd] fp32.  Output
+ * segment i (input channels [seg_start_i, seg_start_{i+1})) is written at channel offset seg_out_i of y. */
+typedef struct dmay_dwconv7_params {
+  const void* x;
+  const void* w;
+  const void* bias;
+  void* y;
+  int N;
+  int H;
+  int W;
+  int Cd;
+  int ldx;
+  int ldy;
+  float scale;
+  int n_seg;
+  int seg_start0;
+  int seg_start1;
+  int seg_start2;
+  int seg_start3;
+  int seg_start4;
+  int seg_out0;
+  int seg_out1;
+  int seg_out2;
+  int seg_out3;
+  int seg_out4;
+} dmay_dwconv7_params;
+int dmay_dwconv7(const dmay_dwconv7_params* p, dmay_stream_t stream);
+
+/* y[pix, 0:d] = a[pix, 0:d] * b[pix, 0:d]  (bf16; d even) — GnConv's first gating step pwa * dw_list[0]. */
+typedef struct dmay_mulch_params {
+  const void* a;
+  const void* b;
+  void* y;
+  long long npix;
+  int d;
+  int lda;
+  int ldb;
+  int ldy;
+} dmay_mulch_params;
+int dmay_mul_channels(const dmay_mulch_params* p, dmay_stream_t stream);
+
+/* y = x + gamma[c] * g  (bf16 activations, fp32 per-channel gamma) — HorBlock layer scale + residual. */
+typedef struct dmay_axpych_params {
+  const void* x;
+  const void* g;
+  const void* gamma;
+  void* y;
+  long long npix;
+  int C;
+  int ldx;
+  int ldg;
+  int ldy;
+} dmay_axpych_params;
+int dmay_axpy_channels(const dmay_axpych_params* p, dmay_stream_t stream);
 
 /* ---- measurement helpers ---------------------------------------------------------------
  * plain vectorised copy (roofline calibration inside bench.py) and L2 flush (memset-like

@@ -227,6 +227,8 @@ def forward_model(cfg: dict, sd: dict, x: torch.Tensor, strides, eps=1e-3):
             x = c3str(xin, sd, p, n, eps)
         elif m == 'C3CA':
             x = c3ca(xin, sd, p, n, a[1] if len(a) > 1 else True, eps)
+        elif m == 'C3HB':
+            x = c3hb(xin, sd, p, n, eps)
         elif m == 'SCConv':
             x = scconv(xin, sd, p, a[1], eps=eps)
         elif m in ('CA', 'CoorAttention'):
@@ -341,4 +343,42 @@ def c3ca(x, sd, p, n=1, shortcut=True, eps=1e-3):
     y = conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps)
     for i in range(n):
         y = ca_bottleneck(y, sd, f'{p}m.{i}.', shortcut, eps)
+    return conv_bn_act(torch.cat((y, conv_bn_act(x, sd, p + 'cv2.', 1, eps=eps)), 1), sd, p + 'cv3.', 1, eps=eps)
+
+
+# ---- 8f-2: HorBlock / GnConv / C3HB (models/common.py:1318-1426) --------------------------------------------------
+def gnconv(x, sd, p, order=5, scale=1.0, eps=1e-3):
+    """GnConv.forward — models/common.py:1336-1346: recursive gating over channel groups c/16, c/8, ..., c."""
+    c = sd[p + 'proj_in.weight'].shape[1]
+    dims = [c // 2 ** i for i in range(order)][::-1]
+    fused = q(F.conv2d(x, sd[p + 'proj_in.weight'], sd[p + 'proj_in.bias']))
+    pwa, abc = fused[:, :dims[0]], fused[:, dims[0]:]
+    dw = q(F.conv2d(abc, sd[p + 'dwconv.weight'], sd[p + 'dwconv.bias'], padding=3, groups=sum(dims)) * scale)
+    offs = [sum(dims[:i]) for i in range(order + 1)]
+    y = q(pwa * dw[:, offs[0]:offs[1]])
+    for i in range(order - 1):
+        y = q(F.conv2d(y, sd[f'{p}pws.{i}.weight'], sd[f'{p}pws.{i}.bias']) * dw[:, offs[i + 1]:offs[i + 2]])
+    return conv_bn_act(y, sd, p + 'proj_out.', 1, eps=eps)
+
+
+def horblock(x, sd, p, eps=1e-3):
+    """HorBlock.forward — models/common.py:1367-1383 (channels_first LayerNorm 1397-1409 written out)."""
+    c = x.shape[1]
+    u = x.mean(1, keepdim=True)
+    s = ((x - u) ** 2).mean(1, keepdim=True)
+    y = q(sd[p + 'norm1.weight'][:, None, None] * ((x - u) / torch.sqrt(s + 1e-6)) + sd[p + 'norm1.bias'][:, None, None])
+    g = gnconv(y, sd, p + 'gnconv.', eps=eps)
+    x1 = q(x + sd[p + 'gamma1'].view(c, 1, 1) * g)
+    t = x1.permute(0, 2, 3, 1)
+    y2 = q(F.layer_norm(t, (c,), sd[p + 'norm2.weight'], sd[p + 'norm2.bias'], 1e-6))
+    h = q(F.gelu(y2 @ sd[p + 'pwconv1.weight'].t() + sd[p + 'pwconv1.bias']))
+    o = sd[p + 'gamma2'] * (h @ sd[p + 'pwconv2.weight'].t() + sd[p + 'pwconv2.bias'])
+    return q(x1 + o.permute(0, 3, 1, 2))
+
+
+def c3hb(x, sd, p, n=1, eps=1e-3):
+    """C3HB.forward — models/common.py:1412-1426."""
+    y = conv_bn_act(x, sd, p + 'cv1.', 1, eps=eps)
+    for i in range(n):
+        y = horblock(y, sd, f'{p}m.{i}.', eps)
     return conv_bn_act(torch.cat((y, conv_bn_act(x, sd, p + 'cv2.', 1, eps=eps)), 1), sd, p + 'cv3.', 1, eps=eps)

@@ -42,6 +42,17 @@ def main():
     fixture('swin_layer_shift_13x10', C.SwinTransformerLayer(64, num_heads=2, window_size=8, shift_size=4), rnd(g, 1, 64, 13, 10), 3)
     fixture('swin_layer_13x10', C.SwinTransformerLayer(32, num_heads=1, window_size=8, shift_size=0), rnd(g, 1, 32, 13, 10), 4)
     fixture('c3str_n2_20x12', C.C3STR(64, 128, 2, False), rnd(g, 2, 64, 20, 12), 5)
+    # HorNet blocks: gamma1 / gamma2 default to 1e-6 (the block would be an identity): randomised to O(1)
+    def hor(name, mod, x, seed):
+        gg = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for n_, p_ in mod.named_parameters():
+                if 'gamma' in n_:
+                    p_.copy_(torch.randn(p_.shape, generator=gg) * 0.5)
+        fixture(name, mod, x, seed)
+    hor('horblock_64_12x10', C.HorBlock(64), rnd(g, 2, 64, 12, 10), 6)
+    hor('horblock_128_9x7', C.HorBlock(128), rnd(g, 1, 128, 9, 7), 7)
+    hor('c3hb_n2_16x12', C.C3HB(64, 128, 2, False), rnd(g, 2, 64, 16, 12), 8)
 
 
 if __name__ == '__main__':

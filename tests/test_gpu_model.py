@@ -95,7 +95,7 @@ def test_half_and_uint8_inputs_and_fuse():
     assert rel(e, a) < 0.15, rel(e, a)
 
 
-@pytest.mark.parametrize('cfg', ['yolov5s', 'ablation-ca-scconv-sppfcspc-bifpn', 'yolov5l-ca-sppfcspc-bifpn-scconv', 'C3CASPD'])
+@pytest.mark.parametrize('cfg', ['yolov5s', 'ablation-ca-scconv-sppfcspc-bifpn', 'yolov5l-ca-sppfcspc-bifpn-scconv', 'C3CASPD', 'spdconv'])
 def test_model_vs_bf16_storage_oracle(cfg):
     """The parity test proper for the bf16 path (north_star tolerance: 1e-2 in bf16).  Both sides hold IDENTICAL
     weights (conv weights rounded to bf16 once) and the oracle rounds to bf16 exactly where the kernel path stores

@@ -28,6 +28,8 @@ CTORS = {
     'swin_layer_shift_13x10': lambda: C.SwinTransformerLayer(64, num_heads=2, window_size=8, shift_size=4),
     'swin_layer_13x10': lambda: C.SwinTransformerLayer(32, num_heads=1, window_size=8, shift_size=0),
     'c3str_n2_20x12': lambda: C.C3STR(64, 128, 2, False),
+    'horblock_64_12x10': lambda: C.HorBlock(64), 'horblock_128_9x7': lambda: C.HorBlock(128),
+    'c3hb_n2_16x12': lambda: C.C3HB(64, 128, 2, False),
 }
 
 
@@ -100,7 +102,7 @@ def test_fuse_only_top_level_convs():
 
 
 def test_unknown_module_is_reported():
-    cfg = dict(nc=2, depth_multiple=1, width_multiple=1, anchors=3, backbone=[[-1, 1, 'C3HB', [64]]],
+    cfg = dict(nc=2, depth_multiple=1, width_multiple=1, anchors=3, backbone=[[-1, 1, 'C3Ghost', [64]]],
                head=[[[0], 1, 'Detect', ['nc', 'anchors']]])
     with pytest.raises(NotImplementedError):
         D.Model(cfg)

@@ -37,6 +37,8 @@ def run_block(name):
     elif name == 'swin_layer_shift_13x10': y = O.swin_layer(x, sd, '', 2, 8, 4)
     elif name == 'swin_layer_13x10': y = O.swin_layer(x, sd, '', 1, 8, 0)
     elif name == 'c3str_n2_20x12': y = O.c3str(x, sd, '', 2)
+    elif name.startswith('horblock'): y = O.horblock(x, sd, '')
+    elif name == 'c3hb_n2_16x12': y = O.c3hb(x, sd, '', 2)
     else: raise KeyError(name)
     return y, d['out']
 
@@ -44,7 +46,8 @@ def run_block(name):
 BLOCKS = ['conv_k3s1', 'conv_k3s2_odd', 'conv_k1', 'conv_stem_k6s2p2', 'conv_c64_k3', 'bottleneck', 'c3_n2',
           'c3_n1_noshortcut', 'coordatt_7x5', 'coordatt_20x20', 'spd', 'scconv_38', 'scconv_16x12', 'scconv_19x23_s1',
           'adconcat2', 'adconcat3', 'adapt_add2', 'adapt_add3', 'sppf_20', 'sppfcspc_12x9', 'spp', 'sppcspc',
-          'swin_layer_16x24', 'swin_layer_shift_16x24', 'swin_layer_shift_13x10', 'swin_layer_13x10', 'c3str_n2_20x12']
+          'swin_layer_16x24', 'swin_layer_shift_16x24', 'swin_layer_shift_13x10', 'swin_layer_13x10', 'c3str_n2_20x12',
+          'horblock_64_12x10', 'horblock_128_9x7', 'c3hb_n2_16x12']
 
 
 @pytest.mark.parametrize('name', BLOCKS)
