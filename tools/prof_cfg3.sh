@@ -1,6 +1,6 @@
 #!/bin/bash
 OUT=gpurun_out/${1:-r2j}; mkdir -p $OUT
-CMD="python tools/prof_one.py model 8 yolov5l-ca-sppfcspc-bifpn-scconv.yaml 1536"
+CMD="python tools/prof_one.py model ${2:-8} ${3:-yolov5l-ca-sppfcspc-bifpn-scconv.yaml} ${4:-1536}"
 $CMD > $OUT/plain_cfg3.log 2>&1 &&
 ncu --clock-control none --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --csv --log-file $OUT/launches_cfg3.csv $CMD > $OUT/ncu_cfg3.log 2>&1
