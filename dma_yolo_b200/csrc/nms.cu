@@ -500,6 +500,169 @@ __global__ void img_counts_kernel(const long long* __restrict__ img_offsets, int
   if (i < N) img_counts[i] = (int)(img_offsets[i + 1] - img_offsets[i]);
 }
 
+// ---- exact top-K pre-selection (utils/general.py:702-703: only the max_nms = 30000 best candidates of an image enter
+// torchvision.ops.nms) ---------------------------------------------------------------------------------------------
+// With val-style thresholds an image has several 100 k candidates; sorting all of them only to look at the first
+// 30000 made the radix sort the second most expensive kernel of the step.  One CTA per image finds the K-th smallest
+// key with a 3-level radix select (11 + 11 + 10 bits of the score key; warp-aggregated shared-memory histograms, so
+// the saturated case "330 k candidates with conf == 1.0" costs one atomic per warp, not per candidate) and then
+// compacts, IN CANDIDATE ORDER, every key below it plus the first (K - #below) keys equal to it.  The stable sort
+// that follows therefore sees exactly the candidates — and the tie order — the full sort would have put first.
+constexpr int kSelThreads = 1024;
+constexpr int kSelPer = 8;   // candidates per thread per chunk in the compaction pass
+
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_tot, int& total) {   // all kSelThreads threads call
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();                 // warp_tot may still be read from the previous call
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = warp_tot[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_tot[lane] = winc - w;
+    if (lane == 31) warp_tot[32] = winc;
+  }
+  __syncthreads();
+  total = warp_tot[32];
+  return warp_tot[warp] + inc - v;
+}
+
+// first bin whose inclusive prefix reaches `want` (bins in ascending order); nbins <= 2 * kSelThreads
+__device__ __forceinline__ void find_bin(const int* hist, int nbins, int want, int* warp_tot, int* res /*[2]*/) {
+  const int b0 = 2 * threadIdx.x, b1 = b0 + 1;
+  const int h0 = b0 < nbins ? hist[b0] : 0, h1 = b1 < nbins ? hist[b1] : 0;
+  int total;
+  const int excl = block_excl_scan(h0 + h1, warp_tot, total);
+  if (excl < want && excl + h0 >= want) { res[0] = b0; res[1] = excl; }
+  else if (excl + h0 < want && excl + h0 + h1 >= want) { res[0] = b1; res[1] = excl + h0; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const unsigned long long* __restrict__ keys,
+                                                                  const int* __restrict__ img_counts,
+                                                                  const long long* __restrict__ img_offsets,
+                                                                  unsigned long long* __restrict__ keys_out,
+                                                                  unsigned* __restrict__ idx_out, int* __restrict__ counts_out,
+                                                                  long long* __restrict__ offsets_out, int N, int K) {
+  __shared__ int hist[2048];
+  __shared__ int warp_tot[33];
+  __shared__ int res[2];
+  __shared__ long long coff_s;
+  const int img = blockIdx.x;
+  const long long off = img_offsets[img];
+  const int cnt = img_counts[img];
+  if (threadIdx.x == 0) {
+    long long c = 0;
+    for (int j = 0; j < img; ++j) c += min(img_counts[j], K);
+    coff_s = c;
+    counts_out[img] = min(cnt, K);
+    offsets_out[img] = c;
+    if (img == N - 1) offsets_out[N] = c + min(cnt, K);
+  }
+  __syncthreads();
+  const long long coff = coff_s;
+  const unsigned long long* kp = keys + off;
+  if (cnt <= K) {   // everything survives: plain copy
+    for (int i = threadIdx.x; i < cnt; i += kSelThreads) {
+      keys_out[coff + i] = kp[i];
+      idx_out[coff + i] = (unsigned)(off + i);
+    }
+    return;
+  }
+  // ---- 3-level radix select of the K-th smallest 32-bit score key ----
+  unsigned prefix = 0;      // bits fixed so far (value of the selected bins)
+  int want = K;             // rank still to find inside the current prefix
+  int n_less = 0;           // keys strictly below the final K-th key
+#pragma unroll 1
+  for (int level = 0; level < 3; ++level) {
+    const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
+    const int nbins = level == 2 ? 1024 : 2048;
+    const unsigned pmask = level == 0 ? 0u : (level == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+    for (int i = threadIdx.x; i < 2048; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+    // 8 independent loads in flight per thread (one CTA streams the image's keys: latency, not bandwidth, is the limit)
+    for (int c0 = 0; c0 < cnt; c0 += kSelThreads * kSelPer) {
+      unsigned k32[kSelPer];
+#pragma unroll
+      for (int u = 0; u < kSelPer; ++u) {
+        const int i = c0 + u * kSelThreads + threadIdx.x;
+        k32[u] = i < cnt ? (unsigned)kp[i] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < kSelPer; ++u) {
+        const int i = c0 + u * kSelThreads + threadIdx.x;
+        unsigned bin = 0xFFFFFFFFu;
+        if (i < cnt && (k32[u] & pmask) == prefix) bin = (k32[u] >> shift) & (unsigned)(nbins - 1);
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != 0xFFFFFFFFu && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+      }
+    }
+    __syncthreads();
+    find_bin(hist, nbins, want, warp_tot, res);
+    prefix |= (unsigned)res[0] << shift;
+    n_less += res[1];
+    want -= res[1];
+  }
+  const unsigned kstar = prefix;
+  const int quota = K - n_less;     // keys equal to kstar that are kept: the first `quota` in candidate order
+  // ---- ordered compaction ----
+  int run_eq = 0, run_keep = 0;
+  const int chunk = kSelThreads * kSelPer;
+#pragma unroll 1
+  for (int c0 = 0; c0 < cnt; c0 += chunk) {
+    const int i0 = c0 + threadIdx.x * kSelPer;
+    unsigned long long kk[kSelPer];
+    int neq = 0;
+#pragma unroll
+    for (int j = 0; j < kSelPer; ++j) {
+      kk[j] = i0 + j < cnt ? kp[i0 + j] : 0xFFFFFFFFFFFFFFFFull;
+      neq += (i0 + j < cnt && (unsigned)kk[j] == kstar) ? 1 : 0;
+    }
+    int tot_eq;
+    int eq_rank = run_eq + block_excl_scan(neq, warp_tot, tot_eq);
+    unsigned keep_mask = 0;
+    int nkeep = 0;
+#pragma unroll
+    for (int j = 0; j < kSelPer; ++j) {
+      if (i0 + j < cnt) {
+        const unsigned k32 = (unsigned)kk[j];
+        bool keep = k32 < kstar;
+        if (k32 == kstar) {
+          keep = eq_rank < quota;
+          ++eq_rank;
+        }
+        if (keep) {
+          keep_mask |= 1u << j;
+          ++nkeep;
+        }
+      }
+    }
+    int tot_keep;
+    int pos = run_keep + block_excl_scan(nkeep, warp_tot, tot_keep);
+#pragma unroll
+    for (int j = 0; j < kSelPer; ++j) {
+      if (keep_mask & (1u << j)) {
+        keys_out[coff + pos] = kk[j];
+        idx_out[coff + pos] = (unsigned)(off + i0 + j);
+        ++pos;
+      }
+    }
+    run_eq += tot_eq;
+    run_keep += tot_keep;
+  }
+}
+
 __global__ void iota_kernel(unsigned* __restrict__ idx, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     idx[i] = (unsigned)i;
@@ -801,13 +964,27 @@ int dmay_nms_sort(const dmay_sort_params* p, dmay_stream_t stream) {
   size_t cub_bytes = cub_ws_bytes(p->n, end_bit);
   if ((long long)cub_bytes + p->n * 4 > p->ws_bytes) return DMAY_ETOOBIG;
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned* idx_in = reinterpret_cast<unsigned*>((char*)p->ws + cub_bytes);
-  iota_kernel<<<grid_for(p->n, 256), 256, 0, s>>>(idx_in, p->n);
+  const unsigned* vals = (const unsigned*)p->vals_in;
+  if (vals == nullptr) {   // payload = position in keys_in
+    unsigned* idx_in = reinterpret_cast<unsigned*>((char*)p->ws + cub_bytes);
+    iota_kernel<<<grid_for(p->n, 256), 256, 0, s>>>(idx_in, p->n);
+    vals = idx_in;
+  }
   cudaError_t e = cub::DeviceRadixSort::SortPairs(p->ws, cub_bytes, (const unsigned long long*)p->keys_in,
-                                                  (unsigned long long*)p->keys_out, (const unsigned*)idx_in,
-                                                  (unsigned*)p->idx_out, p->n, 0, end_bit, s);
+                                                  (unsigned long long*)p->keys_out, vals, (unsigned*)p->idx_out, p->n, 0,
+                                                  end_bit, s);
   if (e != cudaSuccess) return (int)e;
   return finish_launch(2);
+}
+
+int dmay_nms_topk_select(const dmay_topk_params* p, dmay_stream_t stream) {
+  if (!p || !p->keys || !p->img_counts || !p->img_offsets || !p->keys_out || !p->idx_out || !p->counts_out || !p->offsets_out)
+    return DMAY_EINVAL;
+  if (p->N <= 0 || p->K <= 0) return DMAY_EINVAL;
+  topk_select_kernel<<<p->N, kSelThreads, 0, (cudaStream_t)stream>>>(
+      (const unsigned long long*)p->keys, (const int*)p->img_counts, (const long long*)p->img_offsets,
+      (unsigned long long*)p->keys_out, (unsigned*)p->idx_out, (int*)p->counts_out, (long long*)p->offsets_out, p->N, p->K);
+  return finish_launch();
 }
 
 int dmay_nms_greedy(const dmay_nms_params* p, dmay_stream_t stream) {

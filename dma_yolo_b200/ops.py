@@ -532,7 +532,8 @@ def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, 
     if cm is not None:
         common["class_mask"] = cm.data_ptr()
     call("dmay_nms_filter", s, phase=0, **common)
-    total = int(img_offsets[n].item())  # the one sizing sync of the batch
+    offs_host = img_offsets.tolist()    # the one sizing sync of the batch (N+1 values)
+    total = offs_host[-1]
     out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
     out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
     if total == 0:
@@ -540,9 +541,9 @@ def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, 
     keys = torch.empty(total, device=dev, dtype=torch.int64)
     cand = torch.empty((total, 6), device=dev, dtype=torch.float32)
     call("dmay_nms_filter", s, phase=1, keys=keys.data_ptr(), cand=cand.data_ptr(), capacity=total, **common)
-    _keys_out, idx = _sort_candidates(keys, total, n, dev, s)
-    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=img_counts.data_ptr(),
-         img_offsets=img_offsets.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
+    idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
+    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=cnts.data_ptr(),
+         img_offsets=offs.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
          max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
     del keep_alive, cm
     return out, out_counts
@@ -558,16 +559,43 @@ def _class_mask(classes, nc, dev):
     return cm.to(dev)
 
 
-def _sort_candidates(keys, total, n, dev, s):
-    """Stable radix sort of the (image, ~score) keys; payload = candidate index."""
+def _sort_candidates(keys, total, n, dev, s, vals=None):
+    """Stable radix sort of the (image, ~score) keys; payload = candidate index (`vals`, or the position in `keys`)."""
     img_bits = max(1, (n - 1).bit_length())
     ws_bytes = int(_lib.lib().dmay_nms_sort_ws(total, img_bits))
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     keys_out = torch.empty(total, device=dev, dtype=torch.int64)
     idx = torch.empty(total, device=dev, dtype=torch.int32)
-    call("dmay_nms_sort", s, keys_in=keys.data_ptr(), keys_out=keys_out.data_ptr(), idx_out=idx.data_ptr(),
-         ws=ws.data_ptr(), ws_bytes=ws_bytes, n=total, img_bits=img_bits)
+    f = dict(keys_in=keys.data_ptr(), keys_out=keys_out.data_ptr(), idx_out=idx.data_ptr(), ws=ws.data_ptr(),
+             ws_bytes=ws_bytes, n=total, img_bits=img_bits)
+    if vals is not None:
+        f["vals_in"] = vals.data_ptr()
+    call("dmay_nms_sort", s, **f)
     return keys_out, idx
+
+
+TOPK_SELECT = __import__('os').environ.get('DMAY_TOPK_SELECT', '1') != '0'
+
+
+def _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s):
+    """-> (sorted candidate indices, per-image counts, per-image offsets into them) for the greedy kernel.
+    When an image has more than max_nms candidates, the exact top-max_nms pre-selection runs first and only the
+    survivors are sorted (utils/general.py:702-703 keeps just those anyway)."""
+    total = offs_host[-1]
+    counts = [offs_host[i + 1] - offs_host[i] for i in range(n)]
+    if not TOPK_SELECT or max(counts) <= max_nms:
+        _ko, idx = _sort_candidates(keys, total, n, dev, s)
+        return idx, img_counts, img_offsets
+    n_c = sum(min(c, max_nms) for c in counts)
+    keys_c = torch.empty(n_c, device=dev, dtype=torch.int64)
+    idx_c = torch.empty(n_c, device=dev, dtype=torch.int32)
+    counts_c = torch.empty(n, device=dev, dtype=torch.int32)
+    offs_c = torch.empty(n + 1, device=dev, dtype=torch.int64)
+    call("dmay_nms_topk_select", s, keys=keys.data_ptr(), img_counts=img_counts.data_ptr(), img_offsets=img_offsets.data_ptr(),
+         keys_out=keys_c.data_ptr(), idx_out=idx_c.data_ptr(), counts_out=counts_c.data_ptr(), offsets_out=offs_c.data_ptr(),
+         N=n, K=max_nms)
+    _ko, idx = _sort_candidates(keys_c, n_c, n, dev, s, vals=idx_c)
+    return idx, counts_c, offs_c
 
 
 def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
@@ -602,16 +630,17 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
         if cm is not None:
             f["class_mask"] = cm.data_ptr()
         call("dmay_nms_filter_fused", s, **f)
-        total = int(img_offsets[n].item())   # the one sizing sync of the batch
+        offs_host = img_offsets.tolist()     # the one sizing sync of the batch (N+1 values)
+        total = offs_host[-1]
         if total <= capacity:
             break
         capacity = total + total // 8 + 4096   # undersized guess: every candidate was counted, repeat once
     _FUSED_CAP[key] = max(total + total // 4 + 4096, _FUSED_CAP.get(key, 0) // 2)
     if total == 0:
         return out, out_counts
-    _keys_out, idx = _sort_candidates(keys, total, n, dev, s)
-    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=img_counts.data_ptr(),
-         img_offsets=img_offsets.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
+    idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
+    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=cnts.data_ptr(),
+         img_offsets=offs.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
          max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
     return out, out_counts
 

@@ -447,9 +447,29 @@ typedef struct dmay_sort_params {
   long long ws_bytes;
   long long n;
   int img_bits;
+  const void* vals_in;
 } dmay_sort_params;
 long long dmay_nms_sort_ws(long long n, int img_bits);
 int dmay_nms_sort(const dmay_sort_params* p, dmay_stream_t stream);
+
+/* exact pre-selection of the K = max_nms best candidates per image (utils/general.py:702-703) BEFORE the sort:
+ * per image a 3-level radix select finds the K-th smallest score key, then every key below it and the first
+ * (K - #below) keys equal to it are compacted in candidate order (so the stable sort that follows breaks ties exactly
+ * as a full sort would).  keys: u64 [total] as written by the filter, images contiguous; outputs: keys_out u64 and
+ * idx_out u32 (candidate indices) [sum_i min(count_i, K)], counts_out i32 [N], offsets_out i64 [N+1].
+ * dmay_nms_sort then takes idx_out as `vals_in` (payload) instead of generating positions. */
+typedef struct dmay_topk_params {
+  const void* keys;
+  const void* img_counts;
+  const void* img_offsets;
+  void* keys_out;
+  void* idx_out;
+  void* counts_out;
+  void* offsets_out;
+  int N;
+  int K;
+} dmay_topk_params;
+int dmay_nms_topk_select(const dmay_topk_params* p, dmay_stream_t stream);
 
 /* greedy NMS over each image's sorted candidates, stopping after max_det keeps.
  * IoU exactly as torchvision CPU nms_kernel: fp32 inter/(areaA+areaB-inter), compared in

@@ -173,3 +173,28 @@ def test_fused_filter_capacity_overflow_reruns():
         ops._FUSED_CAP[k] = 64          # far too small: the kernel counts everything, the wrapper repeats
     b = ops.nms_batched(None, 0.001, 0.6, levels=levels, na=na, nc=no - 5, multi_label=True)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize('levels', [3, 40], ids=['three-score-values', 'forty-score-values'])
+def test_topk_preselection_is_exact_with_ties(levels):
+    """> max_nms candidates per image with massively tied scores: the radix-select + ordered compaction in front of the
+    sort must give the same detections as sorting everything (and as the oracle's stable truncation)."""
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(17 + levels)
+    pred = torch.rand(3, 9000, 11, generator=g)
+    pred[..., :2] *= 640
+    pred[..., 2:4] = pred[..., 2:4] * 50 + 4
+    pred[..., 4] = 1.0
+    pred[..., 5:] = (torch.randint(1, levels + 1, (3, 9000, 6), generator=g).float() / (levels + 1))
+    pred[2, 4000:] = 0                                     # third image: fewer than max_nms candidates
+    kw = dict(multi_label=True, max_det=300)
+    assert ops.TOPK_SELECT
+    a, ac = ops.nms_batched(pred.cuda(), 0.001, 0.6, **kw)
+    ops.TOPK_SELECT = False
+    try:
+        b, bc = ops.nms_batched(pred.cuda(), 0.001, 0.6, **kw)
+    finally:
+        ops.TOPK_SELECT = True
+    assert torch.equal(ac, bc) and torch.equal(a, b)
+    ref = ON.non_max_suppression(pred[:1].numpy(), 0.001, 0.6, multi_label=True, max_det=300)[0]
+    assert np.array_equal(a[0, :int(ac[0])].cpu().numpy(), ref)
