@@ -503,7 +503,7 @@ __global__ void img_counts_kernel(const long long* __restrict__ img_offsets, int
 // ---- exact top-K pre-selection (utils/general.py:702-703: only the max_nms = 30000 best candidates of an image enter
 // torchvision.ops.nms) ---------------------------------------------------------------------------------------------
 // With val-style thresholds an image has several 100 k candidates; sorting all of them only to look at the first
-// 30000 made the radix sort the second most expensive kernel of the step.  One CTA per image finds the K-th smallest
+// 30000 made the radix sort the second most expensive kernel of the step.  A 4-CTA cluster per image finds the K-th smallest
 // key with a 3-level radix select (11 + 11 + 10 bits of the score key; warp-aggregated shared-memory histograms, so
 // the saturated case "330 k candidates with conf == 1.0" costs one atomic per warp, not per candidate) and then
 // compacts, IN CANDIDATE ORDER, every key below it plus the first (K - #below) keys equal to it.  The stable sort
@@ -549,41 +549,69 @@ __device__ __forceinline__ void find_bin(const int* hist, int nbins, int want, i
   __syncthreads();
 }
 
+// A cluster of kSelCluster CTAs serves one image: each CTA histograms / compacts one contiguous slice of the image's
+// keys, the per-CTA histograms are merged through distributed shared memory (every CTA reads its peers' bins and
+// finds the same bin, so nothing has to be broadcast), and the slices' "keys below" / "keys equal" counts — which
+// fall out of the local histograms — give each CTA its output offset and its share of the tie quota.
+constexpr int kSelCluster = 4;
+
+__device__ __forceinline__ int ld_dsmem_s32(const int* local_ptr, unsigned rank) {
+  unsigned local = (unsigned)__cvta_generic_to_shared(local_ptr), remote;
+  int v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const unsigned long long* __restrict__ keys,
                                                                   const int* __restrict__ img_counts,
                                                                   const long long* __restrict__ img_offsets,
                                                                   unsigned long long* __restrict__ keys_out,
                                                                   unsigned* __restrict__ idx_out, int* __restrict__ counts_out,
                                                                   long long* __restrict__ offsets_out, int N, int K) {
-  __shared__ int hist[2048];
+  __shared__ int hist[2048];        // this CTA's slice
+  __shared__ int merged[2048];      // sum over the cluster
   __shared__ int warp_tot[33];
   __shared__ int res[2];
+  __shared__ int slice_info[2];     // keys of this slice below / equal to the K-th key (read by the peers)
   __shared__ long long coff_s;
-  const int img = blockIdx.x;
+  unsigned crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int img = blockIdx.x / kSelCluster;
   const long long off = img_offsets[img];
   const int cnt = img_counts[img];
   if (threadIdx.x == 0) {
     long long c = 0;
     for (int j = 0; j < img; ++j) c += min(img_counts[j], K);
     coff_s = c;
-    counts_out[img] = min(cnt, K);
-    offsets_out[img] = c;
-    if (img == N - 1) offsets_out[N] = c + min(cnt, K);
+    if (crank == 0) {
+      counts_out[img] = min(cnt, K);
+      offsets_out[img] = c;
+      if (img == N - 1) offsets_out[N] = c + min(cnt, K);
+    }
   }
   __syncthreads();
   const long long coff = coff_s;
-  const unsigned long long* kp = keys + off;
-  if (cnt <= K) {   // everything survives: plain copy
-    for (int i = threadIdx.x; i < cnt; i += kSelThreads) {
-      keys_out[coff + i] = kp[i];
-      idx_out[coff + i] = (unsigned)(off + i);
+  // slice of this CTA (multiples of kSelPer so that the compaction's per-thread runs stay aligned)
+  const int per = ((cnt + kSelCluster - 1) / kSelCluster + kSelPer - 1) / kSelPer * kSelPer;
+  const int s0 = min((int)crank * per, cnt), s1 = min(s0 + per, cnt);
+  const int scnt = s1 - s0;
+  const unsigned long long* kp = keys + off + s0;
+  if (cnt <= K) {   // everything survives: plain copy (uniform across the cluster: no barrier is skipped by a subset)
+    for (int i = threadIdx.x; i < scnt; i += kSelThreads) {
+      keys_out[coff + s0 + i] = kp[i];
+      idx_out[coff + s0 + i] = (unsigned)(off + s0 + i);
     }
     return;
   }
   // ---- 3-level radix select of the K-th smallest 32-bit score key ----
   unsigned prefix = 0;      // bits fixed so far (value of the selected bins)
   int want = K;             // rank still to find inside the current prefix
-  int n_less = 0;           // keys strictly below the final K-th key
+  int n_less = 0;           // keys (whole image) strictly below the final K-th key
+  int my_less = 0;          // same, this slice only
 #pragma unroll 1
   for (int level = 0; level < 3; ++level) {
     const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
@@ -591,43 +619,70 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const unsigned
     const unsigned pmask = level == 0 ? 0u : (level == 1 ? 0xFFE00000u : 0xFFFFFC00u);
     for (int i = threadIdx.x; i < 2048; i += kSelThreads) hist[i] = 0;
     __syncthreads();
-    // 8 independent loads in flight per thread (one CTA streams the image's keys: latency, not bandwidth, is the limit)
-    for (int c0 = 0; c0 < cnt; c0 += kSelThreads * kSelPer) {
+    // 8 independent loads in flight per thread (the CTA streams its slice: latency, not bandwidth, is the limit)
+    for (int c0 = 0; c0 < scnt; c0 += kSelThreads * kSelPer) {
       unsigned k32[kSelPer];
 #pragma unroll
       for (int u = 0; u < kSelPer; ++u) {
         const int i = c0 + u * kSelThreads + threadIdx.x;
-        k32[u] = i < cnt ? (unsigned)kp[i] : 0u;
+        k32[u] = i < scnt ? (unsigned)kp[i] : 0u;
       }
 #pragma unroll
       for (int u = 0; u < kSelPer; ++u) {
         const int i = c0 + u * kSelThreads + threadIdx.x;
         unsigned bin = 0xFFFFFFFFu;
-        if (i < cnt && (k32[u] & pmask) == prefix) bin = (k32[u] >> shift) & (unsigned)(nbins - 1);
+        if (i < scnt && (k32[u] & pmask) == prefix) bin = (k32[u] >> shift) & (unsigned)(nbins - 1);
         const unsigned peers = __match_any_sync(0xffffffffu, bin);
         if (bin != 0xFFFFFFFFu && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
       }
     }
+    cluster_barrier();                                     // every slice's histogram is complete
+    for (int i = threadIdx.x; i < nbins; i += kSelThreads) {
+      int t = 0;
+#pragma unroll
+      for (unsigned r = 0; r < (unsigned)kSelCluster; ++r) t += ld_dsmem_s32(&hist[i], r);
+      merged[i] = t;
+    }
     __syncthreads();
-    find_bin(hist, nbins, want, warp_tot, res);
+    find_bin(merged, nbins, want, warp_tot, res);
+    // this slice's keys below the selected bin at this level
+    {
+      int part = 0;
+      for (int i = threadIdx.x; i < res[0]; i += kSelThreads) part += hist[i];
+      int tot;
+      block_excl_scan(part, warp_tot, tot);
+      my_less += tot;
+    }
+    if (level == 2 && threadIdx.x == 0) slice_info[1] = hist[res[0]];   // keys of this slice equal to the K-th key
     prefix |= (unsigned)res[0] << shift;
     n_less += res[1];
     want -= res[1];
+    cluster_barrier();                                     // peers are done reading this level's histogram
   }
   const unsigned kstar = prefix;
   const int quota = K - n_less;     // keys equal to kstar that are kept: the first `quota` in candidate order
-  // ---- ordered compaction ----
+  if (threadIdx.x == 0) slice_info[0] = my_less;
+  cluster_barrier();
+  // offsets of this slice: what the slices before it keep
   int run_eq = 0, run_keep = 0;
+  for (unsigned r = 0; r < crank; ++r) {
+    const int less_r = ld_dsmem_s32(&slice_info[0], r), eq_r = ld_dsmem_s32(&slice_info[1], r);
+    const int keep_eq = max(0, min(eq_r, quota - run_eq));
+    run_keep += less_r + keep_eq;
+    run_eq += eq_r;
+  }
+  cluster_barrier();                                       // nobody exits (or reuses smem) while a peer still reads it
+  // ---- ordered compaction of this slice ----
   const int chunk = kSelThreads * kSelPer;
 #pragma unroll 1
-  for (int c0 = 0; c0 < cnt; c0 += chunk) {
+  for (int c0 = 0; c0 < scnt; c0 += chunk) {
     const int i0 = c0 + threadIdx.x * kSelPer;
     unsigned long long kk[kSelPer];
     int neq = 0;
 #pragma unroll
     for (int j = 0; j < kSelPer; ++j) {
-      kk[j] = i0 + j < cnt ? kp[i0 + j] : 0xFFFFFFFFFFFFFFFFull;
-      neq += (i0 + j < cnt && (unsigned)kk[j] == kstar) ? 1 : 0;
+      kk[j] = i0 + j < scnt ? kp[i0 + j] : 0xFFFFFFFFFFFFFFFFull;
+      neq += (i0 + j < scnt && (unsigned)kk[j] == kstar) ? 1 : 0;
     }
     int tot_eq;
     int eq_rank = run_eq + block_excl_scan(neq, warp_tot, tot_eq);
@@ -635,7 +690,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const unsigned
     int nkeep = 0;
 #pragma unroll
     for (int j = 0; j < kSelPer; ++j) {
-      if (i0 + j < cnt) {
+      if (i0 + j < scnt) {
         const unsigned k32 = (unsigned)kk[j];
         bool keep = k32 < kstar;
         if (k32 == kstar) {
@@ -654,7 +709,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const unsigned
     for (int j = 0; j < kSelPer; ++j) {
       if (keep_mask & (1u << j)) {
         keys_out[coff + pos] = kk[j];
-        idx_out[coff + pos] = (unsigned)(off + i0 + j);
+        idx_out[coff + pos] = (unsigned)(off + s0 + i0 + j);
         ++pos;
       }
     }
@@ -981,9 +1036,22 @@ int dmay_nms_topk_select(const dmay_topk_params* p, dmay_stream_t stream) {
   if (!p || !p->keys || !p->img_counts || !p->img_offsets || !p->keys_out || !p->idx_out || !p->counts_out || !p->offsets_out)
     return DMAY_EINVAL;
   if (p->N <= 0 || p->K <= 0) return DMAY_EINVAL;
-  topk_select_kernel<<<p->N, kSelThreads, 0, (cudaStream_t)stream>>>(
-      (const unsigned long long*)p->keys, (const int*)p->img_counts, (const long long*)p->img_offsets,
-      (unsigned long long*)p->keys_out, (unsigned*)p->idx_out, (int*)p->counts_out, (long long*)p->offsets_out, p->N, p->K);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p->N * kSelCluster);
+  cfg.blockDim = dim3(kSelThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kSelCluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, topk_select_kernel, (const unsigned long long*)p->keys, (const int*)p->img_counts,
+                                     (const long long*)p->img_offsets, (unsigned long long*)p->keys_out, (unsigned*)p->idx_out,
+                                     (int*)p->counts_out, (long long*)p->offsets_out, p->N, p->K);
+  if (e != cudaSuccess) return (int)e;
   return finish_launch();
 }
 
