@@ -329,8 +329,9 @@ def main():
         config=dict(workload=f'{CFG} forward + Detect decode + NMS(val-style 0.001/0.6/multi_label/300), 640x640, batch {B}/GPU',
                     weights='random-init, seeded, BN-calibrated', l2='inputs (315 MB fp32/batch) and activations exceed the 126 MB L2; no explicit flush',
                     parallelism=f'dp{world} (batch sharded by rank, NCCL all-gather of detections)'),
-        e2e=dict(value=round(e2e_value, 1), unit='img/s', h2d_bytes_per_step=B * 3 * IMG * IMG,
-                 d2h_bytes_per_step=B * max_det * 6 * 4 + B * 4, ms_per_step=round(ms_e2e / args.steps, 3)),
+        e2e=dict(value=round(e2e_value, 1), unit='img/s', h2d_bytes_per_step=world * B * 3 * IMG * IMG,
+                 d2h_bytes_per_step=world * (B * max_det * 6 * 4 + B * 4), ms_per_step=round(ms_e2e / args.steps, 3),
+                 note='bytes summed over ranks; every rank copies its own slice'),
         gpu_launches=launches, clocks=clk,
         roofline=dict(kernel='conv_gemm_kernel (tcgen05 implicit GEMM, all Conv+BN+SiLU layers)', bound='tensor',
                       achieved=round(achieved, 1) if achieved else None, peak=peak_tf, unit='TFLOP/s',

@@ -13,7 +13,8 @@ def box_iou(a, b):
     area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
     wh = np.clip(np.minimum(a[:, None, 2:], b[None, :, 2:]) - np.maximum(a[:, None, :2], b[None, :, :2]), 0, None)
     inter = wh[..., 0] * wh[..., 1]
-    return inter / (area_a[:, None] + area_b[None, :] - inter)
+    with np.errstate(divide='ignore', invalid='ignore'):      # degenerate boxes: 0/0 -> nan, like the reference
+        return inter / (area_a[:, None] + area_b[None, :] - inter)
 
 
 def process_batch(det, labels, iouv):
