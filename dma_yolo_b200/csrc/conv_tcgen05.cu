@@ -1151,7 +1151,10 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     const bool legal = p->block_n != -2 && a.CK == 64 && bn >= 128 && (bn % 32) == 0 && m_tiles_q >= 2 && sms_q >= 2 &&
                        mode != EPI_GENERIC;
     // halo + pair (128-channel 3x3 layers): per CTA one input patch + HALF of the 9-tap weight set per chunk
-    const bool want = (long long)a.taps * p->Cin >= 1024 && (bn == 256 || (halo_auto && bn >= 128)) && m_tiles_q >= sms_q;
+    // (measured: 64->128 3x3 s2 @160, K = 576: 0.390 -> 0.334 ms; 1x1 layers with K <= 512 lose, see r1_conv_notes.md)
+    const long long Ktot = (long long)a.taps * p->Cin;
+    const bool want = m_tiles_q >= sms_q && ((Ktot >= 1024 && (bn == 256 || (halo_auto && bn >= 128))) ||
+                                             (a.taps >= 9 && Ktot >= 512 && bn >= 128));
     a.pair = legal && ((p->flags & 256) || (want && !(p->flags & 512))) ? 1 : 0;
   }
   a.a_bytes = (uint32_t)(BLOCK_M * a.CK * 2);
