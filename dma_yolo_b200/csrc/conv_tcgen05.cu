@@ -311,7 +311,7 @@ constexpr int kMaxCout = 2048;                                                 /
 //   [kEpiWarps x 2 KB] operand staging (residual / gate_x tile of the warp's NEXT item, TMA-loaded) — only when used
 //   barriers, TMEM base slot, scale[kMaxCout], bias[kMaxCout]
 __host__ __device__ constexpr uint32_t tail_bytes(int epi_warps, bool operand_stage, uint32_t sb_floats) {
-  return (uint32_t)epi_warps * 2048u * (operand_stage ? 2u : 1u) + kNumBars * 8 + 16 + 2 * sb_floats * 4;
+  return (uint32_t)epi_warps * 2048u * (operand_stage ? 2u : 1u) + kNumBars * 8 + 32 + 2 * sb_floats * 4;
 }
 
 // one elected lane of a converged warp (the warp stays converged, so operands live in uniform registers)
@@ -356,12 +356,18 @@ __device__ __forceinline__ float sigmoid_t(float x) { return fmaf(0.5f, tanh_app
 template <int MODE>
 __device__ __forceinline__ uint4 epi_compute8(const uint32_t* r, const float* sc, const float* bi, const uint4& aux0,
                                               const uint4& aux1) {
+  // scale / bias live in shared memory, 16-byte aligned: four broadcast LDS.128 per 8 columns
+  const float4 s0 = reinterpret_cast<const float4*>(sc)[0], s1 = reinterpret_cast<const float4*>(sc)[1];
+  const float4 b0 = reinterpret_cast<const float4*>(bi)[0], b1 = reinterpret_cast<const float4*>(bi)[1];
+  const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float f[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(r[j]), sc[j], bi[j]);
+  for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(r[j]), s[j], b[j]);
   if (MODE == EPI_SILU || MODE == EPI_SILU_RES) {
+    // the staged scale / bias of these modes are pre-halved (exact), so f is already h = x/2: silu(x) = h + h*tanh(h)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = silu_t(f[j]);
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], tanh_approx(f[j]), f[j]);
   }
   if (MODE == EPI_GELU) {
 #pragma unroll
@@ -398,7 +404,7 @@ __device__ __forceinline__ void epi_store8(const ConvArgs& a, const uint32_t* r,
   for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(r[j]), sc[j], bi[j]);
   if (MODE == EPI_SILU || MODE == EPI_SILU_RES) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = silu_t(f[j]);
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], tanh_approx(f[j]), f[j]);   // staged scale / bias are pre-halved
   }
   if (MODE == EPI_SILU_RES) {
     float rs[8];
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t opnd_bar = aempty_bar + kMaxABuf * 8;                   // [kEpiWarps]
   const uint32_t tmem_slot = full_bar + kNumBars * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail_ptr + bars_off + kNumBars * 8);
-  float* s_scale = reinterpret_cast<float*>(tail_ptr + bars_off + kNumBars * 8 + 16);
+  float* s_scale = reinterpret_cast<float*>(tail_ptr + ((bars_off + kNumBars * 8 + 16 + 15) & ~15u));
   float* s_bias = s_scale + a.sb_floats;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -493,10 +499,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     fence_barrier_init();
   }
   // folded-BN scale / bias of every output channel, staged once (Cout_pad <= kMaxCout, checked on the host)
+  // (SiLU modes keep them halved -- exact -- so the epilogue's FMA yields x/2 directly, see epi_compute8)
+  const float sb_mul = (MODE == EPI_SILU || MODE == EPI_SILU_RES) ? 0.5f : 1.0f;
   for (int i = threadIdx.x; i < a.sb_floats; i += blockDim.x) {
     const bool in = i < a.Cout_pad;
-    s_scale[i] = in ? a.scale[i] : 0.f;
-    s_bias[i] = in ? a.bias[i] : 0.f;
+    s_scale[i] = in ? sb_mul * a.scale[i] : 0.f;
+    s_bias[i] = in ? sb_mul * a.bias[i] : 0.f;
   }
   if (warp == 2) {
     if (PAIR) tmem_alloc2(tmem_slot, (uint32_t)a.tmem_cols);
