@@ -5,6 +5,7 @@
 // x is read once by `pool` from HBM and once by `apply` (L2-resident at cfg-2 sizes: 52 MB < 126 MB
 // L2); the gate tensors are (H+W)/(H*W) of the activation.  All reductions are deterministic
 // (no atomics): a CTA owns complete rows (for mean_w) and complete columns (for mean_h).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dmay {
@@ -392,6 +393,335 @@ __global__ void __launch_bounds__(256) ca_gate_apply_kernel(const __nv_bfloat16*
   }
 }
 
+// ---- fast path, tensor-core variant (Cm <= 32): the same two launches, with the two small dense layers on mma.sync ----
+// The FMA forms above spend ~3 MAC per activation element on the hidden layer and as many on the gates, each with
+// shared-memory operand loads; ncu showed them instruction-bound (50 us per kernel at cfg-2, 16 % of the HBM roofline).
+// Here both layers run as bf16 m16n8k16 MMAs with fp32 = hi + lo operand splitting: a*b ~= ah*bh + ah*bl + al*bh,
+// accumulated in fp32 (relative error ~2^-16, far below the bf16 output rounding), and the plane is staged with
+// cp.async so that every load of a CTA is in flight at once.
+constexpr int kCmPoolPitch = 64 + 8;   // bf16 per pooled / W1 row (144 B = 9 x 16: conflict-free ldmatrix)
+constexpr int kCmYPitch = 32 + 8;      // bf16 per hidden row (80 B)
+constexpr int kCmMax = 32;
+
+__device__ __forceinline__ void cm_split(float v, float& hi, float& lo) {   // v ~= hi + lo, hi exactly representable in bf16
+  hi = __bfloat162float(__float2bfloat16_rn(v));
+  lo = v - hi;
+}
+__device__ __forceinline__ void cm_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(256) ca_pool_hidden_mma_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                 float* __restrict__ pooled_out, float* __restrict__ partial,
+                                                                 float* __restrict__ yhid, unsigned* __restrict__ counters,
+                                                                 const float* __restrict__ w1T, const float* __restrict__ b1,
+                                                                 const float* __restrict__ s1, const float* __restrict__ t1,
+                                                                 int H, int W, int C, int Cm, int ldx, int G) {
+  extern __shared__ uint4 plane[];                    // [H*W][kCaVL]
+  const int HW = H * W, P = H + W, Pp = (P + 15) & ~15, Cmp = (Cm + 15) & ~15;
+  __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(plane + (size_t)HW * kCaVL);   // [Pp][72] pooled means, hi
+  __nv_bfloat16* pl = ph + Pp * kCmPoolPitch;                                         // ... lo
+  __nv_bfloat16* wh = pl + Pp * kCmPoolPitch;                                         // [Cmp][72] W1 slice (row = hidden unit), hi
+  __nv_bfloat16* wl = wh + Cmp * kCmPoolPitch;                                        // ... lo
+  __shared__ unsigned ticket_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, tq = lane & 3;
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int cvec = C >> 3;
+  const int v0 = g * kCaVL;
+  const int vl = min(kCaVL, cvec - v0);
+  const int nch = vl * 8;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the gate kernel may stage its weights while this grid runs
+  // W1 slice [64][Cm] (contiguous in w1T) -> registers first: its latency hides behind the plane loads
+  float wreg[8];
+  const int wtot = nch * Cm;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid + k * 256;
+    wreg[k] = i < wtot ? w1T[(long long)(v0 * 8) * Cm + i] : 0.f;
+  }
+  {
+    const __nv_bfloat16* xb = x + (long long)n * HW * ldx + v0 * 8;
+    const uint32_t plane_s = (uint32_t)__cvta_generic_to_shared(plane);
+    const int v = tid & 7;
+    if (v < vl) {
+      const __nv_bfloat16* src = xb + (long long)(tid >> 3) * ldx + v * 8;
+      uint32_t dst = plane_s + (uint32_t)tid * 16u;
+      for (int p = tid >> 3; p < HW; p += 32) {
+        cm_cp_async16(dst, src);
+        src += 32LL * ldx;
+        dst += 256u * 16u;
+      }
+    } else {   // channel vectors beyond C (partial last group) read as zero
+      for (int p = tid >> 3; p < HW; p += 32) plane[p * kCaVL + v] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // W1 -> shared, transposed to [unit][channel] and split (rows >= Cm and channels >= nch are zero)
+  for (int i = tid; i < Cmp * kCmPoolPitch / 4; i += 256) reinterpret_cast<uint4*>(wh)[i] = make_uint4(0, 0, 0, 0);   // wh and wl are contiguous
+  __syncthreads();
+  {
+    const bool pow2 = (Cm & (Cm - 1)) == 0;
+    const int sh = 31 - __clz(Cm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = tid + k * 256;
+      if (i < wtot) {
+        const int c = pow2 ? (i >> sh) : i / Cm, j = i - c * Cm;
+        float hi, lo;
+        cm_split(wreg[k], hi, lo);
+        wh[j * kCmPoolPitch + c] = __float2bfloat16_rn(hi);
+        wl[j * kCmPoolPitch + c] = __float2bfloat16_rn(lo);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // pooled means: task = (position, 8-channel vector)
+  const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+  for (int i = tid; i < Pp * kCaVL; i += 256) {
+    const int p = i >> 3, v = i & 7;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (p < P) {
+      int start, step, cnt;
+      float inv;
+      if (p < H) { start = p * W; step = kCaVL; cnt = W; inv = invW; }
+      else { start = p - H; step = W * kCaVL; cnt = H; inv = invH; }
+      const uint4* src = plane + start * kCaVL + v;
+      f32x2_t a2[4] = {0ull, 0ull, 0ull, 0ull};   // packed pairs: 8 unpack + 4 FADD2 per 16-byte vector
+#pragma unroll 4
+      for (int k = 0; k < cnt; ++k) {
+        const uint4 u = *src;
+        src += step;
+        a2[0] = f2_add(a2[0], f2_from_bf2(u.x));
+        a2[1] = f2_add(a2[1], f2_from_bf2(u.y));
+        a2[2] = f2_add(a2[2], f2_from_bf2(u.z));
+        a2[3] = f2_add(a2[3], f2_from_bf2(u.w));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f2_unpack(a2[j], acc[2 * j], acc[2 * j + 1]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= inv;
+      if (pooled_out != nullptr && v < vl) {
+        float4* o = reinterpret_cast<float4*>(pooled_out + ((long long)n * P + p) * C + (v0 + v) * 8);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+    float hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cm_split(acc[j], hi[j], lo[j]);
+    *reinterpret_cast<uint4*>(ph + p * kCmPoolPitch + v * 8) = pack8(hi);
+    *reinterpret_cast<uint4*>(pl + p * kCmPoolPitch + v * 8) = pack8(lo);
+  }
+  __syncthreads();
+  // partial hidden layer of this channel group: [P][Cm] = pooled[P][64] . W1slice^T, tiles of 16 positions x 8 units
+  {
+    float* part = partial + (long long)(n * G + g) * P * Cm;
+    const int mtiles = Pp >> 4, ntiles = Cmp >> 3;
+    const uint32_t ph_s = (uint32_t)__cvta_generic_to_shared(ph), pl_s = (uint32_t)__cvta_generic_to_shared(pl);
+    const uint32_t wh_s = (uint32_t)__cvta_generic_to_shared(wh), wl_s = (uint32_t)__cvta_generic_to_shared(wl);
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kof = (lane >> 4) * 8;
+    const int b_row = lane & 7, b_kof = ((lane >> 3) & 3) * 8;   // x4: two k-steps of one 8-unit tile
+    for (int tile = warp; tile < mtiles * ntiles; tile += 8) {
+      const int mt = tile / ntiles, nt = tile - mt * ntiles;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t aoff = (uint32_t)((mt * 16 + a_row) * kCmPoolPitch + a_kof) * 2u;
+      const uint32_t boff = (uint32_t)((nt * 8 + b_row) * kCmPoolPitch + b_kof) * 2u;
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {   // pairs of k-steps (32 channels)
+        uint32_t bh[4], bl[4];
+        ldsm_x4(wh_s + boff + kp * 64, bh[0], bh[1], bh[2], bh[3]);
+        ldsm_x4(wl_s + boff + kp * 64, bl[0], bl[1], bl[2], bl[3]);
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          uint32_t ah[4], al[4];
+          ldsm_x4(ph_s + aoff + (kp * 2 + k2) * 32, ah[0], ah[1], ah[2], ah[3]);
+          ldsm_x4(pl_s + aoff + (kp * 2 + k2) * 32, al[0], al[1], al[2], al[3]);
+          mma_bf16(acc, ah[0], ah[1], ah[2], ah[3], bh[k2 * 2], bh[k2 * 2 + 1]);
+          mma_bf16(acc, ah[0], ah[1], ah[2], ah[3], bl[k2 * 2], bl[k2 * 2 + 1]);
+          mma_bf16(acc, al[0], al[1], al[2], al[3], bh[k2 * 2], bh[k2 * 2 + 1]);
+        }
+      }
+      const int j = nt * 8 + tq * 2, p0 = mt * 16 + g8, p1 = p0 + 8;
+      if (j < Cm) {   // Cm is a multiple of 8 in every reference model; guard the odd case element-wise
+        if (p0 < P) { part[p0 * Cm + j] = acc[0]; if (j + 1 < Cm) part[p0 * Cm + j + 1] = acc[1]; }
+        if (p1 < P) { part[p1 * Cm + j] = acc[2]; if (j + 1 < Cm) part[p1 * Cm + j + 1] = acc[3]; }
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket_s = atomicAdd(counters + n, 1u);
+  __syncthreads();
+  if (ticket_s == (unsigned)(G - 1)) {   // every other group of this image has published its partial
+    __threadfence();
+    const float* pn = partial + (long long)n * G * P * Cm;
+    for (int o = tid; o < P * Cm; o += 256) {
+      const int j = o % Cm;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int gg = 0; gg < G; ++gg) acc += __ldcg(pn + (long long)gg * P * Cm + o);
+      yhid[(long long)n * P * Cm + o] = hardswish(s1[j] * (acc + b1[j]) + t1[j]);
+    }
+    if (tid == 0) counters[n] = 0u;   // ready for the next launch
+  }
+}
+
+__global__ void __launch_bounds__(256) ca_gate_apply_mma_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ yhid,
+                                                                __nv_bfloat16* __restrict__ out, float* __restrict__ gates_out,
+                                                                const float* __restrict__ whT, const float* __restrict__ bh,
+                                                                const float* __restrict__ wwT, const float* __restrict__ bw,
+                                                                int H, int W, int C, int Cm, int ldx, int ldy, int G) {
+  extern __shared__ __align__(16) unsigned char cg_smem[];
+  const int HW = H * W, P = H + W, Pp = (P + 15) & ~15, Cmp = (Cm + 15) & ~15;
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(cg_smem);          // [Pp][40] hidden activations, hi
+  __nv_bfloat16* yl = yh + Pp * kCmYPitch;                                 // ... lo
+  float* gs = reinterpret_cast<float*>(yl + Pp * kCmYPitch);               // [P][2][8][4]: gates of the group's 64 channels
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, tq = lane & 3;
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int cvec = C >> 3;
+  const int v0 = g * kCaVL;
+  const int vl = min(kCaVL, cvec - v0);
+  const int nch = vl * 8;
+  // pull this CTA's slice of x towards L2 now: it does not depend on the pool kernel, so under programmatic dependent
+  // launch the HBM reads overlap the pool kernel's tail and this kernel's own gate set-up
+  {
+    const __nv_bfloat16* xg = x + (long long)n * HW * ldx + v0 * 8;
+    for (int p = tid; p < HW; p += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(xg + (long long)p * ldx));
+  }
+  // gate weights of this warp's two 8-channel tiles as MMA B fragments, straight from global (L2-resident, read once)
+  uint32_t wgh[2][2][2], wgl[2][2][2];
+  float gb[2][2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int ntile = warp * 2 + t, type = ntile >> 3, vv = ntile & 7;   // tiles 0-7: h gates, 8-15: w gates
+    const float* wT = type ? wwT : whT;
+    const float* bb = type ? bw : bh;
+    const int cl = vv * 8 + g8;
+    const bool cin = cl < nch;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int k0 = ks * 16 + tq * 2 + half * 8;
+        const float a0 = (cin && k0 < Cm) ? wT[(long long)k0 * C + v0 * 8 + cl] : 0.f;
+        const float a1 = (cin && k0 + 1 < Cm) ? wT[(long long)(k0 + 1) * C + v0 * 8 + cl] : 0.f;
+        float h0, l0, h1, l1;
+        cm_split(a0, h0, l0);
+        cm_split(a1, h1, l1);
+        wgh[t][ks][half] = pack_bf2(h0, h1);
+        wgl[t][ks][half] = pack_bf2(l0, l1);
+      }
+    }
+    const int ce = vv * 8 + tq * 2;
+    gb[t][0] = ce < nch ? bb[v0 * 8 + ce] : 0.f;
+    gb[t][1] = ce + 1 < nch ? bb[v0 * 8 + ce + 1] : 0.f;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // y comes from the pool kernel (programmatic dependent launch)
+  for (int i = tid; i < Pp * kCmYPitch; i += 256) {
+    const int p = i / kCmYPitch, j = i - p * kCmYPitch;
+    const float v = (p < P && j < Cm) ? yhid[((long long)n * P + p) * Cm + j] : 0.f;
+    float hi, lo;
+    cm_split(v, hi, lo);
+    yh[i] = __float2bfloat16_rn(hi);
+    yl[i] = __float2bfloat16_rn(lo);
+  }
+  __syncthreads();
+  {
+    const uint32_t yh_s = (uint32_t)__cvta_generic_to_shared(yh), yl_s = (uint32_t)__cvta_generic_to_shared(yl);
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kof = (lane >> 4) * 8;
+    const int ksG = Cmp >> 4, mtiles = Pp >> 4;
+    for (int mt = 0; mt < mtiles; ++mt) {
+      // warps 0-3 hold h-gate tiles (positions < H), warps 4-7 w-gate tiles (positions H .. P-1): skip tiles without rows
+      const bool is_w = warp >= 4;
+      if (is_w ? (mt * 16 + 15 < H || mt * 16 >= P) : (mt * 16 >= H)) continue;
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const uint32_t aoff = (uint32_t)((mt * 16 + a_row) * kCmYPitch + a_kof) * 2u;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks < ksG) {
+          uint32_t ah[4], al[4];
+          ldsm_x4(yh_s + aoff + ks * 32, ah[0], ah[1], ah[2], ah[3]);
+          ldsm_x4(yl_s + aoff + ks * 32, al[0], al[1], al[2], al[3]);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mma_bf16(acc[t], ah[0], ah[1], ah[2], ah[3], wgh[t][ks][0], wgh[t][ks][1]);
+            mma_bf16(acc[t], ah[0], ah[1], ah[2], ah[3], wgl[t][ks][0], wgl[t][ks][1]);
+            mma_bf16(acc[t], al[0], al[1], al[2], al[3], wgh[t][ks][0], wgh[t][ks][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int vv = (warp * 2 + t) & 7;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int pos = mt * 16 + g8 + rr * 8;
+          if (is_w ? (pos >= H && pos < P) : (pos < H)) {
+            const float g0 = sigmoid_fast(acc[t][rr * 2] + gb[t][0]), g1 = sigmoid_fast(acc[t][rr * 2 + 1] + gb[t][1]);
+            // layout [pos][half][vector][4]: the apply loop reads two conflict-free float4 per 8-channel vector
+            *reinterpret_cast<float2*>(gs + pos * 64 + (tq >> 1) * 32 + vv * 4 + (tq & 1) * 2) = make_float2(g0, g1);
+            const int ce = vv * 8 + tq * 2;
+            if (gates_out != nullptr && ce < nch)
+              *reinterpret_cast<float2*>(gates_out + ((long long)n * P + pos) * C + v0 * 8 + ce) = make_float2(g0, g1);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // apply: thread = (8-channel vector, pixel row mod 32); four 16-byte loads in flight, pointer increments only
+  const int v = tid & 7;
+  if (v >= vl) return;
+  constexpr int kRows = 32;
+  int p = tid >> 3;
+  const int h0_ = p / W;
+  int w_ = p - h0_ * W;
+  const int dH = kRows / W, dW = kRows - dH * W;
+  const __nv_bfloat16* xb = x + (long long)n * HW * ldx + v0 * 8 + v * 8;     // per-image offsets fit 32 bits (checked on the host)
+  __nv_bfloat16* ob = out + (long long)n * HW * ldy + v0 * 8 + v * 8;
+  int xo = p * ldx, oo = p * ldy;
+  const int xstep = kRows * ldx, ostep = kRows * ldy;
+  const float* gh = gs + h0_ * 64 + v * 4;
+  const float* gw = gs + (H + w_) * 64 + v * 4;
+  while (p < HW) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = (p + u * kRows < HW) ? ld_nc16(xb + xo + u * xstep) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p < HW) {
+        const float4 h0 = *reinterpret_cast<const float4*>(gh), h1 = *reinterpret_cast<const float4*>(gh + 32);
+        const float4 w0 = *reinterpret_cast<const float4*>(gw), w1 = *reinterpret_cast<const float4*>(gw + 32);
+        // (x * a_w) * a_h on packed pairs: same IEEE roundings as the scalar form, half the issue slots
+        const f32x2_t q0 = f2_mul(f2_mul(f2_from_bf2(r[u].x), f2_pack(w0.x, w0.y)), f2_pack(h0.x, h0.y));
+        const f32x2_t q1 = f2_mul(f2_mul(f2_from_bf2(r[u].y), f2_pack(w0.z, w0.w)), f2_pack(h0.z, h0.w));
+        const f32x2_t q2 = f2_mul(f2_mul(f2_from_bf2(r[u].z), f2_pack(w1.x, w1.y)), f2_pack(h1.x, h1.y));
+        const f32x2_t q3 = f2_mul(f2_mul(f2_from_bf2(r[u].w), f2_pack(w1.z, w1.w)), f2_pack(h1.z, h1.w));
+        float f[8];
+        f2_unpack(q0, f[0], f[1]);
+        f2_unpack(q1, f[2], f[3]);
+        f2_unpack(q2, f[4], f[5]);
+        f2_unpack(q3, f[6], f[7]);
+        st_na16(ob + oo, pack8(f));
+      }
+      p += kRows;
+      xo += xstep;
+      oo += ostep;
+      w_ += dW;
+      gh += dH * 64;
+      gw += dW * 64;
+      if (w_ >= W) {
+        w_ -= W;
+        gh += 64;
+        gw -= W * 64;
+      }
+    }
+  }
+}
+
 }  // namespace dmay
 
 using namespace dmay;
@@ -401,6 +731,7 @@ extern "C" long long dmay_coordatt_ws(int N, int H, int W, int C, int Cm) {
   const long long G = (C / 8 + kCaVL - 1) / kCaVL, P = H + W;
   return ((long long)N * G * P * Cm + (long long)N * P * Cm) * 4 + (long long)N * 4;
 }
+
 
 extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream) {
   if (!p || !p->x || !p->y || !p->w1 || !p->b1 || !p->s1 || !p->t1 || !p->wh || !p->bh || !p->ww || !p->bw)
@@ -426,6 +757,44 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
       float* partial = (float*)p->ws;
       float* yhid = partial + (long long)p->N * G * P * p->Cm;
       unsigned* counters = (unsigned*)(yhid + (long long)p->N * P * p->Cm);   // zero on first use, self-resetting
+      // tensor-core variant of both kernels (hidden layer and gates as split-bf16 MMAs): every reference model has Cm <= 32
+      static const bool no_mma = [] { const char* e = getenv("DMAY_CA_MMA"); return e && e[0] == '0'; }();
+      const int Pp = (P + 15) & ~15, Cmp = (p->Cm + 15) & ~15;
+      const size_t smem1m = (size_t)HW * kCaVL * 16 + (size_t)2 * (Pp + Cmp) * kCmPoolPitch * 2;
+      const size_t smem2m = (size_t)2 * Pp * kCmYPitch * 2 + (size_t)P * 64 * 4;
+      if (!no_mma && p->Cm <= kCmMax && smem1m <= 100 * 1024 && smem2m <= 100 * 1024 &&
+          HW * (long long)(p->ldx > p->ldy ? p->ldx : p->ldy) < 0x7fffffffLL) {
+        static size_t set1 = 48 * 1024, set2 = 48 * 1024;
+        if (smem1m > set1) {
+          cudaError_t e = cudaFuncSetAttribute(ca_pool_hidden_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1m);
+          if (e != cudaSuccess) return (int)e;
+          set1 = smem1m;
+        }
+        if (smem2m > set2) {
+          cudaError_t e = cudaFuncSetAttribute(ca_gate_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2m);
+          if (e != cudaSuccess) return (int)e;
+          set2 = smem2m;
+        }
+        ca_pool_hidden_mma_kernel<<<p->N * G, 256, smem1m, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, partial, yhid,
+                                                               counters, (const float*)p->w1, (const float*)p->b1,
+                                                               (const float*)p->s1, (const float*)p->t1, p->H, p->W, p->C, p->Cm,
+                                                               p->ldx, G);
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3(p->N * G);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem2m;
+        cfg.stream = s;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, ca_gate_apply_mma_kernel, (const __nv_bfloat16*)p->x, (const float*)yhid,
+                                           (__nv_bfloat16*)p->y, (float*)p->gates, (const float*)p->wh, (const float*)p->bh,
+                                           (const float*)p->ww, (const float*)p->bw, p->H, p->W, p->C, p->Cm, p->ldx, p->ldy, G);
+        if (e != cudaSuccess) return (int)e;
+        return finish_launch(2);
+      }
       if (smem1 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(ca_pool_hidden_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) return (int)e;

@@ -305,6 +305,8 @@ int dmay_scconv_gate(const dmay_scgate_params* p, dmay_stream_t stream);
  * dmay_coordatt runs the three steps on the stream.
  * Fast path (two launches; taken when `ws` is given and a 64-channel plane fits in shared memory): pool + partial
  * hidden layer per (image, 64-channel group) with the image's last CTA finishing y, then gates + apply per group.
+ * For Cm <= 32 (every reference model) the two small dense layers run on mma.sync with fp32 = bf16 hi + lo operand
+ * splitting (three products, fp32 accumulate: ~2^-16 relative), the second launch is a programmatic dependent launch.
  * ws: workspace of dmay_coordatt_ws() bytes, ZERO-initialised before its first use (it holds per-image arrival
  * tickets that the kernel resets itself; one workspace per stream).  pooled / gates may then be NULL (they are
  * only written when given). */

@@ -76,13 +76,14 @@ def test_coordatt_stages_vs_oracle(shape):
 
 
 def test_coordatt_fast_path_is_repeatable_without_side_outputs():
-    """Two-launch path (pool + partial hidden layer with a last-CTA reduction, then gates + apply): the arrival
-    tickets reset themselves, so repeated calls on one workspace agree bit for bit and match the 3-stage result."""
+    """Two-launch path (pool + partial hidden layer with a last-CTA reduction, then gates + apply; taken when the channel
+    count is not a multiple of 128): the arrival tickets reset themselves, so repeated calls on one workspace agree bit
+    for bit and match the 3-stage result."""
     from dma_yolo_b200 import ops
     from dma_yolo_b200.models import common as C
     torch.manual_seed(3)
-    m = C.CoorAttention(256, 256).eval()
-    x = ops.as_act(bf(torch.randn(3, 256, 20, 12)).cuda())
+    m = C.CoorAttention(192, 192).eval()
+    x = ops.as_act(bf(torch.randn(3, 192, 20, 12)).cuda())
     pk = ops.pack_coordatt(m.conv1, m.bn1, m.conv_h, m.conv_w, 'cuda')
     y1 = ops.coordatt(x, pk).clone()
     y2 = ops.coordatt(x, pk).clone()
@@ -91,3 +92,60 @@ def test_coordatt_fast_path_is_repeatable_without_side_outputs():
     with torch.no_grad():
         ref = m(back(x))
     assert_close(back(y1), ref, atol=1e-2, rtol=1e-2, what='coordatt fast path')
+
+
+def _ref_gates(m, x):
+    """fp32 gates of the module, [n, h+w, c] (rows 0..h-1: a_h, rows h..: a_w) -- models/common.py:1183-1207."""
+    import torch.nn.functional as F
+    n, c, h, w = x.shape
+    with torch.no_grad():
+        y = torch.cat([x.mean(3, keepdim=True), x.mean(2, keepdim=True).permute(0, 1, 3, 2)], 2)
+        y = F.hardswish(m.bn1(m.conv1(y)))
+        yh, yw = torch.split(y, [h, w], 2)
+        a_h = torch.sigmoid(m.conv_h(yh))[..., 0]                        # [n, c, h]
+        a_w = torch.sigmoid(m.conv_w(yw.permute(0, 1, 3, 2)))[:, :, 0]   # [n, c, w]
+    return torch.cat([a_h, a_w], 2).permute(0, 2, 1).contiguous()
+
+
+@pytest.mark.parametrize('shape', [(3, 1024, 20, 20), (2, 256, 20, 12), (2, 128, 7, 5), (5, 512, 24, 24), (70, 1024, 20, 15),
+                                   (1, 1024, 1, 1), (2, 384, 9, 30), (2, 72, 13, 11), (1, 64, 48, 40)])
+def test_coordatt_mma_fast_path(shape):
+    """Two-launch path with the hidden layer and the gates on mma.sync (fp32 operands split into bf16 hi + lo, three
+    products): bit-repeatable, gates within 3e-5 of the fp32 module (the split keeps ~16 mantissa bits), output within
+    tolerance.  Covers Cm = 8/16/32, H != W, a partial last channel group (C = 72), position counts that are not a
+    multiple of the 16-row MMA tile and tiles that straddle the h / w gate boundary."""
+    from dma_yolo_b200 import ops
+    from dma_yolo_b200.models import common as C
+    n, c, h, w = shape
+    torch.manual_seed(c + h + w)
+    m = C.CoorAttention(c, c).eval()
+    m.bn1.running_mean.normal_(0, 0.2)
+    m.bn1.running_var.uniform_(0.5, 1.5)
+    xc = bf(torch.randn(*shape))
+    x = ops.as_act(xc.cuda())
+    pk = ops.pack_coordatt(m.conv1, m.bn1, m.conv_h, m.conv_w, 'cuda')
+    y1 = ops.coordatt(x, pk).clone()
+    y2 = ops.coordatt(x, pk).clone()
+    y3, pooled, gates = ops.coordatt(x, pk, return_gates=True)
+    assert torch.equal(y1, y2) and torch.equal(y1, y3)
+    assert_close(gates.cpu(), _ref_gates(m, xc), atol=3e-5, rtol=0, what='gates')
+    with torch.no_grad():
+        ref = m(xc)
+    assert_close(back(y1), ref, atol=1e-2, rtol=1e-2, what='coordatt fast path')
+
+
+def test_coordatt_strided_slab():
+    """Input and output are channel slices of wider NHWC slabs (ldx, ldy > C), as inside a C3 concat slab."""
+    from dma_yolo_b200 import ops
+    from dma_yolo_b200.models import common as C
+    torch.manual_seed(11)
+    m = C.CoorAttention(256, 256).eval()
+    slab_in = ops.as_act(bf(torch.randn(2, 640, 12, 16)).cuda())
+    slab_out = ops.as_act(torch.zeros(2, 512, 12, 16).cuda())
+    x = slab_in[:, 128:384]
+    pk = ops.pack_coordatt(m.conv1, m.bn1, m.conv_h, m.conv_w, 'cuda')
+    ops.coordatt(x, pk, out=slab_out[:, 256:])
+    with torch.no_grad():
+        ref = m(back(x))
+    assert_close(back(slab_out[:, 256:]), ref, atol=1e-2, rtol=1e-2, what='coordatt slab')
+    assert float(slab_out[:, :256].abs().max()) == 0.0

@@ -143,7 +143,7 @@ def main():
     conv1, bn1, ch, cw = nn.Conv2d(c, 32, 1), nn.BatchNorm2d(32).eval(), nn.Conv2d(32, c, 1), nn.Conv2d(32, c, 1)
     pk = ops.pack_coordatt(conv1, bn1, ch, cw, dev)
     x, out = act(c, 20, 20), act(c, 20, 20)
-    rec('coordatt c1024@20 (2 kernels)', timeit(lambda: ops.coordatt(x, pk, out=out), flush=flush), gbytes=2 * B * c * 400 * 2 / 1e9)
+    rec('coordatt c1024@20', timeit(lambda: ops.coordatt(x, pk, out=out), flush=flush), gbytes=2 * B * c * 400 * 2 / 1e9)
     del x, out
     # a4 SPD (cfg-4 shape scaled to this batch)
     x = act(64, 320, 320)
