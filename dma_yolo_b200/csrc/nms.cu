@@ -12,6 +12,7 @@
 // Arithmetic contract (bit-exact keep indices): every fp32 operation that the reference performs on
 // boxes / scores is issued with explicit round-to-nearest intrinsics so nvcc cannot contract a
 // multiply into a following add (no FMA), IoU uses IEEE division and is compared in double.
+#include <stdlib.h>
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cstring>
@@ -292,7 +293,9 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 }
 
 // exclusive prefix of `count` over all tiles before `tile` (called by one full warp; 32 predecessors per poll —
-// a 256-wide window was measured slower: 0.71 vs 0.58 ms, the kernel is instruction-bound, not look-back-bound)
+// wider windows were measured slower in both filter kernels: 256-wide 0.71 vs 0.58 ms in the warp-per-row one,
+// 128-wide 0.39 / 0.35 (with back-off) vs 0.34 ms in the thread-per-row one.  What a tile waits for is the slowest of
+// its ~700 in-flight predecessors to publish a count, not the walk over their status words)
 __device__ __forceinline__ long long tile_lookback(unsigned long long* status, int tile, int count, int lane) {
   constexpr unsigned long long kAgg = 1ull << 62, kIncl = 2ull << 62, kVal = (1ull << 62) - 1;
   if (tile == 0) {
@@ -492,6 +495,194 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
       cd[0] = x1; cd[1] = y1; cd[2] = x2; cd[3] = y2; cd[4] = s[4]; cd[5] = s[5];
       keys[g0] = ((unsigned long long)(unsigned)img << 32) | (unsigned long long)(~__float_as_uint(s[4]));
     }
+  }
+}
+
+// ---- fused single-pass filter, one THREAD per row (nc <= 96) -------------------------------------------------
+// ncu of the warp-per-row kernel above: 86 thread-instructions per logit (a 32-lane warp walks one 85-logit row: three
+// passes with the last one two-thirds empty, five shuffles, lane-0-only box decode, a second pass to re-test every
+// class).  Here a thread owns a row.  Multi-label rows do not evaluate sigmoid(c)*obj for every class: since that
+// product is monotonic in the class logit c, a class can only pass when c > logit(thr / obj); the kernel compares the
+// raw logits against that bound minus a safety margin (the bound is clamped, so every class whose exact test could
+// succeed is still evaluated) and runs the reference arithmetic -- fl(fl(sigmoid(c)) * obj) > thr -- only on those.
+// The passing classes are remembered as a 96-bit mask, so the write pass touches nothing else.  Candidate sets, order
+// and values are identical to the kernel above (tests compare both with the CPU restatement).
+constexpr int kRowsThreads = 128;   // rows (pixels of one anchor) per tile == threads per CTA
+constexpr int kRowsMaxNc = 96;
+
+__global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
+                                                                         const unsigned char* __restrict__ class_mask,
+                                                                         unsigned* __restrict__ ticket,
+                                                                         unsigned long long* __restrict__ status,
+                                                                         long long* __restrict__ img_offsets,
+                                                                         unsigned long long* __restrict__ keys,
+                                                                         float* __restrict__ cand) {
+  extern __shared__ float tile[];     // [rows][no]
+  __shared__ int warp_tot[kRowsThreads / 32];
+  __shared__ long long base_s;
+  __shared__ int tile_s;
+  if (threadIdx.x == 0) tile_s = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile_id = tile_s;
+  const int tiles_img = fa.tile0[fa.levels];
+  const int img = tile_id / tiles_img;
+  int t = tile_id - img * tiles_img;
+  int l = 0;
+  while (l + 1 < fa.levels && t >= fa.tile0[l + 1]) ++l;
+  t -= fa.tile0[l];
+  const LevelMeta& m = fa.meta[l];
+  const int a = t / fa.tpa[l], ti = t - a * fa.tpa[l];
+  const int npix = m.ny * m.nx;
+  const int p0 = ti * kRowsThreads;
+  const int np = min(kRowsThreads, npix - p0);
+  const int nc = fa.nc, no = 5 + nc, ld = m.ld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float thr = fa.thr;
+  {   // stage: a warp copies whole rows (coalesced along the row; 4-byte cp.async, rows are only 4-byte aligned)
+    const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * no;
+    const uint32_t tile_sm = (uint32_t)__cvta_generic_to_shared(tile);
+    // per row: nfull unconditional copies (lane, lane + 32, ...) and one partial; addresses advance by constants
+    const int nfull = no >> 5, rem = no & 31;
+    const uint32_t rem_off = (uint32_t)nfull * 128u;
+    uint32_t sdst = tile_sm + (uint32_t)(warp * no + lane) * 4u;
+    const float* g = gsrc + (long long)warp * ld + lane;
+    const uint32_t sstep = (uint32_t)(kRowsThreads / 32) * (uint32_t)no * 4u;
+    const long long gstep = (long long)(kRowsThreads / 32) * ld;
+    for (int row = warp; row < np; row += kRowsThreads / 32) {
+      // no <= 5 + kRowsMaxNc = 101: at most three full 32-lane copies; straight-line code with uniform predicates
+      if (nfull > 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(g) : "memory");
+      if (nfull > 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 128u), "l"(g + 32) : "memory");
+      if (nfull > 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 256u), "l"(g + 64) : "memory");
+      if (lane < rem) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + rem_off), "l"(g + nfull * 32) : "memory");
+      sdst += sstep;
+      g += gstep;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int row = threadIdx.x;
+  float* s = tile + row * no;     // row stride 5 + nc words: conflict-free whenever it is odd (nc = 80, 10, ...)
+  int cnt = 0;
+  uint32_t pm[3] = {0u, 0u, 0u};  // passing classes
+  float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, bconf = 0.f;
+  int bcls = 0;
+  if (row < np) {
+    const float obj = sigmoid_dec(s[4]);
+    if (obj > thr) {
+      if (fa.multi_label) {
+        // conservative pre-filter on the raw logit (see the header comment); exact test only for survivors
+        const float q = (thr / obj) * (1.0f - 4e-6f);
+        float t_lo = -INFINITY;
+        if (q > 0.f) t_lo = q < 1.f ? fminf(__logf(q / (1.0f - q)) - 0.02f, 10.0f) : 10.0f;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {   // 32 classes per mask word (static register indexing)
+          uint32_t mk = 0u;
+          const int cend = min(32, nc - w * 32);
+          const float* sc = s + 5 + w * 32;
+#pragma unroll 8
+          for (int cc = 0; cc < cend; ++cc) {
+            const float v = sc[cc];
+            if (v > t_lo) {
+              const float conf = __fmul_rn(sigmoid_dec(v), obj);
+              if (conf > thr && (class_mask == nullptr || class_mask[w * 32 + cc])) {
+                s[5 + w * 32 + cc] = conf;
+                mk |= 1u << cc;
+                ++cnt;
+              }
+            }
+          }
+          pm[w] = mk;
+        }
+      } else {
+        // best class: first maximum (torch.max on CPU); NaN anywhere -> no candidate
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        bool has_nan = false;
+        for (int c = 0; c < nc; ++c) {
+          const float conf = __fmul_rn(sigmoid_dec(s[5 + c]), obj);
+          if (conf != conf) has_nan = true;
+          if (conf > best) {
+            best = conf;
+            bi = c;
+          }
+        }
+        if (!has_nan && best > thr && bi < nc && (class_mask == nullptr || class_mask[bi])) {
+          cnt = 1;
+          bconf = best;
+          bcls = bi;
+        }
+      }
+      if (cnt > 0) {
+        const int pix = p0 + row;
+        const int gy = pix / m.nx, gx = pix - gy * m.nx;
+        const float sx = sigmoid_dec(s[0]), sy = sigmoid_dec(s[1]), sw = sigmoid_dec(s[2]), sh = sigmoid_dec(s[3]);
+        // models/yolo.py:91-97 operation order, then xywh2xyxy (utils/general.py:539-546)
+        const float x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), m.stride);
+        const float y = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.f), 0.5f), (float)gy), m.stride);
+        const float tw = __fmul_rn(sw, 2.f), th = __fmul_rn(sh, 2.f);
+        const float w = __fmul_rn(__fmul_rn(tw, tw), m.anchor[2 * a]);
+        const float h = __fmul_rn(__fmul_rn(th, th), m.anchor[2 * a + 1]);
+        const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+        x1 = __fsub_rn(x, hw);
+        y1 = __fsub_rn(y, hh);
+        x2 = __fadd_rn(x, hw);
+        y2 = __fadd_rn(y, hh);
+      }
+    }
+  }
+  // ---- exclusive scan of the row counts over the CTA, then this tile's place among all tiles (warp 0) ----
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kRowsThreads / 32; ++w) {
+    const int v = warp_tot[w];
+    if (w < warp) before += v;
+    total += v;
+  }
+  if (warp == 0) {
+    const long long excl = tile_lookback(status, tile_id, total, lane);
+    if (lane == 0) {
+      base_s = excl;
+      if (tile_id == img * tiles_img) img_offsets[img] = excl;                          // first tile of an image
+      if (tile_id == fa.N * tiles_img - 1) img_offsets[fa.N] = excl + total;            // last tile: batch total
+    }
+  }
+  __syncthreads();
+  if (cnt == 0) return;
+  long long g = base_s + before + inc - cnt;
+  const unsigned long long img_hi = (unsigned long long)(unsigned)img << 32;
+  if (fa.multi_label) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      uint32_t mk = pm[w];
+      while (mk) {
+        const int c = w * 32 + __ffs(mk) - 1;
+        mk &= mk - 1;
+        if (g < fa.capacity) {
+          const float conf = s[5 + c];
+          float2* cd = reinterpret_cast<float2*>(cand + g * 6);   // 24-byte rows: three aligned 8-byte stores
+          cd[0] = make_float2(x1, y1);
+          cd[1] = make_float2(x2, y2);
+          cd[2] = make_float2(conf, (float)c);
+          keys[g] = img_hi | (unsigned long long)(~__float_as_uint(conf));
+        }
+        ++g;
+      }
+    }
+  } else if (g < fa.capacity) {
+    float2* cd = reinterpret_cast<float2*>(cand + g * 6);
+    cd[0] = make_float2(x1, y1);
+    cd[1] = make_float2(x2, y2);
+    cd[2] = make_float2(bconf, (float)bcls);
+    keys[g] = img_hi | (unsigned long long)(~__float_as_uint(bconf));
   }
 }
 
@@ -936,11 +1127,11 @@ int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream) {
   return finish_launch();
 }
 
-static long long fused_tiles_per_image(const LevelMeta* hm, int levels, FuseArgs* fa) {
+static long long fused_tiles_per_image(const LevelMeta* hm, int levels, FuseArgs* fa, int P = kFuseP) {
   long long tiles = 0;
   for (int l = 0; l < levels; ++l) {
     const int npix = hm[l].ny * hm[l].nx;
-    const int tpa = (npix + kFuseP - 1) / kFuseP;
+    const int tpa = (npix + P - 1) / P;
     if (fa) {
       fa->tpa[l] = tpa;
       fa->tile0[l] = (int)tiles;
@@ -975,13 +1166,18 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
     fa.meta[l] = m;
     rows += (long long)m.na * m.ny * m.nx;
   }
-  const long long tiles = (long long)p->N * fused_tiles_per_image(hm, p->levels, &fa);
+  // thread-per-row kernel for nc <= 96 (DMAY_FILTER_ROWS=0 keeps the warp-per-row one, for A/B runs and the tests)
+  static const bool no_rows = [] { const char* e = getenv("DMAY_FILTER_ROWS"); return e && e[0] == '0'; }();
+  const bool rows_kernel = !no_rows && p->nc <= kRowsMaxNc && (size_t)kRowsThreads * (5 + p->nc) * sizeof(float) <= 100 * 1024;
+  const int P = rows_kernel ? kRowsThreads : kFuseP;
+  const long long tiles = (long long)p->N * fused_tiles_per_image(hm, p->levels, &fa, P);
   if (tiles > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
   if (p->ws_bytes < 16 + 8 * tiles) return DMAY_ETOOBIG;
-  const size_t smem = (size_t)kFuseP * (5 + p->nc) * sizeof(float);
+  const size_t smem = (size_t)P * (5 + p->nc) * sizeof(float);
   if (smem > 200 * 1024) return DMAY_EUNSUPPORTED;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(filter_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = rows_kernel ? cudaFuncSetAttribute(filter_fused_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(filter_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
   fa.levels = p->levels;
@@ -993,9 +1189,14 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   cudaStream_t s = (cudaStream_t)stream;
   unsigned* ticket = (unsigned*)p->ws;
   unsigned long long* status = (unsigned long long*)((char*)p->ws + 16);
-  filter_fused_kernel<<<(int)tiles, kFuseThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
-                                                           (long long*)p->img_offsets, (unsigned long long*)p->keys,
-                                                           (float*)p->cand);
+  if (rows_kernel)
+    filter_fused_rows_kernel<<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
+                                                                  (long long*)p->img_offsets, (unsigned long long*)p->keys,
+                                                                  (float*)p->cand);
+  else
+    filter_fused_kernel<<<(int)tiles, kFuseThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
+                                                             (long long*)p->img_offsets, (unsigned long long*)p->keys,
+                                                             (float*)p->cand);
   img_counts_kernel<<<(p->N + 255) / 256, 256, 0, s>>>((const long long*)p->img_offsets, (int*)p->img_counts, p->N);
   return finish_launch(2);
 }

@@ -519,6 +519,22 @@ def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, 
         keep_alive = (pred,)
     s = torch.cuda.current_stream(dev).cuda_stream
     multi_label = bool(multi_label) and nc > 1
+    out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
+    out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
+    keys, cand, img_counts, img_offsets, offs_host, total = _ordered_candidates(src, n, rows, nc, conf_thres, multi_label,
+                                                                                classes, dev, s)
+    if total == 0:
+        return out, out_counts
+    idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
+    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=cnts.data_ptr(),
+         img_offsets=offs.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
+         max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
+    del keep_alive
+    return out, out_counts
+
+
+def _ordered_candidates(src, n, rows, nc, conf_thres, multi_label, classes, dev, s):
+    """Three-launch order-preserving filter (count / scan / write) of a dense prediction or of Detect levels."""
     rpb = 128
     nblk = (rows + rpb - 1) // rpb
     blk_counts = torch.empty(n * nblk, device=dev, dtype=torch.int32)
@@ -534,19 +550,13 @@ def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, 
     call("dmay_nms_filter", s, phase=0, **common)
     offs_host = img_offsets.tolist()    # the one sizing sync of the batch (N+1 values)
     total = offs_host[-1]
-    out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
-    out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
     if total == 0:
-        return out, out_counts
+        return None, None, img_counts, img_offsets, offs_host, 0
     keys = torch.empty(total, device=dev, dtype=torch.int64)
     cand = torch.empty((total, 6), device=dev, dtype=torch.float32)
     call("dmay_nms_filter", s, phase=1, keys=keys.data_ptr(), cand=cand.data_ptr(), capacity=total, **common)
-    idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
-    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=cnts.data_ptr(),
-         img_offsets=offs.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
-         max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
-    del keep_alive, cm
-    return out, out_counts
+    del cm
+    return keys, cand, img_counts, img_offsets, offs_host, total
 
 
 def _class_mask(classes, nc, dev):
@@ -605,6 +615,25 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     n = levels[0].logits.shape[0]
     s = torch.cuda.current_stream(dev).cuda_stream
     multi_label = bool(multi_label) and nc > 1
+    out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
+    out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
+    keys, cand, img_counts, img_offsets, offs_host, total = _fused_candidates(levels, na, nc, conf_thres, multi_label, classes)
+    if total == 0:
+        return out, out_counts
+    idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
+    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=cnts.data_ptr(),
+         img_offsets=offs.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
+         max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
+    return out, out_counts
+
+
+def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes):
+    """Single-pass fused decode + filter + order-preserving compaction of the Detect logits (multi_label already
+    reduced by `nc > 1`).  -> keys, cand, img_counts, img_offsets, img_offsets as a host list, total."""
+    import ctypes
+    dev = levels[0].logits.device
+    n = levels[0].logits.shape[0]
+    s = torch.cuda.current_stream(dev).cuda_stream
     raw, rows = _level_meta_host(levels, na)
     meta_host = ctypes.create_string_buffer(raw, len(raw))
     ws_bytes = int(_lib.lib().dmay_nms_filter_fused_ws(ctypes.addressof(meta_host), len(levels), n))
@@ -613,8 +642,6 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     cm = _class_mask(classes, nc, dev)
     key = (dev.index, n, rows, nc, multi_label, float(conf_thres))
     capacity = _FUSED_CAP.get(key, n * rows * (2 if multi_label else 1) // 2 + 4096)
-    out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
-    out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
     img_counts = torch.empty(n, device=dev, dtype=torch.int32)
     img_offsets = torch.empty(n + 1, device=dev, dtype=torch.int64)
     while True:
@@ -636,13 +663,30 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
             break
         capacity = total + total // 8 + 4096   # undersized guess: every candidate was counted, repeat once
     _FUSED_CAP[key] = max(total + total // 4 + 4096, _FUSED_CAP.get(key, 0) // 2)
+    return keys, cand, img_counts, img_offsets, offs_host, total
+
+
+def filter_candidates(pred, conf_thres, *, multi_label=False, classes=None, levels=None, na=0, nc=None):
+    """Candidate generation alone (tests, benchmarks): dense `pred` -> three-launch filter, Detect `levels` -> fused
+    single-pass filter.  -> dict(keys, cand, img_counts, img_offsets (host list), total)."""
+    if levels is not None:
+        multi = bool(multi_label) and nc > 1
+        keys, cand, img_counts, _, offs_host, total = _fused_candidates(levels, na, nc, conf_thres, multi, classes)
+    else:
+        if pred.dtype != torch.float32 or not pred.is_contiguous():
+            pred = pred.float().contiguous()
+        dev = pred.device
+        n, rows, no = pred.shape
+        nc = no - 5
+        multi = bool(multi_label) and nc > 1
+        s = torch.cuda.current_stream(dev).cuda_stream
+        keys, cand, img_counts, _, offs_host, total = _ordered_candidates(dict(levels=0, pred=pred.data_ptr()), n, rows, nc,
+                                                                          conf_thres, multi, classes, dev, s)
     if total == 0:
-        return out, out_counts
-    idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
-    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=cnts.data_ptr(),
-         img_offsets=offs.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
-         max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
-    return out, out_counts
+        dev = img_counts.device
+        keys = torch.empty(0, device=dev, dtype=torch.int64)
+        cand = torch.empty((0, 6), device=dev, dtype=torch.float32)
+    return dict(keys=keys, cand=cand, img_counts=img_counts, img_offsets=offs_host, total=total)
 
 
 # --------------------------------------------------------------------------------------------

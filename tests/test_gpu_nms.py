@@ -198,3 +198,42 @@ def test_topk_preselection_is_exact_with_ties(levels):
     assert torch.equal(ac, bc) and torch.equal(a, b)
     ref = ON.non_max_suppression(pred[:1].numpy(), 0.001, 0.6, multi_label=True, max_det=300)[0]
     assert np.array_equal(a[0, :int(ac[0])].cpu().numpy(), ref)
+
+
+def _continuous_levels(N, nc, shapes, seed, scale, special=False):
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    na, no = 3, 5 + nc
+    ld = ops.round_up(na * no, 8)
+    levels = []
+    for (ny, nx), stride in zip(shapes, (8., 16., 32.)):
+        lg = torch.randn(N, ny, nx, ld, generator=g) * scale
+        if special:   # saturating, infinite and NaN logits, objectness right at the threshold
+            flat = lg.view(-1)
+            idx = torch.randint(0, flat.numel(), (flat.numel() // 50,), generator=g)
+            vals = torch.tensor([40.0, -40.0, float('inf'), float('-inf'), float('nan'), 17.5, 9.99, 10.01])
+            flat[idx] = vals[torch.randint(0, len(vals), (len(idx),), generator=g)]
+        anchors = [(stride * (1 + a), stride * (2 + a)) for a in range(na)]
+        levels.append(ops.DetectLevel(logits=lg.cuda().contiguous(), stride=stride, anchors_px=anchors, ny=ny, nx=nx, ld=ld))
+    return levels, na, no
+
+
+@pytest.mark.parametrize('nc', [2, 10, 80, 96, 100])
+@pytest.mark.parametrize('thr', [0.0, 0.001, 0.25, 0.9])
+@pytest.mark.parametrize('special', [False, True], ids=['finite', 'inf-nan-saturated'])
+def test_fused_filter_candidates_match_dense_filter(nc, thr, special):
+    """Candidate lists of the single-pass fused filter against the three-launch filter on the materialised dense
+    prediction, element for element and in order (keys, boxes, confidences, classes) — multi-label and best-class.
+    nc <= 96 runs the thread-per-row kernel whose logit pre-filter must never drop a class the exact test would keep
+    (thresholds from 0 to 0.9, saturating / infinite / NaN logits); nc = 100 runs the warp-per-row kernel."""
+    from dma_yolo_b200 import ops
+    levels, na, no = _continuous_levels(2, nc, [(19, 11), (10, 6), (5, 3)], seed=nc + int(thr * 1000), scale=3.0, special=special)
+    dense = ops.detect_decode(levels, na, no)
+    for multi in (True, False):
+        a = ops.filter_candidates(None, thr, multi_label=multi, levels=levels, na=na, nc=nc)
+        b = ops.filter_candidates(dense, thr, multi_label=multi)
+        assert torch.equal(a['img_counts'], b['img_counts']), (nc, thr, multi)
+        n = int(b['img_counts'].sum())
+        assert torch.equal(a['keys'][:n], b['keys'][:n])
+        ca, cb = a['cand'][:n], b['cand'][:n]
+        assert torch.equal(ca.view(torch.int32), cb.view(torch.int32))

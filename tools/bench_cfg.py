@@ -26,7 +26,7 @@ def main():
     a = ap.parse_args()
     import dma_yolo_b200 as D
     from dma_yolo_b200.utils.calib import build_calibrated
-    m = build_calibrated(a.cfg, seed=0).cuda().eval()
+    m = build_calibrated(a.cfg, seed=0, calib_hw=(320, 320), calib_bs=4).cuda().eval()   # SURVEY.md F5, as bench.py
     x = torch.rand(a.bs, 3, a.imgsz, a.imgsz, generator=torch.Generator().manual_seed(1)).cuda()
     kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300) if a.style == 'val' else \
         dict(conf_thres=0.25, iou_thres=0.45, max_det=1000)

@@ -31,7 +31,7 @@ elif kind == 'model':
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     cfg = sys.argv[3] if len(sys.argv) > 3 else 'ablation-ca-scconv-sppfcspc-bifpn.yaml'
     S = int(sys.argv[4]) if len(sys.argv) > 4 else 640
-    m = build_calibrated(cfg, seed=0).to(dev).eval()
+    m = build_calibrated(cfg, seed=0, calib_hw=(320, 320), calib_bs=4).to(dev).eval()   # SURVEY.md F5, as bench.py
     x = torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(1)).to(dev)
     with torch.no_grad():
         for it in range(2):
