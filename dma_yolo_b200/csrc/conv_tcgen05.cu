@@ -543,20 +543,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int HoWo = a.Ho * a.Wo;
     if (a.b_resident == 1) {
       // weights once (barrier full[0]), then one input patch per (tile, channel chunk)
+      // (CTA pair: each CTA keeps HALF of the weight set -- its block_n / 2 output channels -- and both halves are
+      //  credited to the even CTA's barrier; the 128-channel 3x3 layers re-streamed 147 KB of weights per tile before)
       if (elect_one()) {
-        mbar_expect_tx(full_bar, (uint32_t)a.total_subs * a.b_bytes);
+        if (!PAIR || crank == 0) mbar_expect_tx(full_bar, (PAIR ? 2u : 1u) * (uint32_t)a.total_subs * a.b_bytes);
         int g = 0;
 #pragma unroll 1
         for (int cc = 0; cc < a.c_chunks; ++cc)
 #pragma unroll 1
-          for (int tap = 0; tap < a.taps; ++tap, ++g)
-            tma_load_2d(bres0 + g * a.b_bytes, &a.tmB, full_bar, tap * a.Cin + cc * a.CK, 0);
+          for (int tap = 0; tap < a.taps; ++tap, ++g) {
+            if (PAIR) tma_load_2d_pair(bres0 + g * a.b_bytes, &a.tmB, full_bar, tap * a.Cin + cc * a.CK, (int)crank * (a.block_n / 2));
+            else tma_load_2d(bres0 + g * a.b_bytes, &a.tmB, full_bar, tap * a.Cin + cc * a.CK, 0);
+          }
       }
       __syncwarp();
       const int per_img = a.tiles_x * a.tiles_y;
 #pragma unroll 1
       for (int st = cluster_id; st < total_super; st += num_clusters) {
-        const int m_tile = st;
+        const int m_tile = PAIR ? st * 2 + (int)crank : st;   // beyond the last tile (odd count): the loads zero-fill
         const int n_img = fdiv(m_tile, a.fd_pi);
         const int rem = m_tile - n_img * per_img;
         const int ty = fdiv(rem, a.fd_tx), tx = rem - ty * a.tiles_x;
@@ -564,9 +568,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         for (int cc = 0; cc < a.c_chunks; ++cc) {
           mbar_wait(aempty_bar + ab * 8, aphase ^ 1u);
           if (elect_one()) {
-            mbar_expect_tx(afull_bar + ab * 8, a.a_halo_tx);
-            tma_load_4d(abuf0 + ab * a.a_halo_bytes, &a.tmA, afull_bar + ab * 8, cc * a.CK, tx * kHaloTW - 1,
-                        ty * kHaloTH - 1, n_img);
+            if (PAIR) {
+              if (crank == 0) mbar_expect_tx(afull_bar + ab * 8, 2u * a.a_halo_tx);
+              tma_load_4d_pair(abuf0 + ab * a.a_halo_bytes, &a.tmA, afull_bar + ab * 8, cc * a.CK, tx * kHaloTW - 1,
+                               ty * kHaloTH - 1, n_img);
+            } else {
+              mbar_expect_tx(afull_bar + ab * 8, a.a_halo_tx);
+              tma_load_4d(abuf0 + ab * a.a_halo_bytes, &a.tmA, afull_bar + ab * 8, cc * a.CK, tx * kHaloTW - 1,
+                          ty * kHaloTH - 1, n_img);
+            }
           }
           __syncwarp();
           if (++ab == a.n_abuf) {
@@ -699,7 +709,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const uint32_t row_bytes = (uint32_t)a.CK * 2u;
     const uint32_t a_step = a.a_bytes >> 4, b_step = a.b_bytes >> 4;
     if (a.b_resident == 1) {
-      mbar_wait(full_bar, 0);   // resident weights have landed
+      if (!(PAIR && crank != 0)) {   // CTA pair: the even CTA issues every MMA
+      mbar_wait(full_bar, 0);   // resident weights have landed (both halves in pair mode)
 #pragma unroll 1
       for (int st = cluster_id; st < total_super; st += num_clusters) {
         mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
@@ -721,12 +732,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                 const uint32_t hlo = ((start >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll 4
                 for (int kk = 0; kk < kk_n; ++kk) {
-                  umma_bf16(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                  if (PAIR) umma_bf16_2(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                  else umma_bf16(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
                   accum = 1;
                 }
                 b_lo += b_step;
               }
-            umma_commit(aempty_bar + ab * 8);
+            if (PAIR) umma_commit_2(aempty_bar + ab * 8);
+            else umma_commit(aempty_bar + ab * 8);
           } else {
             b_lo += 9u * b_step;   // keep the (uniform) running descriptor in step on the non-elected lanes
           }
@@ -737,12 +750,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             aphase ^= 1u;
           }
         }
-        if (elect_one()) umma_commit(tfull_bar + acc * 8);
+        if (elect_one()) {
+          if (PAIR) umma_commit_2(tfull_bar + acc * 8);
+          else umma_commit(tfull_bar + acc * 8);
+        }
         __syncwarp();
         if (++acc == a.nacc) {
           acc = 0;
           acc_phase ^= 1u;
         }
+      }
       }
     } else if (PAIR && crank != 0) {
       // CTA pair: the even CTA issues every MMA (they read both CTAs' shared memory and write both CTAs' TMEM)
@@ -1224,7 +1241,10 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     a.halo_sbo_enc = (uint32_t)(a.halo_pitch * a.CK * 2) >> 4;
     const uint32_t smem_avail = 227u * 1024u - 1024u - kTailBytes - 64u;
     const uint32_t w_bytes = (uint32_t)a.total_subs * a.b_bytes;           // all taps x chunks of this n-tile
-    if (a.num_n_tiles == 1 && w_bytes <= 100u * 1024u && !(p->flags & 4) && !a.pair) {
+    // resident weights: the whole n-tile's taps x chunks (pair mode: this CTA's half) next to >= 2 input patches
+    const bool res_fits = a.pair ? (uint64_t)((w_bytes + 1023u) & ~1023u) + 2ull * a.a_halo_bytes <= smem_avail && !(p->flags & 4096)
+                                 : w_bytes <= 100u * 1024u;
+    if (a.num_n_tiles == 1 && res_fits && !(p->flags & 4)) {
       a.b_resident = 1;
       a.bres_bytes = (w_bytes + 1023u) & ~1023u;
       int nb = (int)((smem_avail - a.bres_bytes) / a.a_halo_bytes);

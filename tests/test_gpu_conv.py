@@ -234,3 +234,19 @@ def test_conv_cta_pair_with_halo(shape, kw):
         pytest.skip('the SCConv gate multiplies by x: needs Cin == Cout')
     y, ref = run_flags(*shape, flags=256 | 2, seed=4, **kw)
     assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'pair+halo {shape} {kw}')
+
+
+@pytest.mark.parametrize('shape', [(2, 128, 32, 24, 128), (3, 128, 16, 8, 128), (3, 64, 16, 8, 128), (1, 128, 19, 23, 128),
+                                   (5, 128, 40, 40, 128)], ids=str)
+@pytest.mark.parametrize('kw', [dict(), dict(residual=True), dict(gate=True)], ids=['plain', 'residual', 'gate'])
+def test_conv_cta_pair_halo_resident_weights(shape, kw):
+    """CTA pair + halo with each CTA's HALF of the 9-tap weight set resident in shared memory (loaded once per CTA, both
+    halves credited to the even CTA's barrier) against the same mode with streamed weights (flags bit2): identical
+    bits, and both within tolerance of the fp32 reference.  Includes an odd number of m-tiles (zero-filled padding tile
+    in the last pair) and a map the 16x8 patches do not tile."""
+    if kw.get('gate') and shape[1] != shape[4]:
+        pytest.skip('the SCConv gate multiplies by x: needs Cin == Cout')
+    y, ref = run_flags(*shape, flags=256 | 2, seed=6, **kw)
+    y0, _ = run_flags(*shape, flags=256 | 2 | 4, seed=6, **kw)
+    assert torch.equal(y, y0), 'resident and streamed weights must give identical results'
+    assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'pair+halo+resident {shape} {kw}')
