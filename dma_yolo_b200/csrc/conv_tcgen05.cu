@@ -317,6 +317,7 @@ struct __align__(64) ConvArgs {
 //   full[8], empty[8], tmem_full[2], tmem_empty[2], afull[4], aempty[4] mbarriers, tmem base ptr, scale[256], bias[256]
 //   (halo mode: [n_abuf halo buffers] precede the stages, which then hold B tiles only)
 constexpr int kMaxABuf = 8;
+constexpr double kHaloMinEff = 0.8;   // fraction of a map's pixels among the pixels of its 16x8 patches
 constexpr int kHaloTH = 16, kHaloTW = 8;
 constexpr int kMaxAcc = 8;                                                     // TMEM accumulator ring (512 columns / block_n)
 constexpr uint32_t kNumBars = 2 * kMaxStages + 2 * kMaxAcc + 2 * kMaxABuf + kEpiWarps;   // + one operand barrier per epilogue warp
@@ -1193,7 +1194,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     const int tx_ = (p->Wo + kHaloTW - 1) / kHaloTW, ty_ = (p->Ho + kHaloTH - 1) / kHaloTH;
     const double eff_ = (double)p->Ho * p->Wo / ((double)tx_ * kHaloTW * ty_ * kHaloTH);
     const bool halo_auto = p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !(p->flags & 1) &&
-                           ((p->flags & 2) || (eff_ >= 0.9 && p->Cin <= 128 && (long long)p->N * tx_ * ty_ >= 2LL * sms_q));
+                           ((p->flags & 2) || (eff_ >= kHaloMinEff && (long long)p->N * tx_ * ty_ >= 2LL * sms_q));
     const bool legal = p->block_n != -2 && a.CK == 64 && bn >= 128 && (bn % 32) == 0 && m_tiles_q >= 2 && sms_q >= 2 &&
                        mode != EPI_GENERIC;
     // halo + pair (128-channel 3x3 layers): per CTA one input patch + HALF of the 9-tap weight set per chunk
@@ -1226,8 +1227,10 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   const double patch_eff = (double)p->Ho * p->Wo / ((double)tiles_x * kHaloTW * tiles_y * kHaloTH);
   bool halo = p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !(p->flags & 1) && (cs == 1 || a.pair);
   if (halo && !(p->flags & 2)) {
-    // worth it where the conv is L2->SM bound: few channels per tile (C <= 128) on maps the patches tile >= 90 %
-    halo = patch_eff >= 0.9 && p->Cin <= 128 && (long long)p->N * tiles_x * tiles_y >= 2LL * sms_q;
+    // every 3x3 s1 layer is L2->SM bound with im2col operands (nine times the input bytes per tile); the patch form wins
+    // as long as the 16x8 patches cover the map reasonably.  Measured (r3u, batch 64): 256->256 @80 1344 -> 1675 TF/s,
+    // 256->256 @40 (83 % cover) 1167 -> 1276, 512->512 @40 1382 -> 1500; 20x20 maps (52 % cover) lose: 1199 -> 825.
+    halo = patch_eff >= kHaloMinEff && (long long)p->N * tiles_x * tiles_y >= 2LL * sms_q;
   }
   uint32_t halo_bytes_total = 0;
   if (halo) {
