@@ -1195,7 +1195,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     const double eff_ = (double)p->Ho * p->Wo / ((double)tx_ * kHaloTW * ty_ * kHaloTH);
     const bool halo_auto = p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !(p->flags & 1) &&
                            ((p->flags & 2) || (eff_ >= kHaloMinEff && (long long)p->N * tx_ * ty_ >= 2LL * sms_q));
-    const bool legal = p->block_n != -2 && a.CK == 64 && bn >= 128 && (bn % 32) == 0 && m_tiles_q >= 2 && sms_q >= 2 &&
+    const bool legal = p->block_n != -2 && a.CK == 64 && bn >= 64 && (bn % 32) == 0 && m_tiles_q >= 2 && sms_q >= 2 &&
                        mode != EPI_GENERIC;
     // halo + pair (128-channel 3x3 layers): per CTA one input patch + HALF of the 9-tap weight set per chunk
     // (measured: 64->128 3x3 s2 @160, K = 576: 0.390 -> 0.334 ms; 1x1 layers with K <= 512 lose, see r1_conv_notes.md)

@@ -237,7 +237,7 @@ def test_conv_cta_pair_with_halo(shape, kw):
 
 
 @pytest.mark.parametrize('shape', [(2, 128, 32, 24, 128), (3, 128, 16, 8, 128), (3, 64, 16, 8, 128), (1, 128, 19, 23, 128),
-                                   (5, 128, 40, 40, 128)], ids=str)
+                                   (5, 128, 40, 40, 128), (2, 64, 32, 16, 64), (3, 64, 40, 24, 64)], ids=str)
 @pytest.mark.parametrize('kw', [dict(), dict(residual=True), dict(gate=True)], ids=['plain', 'residual', 'gate'])
 def test_conv_cta_pair_halo_resident_weights(shape, kw):
     """CTA pair + halo with each CTA's HALF of the 9-tap weight set resident in shared memory (loaded once per CTA, both
