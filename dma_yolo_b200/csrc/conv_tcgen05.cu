@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t tail = base + data_bytes;                               // 1024-aligned (all data regions are)
   uint8_t* tail_ptr = base_ptr + data_bytes;
   const uint32_t epi_stage_bytes = (uint32_t)a.epi_warps * 2048u;
-  const uint32_t bars_off = epi_stage_bytes * (a.opnd_stage ? 2u : 1u);
+  const uint32_t bars_off = epi_stage_bytes * (a.opnd_stage == 1 ? 2u : 1u);   // opnd_stage 2: operand tile shares the output tile
   const uint32_t full_bar = tail + bars_off, empty_bar = full_bar + kMaxStages * 8;
   const uint32_t tfull_bar = full_bar + 2 * kMaxStages * 8, tempty_bar = tfull_bar + kMaxAcc * 8;
   const uint32_t afull_bar = tempty_bar + kMaxAcc * 8, aempty_bar = afull_bar + kMaxABuf * 8;
@@ -882,8 +882,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     constexpr bool kOpnd = (MODE == EPI_SILU_RES || MODE == EPI_GATE || MODE == EPI_LINEAR_RES || MODE == EPI_LINEAR_MUL);
     const uint32_t out_stage = tail + (uint32_t)ew * 2048u;
     uint4* out_ptr = reinterpret_cast<uint4*>(tail_ptr + ew * 2048);
-    const uint32_t op_stage = tail + epi_stage_bytes + (uint32_t)ew * 2048u;
-    const uint4* op_ptr = reinterpret_cast<const uint4*>(tail_ptr + epi_stage_bytes + ew * 2048);
+    // opnd_stage 2 (CTA-pair layers with resident weights: no room for a second tile per warp): the operand tile lands in
+    // the warp's OUTPUT staging tile -- it is consumed into registers before the output is packed, and the next one is
+    // requested only after the store has finished reading the tile.  With 16 epilogue warps (one item per warp and tile)
+    // that request completes while the warp waits for its next accumulator.
+    const bool op_shared = a.opnd_stage == 2;
+    const uint32_t op_stage = op_shared ? out_stage : tail + epi_stage_bytes + (uint32_t)ew * 2048u;
+    const uint4* op_ptr = op_shared ? reinterpret_cast<const uint4*>(tail_ptr + ew * 2048)
+                                    : reinterpret_cast<const uint4*>(tail_ptr + epi_stage_bytes + ew * 2048);
     const uint32_t my_opnd_bar = opnd_bar + (uint32_t)ew * 8u;
     uint32_t opnd_phase = 0;
     auto sidx = [](int r, int j) { return r * 4 + (j ^ ((r >> 1) & 3)); };   // 64-byte rows, TMA SWIZZLE_64B pattern
@@ -951,6 +957,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     // out-of-bounds elements are zero-filled)
     auto issue_opnd = [&](const Item& it) {
       if (lane == 0) {
+        if (op_shared) tma_store_wait_read();   // the previous store of this warp still reads the shared tile
         mbar_expect_tx(my_opnd_bar, 2048u);
         if (a.halo) tma_load_4d(op_stage, &a.tmR, my_opnd_bar, it.n0 + it.c0, it.t1, it.t2, it.t3);
         else tma_load_2d(op_stage, &a.tmR, my_opnd_bar, it.n0 + it.c0, it.t1);
@@ -1172,7 +1179,11 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   if (p->flags & 8) a.epi_warps = 8;
   if (p->flags & 16) a.epi_warps = 16;
   a.epi_groups = (a.epi_warps == 16 && bn <= 64 && !(p->flags & 32)) ? 2 : 1;
-  const uint32_t kTailBytes = tail_bytes(a.epi_warps, a.opnd_stage != 0, (uint32_t)a.sb_floats);
+  if ((p->flags & 8192) && a.opnd_stage && staged && bn > 64) {   // A/B: shared operand tile + 16 warps for every staged operand
+    a.epi_warps = 16;
+    a.opnd_stage = 2;
+  }
+  uint32_t kTailBytes = tail_bytes(a.epi_warps, a.opnd_stage == 1, (uint32_t)a.sb_floats);
 
   if ((bn & 15) || bn > 256 || bn < 16) return DMAY_EUNSUPPORTED;
   a.block_n = bn;
@@ -1250,7 +1261,21 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     if (a.num_n_tiles == 1 && res_fits && !(p->flags & 4)) {
       a.b_resident = 1;
       a.bres_bytes = (w_bytes + 1023u) & ~1023u;
-      int nb = (int)((smem_avail - a.bres_bytes) / a.a_halo_bytes);
+      uint32_t avail_r = smem_avail;
+      // pair + resident: with the weights on chip the tile's MMA time no longer covers two items per epilogue warp
+      // (residual / gate modes: 1072 / 949 vs 1426 TF/s plain at 128->128 @80), so run 16 epilogue warps on 16 single
+      // staging tiles (operand tile shared with the output tile, see the kernel) whenever that still leaves two patches
+      if (a.pair && staged && a.epi_warps == 8 && !(p->flags & 8)) {
+        const uint32_t tail16 = tail_bytes(16, false, (uint32_t)a.sb_floats);
+        const uint32_t avail16 = 227u * 1024u - 1024u - tail16 - 64u;
+        if ((uint64_t)a.bres_bytes + 2ull * a.a_halo_bytes <= avail16) {
+          a.epi_warps = 16;
+          if (a.opnd_stage) a.opnd_stage = 2;
+          kTailBytes = tail16;
+          avail_r = avail16;
+        }
+      }
+      int nb = (int)((avail_r - a.bres_bytes) / a.a_halo_bytes);
       a.n_abuf = nb > kMaxABuf ? kMaxABuf : nb;
       if (a.n_abuf < 2) return DMAY_EUNSUPPORTED;
       subs = 1;

@@ -76,7 +76,9 @@ const char* dmay_strerror(int code);
  *   bit7 = launch without programmatic dependent launch (the kernel's preamble then waits for the previous kernel),
  *   bit8 / bit9 = force / forbid the CTA-pair mode (cta_group::2: a 2-CTA cluster computes one 256 x block_n tile,
  *   each CTA loading its own 128 rows of A and half of the weight tile), bit10 / bit11 = never / always (where legal) keep
- *   the weights resident in shared memory on the plain (non-halo) path. */
+ *   the weights resident in shared memory on the plain (non-halo) path, bit12 = never keep weight halves resident in the
+ *   CTA-pair halo mode, bit13 = 16 epilogue warps with the residual / gate operand tile sharing the output staging tile
+ *   for every staged operand (automatic only for CTA-pair layers with resident weights). */
 typedef struct dmay_conv_params {
   const void* x;
   const void* w;
