@@ -340,6 +340,34 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// Four consecutive k-steps (one 64-channel tap) from ONE asm block: descriptor low words advance by 2 (32 bytes >> 4)
+// inside the block, so ptxas sees the invariant operands (TMEM address, instruction descriptor, descriptor high words)
+// once per tap instead of once per MMA (the per-MMA form re-creates them in uniform registers each time: four R2UR).
+template <bool PAIR>
+__device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+#define DMAY_MMA4(CG)                                                                    \
+  asm volatile(                                                                           \
+      "{\n\t.reg .pred p, t;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"             \
+      "setp.ne.b32 p, %6, 0;\n\t"                                                         \
+      "setp.eq.u32 t, %6, %6;\n\t"                                                        \
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"                                \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %5, p;\n\t"                  \
+      "add.u32 al, %1, 2;\n\tadd.u32 bl, %3, 2;\n\t"                                      \
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"                                \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %5, t;\n\t"                  \
+      "add.u32 al, %1, 4;\n\tadd.u32 bl, %3, 4;\n\t"                                      \
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"                                \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %5, t;\n\t"                  \
+      "add.u32 al, %1, 6;\n\tadd.u32 bl, %3, 6;\n\t"                                      \
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"                                \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %5, t;\n\t}" ::"r"(tmem_d),   \
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)            \
+      : "memory")
+  if (PAIR) DMAY_MMA4("2");
+  else DMAY_MMA4("1");
+#undef DMAY_MMA4
+}
 __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
@@ -731,11 +759,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               for (int s2 = 0; s2 < 3; ++s2) {
                 const uint32_t start = a_patch + (uint32_t)(r * a.halo_pitch + s2) * row_bytes;
                 const uint32_t hlo = ((start >> 4) & 0x3FFFu) | (1u << 16);
-#pragma unroll 4
-                for (int kk = 0; kk < kk_n; ++kk) {
-                  if (PAIR) umma_bf16_2(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
-                  else umma_bf16(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                // (single-CTA tiles only: on the CTA-pair 128-channel layers the tighter issue measured the same for the
+                //  plain / gate epilogues and 14 % slower for the residual one, same box A/B r4k)
+                if (!PAIR && kk_n == 4) {
+                  umma_bf16_x4<PAIR>(tmem_d, hlo, desc_hi_halo, b_lo, desc_hi, a.idesc, accum);
                   accum = 1;
+                } else {
+#pragma unroll 2
+                  for (int kk = 0; kk < kk_n; ++kk) {
+                    if (PAIR) umma_bf16_2(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                    else umma_bf16(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                    accum = 1;
+                  }
                 }
                 b_lo += b_step;
               }
