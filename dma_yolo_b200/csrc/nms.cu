@@ -510,6 +510,12 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
 constexpr int kRowsThreads = 128;   // rows (pixels of one anchor) per tile == threads per CTA
 constexpr int kRowsMaxNc = 96;
 
+// RESERVE = false: tiles take a ticket and place their candidates with the decoupled look-back (final, ordered buffers).
+// RESERVE = true : no ordering inside this kernel -- a tile reserves its run in the TEMPORARY buffers with one atomicAdd
+//                  (`status` then holds tile_base[] / tile_cnt[]), tile_scan_kernel + tile_gather_kernel put the runs
+//                  in order afterwards.  ncu of the look-back form: 46 % of the warp samples wait for the slowest of
+//                  the ~700 in-flight predecessor tiles to publish a count; the gather costs 2 x 32 B per candidate.
+template <bool RESERVE>
 __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
                                                                          const unsigned char* __restrict__ class_mask,
                                                                          unsigned* __restrict__ ticket,
@@ -521,9 +527,11 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
   __shared__ int warp_tot[kRowsThreads / 32];
   __shared__ long long base_s;
   __shared__ int tile_s;
-  if (threadIdx.x == 0) tile_s = (int)atomicAdd(ticket, 1u);
-  __syncthreads();
-  const int tile_id = tile_s;
+  if (!RESERVE) {
+    if (threadIdx.x == 0) tile_s = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+  }
+  const int tile_id = RESERVE ? (int)blockIdx.x : tile_s;
   const int tiles_img = fa.tile0[fa.levels];
   const int img = tile_id / tiles_img;
   int t = tile_id - img * tiles_img;
@@ -647,7 +655,17 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
     if (w < warp) before += v;
     total += v;
   }
-  if (warp == 0) {
+  if (RESERVE) {
+    if (threadIdx.x == 0) {
+      const long long ntiles = (long long)fa.N * tiles_img;
+      long long* tile_base = reinterpret_cast<long long*>(status);
+      int* tile_cnt = reinterpret_cast<int*>(tile_base + ntiles);
+      const long long b = total > 0 ? (long long)atomicAdd(reinterpret_cast<unsigned long long*>(ticket), (unsigned long long)total) : 0;
+      tile_base[tile_id] = b;
+      tile_cnt[tile_id] = total;
+      base_s = b;
+    }
+  } else if (warp == 0) {
     const long long excl = tile_lookback(status, tile_id, total, lane);
     if (lane == 0) {
       base_s = excl;
@@ -683,6 +701,73 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
     cd[1] = make_float2(x2, y2);
     cd[2] = make_float2(bconf, (float)bcls);
     keys[g] = img_hi | (unsigned long long)(~__float_as_uint(bconf));
+  }
+}
+
+// exclusive scan of the per-tile candidate counts (reference tile order == candidate order) -> tile_off[], img_offsets[]
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const int* __restrict__ tile_cnt, long long* __restrict__ tile_off,
+                                                         long long* __restrict__ img_offsets, int* __restrict__ img_counts,
+                                                         long long ntiles, int tiles_img, int N) {
+  __shared__ long long warp_sum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long per = (ntiles + 1023) / 1024;
+  const long long t0 = (long long)tid * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+  long long local = 0;
+  for (long long t = t0; t < t1; ++t) local += tile_cnt[t];
+  long long inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) warp_sum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    long long v = warp_sum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    warp_sum[lane] = v;   // inclusive over warps
+  }
+  __syncthreads();
+  long long run = inc - local + (warp > 0 ? warp_sum[warp - 1] : 0);
+  for (long long t = t0; t < t1; ++t) {
+    tile_off[t] = run;
+    if (t % tiles_img == 0) img_offsets[t / tiles_img] = run;
+    run += tile_cnt[t];
+  }
+  if (tid == 1023) img_offsets[N] = warp_sum[31];
+  __syncthreads();
+  __threadfence_block();
+  // per-image counts from the offsets just written (block-local visibility: same CTA)
+  for (int i = tid; i < N; i += 1024) {
+    const long long a0 = img_offsets[i], a1 = img_offsets[i + 1];
+    img_counts[i] = (int)(a1 - a0);
+  }
+}
+
+// move every tile's run from its reserved place in the temporary buffers to its ordered place
+__global__ void __launch_bounds__(128) tile_gather_kernel(const long long* __restrict__ tile_base, const int* __restrict__ tile_cnt,
+                                                          const long long* __restrict__ tile_off,
+                                                          const unsigned long long* __restrict__ keys_tmp,
+                                                          const float* __restrict__ cand_tmp, unsigned long long* __restrict__ keys,
+                                                          float* __restrict__ cand, long long capacity) {
+  const long long t = blockIdx.x;
+  const int cnt = tile_cnt[t];
+  if (cnt == 0) return;
+  const long long src = tile_base[t], dst = tile_off[t];
+  for (int i = threadIdx.x; i < cnt; i += 128) {
+    if (src + i >= capacity || dst + i >= capacity) break;   // overflow: the caller repeats with larger buffers
+    const float2* cs = reinterpret_cast<const float2*>(cand_tmp + (src + i) * 6);
+    float2* cd = reinterpret_cast<float2*>(cand + (dst + i) * 6);
+    const float2 v0 = cs[0], v1 = cs[1], v2 = cs[2];
+    const unsigned long long k = keys_tmp[src + i];
+    cd[0] = v0;
+    cd[1] = v1;
+    cd[2] = v2;
+    keys[dst + i] = k;
   }
 }
 
@@ -1144,7 +1229,7 @@ static long long fused_tiles_per_image(const LevelMeta* hm, int levels, FuseArgs
 
 long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N) {
   if (!lv_meta_host || levels <= 0 || levels > 5 || N <= 0) return DMAY_EINVAL;
-  return 16 + 8 * N * fused_tiles_per_image((const LevelMeta*)lv_meta_host, levels, nullptr);
+  return 16 + 24 * N * fused_tiles_per_image((const LevelMeta*)lv_meta_host, levels, nullptr);   // status words, or tile base / count / offset
 }
 
 int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t stream) {
@@ -1176,7 +1261,8 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   const size_t smem = (size_t)P * (5 + p->nc) * sizeof(float);
   if (smem > 200 * 1024) return DMAY_EUNSUPPORTED;
   if (smem > 48 * 1024) {
-    cudaError_t e = rows_kernel ? cudaFuncSetAttribute(filter_fused_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+    cudaError_t e = rows_kernel ? (cudaFuncSetAttribute(filter_fused_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                   cudaFuncSetAttribute(filter_fused_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
                                 : cudaFuncSetAttribute(filter_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
@@ -1189,10 +1275,28 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   cudaStream_t s = (cudaStream_t)stream;
   unsigned* ticket = (unsigned*)p->ws;
   unsigned long long* status = (unsigned long long*)((char*)p->ws + 16);
+  static const bool no_reserve = [] { const char* e = getenv("DMAY_FILTER_RESERVE"); return e && e[0] == '0'; }();
+  if (rows_kernel && p->keys_tmp != nullptr && p->cand_tmp != nullptr && !no_reserve) {
+    // reserve + scan + gather: no ordering dependency between the tiles of the big kernel
+    if (p->ws_bytes < 16 + 20 * tiles) return DMAY_ETOOBIG;
+    long long* tile_base = (long long*)status;
+    int* tile_cnt = (int*)(tile_base + tiles);
+    long long* tile_off = (long long*)((char*)p->ws + 16 + ((12 * tiles + 7) & ~7LL));
+    if (p->ws_bytes < 16 + ((12 * tiles + 7) & ~7LL) + 8 * tiles) return DMAY_ETOOBIG;
+    filter_fused_rows_kernel<true><<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
+                                                                        (long long*)p->img_offsets,
+                                                                        (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
+                                        (int)(tiles / p->N), p->N);
+    tile_gather_kernel<<<(int)tiles, 128, 0, s>>>(tile_base, tile_cnt, tile_off, (const unsigned long long*)p->keys_tmp,
+                                                  (const float*)p->cand_tmp, (unsigned long long*)p->keys, (float*)p->cand,
+                                                  p->capacity);
+    return finish_launch(3);
+  }
   if (rows_kernel)
-    filter_fused_rows_kernel<<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
-                                                                  (long long*)p->img_offsets, (unsigned long long*)p->keys,
-                                                                  (float*)p->cand);
+    filter_fused_rows_kernel<false><<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
+                                                                         (long long*)p->img_offsets, (unsigned long long*)p->keys,
+                                                                         (float*)p->cand);
   else
     filter_fused_kernel<<<(int)tiles, kFuseThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
                                                              (long long*)p->img_offsets, (unsigned long long*)p->keys,

@@ -648,10 +648,13 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes):
         ws = torch.zeros(ws_bytes // 8 + 1, device=dev, dtype=torch.int64)   # ticket + tile status words (zeroed)
         keys = torch.empty(capacity, device=dev, dtype=torch.int64)
         cand = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
+        # temporary buffers of the reserve + scan + gather mode (tiles place their runs without waiting for each other)
+        keys_tmp = torch.empty(capacity, device=dev, dtype=torch.int64)
+        cand_tmp = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
         f = dict(lv_meta_host=ctypes.addressof(meta_host), ws=ws.data_ptr(), ws_bytes=ws.numel() * 8,
                  img_counts=img_counts.data_ptr(), img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(),
                  cand=cand.data_ptr(), N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
-                 conf_thres=float(conf_thres))
+                 conf_thres=float(conf_thres), keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr())
         for i, lv in enumerate(levels):
             f[f"lv_logits{i}"] = lv.logits.data_ptr()
         if cm is not None:

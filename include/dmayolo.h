@@ -415,7 +415,10 @@ int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream);
  * ws: caller-ZEROED workspace of dmay_nms_filter_fused_ws() bytes (ticket + one status word per tile).
  * Candidates beyond `capacity` are counted but not written: the caller compares img_offsets[N] with
  * capacity and repeats the call with larger buffers.  lv_meta_host: HOST array of `levels` x 16 words
- * {row0, ny, nx, ld, na, stride(f32), anchor_px[10](f32)}. */
+ * {row0, ny, nx, ld, na, stride(f32), anchor_px[10](f32)}.
+ * keys_tmp / cand_tmp (optional, `capacity` entries each like keys / cand): when given (and nc <= 96) the tiles do not
+ * order themselves with the look-back; each reserves its run in the temporary buffers with one atomic, and a scan over
+ * the per-tile counts plus a gather put the runs in reference order (three launches, same outputs). */
 typedef struct dmay_filter_fused_params {
   const void* lv_logits0;
   const void* lv_logits1;
@@ -436,6 +439,8 @@ typedef struct dmay_filter_fused_params {
   int multi_label;
   long long capacity;
   float conf_thres;
+  void* keys_tmp;
+  void* cand_tmp;
 } dmay_filter_fused_params;
 long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N);
 int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t stream);
