@@ -299,6 +299,7 @@ struct __align__(64) ConvArgs {
   // weights-resident variant of halo mode: the whole [block_n x 9*Cin] weight set (<= ~96 KB) is loaded into
   // smem once per CTA, so the steady state streams input patches only (deep patch ring, no B pipeline)
   int b_resident;
+  int stage_tile;    // bytes of one epilogue warp's staging tile: 2048 (32 rows x 32 bf16) or 4096 (32 rows x 32 fp32)
   uint32_t bres_bytes;
   int ldy, ldr, ldgx, ldgk, gHk, gWk;
   float g_sh, g_sw;
@@ -326,8 +327,8 @@ constexpr int kMaxCout = 2048;                                                 /
 //   [kEpiWarps x 2 KB] output staging (thread == row writes 4 x 16 B, 64-byte-swizzled, a TMA store drains it)
 //   [kEpiWarps x 2 KB] operand staging (residual / gate_x tile of the warp's NEXT item, TMA-loaded) — only when used
 //   barriers, TMEM base slot, scale[kMaxCout], bias[kMaxCout]
-__host__ __device__ constexpr uint32_t tail_bytes(int epi_warps, bool operand_stage, uint32_t sb_floats) {
-  return (uint32_t)epi_warps * 2048u * (operand_stage ? 2u : 1u) + kNumBars * 8 + 32 + 2 * sb_floats * 4;
+__host__ __device__ constexpr uint32_t tail_bytes(int epi_warps, bool operand_stage, uint32_t sb_floats, uint32_t tile = 2048u) {
+  return (uint32_t)epi_warps * tile * (operand_stage ? 2u : 1u) + kNumBars * 8 + 32 + 2 * sb_floats * 4;
 }
 
 // one elected lane of a converged warp (the warp stays converged, so operands live in uniform registers)
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t data_bytes = (stage0 - base) + a.stages * a.stage_bytes;
   const uint32_t tail = base + data_bytes;                               // 1024-aligned (all data regions are)
   uint8_t* tail_ptr = base_ptr + data_bytes;
-  const uint32_t epi_stage_bytes = (uint32_t)a.epi_warps * 2048u;
+  const uint32_t epi_stage_bytes = (uint32_t)a.epi_warps * (uint32_t)a.stage_tile;
   const uint32_t bars_off = epi_stage_bytes * (a.opnd_stage == 1 ? 2u : 1u);   // opnd_stage 2: operand tile shares the output tile
   const uint32_t full_bar = tail + bars_off, empty_bar = full_bar + kMaxStages * 8;
   const uint32_t tfull_bar = full_bar + 2 * kMaxStages * 8, tempty_bar = tfull_bar + kMaxAcc * 8;
@@ -915,15 +916,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     constexpr bool kStaged = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_LINEAR || MODE == EPI_GATE ||
                               MODE == EPI_LINEAR_RES || MODE == EPI_GELU || MODE == EPI_LINEAR_MUL);
     constexpr bool kOpnd = (MODE == EPI_SILU_RES || MODE == EPI_GATE || MODE == EPI_LINEAR_RES || MODE == EPI_LINEAR_MUL);
-    const uint32_t out_stage = tail + (uint32_t)ew * 2048u;
-    uint4* out_ptr = reinterpret_cast<uint4*>(tail_ptr + ew * 2048);
+    const uint32_t out_stage = tail + (uint32_t)ew * (uint32_t)a.stage_tile;
+    uint4* out_ptr = reinterpret_cast<uint4*>(tail_ptr + ew * a.stage_tile);
     // opnd_stage 2 (CTA-pair layers with resident weights: no room for a second tile per warp): the operand tile lands in
     // the warp's OUTPUT staging tile -- it is consumed into registers before the output is packed, and the next one is
     // requested only after the store has finished reading the tile.  With 16 epilogue warps (one item per warp and tile)
     // that request completes while the warp waits for its next accumulator.
     const bool op_shared = a.opnd_stage == 2;
     const uint32_t op_stage = op_shared ? out_stage : tail + epi_stage_bytes + (uint32_t)ew * 2048u;
-    const uint4* op_ptr = op_shared ? reinterpret_cast<const uint4*>(tail_ptr + ew * 2048)
+    const uint4* op_ptr = op_shared ? reinterpret_cast<const uint4*>(tail_ptr + ew * a.stage_tile)
                                     : reinterpret_cast<const uint4*>(tail_ptr + epi_stage_bytes + ew * 2048);
     const uint32_t my_opnd_bar = opnd_bar + (uint32_t)ew * 8u;
     uint32_t opnd_phase = 0;
@@ -1025,7 +1026,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         uint32_t r[32];
         if (cur.width == 32) tmem_ld32(taddr, r);
         else tmem_ld16(taddr, r);
-        if (kStaged) {
+        // fp32 outputs (Detect heads) are staged too when the launch provides 4 KB tiles: a lane's direct 32-byte stores
+        // land 1 KB apart (256 -> 255 @80: 40 % of the HBM rate), the 128-byte-swizzled tile leaves as one TMA store
+        const bool f32_staged = MODE == EPI_LINEAR_F32 && a.stage_tile == 4096;
+        if (kStaged || f32_staged) {
           uint4 own[4];
           if (kOpnd) {
             mbar_wait(my_opnd_bar, opnd_phase);
@@ -1041,6 +1045,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the staging tile
           __syncwarp();
+          if (MODE == EPI_LINEAR_F32) {
+            // 128-byte rows (32 fp32), TMA SWIZZLE_128B pattern: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+            float4* o4 = reinterpret_cast<float4*>(out_ptr);
+#pragma unroll
+            for (int v8 = 0; v8 < 4; ++v8) {
+              const float4 s0 = reinterpret_cast<const float4*>(sc + v8 * 8)[0], s1 = reinterpret_cast<const float4*>(sc + v8 * 8)[1];
+              const float4 b0 = reinterpret_cast<const float4*>(bi + v8 * 8)[0], b1 = reinterpret_cast<const float4*>(bi + v8 * 8)[1];
+              const uint32_t* rr = r + v8 * 8;
+              o4[lane * 8 + ((v8 * 2) ^ (lane & 7))] =
+                  make_float4(fmaf(__uint_as_float(rr[0]), s0.x, b0.x), fmaf(__uint_as_float(rr[1]), s0.y, b0.y),
+                              fmaf(__uint_as_float(rr[2]), s0.z, b0.z), fmaf(__uint_as_float(rr[3]), s0.w, b0.w));
+              o4[lane * 8 + ((v8 * 2 + 1) ^ (lane & 7))] =
+                  make_float4(fmaf(__uint_as_float(rr[4]), s1.x, b1.x), fmaf(__uint_as_float(rr[5]), s1.y, b1.y),
+                              fmaf(__uint_as_float(rr[6]), s1.z, b1.z), fmaf(__uint_as_float(rr[7]), s1.w, b1.w));
+            }
+          } else {
 #pragma unroll
           for (int v8 = 0; v8 < 4; ++v8) {
             uint4 gk = make_uint4(0, 0, 0, 0);
@@ -1049,6 +1069,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               if (cur.row >= 0 && v8 * 8 < cur.width && c + 8 <= a.n_store) gk = ld16(cur.gk_row + c);
             }
             out_ptr[sidx(lane, v8)] = epi_compute8<MODE>(r + v8 * 8, sc + v8 * 8, bi + v8 * 8, own[v8], gk);
+          }
           }
           fence_proxy_async();
           __syncwarp();   // every lane's staging writes are done, and its operand row has been consumed (own[] fed the math)
@@ -1090,7 +1111,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       cur = nxt;
     }
-    if (kStaged && lane == 0) tma_store_wait_all();   // staging tiles stay valid until every store has read them
+    if ((kStaged || (MODE == EPI_LINEAR_F32 && a.stage_tile == 4096)) && lane == 0) tma_store_wait_all();   // staging tiles stay valid until every store has read them
   }
 
   tc_fence_before();
@@ -1214,11 +1235,15 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   if (p->flags & 8) a.epi_warps = 8;
   if (p->flags & 16) a.epi_warps = 16;
   a.epi_groups = (a.epi_warps == 16 && bn <= 64 && !(p->flags & 32)) ? 2 : 1;
+  // fp32 output of a 1x1 conv (Detect heads): staged 4 KB tiles + TMA store (flags bit14 = keep the direct stores)
+  const bool f32_staged = mode == EPI_LINEAR_F32 && p->kh == 1 && p->kw == 1 && p->stride == 1 && !(p->flags & 16384) &&
+                          (p->ldy % 4) == 0 && aligned16(p->y);
+  a.stage_tile = f32_staged ? 4096 : 2048;
   if ((p->flags & 8192) && a.opnd_stage && staged && bn > 64) {   // A/B: shared operand tile + 16 warps for every staged operand
     a.epi_warps = 16;
     a.opnd_stage = 2;
   }
-  uint32_t kTailBytes = tail_bytes(a.epi_warps, a.opnd_stage == 1, (uint32_t)a.sb_floats);
+  uint32_t kTailBytes = tail_bytes(a.epi_warps, a.opnd_stage == 1, (uint32_t)a.sb_floats, (uint32_t)a.stage_tile);
 
   if ((bn & 15) || bn > 256 || bn < 16) return DMAY_EUNSUPPORTED;
   a.block_n = bn;
@@ -1467,6 +1492,14 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
       const int ld = mode == EPI_GATE ? p->ldgx : p->ldr;
       if (!encode_epi(&a.tmR, src, ld)) return DMAY_EDRIVER;
     }
+  } else if (f32_staged) {
+    cuuint64_t gdim[2] = {(cuuint64_t)p->Cout, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)p->ldy * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    r = g_encode_tiled(&a.tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p->y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DMAY_EDRIVER;
   } else {
     a.tmY = a.tmB;   // never used by the direct-store modes; keeps the descriptor prefetch well-defined
   }

@@ -78,7 +78,8 @@ const char* dmay_strerror(int code);
  *   each CTA loading its own 128 rows of A and half of the weight tile), bit10 / bit11 = never / always (where legal) keep
  *   the weights resident in shared memory on the plain (non-halo) path, bit12 = never keep weight halves resident in the
  *   CTA-pair halo mode, bit13 = 16 epilogue warps with the residual / gate operand tile sharing the output staging tile
- *   for every staged operand (automatic only for CTA-pair layers with resident weights). */
+ *   for every staged operand (automatic only for CTA-pair layers with resident weights), bit14 = fp32 outputs of 1x1 convs
+ *   (Detect heads) with direct per-lane stores instead of the staged tile + TMA store. */
 typedef struct dmay_conv_params {
   const void* x;
   const void* w;

@@ -250,3 +250,22 @@ def test_conv_cta_pair_halo_resident_weights(shape, kw):
     y0, _ = run_flags(*shape, flags=256 | 2 | 4, seed=6, **kw)
     assert torch.equal(y, y0), 'resident and streamed weights must give identical results'
     assert_close(y, ref, atol=1e-2, rtol=1e-2, what=f'pair+halo+resident {shape} {kw}')
+
+
+@pytest.mark.parametrize('shape', [(2, 128, 10, 10, 255), (1, 256, 13, 7, 45), (3, 64, 20, 12, 30), (1, 512, 5, 3, 255)], ids=str)
+def test_conv_fp32_output_staged_equals_direct(shape):
+    """Detect-head convs (1x1, bias, fp32 output): the staged 128-byte-swizzled tile + TMA store must write exactly what the
+    direct per-lane stores (flags bit14) write, including Cout that is not a multiple of 8 / 32 and an M tail."""
+    from dma_yolo_b200 import ops
+    n, cin, h, w, cout = shape
+    g = torch.Generator().manual_seed(cout + h)
+    x = ops.as_act(bf(torch.randn(n, cin, h, w, generator=g)).cuda())
+    wt = bf(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5)
+    bias = torch.randn(cout, generator=g)
+    pk = ops.pack_conv(wt, conv_bias=bias, stride=1, pad=0, device='cuda')
+    y = ops.conv(x, pk, 0, out_fp32=True)
+    y0 = ops.conv(x, pk, 0, out_fp32=True, flags=16384)
+    torch.cuda.synchronize()
+    assert y.dtype == torch.float32 and y.shape[1] == cout and torch.equal(y, y0)
+    ref = F.conv2d(back(x), wt, bias)
+    assert_close(y.cpu(), ref, atol=2e-4, rtol=2e-4, what=f'fp32 head {shape}')
