@@ -2,9 +2,12 @@
 //   pool : pooled[n, h, c] = mean_w x ; pooled[n, H+w, c] = mean_h x            (fp32)
 //   mlp  : y = hardswish(s1*(W1.pooled + b1) + t1) ; gates = sigmoid(W{h,w}.y + b{h,w})  (fp32)
 //   apply: out = (x * a_w) * a_h                                                 (bf16)
-// x is read once by `pool` from HBM and once by `apply` (L2-resident at cfg-2 sizes: 52 MB < 126 MB
-// L2); the gate tensors are (H+W)/(H*W) of the activation.  All reductions are deterministic
-// (no atomics): a CTA owns complete rows (for mean_w) and complete columns (for mean_h).
+// x is read once by `pool` and once by `apply` (measured: the second read comes from DRAM too, the L2 does not keep
+// the 52 MB of cfg-2 between the launches); the gate tensors are (H+W)/(H*W) of the activation.  All reductions are
+// deterministic: a CTA owns complete rows (for mean_w) and complete columns (for mean_h); the per-image hidden layer is
+// summed in fixed order by the image's last CTA (an atomic ticket decides who is last, not what is added).
+// Three implementations, chosen in dmay_coordatt: the mma.sync two-launch path (Cm <= 32, plane of 64 channels fits in
+// shared memory: every reference model), the FMA two-launch path (Cm > 32), the three-launch path (large planes).
 #include <stdlib.h>
 #include "common.cuh"
 

@@ -1,9 +1,11 @@
 // a8 + a9: Detect decode (models/yolo.py:81-101) and batched class-aware NMS
 // (utils/general.py:633-725 + torchvision.ops.nms CPU semantics), all on device, whole batch per launch.
 //
-//   filter  : order-preserving candidate generation (count -> scan -> write), reading either a dense
-//             [N,R,5+nc] fp32 prediction or the raw Detect logits (decode fused with the confidence
-//             filter: the dense [N,R,no] tensor is never materialised).
+//   filter  : order-preserving candidate generation.  Dense [N,R,5+nc] fp32 prediction: count -> scan -> write.
+//             Raw Detect logits (decode fused with the confidence filter, the dense [N,R,no] tensor is never
+//             materialised, ONE read of the logits): thread-per-row tiles that reserve their runs + a scan over the
+//             tile counts + a gather (nc <= 96), or the single-launch tile look-back forms.
+//   select  : exact top-max_nms per image (3-level radix select + ordered compaction) when an image exceeds max_nms.
 //   sort    : one stable radix sort of (image, ~score) keys over the whole batch (CUB).
 //   greedy  : one CTA per image walks its sorted candidates in chunks of 128, testing each chunk
 //             against the kept list (<= max_det boxes in shared memory), resolving the chunk's internal
