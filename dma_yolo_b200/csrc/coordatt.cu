@@ -410,8 +410,21 @@ __device__ __forceinline__ void cm_split(float v, float& hi, float& lo) {   // v
   hi = __bfloat162float(__float2bfloat16_rn(v));
   lo = v - hi;
 }
-__device__ __forceinline__ void cm_cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+// 16-byte async copy that asks L2 to keep the line (evict_last): the gate kernel reads the same 52 MB right afterwards
+__device__ __forceinline__ uint64_t cm_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 cm_ld16_evict_first(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void cm_cp_async16(uint32_t dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
 
 __global__ void __launch_bounds__(256) ca_pool_hidden_mma_kernel(const __nv_bfloat16* __restrict__ x,
@@ -449,8 +462,9 @@ __global__ void __launch_bounds__(256) ca_pool_hidden_mma_kernel(const __nv_bflo
     if (v < vl) {
       const __nv_bfloat16* src = xb + (long long)(tid >> 3) * ldx + v * 8;
       uint32_t dst = plane_s + (uint32_t)tid * 16u;
+      const uint64_t pol = cm_policy_evict_last();
       for (int p = tid >> 3; p < HW; p += 32) {
-        cm_cp_async16(dst, src);
+        cm_cp_async16(dst, src, pol);
         src += 32LL * ldx;
         dst += 256u * 16u;
       }
@@ -689,10 +703,12 @@ __global__ void __launch_bounds__(256) ca_gate_apply_mma_kernel(const __nv_bfloa
   const int xstep = kRows * ldx, ostep = kRows * ldy;
   const float* gh = gs + h0_ * 64 + v * 4;
   const float* gw = gs + (H + w_) * 64 + v * 4;
+  uint64_t pol_first;   // last use of x: hand the lines the pool kernel pinned (evict_last) back to the L2
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
   while (p < HW) {
     uint4 r[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = (p + u * kRows < HW) ? ld_nc16(xb + xo + u * xstep) : make_uint4(0, 0, 0, 0);
+    for (int u = 0; u < 4; ++u) r[u] = (p + u * kRows < HW) ? cm_ld16_evict_first(xb + xo + u * xstep, pol_first) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (p < HW) {
