@@ -19,6 +19,15 @@ inline int finish_launch(int n_kernels = 1) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// One-time driver settings (function attributes) are per device: true the first time a call site runs on the current
+// device.  `mask` is that call site's static bit set, one bit per device ordinal (a process normally owns one GPU).
+inline bool first_time_on_device(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (mask.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
+
 // SM count of the current device, cached (immutable after first query).
 int sm_count();
 

@@ -1511,14 +1511,13 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   const int grid = (int)((supers < max_clusters ? supers : max_clusters) * a.cs);
 #define DMAY_LAUNCH_MODE(MODE)                                                                                     \
   case MODE: {                                                                                                      \
-    static bool attr_set = false;                                                                                   \
-    if (!attr_set) {                                                                                                \
+    static std::atomic<unsigned long long> attr_mask{0};                                                            \
+    if (first_time_on_device(attr_mask)) {                                                                          \
       cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            227 * 1024);                                                            \
       if (e != cudaSuccess) return (int)e;                                                                          \
       e = cudaFuncSetAttribute(conv_gemm_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       if (e != cudaSuccess) return (int)e;                                                                          \
-      attr_set = true;                                                                                              \
     }                                                                                                               \
     cudaLaunchConfig_t cfg = {};                                                                                    \
     cfg.gridDim = dim3(grid);                                                                                       \

@@ -783,16 +783,13 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
       const size_t smem2m = (size_t)2 * Pp * kCmYPitch * 2 + (size_t)P * 64 * 4;
       if (!no_mma && p->Cm <= kCmMax && smem1m <= 100 * 1024 && smem2m <= 100 * 1024 &&
           HW * (long long)(p->ldx > p->ldy ? p->ldx : p->ldy) < 0x7fffffffLL) {
-        static size_t set1 = 48 * 1024, set2 = 48 * 1024;
-        if (smem1m > set1) {
+        if (smem1m > 48 * 1024) {
           cudaError_t e = cudaFuncSetAttribute(ca_pool_hidden_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1m);
           if (e != cudaSuccess) return (int)e;
-          set1 = smem1m;
         }
-        if (smem2m > set2) {
+        if (smem2m > 48 * 1024) {
           cudaError_t e = cudaFuncSetAttribute(ca_gate_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2m);
           if (e != cudaSuccess) return (int)e;
-          set2 = smem2m;
         }
         ca_pool_hidden_mma_kernel<<<p->N * G, 256, smem1m, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, partial, yhid,
                                                                counters, (const float*)p->w1, (const float*)p->b1,
