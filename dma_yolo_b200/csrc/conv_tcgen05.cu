@@ -1350,7 +1350,11 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
       for (int sb : {9, 3, 1}) {
         const uint32_t stg = ((uint32_t)sb * a.b_bytes + 1023u) & ~1023u;
         if (stg > 48u * 1024u && sb > 1) continue;
-        for (int nab = 4; nab >= 2 && !ok; --nab)
+        // two input patches are enough (one per ~2.3 k clk of MMAs); every further KB goes to the weight stages, which
+        // are what the L2->SM-bound streamed layers wait for (r4y: 256->256 @40 residual 1163 -> 1295 TF/s, @80 plain
+        // 1665 -> 1809, 512->512 @40 plain 1500 -> 1610).  flags bit15 = the old preference (up to four patches).
+        const int nab_hi = (p->flags & 32768) ? 4 : 2;
+        for (int nab = nab_hi; nab >= 2 && !ok; --nab)
           if ((uint64_t)nab * a.a_halo_bytes + 2ull * stg <= smem_avail) {
             a.n_abuf = nab;
             subs = sb;
