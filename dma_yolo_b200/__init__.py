@@ -26,9 +26,10 @@ __version__ = "0.1.0"
 def install_aliases(force: bool = False):
     """Expose this package as the reference's top-level `models` / `utils` packages."""
     from . import models, utils
-    from .models import common, cspcm, yolo
+    from .models import common, cspcm, detect_t, yolo
     from .utils import general, torch_utils
     table = {"models": models, "models.common": common, "models.cspcm": cspcm, "models.yolo": yolo,
+             "models.detect_t": detect_t,
              "utils": utils, "utils.general": general, "utils.torch_utils": torch_utils}
     for name, mod in table.items():
         if force or name not in sys.modules:

@@ -24,6 +24,7 @@ from .common import (CA, SM, AdConcat2, AdConcat3, Adapt_Add2, Adapt_Add3, Bottl
                      CABottleneck, Concat, Contract, CoorAttention, DWConv, Expand, Focus, SCConv, SPP, SPPCSPC, SPPF,
                      SPPFCSPC, _materialize, _PackMixin, get_conv_pack, kernel_path, space_to_depth)
 from .cspcm import Conv  # shadows common.Conv exactly like `from models.cspcm import *` (models/yolo.py:24)
+from .detect_t import TDetect  # models/yolo.py:9
 
 CFG_DIR = Path(__file__).resolve().parent
 
@@ -154,6 +155,12 @@ class Model(nn.Module):
             check_anchor_order(m)
             self.stride = m.stride
             self._initialize_biases()
+        elif isinstance(m, TDetect):   # models/yolo.py:173-180 — anchor-free head: strides from the train-mode probe, then bias_init
+            s = 256
+            m.inplace = self.inplace
+            m.stride = torch.tensor([s / x.shape[-2] for x in self.forward(torch.zeros(1, ch, s, s))[0]])
+            self.stride = m.stride
+            m.bias_init()
         initialize_weights(self)
 
     def forward(self, x, augment=False, profile=False, visualize=False):
@@ -215,7 +222,7 @@ class Model(nn.Module):
         return _common.torch_body(m, m, x)
 
     def _profile_one_layer(self, m, x, dt):
-        c = isinstance(m, Detect)
+        c = isinstance(m, (Detect, TDetect))
         t = time_sync()
         for _ in range(10):
             m(x.copy() if c else x)
@@ -278,6 +285,10 @@ class Model(nn.Module):
             m.grid = list(map(fn, m.grid))
             if isinstance(m.anchor_grid, list):
                 m.anchor_grid = list(map(fn, m.anchor_grid))
+        elif isinstance(m, TDetect):   # models/yolo.py:345-348
+            m.stride = fn(m.stride)
+            m.anchors = fn(m.anchors)
+            m.strides = fn(m.strides)
         return self
 
 
@@ -330,6 +341,8 @@ def parse_model(d, ch):
             args.append([ch[x] for x in f])
             if isinstance(args[1], int):
                 args[1] = [list(range(args[1] * 2))] * len(f)
+        elif m is TDetect:   # models/yolo.py:438-439
+            args.append([ch[x] for x in f])
         elif m is Contract:
             c2 = ch[f] * args[0] ** 2
         elif m is Expand:

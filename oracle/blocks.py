@@ -192,6 +192,39 @@ def detect(xs, sd, p, anchors_grid, strides, nc):
     return torch.cat(z, 1), raw
 
 
+def tdetect(xs, sd, p, nc, strides, reg_max=16, eps=1e-3):
+    """TDetect.forward (eval) — models/detect_t.py:23-58 with DFL 92-102, make_anchors 66-79, dist2bbox 81-90.
+    Per level: box = 1x1(Conv3(Conv3(x))) [4*reg_max], cls = 1x1(Conv3(Conv3(x))) [nc]; over all levels the softmax
+    expectation of the `reg_max` bins gives (l, t, r, b) distances from the cell centre (+0.5) in grid units.
+    Returns (y [b, 4 + nc, A], box [b, 4*reg_max, A], cls [b, nc, A])."""
+    feats = []
+    for i, x in enumerate(xs):
+        outs = []
+        for br in ('cv2', 'cv3'):
+            t = conv_bn_act(x, sd, f'{p}{br}.{i}.0.', 3, 1, eps=eps)
+            t = conv_bn_act(t, sd, f'{p}{br}.{i}.1.', 3, 1, eps=eps)
+            outs.append(F.conv2d(t, sd[f'{p}{br}.{i}.2.weight'], sd[f'{p}{br}.{i}.2.bias']))
+        feats.append(torch.cat(outs, 1))
+    b = feats[0].shape[0]
+    no = 4 * reg_max + nc
+    allf = torch.cat([f.reshape(b, no, -1) for f in feats], 2)
+    box, cls = allf[:, :4 * reg_max], allf[:, 4 * reg_max:]
+    pts, strs = [], []
+    for f, st in zip(feats, strides):
+        h, w = f.shape[-2:]
+        gy, gx = torch.meshgrid(torch.arange(h).float() + 0.5, torch.arange(w).float() + 0.5, indexing='ij')
+        pts.append(torch.stack((gx, gy), -1).view(-1, 2))
+        strs.append(torch.full((h * w,), float(st)))
+    anchor = torch.cat(pts).t().unsqueeze(0)                  # [1, 2, A]
+    stride = torch.cat(strs).view(1, 1, -1)
+    prob = box.view(b, 4, reg_max, -1).softmax(2)
+    dist = (prob * torch.arange(reg_max).float().view(1, 1, reg_max, 1)).sum(2)     # [b, 4, A]
+    lt, rb = dist[:, :2], dist[:, 2:]
+    x1y1, x2y2 = anchor - lt, anchor + rb
+    dbox = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) * stride
+    return torch.cat((dbox, cls.sigmoid()), 1), box, cls
+
+
 def make_divisible(x, d):
     return math.ceil(x / d) * d
 

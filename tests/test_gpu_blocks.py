@@ -96,3 +96,29 @@ def test_window_attention_mma_vs_scalar_kernel(shape):
     b = ops.window_attention(qkv, rel, mask, c // 32, shift, layer.attn.scale, variant=1)
     torch.cuda.synchronize()
     assert_close(a.float().cpu(), b.float().cpu(), atol=2e-2, rtol=2e-2, what=f'attention mma vs scalar {shape}')
+
+
+@pytest.mark.parametrize('name,nc', [('tdetect_nc10_3lv', 10), ('tdetect_nc20_4lv', 20)])
+def test_tdetect_kernel_path(name, nc):
+    """8f-4: TDetect (models/detect_t.py) on the kernel path -- six tcgen05 convs per level (the 1x1 heads with staged fp32
+    output), DFL expectation + box arithmetic in fp32 -- against the executed reference's outputs."""
+    from dma_yolo_b200.models.detect_t import TDetect
+    d, sd, ins = load_golden(name)
+    m = TDetect(nc, tuple(x.shape[1] for x in ins))
+    m.stride = d['strides'].clone()
+    m.load_state_dict(sd)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eps = 1e-3
+    m = m.cuda().eval()
+    m.stride = m.stride.cuda()
+    with torch.no_grad():
+        y, (feats, box, cls) = m([x.cuda() for x in ins])
+    assert y.dtype == torch.float32 and y.shape == d['out'].shape
+    assert_close(box, d['box'], atol=4e-2, rtol=3e-2, what='box logits')         # three chained bf16 convs
+    assert_close(cls, d['cls'], atol=4e-2, rtol=3e-2, what='cls logits')
+    assert_close(y[:, 4:], d['out'][:, 4:], atol=1e-2, rtol=1e-2, what='class confidences')
+    # boxes: the DFL expectation is a softmax average over 16 bins; tolerance in units of each point's stride
+    per_point_stride = torch.cat([torch.full((x.shape[-2] * x.shape[-1],), float(s)) for x, s in zip(ins, d['strides'])])
+    err = (y[:, :4].cpu() - d['out'][:, :4]).abs() / per_point_stride.view(1, 1, -1)
+    assert float(err.max()) < 0.1, float(err.max())

@@ -136,3 +136,19 @@ def test_cuda_path_fails_loudly_without_library(monkeypatch):
     monkeypatch.setattr(_lib, 'SO', _lib.SO.with_name('missing.so'))
     with pytest.raises(D.DmayError):
         _lib.lib()
+
+
+def test_tdetect_config_builds_and_runs_on_cpu():
+    """CASPD_ODRTA.yaml (SPD-Conv backbone, C3CA neck, four-level anchor-free TDetect head): parse_model,
+    the stride probe and bias_init of the TDetect branch (models/yolo.py:173-180, 438-439), eval output layout."""
+    from dma_yolo_b200.models.detect_t import TDetect
+    m = Y.Model('CASPD_ODRTA.yaml', nc=6)
+    head = m.model[-1]
+    assert isinstance(head, TDetect) and m.stride.tolist() == [4., 8., 16., 32.]
+    assert float(head.cv2[0][-1].bias[0]) == 1.0
+    m.eval()
+    with torch.no_grad():
+        y, (feats, box, cls) = m(torch.rand(1, 3, 64, 64))
+    a = 16 * 16 + 8 * 8 + 4 * 4 + 2 * 2
+    assert y.shape == (1, 4 + 6, a) and box.shape == (1, 64, a) and cls.shape == (1, 6, a) and len(feats) == 4
+    assert torch.isfinite(y).all() and float(y[:, 4:].min()) >= 0.0 and float(y[:, 4:].max()) <= 1.0

@@ -73,6 +73,30 @@ def test_detect_oracle():
         assert_close(r, d[f'raw{i}'], what=f'raw{i}', **TOL)
 
 
+@pytest.mark.parametrize('name,nc', [('tdetect_nc10_3lv', 10), ('tdetect_nc20_4lv', 20)])
+def test_tdetect_oracle_and_host_mirror(name, nc):
+    """Anchor-free TDetect head with DFL decoding (models/detect_t.py): the restatement and the product's host mirror
+    (torch body on the CPU, same state_dict keys) against the executed reference."""
+    from dma_yolo_b200.models.detect_t import TDetect
+    d, sd, ins = load_golden(name)
+    strides = d['strides'].tolist()
+    y, box, cls = O.tdetect(ins, sd, '', nc, strides)
+    assert_close(box, d['box'], what='box logits', **TOL)
+    assert_close(cls, d['cls'], what='cls logits', **TOL)
+    assert_close(y, d['out'], what='decoded', atol=1e-4, rtol=1e-5)
+    m = TDetect(nc, tuple(x.shape[1] for x in ins))
+    m.stride = d['strides'].clone()
+    m.load_state_dict(sd)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eps = 1e-3
+    m.eval()
+    with torch.no_grad():
+        ym, (_, bm, cm) = m([x.clone() for x in ins])
+    assert_close(ym, d['out'], what='host mirror decoded', atol=1e-4, rtol=1e-5)
+    assert_close(bm, d['box'], what='host mirror box', **TOL)
+
+
 STYLES = {'detect': dict(conf_thres=0.25, iou_thres=0.45, max_det=1000),
           'val': dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300),
           'agnostic': dict(conf_thres=0.3, iou_thres=0.5, agnostic=True, max_det=50),
