@@ -27,10 +27,11 @@ def install_aliases(force: bool = False):
     """Expose this package as the reference's top-level `models` / `utils` packages."""
     from . import models, utils
     from .models import common, cspcm, detect_t, yolo
-    from .utils import general, torch_utils
+    from .utils import augmentations, general, metrics, torch_utils
     table = {"models": models, "models.common": common, "models.cspcm": cspcm, "models.yolo": yolo,
              "models.detect_t": detect_t,
-             "utils": utils, "utils.general": general, "utils.torch_utils": torch_utils}
+             "utils": utils, "utils.general": general, "utils.torch_utils": torch_utils,
+             "utils.augmentations": augmentations, "utils.metrics": metrics}
     for name, mod in table.items():
         if force or name not in sys.modules:
             sys.modules[name] = mod

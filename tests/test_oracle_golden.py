@@ -197,3 +197,17 @@ def test_metrics_oracle_and_host_port_match_the_executed_reference():
     p, r, ap, f1, cls = PM.ap_per_class(tp, conf, pcls, tcls)
     assert np.allclose(ap, d['ap'], atol=1e-9) and np.allclose(p, d['p'], atol=1e-9) and np.allclose(r, d['r'], atol=1e-9)
     assert np.array_equal(cls, d['ap_class'])
+
+
+def test_letterbox_host_mirror_matches_executed_reference():
+    """8f-3: `letterbox` (utils/augmentations.py:91-122) -- resize + pad geometry, ratios and per-side padding, for the
+    auto / fixed / scaleFill / no-scale-up branches and non-default stride and colour; pixels bit-exact (same cv2 calls)."""
+    from dma_yolo_b200.utils.augmentations import letterbox
+    from oracle.make_golden_letterbox import CASES
+    z = np.load(__import__('tests.util', fromlist=['GOLD']).GOLD / 'letterbox.npz')
+    for i, (h, w, kw) in enumerate(CASES):
+        im = z[f'im{i}']
+        assert im.shape == (h, w, 3)
+        out, ratio, pad = letterbox(im.copy(), **kw)
+        assert out.shape == z[f'out{i}'].shape and np.array_equal(out, z[f'out{i}']), (i, kw)
+        assert np.allclose([ratio[0], ratio[1], pad[0], pad[1]], z[f'meta{i}'], rtol=0, atol=1e-12), (i, kw)
