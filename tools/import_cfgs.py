@@ -13,7 +13,7 @@ import yaml
 SRC = Path('/root/reference/models')
 DST = Path(__file__).resolve().parent.parent / 'dma_yolo_b200' / 'models'
 DEFAULT = ['yolov5s', 'yolov5n', 'yolov5m', 'yolov5l', 'yolov5x', 'ablation-ca-scconv-sppfcspc-bifpn',
-           'yolov5l-ca-sppfcspc-bifpn-scconv', 'spdconv', 'C3CASPD']
+           'yolov5l-ca-sppfcspc-bifpn-scconv', 'spdconv', 'C3CASPD', 'CASPD_ODRTA']
 
 
 def emit(name: str):
