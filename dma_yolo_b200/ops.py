@@ -494,11 +494,25 @@ def detect_decode(levels, na: int, no: int) -> torch.Tensor:
     return pred
 
 
+def _det_buffers(n, max_det, dev):
+    """One zeroed fp32 buffer [N*max_det*6 | N counts (int32 bits)] and its two views: the layout the one-collective
+    all-gather of dist.py moves as is."""
+    buf = torch.zeros(n * max_det * 6 + n, device=dev, dtype=torch.float32)
+    return buf, buf[:n * max_det * 6].view(n, max_det, 6), buf[n * max_det * 6:].view(torch.int32)
+
+
 def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, *, levels=None, na=0, nc=None,
-                classes=None, agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=4096.0):
+                classes=None, agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=4096.0,
+                return_packed=False):
     """Whole-batch NMS.  Source is a dense fp32 `pred` [N,R,5+nc] or Detect `levels` (fused decode).
     Returns (out [N,max_det,6] fp32, counts [N] int32) on the device; out[i,:counts[i]] are image i's
-    detections (xyxy, conf, cls) in descending score order — utils/general.py:633-725."""
+    detections (xyxy, conf, cls) in descending score order — utils/general.py:633-725.  `return_packed` appends the
+    flat buffer both are views of."""
+    r = _nms_batched(pred, conf_thres, iou_thres, levels, na, nc, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    return r if return_packed else r[:2]
+
+
+def _nms_batched(pred, conf_thres, iou_thres, levels, na, nc, classes, agnostic, multi_label, max_det, max_nms, max_wh):
     if levels is not None:
         dev = levels[0].logits.device
         n = levels[0].logits.shape[0]
@@ -519,18 +533,17 @@ def nms_batched(pred: torch.Tensor | None, conf_thres: float, iou_thres: float, 
         keep_alive = (pred,)
     s = torch.cuda.current_stream(dev).cuda_stream
     multi_label = bool(multi_label) and nc > 1
-    out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
-    out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
+    buf, out, out_counts = _det_buffers(n, max_det, dev)
     keys, cand, img_counts, img_offsets, offs_host, total = _ordered_candidates(src, n, rows, nc, conf_thres, multi_label,
                                                                                 classes, dev, s)
     if total == 0:
-        return out, out_counts
+        return out, out_counts, buf
     idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
     call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=cnts.data_ptr(),
          img_offsets=offs.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
          max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
     del keep_alive
-    return out, out_counts
+    return out, out_counts, buf
 
 
 def _ordered_candidates(src, n, rows, nc, conf_thres, multi_label, classes, dev, s):
@@ -615,16 +628,15 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     n = levels[0].logits.shape[0]
     s = torch.cuda.current_stream(dev).cuda_stream
     multi_label = bool(multi_label) and nc > 1
-    out = torch.zeros((n, max_det, 6), device=dev, dtype=torch.float32)
-    out_counts = torch.zeros(n, device=dev, dtype=torch.int32)
+    buf, out, out_counts = _det_buffers(n, max_det, dev)
     keys, cand, img_counts, img_offsets, offs_host, total = _fused_candidates(levels, na, nc, conf_thres, multi_label, classes)
     if total == 0:
-        return out, out_counts
+        return out, out_counts, buf
     idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
     call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=cnts.data_ptr(),
          img_offsets=offs.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
          max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
-    return out, out_counts
+    return out, out_counts, buf
 
 
 def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes):

@@ -159,19 +159,59 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
             res.append(out[0, :int(cnt[0].item())])
         return res
     if isinstance(prediction, LazyPred) and prediction._dense is None:
-        out, cnt = ops.nms_batched(None, conf_thres, iou_thres, levels=prediction._levels, na=prediction._na,
-                                   nc=prediction._no - 5, **kw)
+        out, cnt, packed = ops.nms_batched(None, conf_thres, iou_thres, levels=prediction._levels, na=prediction._na,
+                                           nc=prediction._no - 5, return_packed=True, **kw)
     else:
         dense = prediction.dense() if isinstance(prediction, LazyPred) else prediction
-        out, cnt = ops.nms_batched(dense, conf_thres, iou_thres, **kw)
-    counts = cnt.tolist()  # one D2H of N ints: the list-of-tensors return type needs the sizes
-    dets = Detections(out[i, :c] for i, c in enumerate(counts))
-    dets.padded, dets.counts = out, cnt
-    return dets
+        out, cnt, packed = ops.nms_batched(dense, conf_thres, iou_thres, return_packed=True, **kw)
+    return Detections(out, cnt, packed)
 
 
 class Detections(list):
-    """The reference's return type (a list of (n,6) tensors) plus the batch buffers its elements are views of:
-    `padded` [N, max_det, 6] fp32 and `counts` [N] int32 on the device — one D2H / one all_gather moves the batch."""
-    padded = None
-    counts = None
+    """The reference's return type — a list of (n,6) tensors, one per image — plus the batch buffers its elements are
+    views of: `padded` [N, max_det, 6] fp32, `counts` [N] int32 and `packed` (the flat buffer both live in) on the
+    device, so one D2H / one all_gather moves the batch.  The list elements need the per-image counts on the host:
+    that one D2H of N ints happens on first access to an element (iteration, indexing, comparison ...), not inside
+    `non_max_suppression` — a caller that only forwards `padded` / `counts` / `packed` never synchronises."""
+
+    def __init__(self, padded, counts, packed=None):
+        super().__init__([None] * padded.shape[0])
+        self.padded, self.counts, self.packed = padded, counts, packed
+        self._pending = True
+
+    def _fill(self):
+        if self._pending:
+            self._pending = False
+            c = self.counts.tolist()
+            for i, n in enumerate(c):
+                list.__setitem__(self, i, self.padded[i, :n])
+        return self
+
+    def __iter__(self):
+        return list.__iter__(self._fill())
+
+    def __getitem__(self, i):
+        return list.__getitem__(self._fill(), i)
+
+    def __reversed__(self):
+        return list.__reversed__(self._fill())
+
+    def __contains__(self, v):
+        return list.__contains__(self._fill(), v)
+
+    def __eq__(self, o):
+        return list.__eq__(self._fill(), o)
+
+    __hash__ = None
+
+    def __add__(self, o):
+        return list(self._fill()) + list(o)
+
+    def __repr__(self):
+        return list.__repr__(self._fill())
+
+    def copy(self):
+        return list(self._fill())
+
+    def __reduce__(self):
+        return (list, (list(self._fill()),))

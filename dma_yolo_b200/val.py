@@ -54,8 +54,11 @@ def run(data, model=None, dataloader=None, batch_size=32, imgsz=640, conf_thres=
         targets[:, 2:] *= torch.tensor([width, height, width, height], dtype=targets.dtype)
         out = non_max_suppression(out, conf_thres, iou_thres, multi_label=True, agnostic=single_cls, max_det=max_det)
         if world_size > 1:   # rank-then-image order (np.argsort in ap_per_class is order sensitive)
-            p, c = pad_detections(out, max_det, device)
-            out = unpad(*all_gather_detections(p, c))
+            if getattr(out, 'packed', None) is not None:     # the NMS output buffer is already the exchange layout
+                out = unpad(*all_gather_detections(out.padded, out.counts, packed=out.packed))
+            else:
+                p, c = pad_detections(out, max_det, device)
+                out = unpad(*all_gather_detections(p, c))
             if rank != 0:
                 continue
         for si, pred in enumerate(out):

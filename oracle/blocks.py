@@ -229,10 +229,12 @@ def make_divisible(x, d):
     return math.ceil(x / d) * d
 
 
-def forward_model(cfg: dict, sd: dict, x: torch.Tensor, strides, eps=1e-3):
+def forward_model(cfg: dict, sd: dict, x: torch.Tensor, strides, eps=1e-3, teacher=None):
     """Model._forward_once (eval) — models/yolo.py:211-239 + the channel/arg bookkeeping of parse_model
     (models/yolo.py:353-478), as a functional interpreter over the hot-path module set.
-    `sd` = state_dict of the model (keys `model.{i}....`).  Returns (pred, raw_list, per-layer outputs)."""
+    `sd` = state_dict of the model (keys `model.{i}....`).  Returns (pred, raw_list, per-layer outputs).
+    `teacher` (a list of per-layer tensors): every layer reads ITS inputs from that list instead of from this run's
+    own outputs (teacher forcing — used to measure one layer's sensitivity to storage precision on given inputs)."""
     gd, nc = cfg['depth_multiple'], cfg['nc']
     ys, outs = [], []
     x = q(x)
@@ -292,8 +294,10 @@ def forward_model(cfg: dict, sd: dict, x: torch.Tensor, strides, eps=1e-3):
             return pred, raw, outs
         else:
             raise NotImplementedError(f'oracle: layer {i} module {m}')
-        ys.append(x)
         outs.append(x)
+        if teacher is not None:
+            x = teacher[i]
+        ys.append(x)
     return x, None, outs
 
 

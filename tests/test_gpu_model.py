@@ -95,30 +95,20 @@ def test_half_and_uint8_inputs_and_fuse():
     assert rel(e, a) < 0.15, rel(e, a)
 
 
-@pytest.mark.parametrize('cfg', ['yolov5s', 'ablation-ca-scconv-sppfcspc-bifpn', 'yolov5l-ca-sppfcspc-bifpn-scconv', 'C3CASPD', 'spdconv'])
-def test_model_vs_bf16_storage_oracle(cfg):
-    """The parity test proper for the bf16 path (north_star tolerance: 1e-2 in bf16).  Both sides hold IDENTICAL
-    weights (conv weights rounded to bf16 once) and the oracle rounds to bf16 exactly where the kernel path stores
-    bf16 (oracle.blocks.bf16_storage).  Every layer of the model is run on the kernel path with the ORACLE's
-    tensors as its inputs (teacher forcing), so each comparison is "same inputs, same weights": what is left is
-    arithmetic (accumulation order, tanh.approx SiLU, a one-ulp flip now and then).  A free-running chain is
-    printed for information only: an untrained net amplifies one-ulp flips ~1.3x per layer (oracle-vs-oracle shows
-    the same growth for fp32-vs-bf16 storage), which says nothing about any single kernel.
-    Tolerance per layer: max|err| <= 1e-2 * max(1, max|ref|) (1e-2 absolute for O(1) activations; the calibrated
-    random-init head reaches |activations| ~ 5e3 at this input size, where one bf16 ulp is 16-32) and relative L2
-    <= 1e-2; decoded boxes within 1e-2 of the image size, confidences within 1e-2 absolute."""
+def _teacher_forced(cfg, S, B, calib=None, seed_x=11):
+    """Run every layer of `cfg` on the kernel path with the bf16-storage ORACLE's tensors as its inputs.
+    -> (per-layer max|err|/max(1,max|ref|), per-layer rel-L2, box error / S, confidence error, model, x, oracle layers)."""
     from dma_yolo_b200.models import yolo as Y
     from dma_yolo_b200.ops import Up
     from dma_yolo_b200.utils.calib import build_calibrated
-    m = build_calibrated(cfg + '.yaml', seed=0)
+    m = build_calibrated(cfg + '.yaml', seed=0, **(calib or {}))
     with torch.no_grad():
         for p in m.parameters():
             if p.dim() == 4:
                 p.copy_(p.bfloat16().float())
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     strides = m.stride.tolist()
-    S = 128
-    x = torch.rand(2, 3, S, S, generator=torch.Generator().manual_seed(11)).bfloat16().float()
+    x = torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(seed_x)).bfloat16().float()
     cfgd = yaml.safe_load(open(Y.CFG_DIR / (cfg + '.yaml')))
     with torch.no_grad(), O.bf16_storage():
         ref_pred, _, ref_layers = O.forward_model(cfgd, sd, x, strides)
@@ -142,28 +132,63 @@ def test_model_vs_bf16_storage_oracle(cfg):
             assert y.shape == r.shape, (i, y.shape, r.shape)
             worst.append(float((y - r).abs().max() / max(1.0, float(r.abs().max()))))
             rl2.append(float((y - r).norm() / (r.norm() + 1e-12)))
+    return worst, rl2, box_err, conf_err, m, x, ref_layers
+
+
+@pytest.mark.parametrize('cfg', ['yolov5s', 'ablation-ca-scconv-sppfcspc-bifpn', 'yolov5l-ca-sppfcspc-bifpn-scconv', 'C3CASPD', 'spdconv'])
+def test_model_vs_bf16_storage_oracle(cfg):
+    """The parity test proper for the bf16 path (north_star tolerance: 1e-2 in bf16).  Both sides hold IDENTICAL
+    weights (conv weights rounded to bf16 once) and the oracle rounds to bf16 exactly where the kernel path stores
+    bf16 (oracle.blocks.bf16_storage).  Every layer of the model is run on the kernel path with the ORACLE's
+    tensors as its inputs (teacher forcing), so each comparison is "same inputs, same weights": what is left is
+    arithmetic (accumulation order, tanh.approx SiLU, a one-ulp flip now and then).  A free-running chain is
+    printed for information only: an untrained net amplifies one-ulp flips ~1.3x per layer (oracle-vs-oracle shows
+    the same growth for fp32-vs-bf16 storage), which says nothing about any single kernel.
+    Tolerance per layer: max|err| <= 1e-2 * max(1, max|ref|) (1e-2 absolute for O(1) activations; the calibrated
+    random-init head reaches |activations| ~ 5e3 at this input size, where one bf16 ulp is 16-32) and relative L2
+    <= 1e-2; decoded boxes within 1e-2 of the image size, confidences within 1e-2 absolute."""
+    worst, rl2, box_err, conf_err, m, x, ref_layers = _teacher_forced(cfg, 128, 2)
     print('teacher-forced per-layer max|err|/max(1,max|ref|):', ' '.join(f'{v:.4f}' for v in worst))
     print('teacher-forced per-layer rel L2:', ' '.join(f'{v:.4f}' for v in rl2))
     print(f'decoded prediction: max box error {box_err:.5f} of the image size, max confidence error {conf_err:.5f}')
     # a "layer" of the YAML can be a chain of up to 19 convs (C3 with n=9): its internal storage roundings compound
     # a little (measured max 1.08e-2 there; every other layer <= 6.5e-3), hence 1.5e-2 on the max norm
-    if cfg == 'C3CASPD':
-        # C3CA blocks (CoordAtt bottlenecks chained, |activations| up to 3e4 on this random-init net) are chaotic at this
-        # input size: the ORACLE ITSELF moves by rel-L2 2.4 / 4.2 / 10.7 / 12.7 % on layers 25 / 29 / 33 / 37 when only
-        # its storage precision changes (fp32 vs bf16, same inputs).  The kernel path stays inside that envelope
-        # (measured 0.5 / 0.9 / 4.0 / 12.3 %); every other layer meets the 1e-2 bar.
-        chaotic = {25: 0.03, 29: 0.05, 33: 0.12, 37: 0.15}
-        for i, (w_, r_) in enumerate(zip(worst, rl2)):
-            lim = chaotic.get(i)
-            assert r_ <= (lim if lim else 1e-2), (i, r_)
-            assert w_ <= (2 * lim if lim else 1.5e-2), (i, w_)
-    else:
-        assert max(worst) <= 1.5e-2, worst
-        assert max(rl2) <= 1e-2, rl2
+    bad = [i for i, (w_, r_) in enumerate(zip(worst, rl2)) if r_ > 1e-2 or w_ > 1.5e-2]
+    if bad:
+        # A layer that misses the bar is only excused when the ORACLE ITSELF cannot resolve it: the same layer of the
+        # fp32-storage oracle, fed the SAME inputs (teacher forcing by the bf16-storage oracle's tensors), must move by
+        # at least as much when nothing but its storage precision changes.  (C3CA layers of the random-init C3CASPD
+        # net: CoordAtt bottlenecks chained at |activations| ~ 3e4.)  The envelope is measured here, not hard-coded;
+        # the conditioned-checkpoint tests below hold the same layers to the plain 1e-2 bar.
+        from dma_yolo_b200.models import yolo as Y
+        cfgd = yaml.safe_load(open(Y.CFG_DIR / (cfg + '.yaml')))
+        sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
+        with torch.no_grad():
+            _, _, fp32_layers = O.forward_model(cfgd, sd, x, m.stride.tolist(), teacher=ref_layers)
+        for i in bad:
+            env = float((fp32_layers[i] - ref_layers[i]).norm() / (ref_layers[i].norm() + 1e-12))
+            print(f'layer {i}: kernel-vs-oracle rel-L2 {rl2[i]:.4f}, oracle fp32-vs-bf16-storage on the same inputs {env:.4f}')
+            assert rl2[i] <= 1.25 * env, (i, rl2[i], env)
     assert box_err < 1e-2 and conf_err < 1e-2, (box_err, conf_err)
     # information: the free-running chain
     _, _, outs = layer_outputs(m, x.cuda())
     print('free-running chain, per-layer rel L2:', ' '.join(f'{float((o - r).norm() / (r.norm() + 1e-12)):.4f}' for o, r in zip(outs, ref_layers)))
+
+
+def test_cfg2_teacher_forced_at_baseline_shapes():
+    """The same teacher-forced parity check at the BASELINE shapes of cfg-2 — 640x640, batch 8, bench.py's calibration —
+    so that the conv modes `conv_launch` selects at full size (CTA-pair tiles with resident weight halves for the
+    128-channel 3x3 layers, streamed halo patches for 256 channels at 80x80 / 40x40, im2col pairs on the 20x20 maps,
+    staged fp32 Detect stores, register-window pool cascade, mma CoordAtt) are compared with the oracle, not only
+    forced by flags at toy sizes.  Tolerances as above: no waivers."""
+    worst, rl2, box_err, conf_err, *_ = _teacher_forced('ablation-ca-scconv-sppfcspc-bifpn', 640, 8,
+                                                        calib=dict(calib_hw=(320, 320), calib_bs=4))
+    print('640x640 batch 8 teacher-forced max|err|/max(1,max|ref|):', ' '.join(f'{v:.4f}' for v in worst))
+    print('640x640 batch 8 teacher-forced rel L2:', ' '.join(f'{v:.4f}' for v in rl2))
+    print(f'decoded prediction: max box error {box_err:.5f} of the image size, max confidence error {conf_err:.5f}')
+    assert max(worst) <= 1.5e-2, worst
+    assert max(rl2) <= 1e-2, rl2
+    assert box_err < 1e-2 and conf_err < 1e-2, (box_err, conf_err)
 
 
 def test_map_on_synthetic_labelled_set():

@@ -74,6 +74,35 @@ def test_nms_class_offset_rounding_and_big_random(style):
         assert np.array_equal(outs[i].cpu().numpy(), ref), (style, i)
 
 
+def cfg5_pred(n=256, seed=1):
+    """BASELINE cfg-5 / SURVEY 8d: rand(256, 25200, 15) with pixel-scale xywh; every row passes conf 0.001."""
+    pred = torch.rand(n, 25200, 15, generator=torch.Generator().manual_seed(seed))
+    pred[..., :2] *= 640
+    pred[..., 2:4] = pred[..., 2:4] * 60 + 4
+    return pred
+
+
+@pytest.mark.parametrize('style', ['detect', 'val'])
+def test_nms_cfg5_stress_full_size(style):
+    """cfg-5 at its full size (256 x 25,200 x 15, ~252 k multi-label rows per image truncated to the top 30,000 in the
+    val style): the whole batch in one call; 8 of the 256 images compared BIT-EXACT with the oracle
+    (utils/general.py:633-725), every image checked for the size-independent properties (descending scores, count <=
+    max_det, finite boxes)."""
+    import dma_yolo_b200 as D
+    pred = cfg5_pred()
+    kw = dict(STYLES[style])
+    outs = D.non_max_suppression(pred.cuda(), **kw)
+    assert len(outs) == 256
+    for o in outs:
+        o = o.cpu()
+        assert o.shape[0] <= kw.get('max_det', 300) and o.shape[0] > 0
+        assert torch.isfinite(o).all()
+        assert bool((o[1:, 4] <= o[:-1, 4]).all())
+    for i in (0, 1, 37, 100, 128, 200, 254, 255):
+        ref = ON.non_max_suppression(pred[i:i + 1].numpy(), **kw)[0]
+        assert np.array_equal(outs[i].cpu().numpy(), ref), (style, i)
+
+
 def test_nms_empty_and_ragged():
     import dma_yolo_b200 as D
     pred = torch.zeros(3, 100, 9)
