@@ -16,6 +16,7 @@ import sys
 
 from . import _lib, ops  # noqa: F401
 from ._lib import DmayError, launch_count  # noqa: F401
+from .graph import GraphedDetector  # noqa: F401
 from .models.common import set_backend  # noqa: F401
 from .models.yolo import Detect, Model, parse_model  # noqa: F401
 from .utils.general import non_max_suppression, scale_coords, xywh2xyxy, xyxy2xywh  # noqa: F401

@@ -26,6 +26,9 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
 
 namespace dmay {
 
@@ -1171,7 +1174,18 @@ static int pow2ceil(int v) {
   return p;
 }
 
-static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
+// A launch plan: everything conv_plan derives from the parameter struct (mode / tile / pipeline decisions and the
+// encoded CUtensorMaps).  Plans are immutable and cached per (device, parameter struct) — SURVEY.md 8b "immutable
+// CUtensorMap caches keyed by pointer + shape" — so a steady-state step re-encodes nothing on the host.
+struct ConvPlan {
+  ConvArgs a;
+  int mode;
+  int grid;
+  int pdl;
+  size_t smem;
+};
+
+static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   if (!p || !p->x || !p->w || !p->scale || !p->bias || !p->y) return DMAY_EINVAL;
   if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->kh <= 0 || p->kw <= 0 || p->stride <= 0 ||
       p->pad < 0 || p->Ho <= 0 || p->Wo <= 0)
@@ -1193,7 +1207,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   if (p->pad > 127 || p->kh > 64 || p->kw > 64 || p->stride > 8) return DMAY_EUNSUPPORTED;
   if (!load_driver_fns()) return DMAY_EDRIVER;
 
-  ConvArgs a;
+  ConvArgs& a = pl.a;
   memset(&a, 0, sizeof(a));
   const long long M = (long long)p->N * p->Ho * p->Wo;
   if (M > 0x7fffff00LL) return DMAY_EUNSUPPORTED;
@@ -1512,7 +1526,17 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   const int sms = p->num_sms > 0 ? p->num_sms : sm_count();
   const long long supers = (long long)((a.num_m_tiles + a.cs - 1) / a.cs) * a.num_n_tiles;
   const long long max_clusters = sms / a.cs;
-  const int grid = (int)((supers < max_clusters ? supers : max_clusters) * a.cs);
+  pl.grid = (int)((supers < max_clusters ? supers : max_clusters) * a.cs);
+  pl.mode = mode;
+  pl.smem = smem;
+  pl.pdl = (p->flags & 128) ? 0 : 1;
+  return DMAY_OK;
+}
+
+static int conv_issue(const ConvPlan& pl, cudaStream_t stream) {
+  const ConvArgs& a = pl.a;
+  const int grid = pl.grid;
+  const size_t smem = pl.smem;
 #define DMAY_LAUNCH_MODE(MODE)                                                                                     \
   case MODE: {                                                                                                      \
     static std::atomic<unsigned long long> attr_mask{0};                                                            \
@@ -1530,7 +1554,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     cfg.stream = stream;                                                                                            \
     cudaLaunchAttribute at[2];                                                                                      \
     int nat = 0;                                                                                                    \
-    if (!(p->flags & 128)) {                                                                                        \
+    if (pl.pdl) {                                                                                                   \
       at[nat].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                              \
       at[nat].val.programmaticStreamSerializationAllowed = 1;                                                       \
       ++nat;                                                                                                        \
@@ -1549,7 +1573,7 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;                                                                            \
     break;                                                                                                          \
   }
-  switch (mode) {
+  switch (pl.mode) {
     DMAY_LAUNCH_MODE(EPI_SILU)
     DMAY_LAUNCH_MODE(EPI_SILU_RES)
     DMAY_LAUNCH_MODE(EPI_LINEAR)
@@ -1564,8 +1588,67 @@ static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
   return finish_launch();
 }
 
+// ---- plan cache -----------------------------------------------------------------------------------------------------
+// Key = the raw bytes of the parameter struct + the device ordinal.  The caching allocator of the host framework hands the
+// same addresses back step after step, so after the first step of a (batch, H, W) every launch is a cache hit.  A plan
+// holds no reference to device memory (tensor maps carry addresses, not ownership); a stale entry is merely never hit again.
+struct PlanKey {
+  dmay_conv_params p;
+  int dev;
+  int pad_;
+};
+struct PlanKeyHash {
+  size_t operator()(const PlanKey& k) const {
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(PlanKey); ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+struct PlanKeyEq {
+  bool operator()(const PlanKey& a, const PlanKey& b) const { return memcmp(&a, &b, sizeof(PlanKey)) == 0; }
+};
+static std::mutex g_plan_mu;
+static std::unordered_map<PlanKey, std::unique_ptr<ConvPlan>, PlanKeyHash, PlanKeyEq> g_plans;
+static std::atomic<long long> g_plan_hits{0}, g_plan_misses{0};
+static const size_t kMaxPlans = 16384;
+
+static int conv_launch(const dmay_conv_params* p, cudaStream_t stream) {
+  if (!p) return DMAY_EINVAL;
+  PlanKey key;
+  memset(&key, 0, sizeof(key));
+  key.p = *p;
+  if (cudaGetDevice(&key.dev) != cudaSuccess) key.dev = -1;
+  const ConvPlan* pl = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) pl = it->second.get();
+  }
+  if (pl) {
+    g_plan_hits.fetch_add(1, std::memory_order_relaxed);
+    return conv_issue(*pl, stream);
+  }
+  std::unique_ptr<ConvPlan> np(new ConvPlan);
+  const int rc = conv_plan(p, *np);
+  if (rc != DMAY_OK) return rc;
+  g_plan_misses.fetch_add(1, std::memory_order_relaxed);
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (g_plans.size() < kMaxPlans) {   // entries are never erased, so a pointer obtained under the lock stays valid
+      auto ins = g_plans.emplace(key, std::move(np));
+      pl = ins.first->second.get();
+    }
+  }
+  return conv_issue(pl ? *pl : *np, stream);
+}
+
 }  // namespace dmay
 
 extern "C" int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream) {
   return dmay::conv_launch(p, (cudaStream_t)stream);
+}
+
+extern "C" long long dmay_conv_plan_stats(int what) {
+  return what == 0 ? dmay::g_plan_hits.load() : what == 1 ? dmay::g_plan_misses.load() : (long long)dmay::g_plans.size();
 }

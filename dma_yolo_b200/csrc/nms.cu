@@ -996,6 +996,18 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const unsigned
   }
 }
 
+__global__ void clamp_offsets_kernel(const long long* __restrict__ img_offsets, long long* __restrict__ offsets_out,
+                                     int* __restrict__ counts_out, int N, long long capacity) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > N) return;
+  const long long a = img_offsets[i] < capacity ? img_offsets[i] : capacity;
+  offsets_out[i] = a;
+  if (i < N) {
+    const long long b = img_offsets[i + 1] < capacity ? img_offsets[i + 1] : capacity;
+    counts_out[i] = (int)(b - a);
+  }
+}
+
 __global__ void iota_kernel(unsigned* __restrict__ idx, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     idx[i] = (unsigned)i;
@@ -1359,6 +1371,14 @@ int dmay_nms_topk_select(const dmay_topk_params* p, dmay_stream_t stream) {
                                      (const long long*)p->img_offsets, (unsigned long long*)p->keys_out, (unsigned*)p->idx_out,
                                      (int*)p->counts_out, (long long*)p->offsets_out, p->N, p->K);
   if (e != cudaSuccess) return (int)e;
+  return finish_launch();
+}
+
+int dmay_nms_clamp_offsets(const dmay_clamp_params* p, dmay_stream_t stream) {
+  if (!p || !p->img_offsets || !p->offsets_out || !p->counts_out || p->N <= 0 || p->capacity <= 0) return DMAY_EINVAL;
+  if (p->img_offsets == p->offsets_out) return DMAY_EINVAL;   // out of place: threads read their neighbour's input
+  clamp_offsets_kernel<<<(p->N + 256) / 256, 256, 0, (cudaStream_t)stream>>>((const long long*)p->img_offsets, (long long*)p->offsets_out,
+                                                                          (int*)p->counts_out, p->N, p->capacity);
   return finish_launch();
 }
 

@@ -11,6 +11,7 @@ Every class has two bodies:
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import warnings
 
@@ -31,6 +32,18 @@ def set_backend(name: str):
     """'b200' (default): CUDA eval runs on the kernels.  'torch': reference torch-op bodies."""
     assert name in ("b200", "torch")
     _State.enabled = name == "b200"
+
+
+@contextlib.contextmanager
+def reference_ops():
+    """Inside this context every module of the package runs its reference torch-op body (used by the torch-only module
+    mirrors of models/extra.py so that a whole subtree stays in one dtype / layout)."""
+    prev = _State.enabled
+    _State.enabled = False
+    try:
+        yield
+    finally:
+        _State.enabled = prev
 
 
 def _first_tensor(x):

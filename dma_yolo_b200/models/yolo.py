@@ -23,6 +23,9 @@ from .common import *  # noqa: F401,F403  (module names are looked up by parse_m
 from .common import (CA, SM, AdConcat2, AdConcat3, Adapt_Add2, Adapt_Add3, Bottleneck, BottleneckCSP, C3, C3CA, C3HB, C3STR,
                      CABottleneck, Concat, Contract, CoorAttention, DWConv, Expand, Focus, SCConv, SPP, SPPCSPC, SPPF,
                      SPPFCSPC, _materialize, _PackMixin, get_conv_pack, kernel_path, space_to_depth)
+from .common import GnConv, HorBlock
+from .extra import (ASPP, BAM, C3SPP, C3TR, CBAM, CSPCM, AdaptADD, AdaptConcat, C3Ghost, C3GhostV2, ConvMix, CrossConv, DMConv,
+                    DMMConv, DMMConv2, GhostBottleneck, GhostConv, MixConv2d, MP, SMMConv)
 from .cspcm import Conv  # shadows common.Conv exactly like `from models.cspcm import *` (models/yolo.py:24)
 from .detect_t import TDetect  # models/yolo.py:9
 
@@ -192,20 +195,24 @@ class Model(nn.Module):
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
             if profile:
                 self._profile_one_layer(m, x, dt)
-            if fast and isinstance(m, nn.Upsample):
-                x = self._upsample_b200(m, x)
-            else:
-                if fast and not isinstance(m, (_common.AdConcat2, _common.AdConcat3, _common.Concat)):
-                    x = _materialize(x)
-                if fast and not _has_kernel_path(m):
-                    x = _common.torch_body(m, m, x)
-                else:
-                    x = m(x)
+            x = self._run_layer(m, x, fast)
             y.append(x if m.i in self.save else None)
             tr = self.__dict__.get('_trace')
             if tr is not None:  # test/debug hook: per-layer outputs (incl. layers that bypass nn.Module.__call__)
                 tr.append(x)
         return x
+
+    def _run_layer(self, m, x, fast=None):
+        """One layer of the loop: kernel path where the module has one, torch body on CUDA otherwise."""
+        if fast is None:
+            fast = kernel_path(self, x)
+        if fast and isinstance(m, nn.Upsample):
+            return self._upsample_b200(m, x)
+        if fast and not isinstance(m, (_common.AdConcat2, _common.AdConcat3, _common.Concat)):
+            x = _materialize(x)
+        if fast and not _has_kernel_path(m):
+            return _common.torch_body(m, m, x)
+        return m(x)
 
     @staticmethod
     def _upsample_b200(m, x):
@@ -306,9 +313,11 @@ def parse_model(d, ch):
     anchors, nc, gd, gw = d['anchors'], d['nc'], d['depth_multiple'], d['width_multiple']
     na = (len(anchors[0]) // 2) if isinstance(anchors, list) else anchors
     no = na * (nc + 5)
-    scaled = [Conv, _common.Conv, Bottleneck, SPP, SPPF, DWConv, Focus, BottleneckCSP, C3, nn.ConvTranspose2d,
-              CoorAttention, CABottleneck, C3CA, C3STR, C3HB, SPPCSPC, SPPFCSPC, SCConv]
-    repeated = [BottleneckCSP, C3, C3CA, C3STR, C3HB]
+    # models/yolo.py:387-388 (the channel-aware list) and 399 (modules that take the repeat count as an argument)
+    scaled = [Conv, _common.Conv, GhostConv, Bottleneck, GhostBottleneck, SPP, SPPF, DWConv, MixConv2d, Focus, CrossConv,
+              BottleneckCSP, C3, C3TR, C3STR, C3SPP, C3Ghost, ASPP, CBAM, nn.ConvTranspose2d, CoorAttention, CABottleneck, C3CA,
+              SPPCSPC, SPPFCSPC, SCConv, HorBlock, C3HB, GnConv]
+    repeated = [BottleneckCSP, C3, C3TR, C3STR, C3Ghost, C3CA, C3HB, BAM]
     layers, save, c2 = [], [], ch[-1]
     for i, (f, n, m, args) in enumerate(d['backbone'] + d['head']):
         if isinstance(m, str):
@@ -335,8 +344,23 @@ def parse_model(d, ch):
             args = [ch[f]]
         elif m in (Concat, AdConcat2, AdConcat3):
             c2 = sum(ch[x] for x in f)
+        elif m in (ConvMix, CSPCM):                       # models/yolo.py:410-414
+            c1, c2 = ch[f], args[0]
+            if c2 != no:
+                c2 = make_divisible(c2 * gw, 8)
+            args = [c1, c2, *args[1:]]
+        elif m in (AdaptConcat, AdaptADD):                # models/yolo.py:416-420
+            c2 = sum(ch[x] for x in f)
+            args = [len(f), *args]
         elif m in (Adapt_Add2, Adapt_Add3):
             c2 = max([ch[x] for x in f])
+        elif m is C3GhostV2:                              # models/yolo.py:424-431
+            c1, c2 = ch[f], args[0]
+            if c2 != no:
+                c2 = make_divisible(c2 * gw, 8)
+            args = [c1, c2, *args[1:]]
+            args.insert(2, n)
+            n = 1
         elif m is Detect:
             args.append([ch[x] for x in f])
             if isinstance(args[1], int):
@@ -347,8 +371,21 @@ def parse_model(d, ch):
             c2 = ch[f] * args[0] ** 2
         elif m is Expand:
             c2 = ch[f] // args[0] ** 2
-        elif m in (space_to_depth, SM):
+        elif m is space_to_depth:                        # models/yolo.py:446-447 (`SM` is not listed there: c2 = ch[f])
             c2 = 4 * ch[f]
+        elif m is SMMConv:                                # models/yolo.py:448-463
+            c1, c2 = ch[f], 4 * args[0]
+            args = [c1, args[0]]
+        elif m is DMMConv:
+            c1, c2 = ch[f], 5 * args[0]
+            args = [c1, args[0]]
+        elif m is DMMConv2:
+            c1 = ch[f]
+            c2 = args[0] + 4 * c1
+            args = [c1, args[0]]
+        elif m is DMConv:
+            c1, c2 = ch[f], 4 * args[0]
+            args = [c1, args[0]]
         else:
             c2 = ch[f]
         m_ = nn.Sequential(*(m(*args) for _ in range(n))) if n > 1 else m(*args)

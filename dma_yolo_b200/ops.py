@@ -681,6 +681,63 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes):
     return keys, cand, img_counts, img_offsets, offs_host, total
 
 
+def nms_fused_static(levels, na: int, nc: int, conf_thres: float, iou_thres: float, capacity: int, *, classes=None,
+                     agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=4096.0):
+    """Sync-free form of the Detect-logits NMS chain for CUDA-graph capture: the candidate buffers have a FIXED `capacity`,
+    nothing is read back by the host, every buffer size is a function of (capacity, N) only.
+      filter (reserve + scan + gather) -> clamp offsets to capacity -> exact top-max_nms selection (a plain copy for images
+      at or below max_nms) into a sentinel-filled key buffer -> stable sort of the whole buffer (sentinel keys sort last
+      within the last image and are never read: the per-image counts bound the greedy kernel) -> greedy.
+    Returns (out, counts, packed, img_offsets); img_offsets[N] is the TRUE candidate total: when it exceeds `capacity` the
+    result of this call is invalid and the caller must repeat the step with larger buffers (GraphedDetector does)."""
+    import ctypes
+    dev = levels[0].logits.device
+    n = levels[0].logits.shape[0]
+    s = torch.cuda.current_stream(dev).cuda_stream
+    multi_label = bool(multi_label) and nc > 1
+    buf, out, out_counts = _det_buffers(n, max_det, dev)
+    raw, rows = _level_meta_host(levels, na)
+    meta_host = ctypes.create_string_buffer(raw, len(raw))
+    ws_bytes = int(_lib.lib().dmay_nms_filter_fused_ws(ctypes.addressof(meta_host), len(levels), n))
+    if ws_bytes < 0:
+        raise DmayError(f"dmay_nms_filter_fused_ws failed: {ws_bytes}")
+    cm = _class_mask(classes, nc, dev)
+    capacity = int(capacity)
+    img_counts = torch.empty(n, device=dev, dtype=torch.int32)
+    img_offsets = torch.empty(n + 1, device=dev, dtype=torch.int64)
+    ws = torch.zeros(ws_bytes // 8 + 1, device=dev, dtype=torch.int64)
+    keys = torch.empty(capacity, device=dev, dtype=torch.int64)
+    cand = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
+    keys_tmp = torch.empty(capacity, device=dev, dtype=torch.int64)
+    cand_tmp = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
+    f = dict(lv_meta_host=ctypes.addressof(meta_host), ws=ws.data_ptr(), ws_bytes=ws.numel() * 8,
+             img_counts=img_counts.data_ptr(), img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(),
+             cand=cand.data_ptr(), N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
+             conf_thres=float(conf_thres), keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr())
+    for i, lv in enumerate(levels):
+        f[f"lv_logits{i}"] = lv.logits.data_ptr()
+    if cm is not None:
+        f["class_mask"] = cm.data_ptr()
+    call("dmay_nms_filter_fused", s, **f)
+    offs_cl = torch.empty(n + 1, device=dev, dtype=torch.int64)
+    cnts_cl = torch.empty(n, device=dev, dtype=torch.int32)
+    call("dmay_nms_clamp_offsets", s, img_offsets=img_offsets.data_ptr(), offsets_out=offs_cl.data_ptr(),
+         counts_out=cnts_cl.data_ptr(), N=n, capacity=capacity)
+    n_c = min(capacity, n * max_nms)
+    keys_c = torch.full((n_c,), -1, device=dev, dtype=torch.int64)           # sentinel: sorts after every real key
+    idx_c = torch.zeros(n_c, device=dev, dtype=torch.int32)
+    counts_c = torch.empty(n, device=dev, dtype=torch.int32)
+    offs_c = torch.empty(n + 1, device=dev, dtype=torch.int64)
+    call("dmay_nms_topk_select", s, keys=keys.data_ptr(), img_counts=cnts_cl.data_ptr(), img_offsets=offs_cl.data_ptr(),
+         keys_out=keys_c.data_ptr(), idx_out=idx_c.data_ptr(), counts_out=counts_c.data_ptr(), offsets_out=offs_c.data_ptr(),
+         N=n, K=max_nms)
+    _ko, idx = _sort_candidates(keys_c, n_c, n, dev, s, vals=idx_c)
+    call("dmay_nms_greedy", s, cand=cand.data_ptr(), sorted_idx=idx.data_ptr(), img_counts=counts_c.data_ptr(),
+         img_offsets=offs_c.data_ptr(), out=out.data_ptr(), out_counts=out_counts.data_ptr(), N=n, max_det=max_det,
+         max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
+    return out, out_counts, buf, img_offsets
+
+
 def filter_candidates(pred, conf_thres, *, multi_label=False, classes=None, levels=None, na=0, nc=None):
     """Candidate generation alone (tests, benchmarks): dense `pred` -> three-launch filter, Detect `levels` -> fused
     single-pass filter.  -> dict(keys, cand, img_counts, img_offsets (host list), total)."""

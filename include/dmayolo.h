@@ -116,6 +116,9 @@ typedef struct dmay_conv_params {
   int res_op;
 } dmay_conv_params;
 int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream);
+/* launch-plan cache of dmay_conv_bn_act (mode / tile decisions + encoded CUtensorMaps, keyed by the parameter struct and the
+ * device): what = 0 -> hits, 1 -> misses, 2 -> entries.  Immutable entries; no device memory is owned. */
+long long dmay_conv_plan_stats(int what);
 
 /* ---- input prep: NCHW {f32,f16,bf16,u8} image -> NHWC bf16 ------------------------------
  * replaces val.py:199-202 (`img.float()/255`) + the layout change the first conv needs.
@@ -481,6 +484,20 @@ typedef struct dmay_topk_params {
   int K;
 } dmay_topk_params;
 int dmay_nms_topk_select(const dmay_topk_params* p, dmay_stream_t stream);
+
+/* Sync-free guard for capacity-bounded candidate buffers (CUDA-graph replay of the NMS chain, where the host cannot
+ * re-size the buffers after the filter): offsets_out[i] = min(img_offsets[i], capacity), counts_out[i] =
+ * offsets_out[i+1] - offsets_out[i].  The filter counts every candidate but writes only those below `capacity`; with
+ * the clamped counts no later kernel reads past it.  img_offsets[N] (the true total) is left untouched: the caller
+ * compares it with `capacity` after the replay and repeats the step with larger buffers when it overflowed. */
+typedef struct dmay_clamp_params {
+  const void* img_offsets;
+  void* offsets_out;
+  void* counts_out;
+  int N;
+  long long capacity;
+} dmay_clamp_params;
+int dmay_nms_clamp_offsets(const dmay_clamp_params* p, dmay_stream_t stream);
 
 /* greedy NMS over each image's sorted candidates, stopping after max_det keeps.
  * IoU exactly as torchvision CPU nms_kernel: fp32 inter/(areaA+areaB-inter), compared in

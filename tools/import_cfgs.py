@@ -16,8 +16,19 @@ DEFAULT = ['yolov5s', 'yolov5n', 'yolov5m', 'yolov5l', 'yolov5x', 'ablation-ca-s
            'yolov5l-ca-sppfcspc-bifpn-scconv', 'spdconv', 'C3CASPD', 'CASPD_ODRTA']
 
 
+def all_names():
+    """Every reference config with a layer table (models/*.yaml and models/hub/*.yaml; hub/anchors.yaml is a list of anchors)."""
+    out = []
+    for f in sorted(SRC.glob('*.yaml')) + sorted((SRC / 'hub').glob('*.yaml')):
+        d = yaml.safe_load(f.read_text(errors='ignore'))
+        if isinstance(d, dict) and 'backbone' in d and 'anchors' in d:
+            out.append(str(f.relative_to(SRC))[:-5])
+    return out
+
+
 def emit(name: str):
     d = yaml.safe_load((SRC / f'{name}.yaml').read_text(errors='ignore'))
+    (DST / f'{name}.yaml').parent.mkdir(exist_ok=True)
     flow = lambda v: yaml.safe_dump(v, default_flow_style=True, width=10 ** 6).strip()
     lines = [f'# {name}: layer table for dma_yolo_b200.Model (normalised by tools/import_cfgs.py)',
              f"nc: {d['nc']}", f"depth_multiple: {d['depth_multiple']}", f"width_multiple: {d['width_multiple']}"]
@@ -36,5 +47,8 @@ def emit(name: str):
 
 
 if __name__ == '__main__':
-    for n in (sys.argv[1:] or DEFAULT):
+    names = sys.argv[1:] or DEFAULT
+    if names == ['--all']:
+        names = all_names()
+    for n in names:
         emit(n)
