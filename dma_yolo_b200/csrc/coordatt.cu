@@ -741,6 +741,331 @@ __global__ void __launch_bounds__(256) ca_gate_apply_mma_kernel(const __nv_bfloa
   }
 }
 
+
+// ---- ONE launch: pool + hidden layer + gates + apply, x read from HBM exactly once ------------------------------------
+// The two launches above read x twice (the 52 MB of cfg-2 do not survive in L2 between them: ncu shows 105 MB of DRAM
+// reads) and each is wave / latency-bound.  Here a CTA keeps its (image, 64-channel) plane in shared memory across both
+// phases: phase 1 is ca_pool_hidden_mma_kernel (pooled means, partial hidden layer, the image's last CTA finishes y),
+// then the CTAs of the image meet at a per-image flag, phase 2 is ca_gate_apply_mma_kernel with the apply loop reading the
+// plane from shared memory.  Work items come from an atomic ticket, so the CTAs of an image are the ones that started
+// before any later image's: a waiting CTA only ever waits for CTAs that are already running (at most one image can have
+// tickets not yet taken, every other image in flight is complete and frees its slots) -- no co-scheduling assumption.
+// Algorithmic traffic = read x once + write out once.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) ca_fused_mma_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           float* __restrict__ pooled_out, float* __restrict__ gates_out,
+                                                           float* __restrict__ partial, float* __restrict__ yhid,
+                                                           unsigned* __restrict__ sync_words,   // [3N + 2], zero on first use
+                                                           const float* __restrict__ w1T, const float* __restrict__ b1,
+                                                           const float* __restrict__ s1, const float* __restrict__ t1,
+                                                           const float* __restrict__ whT, const float* __restrict__ bh,
+                                                           const float* __restrict__ wwT, const float* __restrict__ bw,
+                                                           int N, int H, int W, int C, int Cm, int ldx, int ldy, int G) {
+  extern __shared__ uint4 plane[];                    // [H*W][kCaVL], lives through both phases
+  const int HW = H * W, P = H + W, Pp = (P + 15) & ~15, Cmp = (Cm + 15) & ~15;
+  __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(plane + (size_t)HW * kCaVL);   // phase 1: [Pp][72] pooled means, hi
+  __nv_bfloat16* pl = ph + Pp * kCmPoolPitch;
+  __nv_bfloat16* wh = pl + Pp * kCmPoolPitch;                                         // [Cmp][72] W1 slice, hi
+  __nv_bfloat16* wl = wh + Cmp * kCmPoolPitch;
+  __nv_bfloat16* yh = ph;                                                             // phase 2 re-uses the same bytes:
+  __nv_bfloat16* yl = yh + Pp * kCmYPitch;                                            // [Pp][40] hidden activations hi / lo
+  float* gs = reinterpret_cast<float*>(yl + Pp * kCmYPitch);                          // [P][2][8][4] gates of the 64 channels
+  __shared__ unsigned work_s, ticket_s;
+  unsigned* counters = sync_words;          // [N] arrivals after phase 1
+  unsigned* ready = sync_words + N;         // [N] y of the image is complete
+  unsigned* passed = sync_words + 2 * N;    // [N] CTAs that have consumed `ready`
+  unsigned* work_ticket = sync_words + 3 * N;
+  unsigned* finished = sync_words + 3 * N + 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, tq = lane & 3;
+  if (tid == 0) work_s = atomicAdd(work_ticket, 1u);
+  __syncthreads();
+  const int n = (int)work_s / G, g = (int)work_s % G;
+  const int cvec = C >> 3;
+  const int v0 = g * kCaVL;
+  const int vl = min(kCaVL, cvec - v0);
+  const int nch = vl * 8;
+  // ---------------- phase 1: plane -> shared, pooled means, partial hidden layer ----------------
+  float wreg[8];
+  const int wtot = nch * Cm;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid + k * 256;
+    wreg[k] = i < wtot ? w1T[(long long)(v0 * 8) * Cm + i] : 0.f;
+  }
+  {
+    const __nv_bfloat16* xb = x + (long long)n * HW * ldx + v0 * 8;
+    const uint32_t plane_s = (uint32_t)__cvta_generic_to_shared(plane);
+    const int v = tid & 7;
+    if (v < vl) {
+      const __nv_bfloat16* src = xb + (long long)(tid >> 3) * ldx + v * 8;
+      uint32_t dst = plane_s + (uint32_t)tid * 16u;
+      for (int p = tid >> 3; p < HW; p += 32) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");   // single use: no L2 hint
+        src += 32LL * ldx;
+        dst += 256u * 16u;
+      }
+    } else {
+      for (int p = tid >> 3; p < HW; p += 32) plane[p * kCaVL + v] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = tid; i < Cmp * kCmPoolPitch / 4; i += 256) reinterpret_cast<uint4*>(wh)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    const bool pow2 = (Cm & (Cm - 1)) == 0;
+    const int sh = 31 - __clz(Cm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = tid + k * 256;
+      if (i < wtot) {
+        const int c = pow2 ? (i >> sh) : i / Cm, j = i - c * Cm;
+        float hi, lo;
+        cm_split(wreg[k], hi, lo);
+        wh[j * kCmPoolPitch + c] = __float2bfloat16_rn(hi);
+        wl[j * kCmPoolPitch + c] = __float2bfloat16_rn(lo);
+      }
+    }
+  }
+  // gate weights of this warp's two 8-channel tiles as MMA B fragments (phase 2 operands; the loads overlap the plane's)
+  uint32_t wgh[2][2][2], wgl[2][2][2];
+  float gb[2][2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int ntile = warp * 2 + t, type = ntile >> 3, vv = ntile & 7;   // tiles 0-7: h gates, 8-15: w gates
+    const float* wT = type ? wwT : whT;
+    const float* bb = type ? bw : bh;
+    const int cl = vv * 8 + g8;
+    const bool cin = cl < nch;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int k0 = ks * 16 + tq * 2 + half * 8;
+        const float a0 = (cin && k0 < Cm) ? wT[(long long)k0 * C + v0 * 8 + cl] : 0.f;
+        const float a1 = (cin && k0 + 1 < Cm) ? wT[(long long)(k0 + 1) * C + v0 * 8 + cl] : 0.f;
+        float h0, l0, h1, l1;
+        cm_split(a0, h0, l0);
+        cm_split(a1, h1, l1);
+        wgh[t][ks][half] = pack_bf2(h0, h1);
+        wgl[t][ks][half] = pack_bf2(l0, l1);
+      }
+    }
+    const int ce = vv * 8 + tq * 2;
+    gb[t][0] = ce < nch ? bb[v0 * 8 + ce] : 0.f;
+    gb[t][1] = ce + 1 < nch ? bb[v0 * 8 + ce + 1] : 0.f;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const float invW = 1.0f / (float)W, invH = 1.0f / (float)H;
+  for (int i = tid; i < Pp * kCaVL; i += 256) {
+    const int p = i >> 3, v = i & 7;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (p < P) {
+      int start, step, cnt;
+      float inv;
+      if (p < H) { start = p * W; step = kCaVL; cnt = W; inv = invW; }
+      else { start = p - H; step = W * kCaVL; cnt = H; inv = invH; }
+      const uint4* src = plane + start * kCaVL + v;
+      f32x2_t a2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll 4
+      for (int k = 0; k < cnt; ++k) {
+        const uint4 u = *src;
+        src += step;
+        a2[0] = f2_add(a2[0], f2_from_bf2(u.x));
+        a2[1] = f2_add(a2[1], f2_from_bf2(u.y));
+        a2[2] = f2_add(a2[2], f2_from_bf2(u.z));
+        a2[3] = f2_add(a2[3], f2_from_bf2(u.w));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f2_unpack(a2[j], acc[2 * j], acc[2 * j + 1]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= inv;
+      if (pooled_out != nullptr && v < vl) {
+        float4* o = reinterpret_cast<float4*>(pooled_out + ((long long)n * P + p) * C + (v0 + v) * 8);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+    float hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cm_split(acc[j], hi[j], lo[j]);
+    *reinterpret_cast<uint4*>(ph + p * kCmPoolPitch + v * 8) = pack8(hi);
+    *reinterpret_cast<uint4*>(pl + p * kCmPoolPitch + v * 8) = pack8(lo);
+  }
+  __syncthreads();
+  {
+    float* part = partial + (long long)(n * G + g) * P * Cm;
+    const int mtiles = Pp >> 4, ntiles = Cmp >> 3;
+    const uint32_t ph_s = (uint32_t)__cvta_generic_to_shared(ph), pl_s = (uint32_t)__cvta_generic_to_shared(pl);
+    const uint32_t wh_s = (uint32_t)__cvta_generic_to_shared(wh), wl_s = (uint32_t)__cvta_generic_to_shared(wl);
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kof = (lane >> 4) * 8;
+    const int b_row = lane & 7, b_kof = ((lane >> 3) & 3) * 8;
+    for (int tile = warp; tile < mtiles * ntiles; tile += 8) {
+      const int mt = tile / ntiles, nt = tile - mt * ntiles;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t aoff = (uint32_t)((mt * 16 + a_row) * kCmPoolPitch + a_kof) * 2u;
+      const uint32_t boff = (uint32_t)((nt * 8 + b_row) * kCmPoolPitch + b_kof) * 2u;
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {
+        uint32_t bhf[4], blf[4];
+        ldsm_x4(wh_s + boff + kp * 64, bhf[0], bhf[1], bhf[2], bhf[3]);
+        ldsm_x4(wl_s + boff + kp * 64, blf[0], blf[1], blf[2], blf[3]);
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          uint32_t ah[4], al[4];
+          ldsm_x4(ph_s + aoff + (kp * 2 + k2) * 32, ah[0], ah[1], ah[2], ah[3]);
+          ldsm_x4(pl_s + aoff + (kp * 2 + k2) * 32, al[0], al[1], al[2], al[3]);
+          mma_bf16(acc, ah[0], ah[1], ah[2], ah[3], bhf[k2 * 2], bhf[k2 * 2 + 1]);
+          mma_bf16(acc, ah[0], ah[1], ah[2], ah[3], blf[k2 * 2], blf[k2 * 2 + 1]);
+          mma_bf16(acc, al[0], al[1], al[2], al[3], bhf[k2 * 2], bhf[k2 * 2 + 1]);
+        }
+      }
+      const int j = nt * 8 + tq * 2, p0 = mt * 16 + g8, p1 = p0 + 8;
+      if (j < Cm) {
+        if (p0 < P) { part[p0 * Cm + j] = acc[0]; if (j + 1 < Cm) part[p0 * Cm + j + 1] = acc[1]; }
+        if (p1 < P) { part[p1 * Cm + j] = acc[2]; if (j + 1 < Cm) part[p1 * Cm + j + 1] = acc[3]; }
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket_s = atomicAdd(counters + n, 1u);
+  __syncthreads();
+  if (ticket_s == (unsigned)(G - 1)) {   // every other group of this image has published its partial: finish y, open the gate
+    __threadfence();
+    const float* pn = partial + (long long)n * G * P * Cm;
+    for (int o = tid; o < P * Cm; o += 256) {
+      const int j = o % Cm;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int gg = 0; gg < G; ++gg) acc += __ldcg(pn + (long long)gg * P * Cm + o);   // fixed order: deterministic
+      yhid[(long long)n * P * Cm + o] = hardswish(s1[j] * (acc + b1[j]) + t1[j]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      counters[n] = 0u;
+      st_release_u32(ready + n, 1u);
+    }
+  } else {
+    if (tid == 0) {
+      while (ld_acquire_u32(ready + n) == 0u) __nanosleep(100);
+    }
+    __syncthreads();
+  }
+  // ---------------- phase 2: gates of this group's 64 channels, apply from the resident plane ----------------
+  for (int i = tid; i < Pp * kCmYPitch; i += 256) {
+    const int p = i / kCmYPitch, j = i - p * kCmYPitch;
+    const float v = (p < P && j < Cm) ? __ldcg(yhid + ((long long)n * P + p) * Cm + j) : 0.f;
+    float hi, lo;
+    cm_split(v, hi, lo);
+    yh[i] = __float2bfloat16_rn(hi);
+    yl[i] = __float2bfloat16_rn(lo);
+  }
+  __syncthreads();
+  if (tid == 0) {   // the flag may be cleared once every CTA of the image has read it (self-resetting workspace)
+    if (atomicAdd(passed + n, 1u) == (unsigned)(G - 1)) {
+      passed[n] = 0u;
+      ready[n] = 0u;
+    }
+    if (atomicAdd(finished, 1u) == (unsigned)(N * G - 1)) {
+      *finished = 0u;
+      *work_ticket = 0u;
+    }
+  }
+  {
+    const uint32_t yh_s = (uint32_t)__cvta_generic_to_shared(yh), yl_s = (uint32_t)__cvta_generic_to_shared(yl);
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kof = (lane >> 4) * 8;
+    const int ksG = Cmp >> 4, mtiles = Pp >> 4;
+    for (int mt = 0; mt < mtiles; ++mt) {
+      const bool is_w = warp >= 4;
+      if (is_w ? (mt * 16 + 15 < H || mt * 16 >= P) : (mt * 16 >= H)) continue;
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const uint32_t aoff = (uint32_t)((mt * 16 + a_row) * kCmYPitch + a_kof) * 2u;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks < ksG) {
+          uint32_t ah[4], al[4];
+          ldsm_x4(yh_s + aoff + ks * 32, ah[0], ah[1], ah[2], ah[3]);
+          ldsm_x4(yl_s + aoff + ks * 32, al[0], al[1], al[2], al[3]);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mma_bf16(acc[t], ah[0], ah[1], ah[2], ah[3], wgh[t][ks][0], wgh[t][ks][1]);
+            mma_bf16(acc[t], ah[0], ah[1], ah[2], ah[3], wgl[t][ks][0], wgl[t][ks][1]);
+            mma_bf16(acc[t], al[0], al[1], al[2], al[3], wgh[t][ks][0], wgh[t][ks][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int vv = (warp * 2 + t) & 7;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int pos = mt * 16 + g8 + rr * 8;
+          if (is_w ? (pos >= H && pos < P) : (pos < H)) {
+            const float g0 = sigmoid_fast(acc[t][rr * 2] + gb[t][0]), g1 = sigmoid_fast(acc[t][rr * 2 + 1] + gb[t][1]);
+            *reinterpret_cast<float2*>(gs + pos * 64 + (tq >> 1) * 32 + vv * 4 + (tq & 1) * 2) = make_float2(g0, g1);
+            const int ce = vv * 8 + tq * 2;
+            if (gates_out != nullptr && ce < nch)
+              *reinterpret_cast<float2*>(gates_out + ((long long)n * P + pos) * C + v0 * 8 + ce) = make_float2(g0, g1);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int v = tid & 7;
+  if (v >= vl) return;
+  constexpr int kRows = 32;
+  int p = tid >> 3;
+  const int h0_ = p / W;
+  int w_ = p - h0_ * W;
+  const int dH = kRows / W, dW = kRows - dH * W;
+  __nv_bfloat16* ob = out + (long long)n * HW * ldy + v0 * 8 + v * 8;
+  int oo = p * ldy;
+  const int ostep = kRows * ldy;
+  const float* gh = gs + h0_ * 64 + v * 4;
+  const float* gw = gs + (H + w_) * 64 + v * 4;
+  const uint4* xs = plane + p * kCaVL + v;
+  while (p < HW) {
+    const uint4 r = *xs;
+    const float4 h0 = *reinterpret_cast<const float4*>(gh), h1 = *reinterpret_cast<const float4*>(gh + 32);
+    const float4 w0 = *reinterpret_cast<const float4*>(gw), w1 = *reinterpret_cast<const float4*>(gw + 32);
+    // (x * a_w) * a_h on packed pairs: same IEEE roundings as the scalar form
+    const f32x2_t q0 = f2_mul(f2_mul(f2_from_bf2(r.x), f2_pack(w0.x, w0.y)), f2_pack(h0.x, h0.y));
+    const f32x2_t q1 = f2_mul(f2_mul(f2_from_bf2(r.y), f2_pack(w0.z, w0.w)), f2_pack(h0.z, h0.w));
+    const f32x2_t q2 = f2_mul(f2_mul(f2_from_bf2(r.z), f2_pack(w1.x, w1.y)), f2_pack(h1.x, h1.y));
+    const f32x2_t q3 = f2_mul(f2_mul(f2_from_bf2(r.w), f2_pack(w1.z, w1.w)), f2_pack(h1.z, h1.w));
+    float f[8];
+    f2_unpack(q0, f[0], f[1]);
+    f2_unpack(q1, f[2], f[3]);
+    f2_unpack(q2, f[4], f[5]);
+    f2_unpack(q3, f[6], f[7]);
+    st_na16(ob + oo, pack8(f));
+    p += kRows;
+    xs += kRows * kCaVL;
+    oo += ostep;
+    w_ += dW;
+    gh += dH * 64;
+    gw += dW * 64;
+    if (w_ >= W) {
+      w_ -= W;
+      gh += 64;
+      gw -= W * 64;
+    }
+  }
+}
+
 }  // namespace dmay
 
 using namespace dmay;
@@ -748,7 +1073,7 @@ using namespace dmay;
 extern "C" long long dmay_coordatt_ws(int N, int H, int W, int C, int Cm) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cm <= 0) return DMAY_EINVAL;
   const long long G = (C / 8 + kCaVL - 1) / kCaVL, P = H + W;
-  return ((long long)N * G * P * Cm + (long long)N * P * Cm) * 4 + (long long)N * 4;
+  return ((long long)N * G * P * Cm + (long long)N * P * Cm) * 4 + ((long long)3 * N + 2) * 4;   // partial, y, sync words
 }
 
 
@@ -770,7 +1095,7 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
     const int G = (cvec + kCaVL - 1) / kCaVL, P = p->H + p->W;
     const size_t smem1 = (size_t)HW * kCaVL * 16 + (size_t)P * 64 * 4 + (size_t)64 * p->Cm * 4;
     const size_t smem2 = ((size_t)P * p->Cm + (size_t)P * 64 + 2 * (size_t)p->Cm * 64) * 4;
-    const long long need = ((long long)p->N * G * P * p->Cm + (long long)p->N * P * p->Cm) * 4 + (long long)p->N * 4;
+    const long long need = ((long long)p->N * G * P * p->Cm + (long long)p->N * P * p->Cm) * 4 + ((long long)3 * p->N + 2) * 4;
     if (p->ws != nullptr && p->ws_bytes >= need && smem1 <= 100 * 1024 && smem2 <= 100 * 1024 && aligned16(p->ws) &&
         p->Cm <= 256) {
       float* partial = (float*)p->ws;
@@ -781,6 +1106,25 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
       const int Pp = (P + 15) & ~15, Cmp = (p->Cm + 15) & ~15;
       const size_t smem1m = (size_t)HW * kCaVL * 16 + (size_t)2 * (Pp + Cmp) * kCmPoolPitch * 2;
       const size_t smem2m = (size_t)2 * Pp * kCmYPitch * 2 + (size_t)P * 64 * 4;
+      // opt-in (DMAY_CA_FUSED=1): measured 88 us vs 60 us for the two launches at cfg-2 (3 instead of 4 CTAs per SM and the
+      // CTAs of an image idle at the flag while its last CTA finishes y) -- profiles/r2_notes.md
+      static const bool no_fused = [] { const char* e = getenv("DMAY_CA_FUSED"); return !(e && e[0] == '1'); }();
+      const size_t smem_a = (size_t)2 * (Pp + Cmp) * kCmPoolPitch * 2, smem_b = (size_t)2 * Pp * kCmYPitch * 2 + (size_t)P * 64 * 4;
+      const size_t smemf = (size_t)HW * kCaVL * 16 + (smem_a > smem_b ? smem_a : smem_b);
+      if (!no_mma && !no_fused && p->Cm <= kCmMax && smemf <= 100 * 1024 && G <= 64 &&
+          HW * (long long)(p->ldx > p->ldy ? p->ldx : p->ldy) < 0x7fffffffLL) {
+        // single launch: x is read once (see ca_fused_mma_kernel)
+        if (smemf > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(ca_fused_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemf);
+          if (e != cudaSuccess) return (int)e;
+        }
+        ca_fused_mma_kernel<<<p->N * G, 256, smemf, s>>>((const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, (float*)p->pooled,
+                                                         (float*)p->gates, partial, yhid, counters, (const float*)p->w1,
+                                                         (const float*)p->b1, (const float*)p->s1, (const float*)p->t1,
+                                                         (const float*)p->wh, (const float*)p->bh, (const float*)p->ww,
+                                                         (const float*)p->bw, p->N, p->H, p->W, p->C, p->Cm, p->ldx, p->ldy, G);
+        return finish_launch(1);
+      }
       if (!no_mma && p->Cm <= kCmMax && smem1m <= 100 * 1024 && smem2m <= 100 * 1024 &&
           HW * (long long)(p->ldx > p->ldy ? p->ldx : p->ldy) < 0x7fffffffLL) {
         if (smem1m > 48 * 1024) {

@@ -38,6 +38,7 @@ struct RowSrc {
   const LevelMeta* meta;
   int levels;
   int R, nc;
+  int pitch;                 // floats per anchor row inside a pixel's channel vector (0 = 5 + nc)
 };
 
 // Loads one prediction row for the whole warp: returns obj and xywh (valid in all lanes); class
@@ -71,7 +72,7 @@ __device__ __forceinline__ RowView load_row(const RowSrc& s, int img, int r) {
   const int gy = rr % m.ny;
   const int a = rr / m.ny;
   const int no = 5 + s.nc;
-  v.base = s.logits[l] + (((long long)img * m.ny + gy) * m.nx + gx) * m.ld + a * no;
+  v.base = s.logits[l] + (((long long)img * m.ny + gy) * m.nx + gx) * m.ld + a * (s.pitch > 0 ? s.pitch : no);
   const float sx = sigmoid_dec(v.base[0]), sy = sigmoid_dec(v.base[1]);
   const float sw = sigmoid_dec(v.base[2]), sh = sigmoid_dec(v.base[3]);
   v.obj = sigmoid_dec(v.base[4]);
@@ -283,6 +284,7 @@ struct FuseArgs {
   int levels, nc, multi_label, N;
   float thr;
   long long capacity;
+  int pitch;           // floats between the rows of two anchors inside a pixel's channel vector (5 + nc, or padded to 4n)
 };
 
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
   const int nc = fa.nc, no = 5 + nc, ld = m.ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float thr = fa.thr;
-  const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * no;
+  const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * fa.pitch;
 
   // ---- stage + phase 1 (the warp that loads a row also processes it: only warp-level sync needed) ----
   // (rows start on 4-byte boundaries only — a*no floats into the pixel — hence 4-byte cp.async: every lane's copy is
@@ -517,7 +519,13 @@ constexpr int kRowsMaxNc = 96;
 //                  (`status` then holds tile_base[] / tile_cnt[]), tile_scan_kernel + tile_gather_kernel put the runs
 //                  in order afterwards.  ncu of the look-back form: 46 % of the warp samples wait for the slowest of
 //                  the ~700 in-flight predecessor tiles to publish a count; the gather costs 2 x 32 B per candidate.
-template <bool RESERVE>
+// KIND 0: Detect logits, anchor rows of 5 + nc floats (only 4-byte aligned: 4-byte cp.async staging, scalar LDS).
+// KIND 1: Detect logits whose anchor rows are padded to a multiple of 4 floats by the head GEMM (zero weight rows; the
+//         layout is ours): rows are 16-byte aligned, staged with 16-byte cp.async into shared rows of pitch + 4 words (an
+//         odd number of 16-byte chunks: conflict-free LDS.128), and the multi-label scan reads four logits per load.
+// KIND 2: dense prediction [N, R, 5 + nc] (already decoded: utils/general.py's input when the caller holds a tensor):
+//         values are used as they are (no sigmoid, no grid decode); the tile is one contiguous run of memory.
+template <bool RESERVE, int KIND>
 __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
                                                                          const unsigned char* __restrict__ class_mask,
                                                                          unsigned* __restrict__ ticket,
@@ -546,63 +554,134 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
   const int p0 = ti * kRowsThreads;
   const int np = min(kRowsThreads, npix - p0);
   const int nc = fa.nc, no = 5 + nc, ld = m.ld;
+  const int pitch = KIND == 1 ? fa.pitch : no;              // global floats per anchor row
+  const int srow = KIND == 1 ? fa.pitch + 4 : no;           // shared-memory words per row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float thr = fa.thr;
-  {   // stage: a warp copies whole rows (coalesced along the row; 4-byte cp.async, rows are only 4-byte aligned)
-    const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * no;
+  {
+    const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * pitch;
     const uint32_t tile_sm = (uint32_t)__cvta_generic_to_shared(tile);
-    // per row: nfull unconditional copies (lane, lane + 32, ...) and one partial; addresses advance by constants
-    const int nfull = no >> 5, rem = no & 31;
-    const uint32_t rem_off = (uint32_t)nfull * 128u;
-    uint32_t sdst = tile_sm + (uint32_t)(warp * no + lane) * 4u;
-    const float* g = gsrc + (long long)warp * ld + lane;
-    const uint32_t sstep = (uint32_t)(kRowsThreads / 32) * (uint32_t)no * 4u;
-    const long long gstep = (long long)(kRowsThreads / 32) * ld;
-    for (int row = warp; row < np; row += kRowsThreads / 32) {
-      // no <= 5 + kRowsMaxNc = 101: at most three full 32-lane copies; straight-line code with uniform predicates
-      if (nfull > 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(g) : "memory");
-      if (nfull > 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 128u), "l"(g + 32) : "memory");
-      if (nfull > 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 256u), "l"(g + 64) : "memory");
-      if (lane < rem) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + rem_off), "l"(g + nfull * 32) : "memory");
-      sdst += sstep;
-      g += gstep;
+    bool staged = false;
+    if (KIND == 1) {   // a warp copies whole rows, one 16-byte chunk per lane
+      const int cpr = pitch >> 2;
+      uint32_t sdst = tile_sm + (uint32_t)(warp * srow) * 4u + (uint32_t)lane * 16u;
+      const float* g = gsrc + (long long)warp * ld + lane * 4;
+      const uint32_t sstep = (uint32_t)(kRowsThreads / 32) * (uint32_t)srow * 4u;
+      const long long gstep = (long long)(kRowsThreads / 32) * ld;
+      for (int row = warp; row < np; row += kRowsThreads / 32) {
+        if (lane < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
+        if (lane + 32 < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 512u), "l"(g + 128) : "memory");
+        sdst += sstep;
+        g += gstep;
+      }
+      staged = true;
+    } else if (KIND == 2) {   // the tile is contiguous: flat 16-byte copies when base and length allow
+      const int words = np * no;
+      if (((reinterpret_cast<uintptr_t>(gsrc) & 15u) == 0) && (words & 3) == 0) {
+        for (int i = threadIdx.x; i < (words >> 2); i += kRowsThreads)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_sm + (uint32_t)i * 16u), "l"(gsrc + i * 4) : "memory");
+        staged = true;
+      }
+    }
+    if (!staged) {   // a warp copies whole rows (coalesced along the row; 4-byte cp.async, rows are only 4-byte aligned)
+      // per row: nfull unconditional copies (lane, lane + 32, ...) and one partial; addresses advance by constants
+      const int nfull = no >> 5, rem = no & 31;
+      const uint32_t rem_off = (uint32_t)nfull * 128u;
+      uint32_t sdst = tile_sm + (uint32_t)(warp * srow + lane) * 4u;
+      const float* g = gsrc + (long long)warp * ld + lane;
+      const uint32_t sstep = (uint32_t)(kRowsThreads / 32) * (uint32_t)srow * 4u;
+      const long long gstep = (long long)(kRowsThreads / 32) * ld;
+      for (int row = warp; row < np; row += kRowsThreads / 32) {
+        // no <= 5 + kRowsMaxNc = 101: at most three full 32-lane copies; straight-line code with uniform predicates
+        if (nfull > 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(g) : "memory");
+        if (nfull > 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 128u), "l"(g + 32) : "memory");
+        if (nfull > 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 256u), "l"(g + 64) : "memory");
+        if (lane < rem) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + rem_off), "l"(g + nfull * 32) : "memory");
+        sdst += sstep;
+        g += gstep;
+      }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
 
   const int row = threadIdx.x;
-  float* s = tile + row * no;     // row stride 5 + nc words: conflict-free whenever it is odd (nc = 80, 10, ...)
+  float* s = tile + row * srow;   // KIND 0 / 2: row stride 5 + nc words, conflict-free whenever it is odd (nc = 80, 10, ...)
   int cnt = 0;
-  uint32_t pm[3] = {0u, 0u, 0u};  // passing classes
+  uint32_t pm[4] = {0u, 0u, 0u, 0u};  // passing classes (bit = class; KIND 1 indexes words 0..3 statically)
   float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, bconf = 0.f;
   int bcls = 0;
   if (row < np) {
-    const float obj = sigmoid_dec(s[4]);
+    const float obj = KIND == 2 ? s[4] : sigmoid_dec(s[4]);
     if (obj > thr) {
       if (fa.multi_label) {
-        // conservative pre-filter on the raw logit (see the header comment); exact test only for survivors
-        const float q = (thr / obj) * (1.0f - 4e-6f);
-        float t_lo = -INFINITY;
-        if (q > 0.f) t_lo = q < 1.f ? fminf(__logf(q / (1.0f - q)) - 0.02f, 10.0f) : 10.0f;
+        if (KIND == 2) {
+          // dense rows hold the class confidences themselves: the reference arithmetic is one multiply (general.py:677)
 #pragma unroll
-        for (int w = 0; w < 3; ++w) {   // 32 classes per mask word (static register indexing)
-          uint32_t mk = 0u;
-          const int cend = min(32, nc - w * 32);
-          const float* sc = s + 5 + w * 32;
+          for (int w = 0; w < 3; ++w) {
+            uint32_t mk = 0u;
+            const int cend = min(32, nc - w * 32);
+            float* sc = s + 5 + w * 32;
 #pragma unroll 8
-          for (int cc = 0; cc < cend; ++cc) {
-            const float v = sc[cc];
-            if (v > t_lo) {
-              const float conf = __fmul_rn(sigmoid_dec(v), obj);
+            for (int cc = 0; cc < cend; ++cc) {
+              const float conf = __fmul_rn(sc[cc], obj);
               if (conf > thr && (class_mask == nullptr || class_mask[w * 32 + cc])) {
-                s[5 + w * 32 + cc] = conf;
+                sc[cc] = conf;
                 mk |= 1u << cc;
                 ++cnt;
               }
             }
+            pm[w] = mk;
           }
-          pm[w] = mk;
+        } else {
+          // conservative pre-filter on the raw logit (see the header comment); exact test only for survivors
+          const float q = (thr / obj) * (1.0f - 4e-6f);
+          float t_lo = -INFINITY;
+          if (q > 0.f) t_lo = q < 1.f ? fminf(__logf(q / (1.0f - q)) - 0.02f, 10.0f) : 10.0f;
+          if (KIND == 1) {
+            // four logits per LDS.128; chunk k holds words 4k .. 4k+3 of the row, class c sits at word 5 + c
+            const float4* s4 = reinterpret_cast<const float4*>(s);
+            const int nchunk = (no + 3) >> 2;
+#pragma unroll
+            for (int k = 1; k < (5 + kRowsMaxNc + 3) / 4; ++k) {
+              if (k < nchunk) {
+                const float4 v4 = s4[k];
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int c = 4 * k + e - 5;
+                  if (c >= 0 && c < nc && vv[e] > t_lo) {
+                    const float conf = __fmul_rn(sigmoid_dec(vv[e]), obj);
+                    if (conf > thr && (class_mask == nullptr || class_mask[c])) {
+                      s[5 + c] = conf;
+                      pm[c >> 5] |= 1u << (c & 31);
+                      ++cnt;
+                    }
+                  }
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {   // 32 classes per mask word (static register indexing)
+              uint32_t mk = 0u;
+              const int cend = min(32, nc - w * 32);
+              const float* sc = s + 5 + w * 32;
+#pragma unroll 8
+              for (int cc = 0; cc < cend; ++cc) {
+                const float v = sc[cc];
+                if (v > t_lo) {
+                  const float conf = __fmul_rn(sigmoid_dec(v), obj);
+                  if (conf > thr && (class_mask == nullptr || class_mask[w * 32 + cc])) {
+                    s[5 + w * 32 + cc] = conf;
+                    mk |= 1u << cc;
+                    ++cnt;
+                  }
+                }
+              }
+              pm[w] = mk;
+            }
+          }
         }
       } else {
         // best class: first maximum (torch.max on CPU); NaN anywhere -> no candidate
@@ -610,7 +689,7 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
         int bi = 0x7fffffff;
         bool has_nan = false;
         for (int c = 0; c < nc; ++c) {
-          const float conf = __fmul_rn(sigmoid_dec(s[5 + c]), obj);
+          const float conf = __fmul_rn(KIND == 2 ? s[5 + c] : sigmoid_dec(s[5 + c]), obj);
           if (conf != conf) has_nan = true;
           if (conf > best) {
             best = conf;
@@ -624,15 +703,21 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
         }
       }
       if (cnt > 0) {
-        const int pix = p0 + row;
-        const int gy = pix / m.nx, gx = pix - gy * m.nx;
-        const float sx = sigmoid_dec(s[0]), sy = sigmoid_dec(s[1]), sw = sigmoid_dec(s[2]), sh = sigmoid_dec(s[3]);
-        // models/yolo.py:91-97 operation order, then xywh2xyxy (utils/general.py:539-546)
-        const float x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), m.stride);
-        const float y = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.f), 0.5f), (float)gy), m.stride);
-        const float tw = __fmul_rn(sw, 2.f), th = __fmul_rn(sh, 2.f);
-        const float w = __fmul_rn(__fmul_rn(tw, tw), m.anchor[2 * a]);
-        const float h = __fmul_rn(__fmul_rn(th, th), m.anchor[2 * a + 1]);
+        float x, y, w, h;
+        if (KIND == 2) {
+          x = s[0]; y = s[1]; w = s[2]; h = s[3];
+        } else {
+          const int pix = p0 + row;
+          const int gy = pix / m.nx, gx = pix - gy * m.nx;
+          const float sx = sigmoid_dec(s[0]), sy = sigmoid_dec(s[1]), sw = sigmoid_dec(s[2]), sh = sigmoid_dec(s[3]);
+          // models/yolo.py:91-97 operation order
+          x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), m.stride);
+          y = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.f), 0.5f), (float)gy), m.stride);
+          const float tw = __fmul_rn(sw, 2.f), th = __fmul_rn(sh, 2.f);
+          w = __fmul_rn(__fmul_rn(tw, tw), m.anchor[2 * a]);
+          h = __fmul_rn(__fmul_rn(th, th), m.anchor[2 * a + 1]);
+        }
+        // xywh2xyxy (utils/general.py:539-546)
         const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
         x1 = __fsub_rn(x, hw);
         y1 = __fsub_rn(y, hh);
@@ -1147,7 +1232,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float* __
 
 // ---- dense Detect decode (API-compat materialisation of `pred`) ------------------------------------------
 __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ logits, float* __restrict__ pred, int N,
-                                                     int ny, int nx, int na, int no, int ld, int row0, int rows_total,
+                                                     int ny, int nx, int na, int no, int ld, int pitch, int row0, int rows_total,
                                                      float stride, float aw0,
                                                      float ah0, float aw1, float ah1, float aw2, float ah2, float aw3,
                                                      float ah3, float aw4, float ah4) {
@@ -1163,7 +1248,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ l
     t /= ny;
     int a = (int)(t % na);
     int n = (int)(t / na);
-    const float s = sigmoid_dec(logits[(((long long)n * ny + gy) * nx + gx) * ld + a * no + o]);
+    const float s = sigmoid_dec(logits[(((long long)n * ny + gy) * nx + gx) * ld + a * pitch + o]);
     float v = s;
     if (o == 0) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.f), 0.5f), (float)gx), stride);
     else if (o == 1) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.f), 0.5f), (float)gy), stride);
@@ -1182,10 +1267,11 @@ extern "C" {
 int dmay_detect_decode(const dmay_decode_params* p, dmay_stream_t stream) {
   if (!p || !p->logits || !p->pred) return DMAY_EINVAL;
   if (p->N <= 0 || p->ny <= 0 || p->nx <= 0 || p->na <= 0 || p->no <= 5) return DMAY_EINVAL;
-  if (p->na > 5 || p->ld < p->na * p->no) return DMAY_EUNSUPPORTED;
+  const int pitch = p->row_pitch > 0 ? p->row_pitch : p->no;
+  if (p->na > 5 || pitch < p->no || p->ld < p->na * pitch) return DMAY_EUNSUPPORTED;
   long long items = (long long)p->N * p->na * p->ny * p->nx * p->no;
   decode_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float*)p->logits, (float*)p->pred, p->N, p->ny, p->nx, p->na, p->no, p->ld, p->row0, p->rows_total,
+      (const float*)p->logits, (float*)p->pred, p->N, p->ny, p->nx, p->na, p->no, p->ld, pitch, p->row0, p->rows_total,
       p->stride, p->aw0, p->ah0, p->aw1, p->ah1, p->aw2, p->ah2, p->aw3, p->ah3, p->aw4, p->ah4);
   return finish_launch();
 }
@@ -1210,6 +1296,7 @@ int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream) {
   src.levels = p->levels;
   src.R = p->R;
   src.nc = p->nc;
+  src.pitch = p->row_pitch;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned char* cm = (const unsigned char*)p->class_mask;
   if (p->phase == 0) {
@@ -1254,12 +1341,18 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   memset(&fa, 0, sizeof(fa));
   const void* lg[5] = {p->lv_logits0, p->lv_logits1, p->lv_logits2, p->lv_logits3, p->lv_logits4};
   const LevelMeta* hm = (const LevelMeta*)p->lv_meta_host;
+  const int no = 5 + p->nc;
+  const int pitch = p->row_pitch > 0 ? p->row_pitch : no;
+  if (pitch < no) return DMAY_EINVAL;
+  if (p->dense && (p->levels != 1 || hm[0].na != 1 || pitch != no)) return DMAY_EINVAL;
+  const bool padded = !p->dense && pitch != no;
   long long rows = 0;
   for (int l = 0; l < p->levels; ++l) {
     const LevelMeta& m = hm[l];
     if (!lg[l] || (reinterpret_cast<uintptr_t>(lg[l]) & 3u)) return DMAY_EINVAL;
     if (m.na <= 0 || m.na > 5 || m.ny <= 0 || m.nx <= 0) return DMAY_EINVAL;
-    if (m.ld < m.na * (5 + p->nc)) return DMAY_EUNSUPPORTED;
+    if (m.ld < m.na * pitch) return DMAY_EUNSUPPORTED;
+    if (padded && ((pitch & 3) || (m.ld & 3) || (reinterpret_cast<uintptr_t>(lg[l]) & 15u))) return DMAY_EUNSUPPORTED;
     if (m.row0 != rows) return DMAY_EINVAL;
     fa.logits[l] = (const float*)lg[l];
     fa.meta[l] = m;
@@ -1267,54 +1360,63 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   }
   // thread-per-row kernel for nc <= 96 (DMAY_FILTER_ROWS=0 keeps the warp-per-row one, for A/B runs and the tests)
   static const bool no_rows = [] { const char* e = getenv("DMAY_FILTER_ROWS"); return e && e[0] == '0'; }();
-  const bool rows_kernel = !no_rows && p->nc <= kRowsMaxNc && (size_t)kRowsThreads * (5 + p->nc) * sizeof(float) <= 100 * 1024;
+  const int srow = padded ? pitch + 4 : no;
+  const bool rows_kernel = (!no_rows || padded || p->dense) && p->nc <= kRowsMaxNc && (size_t)kRowsThreads * srow * sizeof(float) <= 100 * 1024;
+  if ((padded || p->dense) && !rows_kernel) return DMAY_EUNSUPPORTED;   // those layouts exist for the thread-per-row kernel only
   const int P = rows_kernel ? kRowsThreads : kFuseP;
   const long long tiles = (long long)p->N * fused_tiles_per_image(hm, p->levels, &fa, P);
   if (tiles > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
   if (p->ws_bytes < 16 + 8 * tiles) return DMAY_ETOOBIG;
-  const size_t smem = (size_t)P * (5 + p->nc) * sizeof(float);
+  const size_t smem = (size_t)P * srow * sizeof(float);
   if (smem > 200 * 1024) return DMAY_EUNSUPPORTED;
-  if (smem > 48 * 1024) {
-    cudaError_t e = rows_kernel ? (cudaFuncSetAttribute(filter_fused_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                                   cudaFuncSetAttribute(filter_fused_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-                                : cudaFuncSetAttribute(filter_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
   fa.levels = p->levels;
   fa.nc = p->nc;
   fa.multi_label = p->multi_label;
   fa.N = p->N;
   fa.thr = p->conf_thres;
   fa.capacity = p->capacity;
+  fa.pitch = pitch;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned* ticket = (unsigned*)p->ws;
   unsigned long long* status = (unsigned long long*)((char*)p->ws + 16);
   static const bool no_reserve = [] { const char* e = getenv("DMAY_FILTER_RESERVE"); return e && e[0] == '0'; }();
-  if (rows_kernel && p->keys_tmp != nullptr && p->cand_tmp != nullptr && !no_reserve) {
-    // reserve + scan + gather: no ordering dependency between the tiles of the big kernel
-    if (p->ws_bytes < 16 + 20 * tiles) return DMAY_ETOOBIG;
-    long long* tile_base = (long long*)status;
-    int* tile_cnt = (int*)(tile_base + tiles);
-    long long* tile_off = (long long*)((char*)p->ws + 16 + ((12 * tiles + 7) & ~7LL));
-    if (p->ws_bytes < 16 + ((12 * tiles + 7) & ~7LL) + 8 * tiles) return DMAY_ETOOBIG;
-    filter_fused_rows_kernel<true><<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
-                                                                        (long long*)p->img_offsets,
-                                                                        (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
-                                        (int)(tiles / p->N), p->N);
-    tile_gather_kernel<<<(int)tiles, 128, 0, s>>>(tile_base, tile_cnt, tile_off, (const unsigned long long*)p->keys_tmp,
-                                                  (const float*)p->cand_tmp, (unsigned long long*)p->keys, (float*)p->cand,
-                                                  p->capacity);
-    return finish_launch(3);
-  }
-  if (rows_kernel)
-    filter_fused_rows_kernel<false><<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
-                                                                         (long long*)p->img_offsets, (unsigned long long*)p->keys,
-                                                                         (float*)p->cand);
-  else
+  const bool reserve = rows_kernel && p->keys_tmp != nullptr && p->cand_tmp != nullptr && !no_reserve;
+  const int kind = p->dense ? 2 : (padded ? 1 : 0);
+  if (rows_kernel) {
+    void (*kern)(const FuseArgs, const unsigned char*, unsigned*, unsigned long long*, long long*, unsigned long long*, float*) =
+        reserve ? (kind == 0 ? filter_fused_rows_kernel<true, 0> : kind == 1 ? filter_fused_rows_kernel<true, 1> : filter_fused_rows_kernel<true, 2>)
+                : (kind == 0 ? filter_fused_rows_kernel<false, 0> : kind == 1 ? filter_fused_rows_kernel<false, 1> : filter_fused_rows_kernel<false, 2>);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    if (reserve) {
+      // reserve + scan + gather: no ordering dependency between the tiles of the big kernel
+      if (p->ws_bytes < 16 + 20 * tiles) return DMAY_ETOOBIG;
+      long long* tile_base = (long long*)status;
+      int* tile_cnt = (int*)(tile_base + tiles);
+      long long* tile_off = (long long*)((char*)p->ws + 16 + ((12 * tiles + 7) & ~7LL));
+      if (p->ws_bytes < 16 + ((12 * tiles + 7) & ~7LL) + 8 * tiles) return DMAY_ETOOBIG;
+      kern<<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
+                                                  (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
+      tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
+                                          (int)(tiles / p->N), p->N);
+      tile_gather_kernel<<<(int)tiles, 128, 0, s>>>(tile_base, tile_cnt, tile_off, (const unsigned long long*)p->keys_tmp,
+                                                    (const float*)p->cand_tmp, (unsigned long long*)p->keys, (float*)p->cand,
+                                                    p->capacity);
+      return finish_launch(3);
+    }
+    kern<<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
+                                                (unsigned long long*)p->keys, (float*)p->cand);
+  } else {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(filter_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
     filter_fused_kernel<<<(int)tiles, kFuseThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
                                                              (long long*)p->img_offsets, (unsigned long long*)p->keys,
                                                              (float*)p->cand);
+  }
   img_counts_kernel<<<(p->N + 255) / 256, 256, 0, s>>>((const long long*)p->img_offsets, (int*)p->img_counts, p->N);
   return finish_launch(2);
 }

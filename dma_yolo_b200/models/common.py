@@ -187,7 +187,15 @@ class Focus(nn.Module):
 
     def forward(self, x):
         if kernel_path(self, x):
-            return self.conv.forward_b200(ops.spd(x))
+            c = x.shape[1]
+            if c % 8 == 0 and x.dtype == torch.bfloat16:
+                return self.conv.forward_b200(ops.spd(x))
+            # an image (3 channels, any input dtype): the prep kernel writes the pixel-unshuffled NHWC bf16 form directly,
+            # channel (dy + 2 dx) * C + c as the torch.cat below, zero-padded to the conv pack's channel count
+            if c * 4 <= 16 and _conv_supported(self.conv.conv) and self.conv.conv.groups == 1:
+                mul = 1.0 / 255.0 if x.dtype == torch.uint8 else 1.0
+                return self.conv.forward_b200(ops.input_prep(x, spd=True, cpad=ops.round_up(4 * c, 16), mul=mul))
+            return self.conv.forward_b200(ops.spd(ops.as_act(x)))
         return self.conv(torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1))
 
 

@@ -30,6 +30,7 @@ from .cspcm import Conv  # shadows common.Conv exactly like `from models.cspcm i
 from .detect_t import TDetect  # models/yolo.py:9
 
 CFG_DIR = Path(__file__).resolve().parent
+PAD_HEAD_ROWS = __import__('os').environ.get('DMAY_PAD_HEAD', '1') != '0'   # A/B switch: anchor rows of the head logits padded to 4n floats
 
 
 def check_anchor_order(m):
@@ -100,6 +101,29 @@ class Detect(_PackMixin, nn.Module):
             self.__dict__['_b200_consts'] = c
         return c[1], c[2]
 
+    def _head_pack(self, i, device):
+        """1x1 head conv i as a GEMM pack.  When no = 5 + nc is not a multiple of 4, every anchor's `no` output rows are
+        padded to `pitch` = round_up(no, 4) with zero weight rows (the layout of the logits is ours): anchor rows of the fp32
+        logits are then 16-byte aligned, which the fused decode + filter kernel needs for 16-byte staging."""
+        conv = self.m[i]
+        pitch = ops.round_up(self.no, 4)
+        if pitch == self.no or not PAD_HEAD_ROWS:
+            return get_conv_pack(self, f'm{i}', conv, None, device), 0
+        key = (str(device), conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version, pitch)
+        cache = self.__dict__.setdefault('_b200_packs', {})
+        pk = cache.get(f'mp{i}')
+        if pk is None or pk.key != key:
+            w = conv.weight.detach().float()
+            cin = w.shape[1]
+            wp = torch.zeros((self.na, pitch, cin, 1, 1), dtype=torch.float32, device=w.device)
+            wp[:, :self.no] = w.view(self.na, self.no, cin, 1, 1)
+            bp = torch.zeros((self.na, pitch), dtype=torch.float32, device=w.device)
+            bp[:, :self.no] = conv.bias.detach().float().view(self.na, self.no)
+            pk = ops.pack_conv(wp.view(self.na * pitch, cin, 1, 1), conv_bias=bp.view(-1), device=device)
+            pk.key = key
+            cache[f'mp{i}'] = pk
+        return pk, pitch
+
     def forward_b200(self, x):
         """Raw fp32 head logits (NHWC) from the tcgen05 GEMM; decode is deferred to LazyPred /
         non_max_suppression so that it can be fused with the confidence filter."""
@@ -107,14 +131,18 @@ class Detect(_PackMixin, nn.Module):
         levels, xs = [], []
         for i in range(self.nl):
             t = _materialize(x[i])
-            pk = get_conv_pack(self, f'm{i}', self.m[i], None, t.device)
-            lg = ops.conv(t, pk, ACT_NONE, out_fp32=True)          # [bs, na*no, ny, nx] view of an NHWC slab
+            pk, pitch = self._head_pack(i, t.device)
+            # two N tiles of 160 columns cover a padded 3 x 88 = 264-channel head with 21 % spare columns (256 + 16 would
+            # spend a whole second tile on 8 channels)
+            bn = 160 if (pitch and 256 < pk.cout_pad <= 320) else 0
+            lg = ops.conv(t, pk, ACT_NONE, out_fp32=True, block_n=bn)   # [bs, na*pitch, ny, nx] view of an NHWC slab
             bs, _, ny, nx = lg.shape
             ld = ops.ld_of(lg)
-            nhwc = lg.permute(0, 2, 3, 1)                          # [bs, ny, nx, na*no], strides (.., ld, 1)
+            nhwc = lg.permute(0, 2, 3, 1)                          # [bs, ny, nx, na*pitch], strides (.., ld, 1)
             levels.append(ops.DetectLevel(logits=lg, stride=strides[i], anchors_px=[tuple(a) for a in anchors_px[i]],
-                                          ny=ny, nx=nx, ld=ld))
-            xs.append(nhwc.unflatten(-1, (self.na, self.no)).permute(0, 3, 1, 2, 4))  # (bs,na,ny,nx,no) view
+                                          ny=ny, nx=nx, ld=ld, pitch=pitch))
+            v = nhwc.unflatten(-1, (self.na, pitch or self.no))
+            xs.append((v[..., :self.no] if pitch else v).permute(0, 3, 1, 2, 4))   # (bs,na,ny,nx,no) view
         return LazyPred(levels, self.na, self.no), xs
 
     def __getstate__(self):
@@ -133,8 +161,11 @@ class Model(nn.Module):
         else:
             import yaml
             p = Path(cfg)
-            if not p.exists() and (CFG_DIR / p.name).exists():
-                p = CFG_DIR / p.name
+            if not p.exists():   # a bare config name (optionally hub/<name>) resolves against the packaged layer tables
+                for cand in (CFG_DIR / cfg, CFG_DIR / p.name):
+                    if cand.exists():
+                        p = cand
+                        break
             self.yaml_file = p.name
             with open(p, errors='ignore') as f:
                 self.yaml = yaml.safe_load(f)

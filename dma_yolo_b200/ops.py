@@ -456,6 +456,7 @@ class DetectLevel:
     ny: int
     nx: int
     ld: int
+    pitch: int = 0            # floats per anchor row inside a pixel's channel vector (0 = no; 4n when the head pads the rows)
 
 
 def _level_meta_host(levels, na):
@@ -488,7 +489,7 @@ def detect_decode(levels, na: int, no: int) -> torch.Tensor:
     for lv in levels:
         a = [v for wh in lv.anchors_px for v in wh] + [0.0] * (10 - 2 * na)
         call("dmay_detect_decode", _stream(pred), logits=lv.logits.data_ptr(), pred=pred.data_ptr(), N=n, ny=lv.ny,
-             nx=lv.nx, na=na, no=no, ld=lv.ld, row0=row0, rows_total=rows, stride=float(lv.stride),
+             nx=lv.nx, na=na, no=no, ld=lv.ld, row_pitch=lv.pitch, row0=row0, rows_total=rows, stride=float(lv.stride),
              aw0=a[0], ah0=a[1], aw1=a[2], ah1=a[3], aw2=a[4], ah2=a[5], aw3=a[6], ah3=a[7], aw4=a[8], ah4=a[9])
         row0 += na * lv.ny * lv.nx
     return pred
@@ -519,7 +520,7 @@ def _nms_batched(pred, conf_thres, iou_thres, levels, na, nc, classes, agnostic,
         if FUSED_FILTER:
             return _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
         meta, rows = _level_meta(levels, na, dev)
-        src = dict(levels=len(levels), lv_meta=meta.data_ptr())
+        src = dict(levels=len(levels), lv_meta=meta.data_ptr(), row_pitch=levels[0].pitch)
         for i, lv in enumerate(levels):
             src[f"lv_logits{i}"] = lv.logits.data_ptr()
         keep_alive = (meta,)
@@ -534,8 +535,14 @@ def _nms_batched(pred, conf_thres, iou_thres, levels, na, nc, classes, agnostic,
     s = torch.cuda.current_stream(dev).cuda_stream
     multi_label = bool(multi_label) and nc > 1
     buf, out, out_counts = _det_buffers(n, max_det, dev)
-    keys, cand, img_counts, img_offsets, offs_host, total = _ordered_candidates(src, n, rows, nc, conf_thres, multi_label,
-                                                                                classes, dev, s)
+    if levels is None and DENSE_ROWS_FILTER and nc <= 96:
+        # dense prediction through the thread-per-row single-pass filter (one read of the tensor instead of the
+        # count + write passes of the warp-per-row kernels)
+        keys, cand, img_counts, img_offsets, offs_host, total = _fused_candidates(_dense_level(pred), 1, nc, conf_thres,
+                                                                                  multi_label, classes, dense=True)
+    else:
+        keys, cand, img_counts, img_offsets, offs_host, total = _ordered_candidates(src, n, rows, nc, conf_thres, multi_label,
+                                                                                    classes, dev, s)
     if total == 0:
         return out, out_counts, buf
     idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
@@ -544,6 +551,15 @@ def _nms_batched(pred, conf_thres, iou_thres, levels, na, nc, classes, agnostic,
          max_nms=max_nms, agnostic=int(bool(agnostic)), max_wh=float(max_wh), iou_thres=float(iou_thres))
     del keep_alive
     return out, out_counts, buf
+
+
+DENSE_ROWS_FILTER = __import__('os').environ.get('DMAY_DENSE_ROWS', '1') != '0'
+
+
+def _dense_level(pred: torch.Tensor):
+    """A dense prediction [N, R, no] described as ONE pseudo level (na = 1, ny = 1, nx = R, ld = no) for the fused filter."""
+    n, rows, no = pred.shape
+    return [DetectLevel(logits=pred, stride=0.0, anchors_px=[(0.0, 0.0)], ny=1, nx=rows, ld=no, pitch=0)]
 
 
 def _ordered_candidates(src, n, rows, nc, conf_thres, multi_label, classes, dev, s):
@@ -639,9 +655,10 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     return out, out_counts, buf
 
 
-def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes):
+def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=False):
     """Single-pass fused decode + filter + order-preserving compaction of the Detect logits (multi_label already
-    reduced by `nc > 1`).  -> keys, cand, img_counts, img_offsets, img_offsets as a host list, total."""
+    reduced by `nc > 1`).  `dense`: `levels` is one pseudo level wrapping a dense prediction [N, R, 5 + nc] (values used
+    as they are).  -> keys, cand, img_counts, img_offsets, img_offsets as a host list, total."""
     import ctypes
     dev = levels[0].logits.device
     n = levels[0].logits.shape[0]
@@ -652,7 +669,7 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes):
     if ws_bytes < 0:
         raise DmayError(f"dmay_nms_filter_fused_ws failed: {ws_bytes}")
     cm = _class_mask(classes, nc, dev)
-    key = (dev.index, n, rows, nc, multi_label, float(conf_thres))
+    key = (dev.index, n, rows, nc, multi_label, float(conf_thres), bool(dense))
     capacity = _FUSED_CAP.get(key, n * rows * (2 if multi_label else 1) // 2 + 4096)
     img_counts = torch.empty(n, device=dev, dtype=torch.int32)
     img_offsets = torch.empty(n + 1, device=dev, dtype=torch.int64)
@@ -666,7 +683,8 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes):
         f = dict(lv_meta_host=ctypes.addressof(meta_host), ws=ws.data_ptr(), ws_bytes=ws.numel() * 8,
                  img_counts=img_counts.data_ptr(), img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(),
                  cand=cand.data_ptr(), N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
-                 conf_thres=float(conf_thres), keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr())
+                 conf_thres=float(conf_thres), keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr(),
+                 row_pitch=levels[0].pitch, dense=int(dense))
         for i, lv in enumerate(levels):
             f[f"lv_logits{i}"] = lv.logits.data_ptr()
         if cm is not None:
@@ -713,7 +731,8 @@ def nms_fused_static(levels, na: int, nc: int, conf_thres: float, iou_thres: flo
     f = dict(lv_meta_host=ctypes.addressof(meta_host), ws=ws.data_ptr(), ws_bytes=ws.numel() * 8,
              img_counts=img_counts.data_ptr(), img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(),
              cand=cand.data_ptr(), N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
-             conf_thres=float(conf_thres), keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr())
+             conf_thres=float(conf_thres), keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr(),
+             row_pitch=levels[0].pitch)
     for i, lv in enumerate(levels):
         f[f"lv_logits{i}"] = lv.logits.data_ptr()
     if cm is not None:
@@ -738,7 +757,7 @@ def nms_fused_static(levels, na: int, nc: int, conf_thres: float, iou_thres: flo
     return out, out_counts, buf, img_offsets
 
 
-def filter_candidates(pred, conf_thres, *, multi_label=False, classes=None, levels=None, na=0, nc=None):
+def filter_candidates(pred, conf_thres, *, multi_label=False, classes=None, levels=None, na=0, nc=None, rows_kernel=False):
     """Candidate generation alone (tests, benchmarks): dense `pred` -> three-launch filter, Detect `levels` -> fused
     single-pass filter.  -> dict(keys, cand, img_counts, img_offsets (host list), total)."""
     if levels is not None:
@@ -752,8 +771,12 @@ def filter_candidates(pred, conf_thres, *, multi_label=False, classes=None, leve
         nc = no - 5
         multi = bool(multi_label) and nc > 1
         s = torch.cuda.current_stream(dev).cuda_stream
-        keys, cand, img_counts, _, offs_host, total = _ordered_candidates(dict(levels=0, pred=pred.data_ptr()), n, rows, nc,
-                                                                          conf_thres, multi, classes, dev, s)
+        if rows_kernel and nc <= 96:
+            keys, cand, img_counts, _, offs_host, total = _fused_candidates(_dense_level(pred), 1, nc, conf_thres, multi, classes,
+                                                                            dense=True)
+        else:
+            keys, cand, img_counts, _, offs_host, total = _ordered_candidates(dict(levels=0, pred=pred.data_ptr()), n, rows, nc,
+                                                                              conf_thres, multi, classes, dev, s)
     if total == 0:
         dev = img_counts.device
         keys = torch.empty(0, device=dev, dtype=torch.int64)

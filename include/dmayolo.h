@@ -345,7 +345,8 @@ long long dmay_coordatt_ws(int N, int H, int W, int C, int Cm);
 int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream);
 
 /* ---- a8: Detect grid/anchor decode, models/yolo.py:81-101 -------------------------------
- * logits: fp32 NHWC [N, ny, nx, ld] per level, channel = a*no + o  (1x1 conv + bias output).
+ * logits: fp32 NHWC [N, ny, nx, ld] per level, channel = a*row_pitch + o  (1x1 conv + bias output; row_pitch = 0 means no,
+ *         a head GEMM may pad each anchor's no outputs to a multiple of 4 floats, see dmay_nms_filter_fused).
  * dense:  pred[n, row0 + (a*ny + y)*nx + x, :] = decode(sigmoid(logit)) — rows ordered
  *         (level, anchor, y, x), out [N, rows_total, no] fp32. anchors_px = anchors*stride. */
 typedef struct dmay_decode_params {
@@ -370,6 +371,7 @@ typedef struct dmay_decode_params {
   float ah3;
   float aw4;
   float ah4;
+  int row_pitch;
 } dmay_decode_params;
 int dmay_detect_decode(const dmay_decode_params* p, dmay_stream_t stream);
 
@@ -409,6 +411,7 @@ typedef struct dmay_filter_params {
   int phase;
   long long capacity;
   float conf_thres;
+  int row_pitch;
 } dmay_filter_params;
 int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream);
 
@@ -423,7 +426,13 @@ int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream);
  * {row0, ny, nx, ld, na, stride(f32), anchor_px[10](f32)}.
  * keys_tmp / cand_tmp (optional, `capacity` entries each like keys / cand): when given (and nc <= 96) the tiles do not
  * order themselves with the look-back; each reserves its run in the temporary buffers with one atomic, and a scan over
- * the per-tile counts plus a gather put the runs in reference order (three launches, same outputs). */
+ * the per-tile counts plus a gather put the runs in reference order (three launches, same outputs).
+ * row_pitch (0 = 5 + nc): floats between the rows of two anchors inside a pixel's channel vector.  A head GEMM that pads
+ *   every anchor's 5 + nc outputs to a multiple of 4 floats (zero weight rows) makes the rows 16-byte aligned: they are
+ *   then staged with 16-byte copies and scanned four logits per shared-memory load (ld and the base pointers must be
+ *   16-byte multiples).
+ * dense = 1: the source is a DENSE prediction [N, R, 5 + nc] (utils/general.py:633 input, already decoded) passed as
+ *   lv_logits0 with one level {row0 0, ny 1, nx R, ld 5 + nc, na 1}: same kernels, values used as they are. */
 typedef struct dmay_filter_fused_params {
   const void* lv_logits0;
   const void* lv_logits1;
@@ -446,6 +455,8 @@ typedef struct dmay_filter_fused_params {
   float conf_thres;
   void* keys_tmp;
   void* cand_tmp;
+  int row_pitch;
+  int dense;
 } dmay_filter_fused_params;
 long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N);
 int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t stream);

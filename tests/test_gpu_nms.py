@@ -266,3 +266,100 @@ def test_fused_filter_candidates_match_dense_filter(nc, thr, special):
         assert torch.equal(a['keys'][:n], b['keys'][:n])
         ca, cb = a['cand'][:n], b['cand'][:n]
         assert torch.equal(ca.view(torch.int32), cb.view(torch.int32))
+
+
+def _pad_levels(levels, na, no):
+    """The same logits with every anchor's row padded to a multiple of 4 floats (the layout the Detect head GEMM writes)."""
+    from dma_yolo_b200 import ops
+    pitch = ops.round_up(no, 4)
+    out = []
+    for lv in levels:
+        n = lv.logits.shape[0]
+        ld = ops.round_up(na * pitch, 4)
+        lg = torch.full((n, lv.ny, lv.nx, ld), 123.0, device=lv.logits.device)       # pad words must never be read as data
+        lg[..., :na * pitch].view(n, lv.ny, lv.nx, na, pitch)[..., :no] = lv.logits[..., :na * no].reshape(n, lv.ny, lv.nx, na, no)
+        out.append(ops.DetectLevel(logits=lg, stride=lv.stride, anchors_px=lv.anchors_px, ny=lv.ny, nx=lv.nx, ld=ld, pitch=pitch))
+    return out
+
+
+@pytest.mark.parametrize('nc', [2, 4, 10, 80, 96])
+@pytest.mark.parametrize('thr', [0.0, 0.001, 0.25])
+@pytest.mark.parametrize('special', [False, True], ids=['finite', 'inf-nan-saturated'])
+def test_padded_row_filter_matches_unpadded(nc, thr, special):
+    """16-byte-aligned anchor rows (row pitch 4n floats, 16-byte staging, LDS.128 scan) against the unpadded layout:
+    candidate keys / boxes / confidences / classes identical bit for bit and in order; the dense decode agrees too."""
+    from dma_yolo_b200 import ops
+    levels, na, no = _continuous_levels(2, nc, [(19, 11), (10, 6), (5, 3)], seed=7 * nc + int(thr * 1000), scale=3.0, special=special)
+    padded = _pad_levels(levels, na, no)
+    da, db = ops.detect_decode(levels, na, no), ops.detect_decode(padded, na, no)
+    assert torch.equal(da.view(torch.int32), db.view(torch.int32))
+    for multi in (True, False):
+        a = ops.filter_candidates(None, thr, multi_label=multi, levels=levels, na=na, nc=nc)
+        b = ops.filter_candidates(None, thr, multi_label=multi, levels=padded, na=na, nc=nc)
+        assert torch.equal(a['img_counts'], b['img_counts']), (nc, thr, multi)
+        n = int(a['img_counts'].sum())
+        assert torch.equal(a['keys'][:n], b['keys'][:n])
+        assert torch.equal(a['cand'][:n].view(torch.int32), b['cand'][:n].view(torch.int32))
+
+
+@pytest.mark.parametrize('nc', [2, 10, 15, 80])
+@pytest.mark.parametrize('thr', [0.0, 0.001, 0.25])
+def test_dense_rows_filter_matches_three_launch_filter(nc, thr):
+    """Dense predictions through the thread-per-row single-pass filter (KIND 2) against the count / scan / write filter:
+    identical candidates in identical order, multi-label and best-class, including NaN / inf rows and rows whose tile is
+    not 16-byte aligned (R * no odd)."""
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(31 * nc + int(thr * 1000))
+    for R in (777, 1280):
+        pred = torch.rand(3, R, 5 + nc, generator=g)
+        pred[..., :2] *= 640
+        pred[..., 2:4] = pred[..., 2:4] * 60 + 4
+        pred[..., 4] = pred[..., 4] ** 2
+        flat = pred.view(-1)
+        idx = torch.randint(0, flat.numel(), (flat.numel() // 200,), generator=g)
+        vals = torch.tensor([float('nan'), float('inf'), -1.0, 0.0, 1.0, 1e-3])
+        flat[idx] = vals[torch.randint(0, len(vals), (len(idx),), generator=g)]
+        pred = pred.cuda()
+        for multi in (True, False):
+            a = ops.filter_candidates(pred, thr, multi_label=multi, rows_kernel=True)
+            b = ops.filter_candidates(pred, thr, multi_label=multi, rows_kernel=False)
+            assert torch.equal(a['img_counts'], b['img_counts']), (nc, thr, multi, R)
+            n = int(b['img_counts'].sum())
+            assert torch.equal(a['keys'][:n], b['keys'][:n])
+            assert torch.equal(a['cand'][:n].view(torch.int32), b['cand'][:n].view(torch.int32))
+
+
+def test_detect_head_padded_rows_equal_unpadded():
+    """Detect.forward_b200 with the head rows padded to 4n floats (default) against the unpadded layout: same raw
+    outputs, same dense prediction, same detections."""
+    import dma_yolo_b200 as D
+    from dma_yolo_b200.models import yolo as Y
+    torch.manual_seed(0)
+    det = Y.Detect(nc=80, anchors=[[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]],
+                   ch=(64, 128, 256))
+    det.stride = torch.tensor([8., 16., 32.])
+    det.anchors /= det.stride.view(-1, 1, 1)
+    for mi in det.m:
+        mi.weight.data.mul_(3.0)
+        mi.bias.data.normal_(-1.0, 1.0)
+    det = det.cuda().eval()
+    det.stride = det.stride.cuda()
+    xs = [torch.randn(3, 64, 20, 12).cuda(), torch.randn(3, 128, 10, 6).cuda(), torch.randn(3, 256, 5, 3).cuda()]
+    kw = dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)
+    res = {}
+    for pad in (True, False):
+        Y.PAD_HEAD_ROWS = pad
+        try:
+            with torch.no_grad():
+                pred, raw = det(list(xs))
+                assert (pred._levels[0].pitch == 88) == pad
+                dets = D.non_max_suppression(pred, **kw)
+                res[pad] = (pred.dense().clone(), [r.clone() for r in raw], [d.clone() for d in dets])
+        finally:
+            Y.PAD_HEAD_ROWS = True
+    assert torch.equal(res[True][0], res[False][0])
+    for a, b in zip(res[True][1], res[False][1]):
+        assert a.shape == b.shape and torch.equal(a, b)
+    for a, b in zip(res[True][2], res[False][2]):
+        assert torch.equal(a, b)
+    assert sum(len(d) for d in res[True][2]) > 0
