@@ -8,8 +8,9 @@ distribution-focal-loss (DFL) box decoding, used by CASPD_ODRTA.yaml.
                 y = cat(xywh, sigmoid(cls))  ->  (y, (x, box, cls))
 
 Kernel path (CUDA, eval): the six convs of every level run on the tcgen05 conv kernel (the two 1x1 heads with fp32 output);
-the DFL expectation and the box arithmetic are a few small fp32 torch ops on [b, 64 + nc, A] (A = 34 k at 640^2:
-~13 MB) -- not worth a kernel of their own next to 2 x 4 convs per level.
+the DFL softmax-expectation, dist2bbox, * stride and the class sigmoid are ONE kernel per level reading the fp32 head logits
+once (`dmay_dfl_decode`, csrc/post.cu) -- no cuDNN / eager arithmetic on the path.  The raw tuple `(x, box, cls)` the
+reference returns next to `y` is re-laid by plain copies (torch.cat of views).
 """
 from __future__ import annotations
 
@@ -22,6 +23,7 @@ from .. import ops
 from .common import Conv, get_conv_pack, kernel_path
 
 __all__ = ['TDetect', 'DFL', 'make_anchors', 'dist2bbox']
+DFL_KERNEL = __import__('os').environ.get('DMAY_DFL_KERNEL', '1') != '0'   # A/B switch (tests compare both forms)
 
 
 def make_anchors(feats, strides, grid_cell_offset=0.5):
@@ -96,12 +98,19 @@ class TDetect(nn.Module):
         fast = kernel_path(self, x)
         x = list(x)
         shape = x[0].shape
+        heads = []
         for i in range(self.nl):
-            x[i] = torch.cat((self._branch(self.cv2[i], f'cv2.{i}.2', x[i], fast),
-                              self._branch(self.cv3[i], f'cv3.{i}.2', x[i], fast)), 1)
+            heads.append((self._branch(self.cv2[i], f'cv2.{i}.2', x[i], fast), self._branch(self.cv3[i], f'cv3.{i}.2', x[i], fast)))
+            x[i] = torch.cat(heads[-1], 1)
         box, cls = torch.cat([xi.reshape(shape[0], self.no, -1) for xi in x], 2).split((self.reg_max * 4, self.nc), 1)
         if self.training:
             return x, box, cls
+        if fast and DFL_KERNEL and self.dfl.c1 == self.reg_max:
+            strides = self.__dict__.get('_b200_strides')
+            if strides is None or strides[0] is not self.stride:
+                strides = self.__dict__['_b200_strides'] = (self.stride, [float(v) for v in self.stride.tolist()])
+            y = ops.dfl_decode([h[0] for h in heads], [h[1] for h in heads], self.nc, self.reg_max, strides[1])
+            return y if self.export else (y, (x, box, cls))
         if self.dynamic or self.shape != shape or self.anchors.device != box.device:
             self.anchors, self.strides = (t.transpose(0, 1) for t in make_anchors(x, self.stride, 0.5))
             self.shape = shape

@@ -554,6 +554,7 @@ def _nms_batched(pred, conf_thres, iou_thres, levels, na, nc, classes, agnostic,
 
 
 DENSE_ROWS_FILTER = __import__('os').environ.get('DMAY_DENSE_ROWS', '1') != '0'
+_DENSE_RESERVE = __import__('os').environ.get('DMAY_DENSE_RESERVE')
 
 
 def _dense_level(pred: torch.Tensor):
@@ -655,7 +656,7 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     return out, out_counts, buf
 
 
-def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=False):
+def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=False, reserve=None):
     """Single-pass fused decode + filter + order-preserving compaction of the Detect logits (multi_label already
     reduced by `nc > 1`).  `dense`: `levels` is one pseudo level wrapping a dense prediction [N, R, 5 + nc] (values used
     as they are).  -> keys, cand, img_counts, img_offsets, img_offsets as a host list, total."""
@@ -677,14 +678,20 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=Fa
         ws = torch.zeros(ws_bytes // 8 + 1, device=dev, dtype=torch.int64)   # ticket + tile status words (zeroed)
         keys = torch.empty(capacity, device=dev, dtype=torch.int64)
         cand = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
-        # temporary buffers of the reserve + scan + gather mode (tiles place their runs without waiting for each other)
-        keys_tmp = torch.empty(capacity, device=dev, dtype=torch.int64)
-        cand_tmp = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
         f = dict(lv_meta_host=ctypes.addressof(meta_host), ws=ws.data_ptr(), ws_bytes=ws.numel() * 8,
                  img_counts=img_counts.data_ptr(), img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(),
                  cand=cand.data_ptr(), N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
-                 conf_thres=float(conf_thres), keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr(),
-                 row_pitch=levels[0].pitch, dense=int(dense))
+                 conf_thres=float(conf_thres), row_pitch=levels[0].pitch, dense=int(dense))
+        # temporary buffers of the reserve + scan + gather mode (tiles place their runs without waiting for each other).
+        # It moves every candidate twice more (32 B each way), so it is for sparse outputs: where most (row, class) pairs
+        # become candidates (dense multi-label predictions: cfg-5 writes 2 GB of candidates for 0.39 GB of input) the
+        # single-launch look-back form writes them once, in place.
+        if dense and _DENSE_RESERVE is not None and reserve is None:
+            reserve = _DENSE_RESERVE == '1'           # A/B switch
+        if reserve if reserve is not None else not (dense and multi_label):
+            keys_tmp = torch.empty(capacity, device=dev, dtype=torch.int64)
+            cand_tmp = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
+            f.update(keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr())
         for i, lv in enumerate(levels):
             f[f"lv_logits{i}"] = lv.logits.data_ptr()
         if cm is not None:
@@ -827,3 +834,23 @@ def axpy_channels(x: torch.Tensor, g: torch.Tensor, gamma: torch.Tensor, out=Non
 
 def device_copy(dst: torch.Tensor, src: torch.Tensor):
     call("dmay_copy", _stream(src), src=src.data_ptr(), dst=dst.data_ptr(), bytes=src.numel() * src.element_size())
+
+
+# --------------------------------------------------------------------------------------------
+# 8f-4 TDetect eval tail: DFL expectation + dist2bbox + sigmoid in one kernel
+# --------------------------------------------------------------------------------------------
+def dfl_decode(boxes, clss, nc: int, reg_max: int, strides) -> torch.Tensor:
+    """Per-level fp32 NHWC head logits (`boxes[i]` [N, 4*reg_max, ny, nx], `clss[i]` [N, nc, ny, nx], channels_last strides)
+    -> y [N, 4 + nc, A] exactly as TDetect.forward's eval branch builds it (models/detect_t.py:46-58)."""
+    n = boxes[0].shape[0]
+    A = sum(b.shape[2] * b.shape[3] for b in boxes)
+    y = torch.empty((n, 4 + nc, A), device=boxes[0].device, dtype=torch.float32)
+    a0 = 0
+    for b, c, st in zip(boxes, clss, strides):
+        if b.dtype != torch.float32 or c.dtype != torch.float32 or not is_nhwc(b) or not is_nhwc(c):
+            raise DmayError("dfl_decode: fp32 NHWC head logits expected")
+        ny, nx = b.shape[2], b.shape[3]
+        call("dmay_dfl_decode", _stream(b), box=b.data_ptr(), cls=c.data_ptr(), y=y.data_ptr(), N=n, ny=ny, nx=nx, nc=nc,
+             reg_max=reg_max, ld_box=ld_of(b), ld_cls=ld_of(c), a0=a0, A=A, stride=float(st))
+        a0 += ny * nx
+    return y

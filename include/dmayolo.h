@@ -644,6 +644,56 @@ typedef struct dmay_copy_params {
 } dmay_copy_params;
 int dmay_copy(const dmay_copy_params* p, dmay_stream_t stream);
 
+/* ---- 8f-4: TDetect eval tail, models/detect_t.py:46-58, 81-102 -------------------------------------------------
+ * One level per call.  box: fp32 NHWC [N, ny, nx, ld_box], channel = side * reg_max + bin (the 4 * reg_max outputs of the
+ * cv2 head); cls: fp32 NHWC [N, ny, nx, ld_cls] (nc class logits).  y: fp32 [N, 4 + nc, A] (A = anchor points of all
+ * levels, this level's start at a0, row-major (y, x)):
+ *   d_s = sum_j j * softmax_j(box[s * reg_max + j])   (DFL.forward: softmax over the bins, frozen conv with weights 0..15)
+ *   (x1, y1) = (gx + .5, gy + .5) - (d_0, d_1), (x2, y2) = (gx + .5, gy + .5) + (d_2, d_3)      (dist2bbox, xywh=True)
+ *   y[0:4] = ((x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1) * stride,   y[4 + c] = sigmoid(cls[c]). */
+typedef struct dmay_dfl_params {
+  const void* box;
+  const void* cls;
+  void* y;
+  int N;
+  int ny;
+  int nx;
+  int nc;
+  int reg_max;
+  int ld_box;
+  int ld_cls;
+  int a0;
+  long long A;
+  float stride;
+} dmay_dfl_params;
+int dmay_dfl_decode(const dmay_dfl_params* p, dmay_stream_t stream);
+
+/* ---- 8f-3: val.py:62-83 process_batch for a whole batch, after scale_coords / clip_coords (utils/general.py:605-630) ----
+ * det: fp32 [B, max_det, 6] (x1, y1, x2, y2, conf, cls) as dmay_nms_greedy writes it, counts i32 [B].
+ * labels: fp32 [L, 5] (cls, x1, y1, x2, y2) in ORIGINAL-image pixels, images contiguous; lab_off i32 [B + 1].
+ * geom: fp32 [B, 5] = (gain, pad_x, pad_y, h0, w0) of scale_coords (img1 -> img0).  iouv: fp32 [niou] IoU levels.
+ * correct: u8 [B, max_det, niou]: detection j is the matched detection of a label of its class at level t:
+ *   every detection takes the label of its class with the highest IoU >= iouv[0]; every label keeps the first (most
+ *   confident) detection that took it; correct = (that IoU >= iouv[t]).  IoU in fp32 exactly as utils/metrics.py:254-276.
+ * predn (optional): fp32 [B, max_det, 6], the rescaled detections (what val.py stores as `predn`).
+ * max_labels: an upper bound of the labels of one image (shared-memory sizing). */
+typedef struct dmay_match_params {
+  const void* det;
+  const void* counts;
+  const void* labels;
+  const void* lab_off;
+  const void* geom;
+  const void* iouv;
+  void* correct;
+  void* predn;
+  int B;
+  int max_det;
+  int niou;
+  int max_labels;
+  int single_cls;
+} dmay_match_params;
+int dmay_val_match(const dmay_match_params* p, dmay_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

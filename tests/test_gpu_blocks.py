@@ -122,3 +122,30 @@ def test_tdetect_kernel_path(name, nc):
     per_point_stride = torch.cat([torch.full((x.shape[-2] * x.shape[-1],), float(s)) for x, s in zip(ins, d['strides'])])
     err = (y[:, :4].cpu() - d['out'][:, :4]).abs() / per_point_stride.view(1, 1, -1)
     assert float(err.max()) < 0.1, float(err.max())
+
+
+@pytest.mark.parametrize('name,nc', [('tdetect_nc10_3lv', 10), ('tdetect_nc20_4lv', 20)])
+def test_dfl_decode_kernel_equals_reference_arithmetic(name, nc):
+    """The one-kernel TDetect tail (DFL softmax expectation + dist2bbox + stride + class sigmoid) against the reference's
+    own fp32 arithmetic (DFL module, dist2bbox, make_anchors of models/detect_t.py) applied to the SAME head logits:
+    1e-4 relative on the boxes, 1e-6 on the confidences."""
+    from dma_yolo_b200.models import detect_t as T
+    d, sd, ins = load_golden(name)
+    m = T.TDetect(nc, tuple(x.shape[1] for x in ins))
+    m.stride = d['strides'].clone()
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    m.stride = m.stride.cuda()
+    xs = [x.cuda() for x in ins]
+    with torch.no_grad():
+        y_k, (_, box, cls) = m(list(xs))
+        T.DFL_KERNEL = False
+        try:
+            m.shape = None
+            y_t, (_, box2, cls2) = m(list(xs))
+        finally:
+            T.DFL_KERNEL = True
+    assert torch.equal(box, box2) and torch.equal(cls, cls2)
+    assert y_k.shape == y_t.shape
+    assert_close(y_k[:, :4], y_t[:, :4], atol=1e-3, rtol=1e-4, what='DFL boxes')
+    assert_close(y_k[:, 4:], y_t[:, 4:], atol=1e-6, rtol=1e-5, what='class confidences')

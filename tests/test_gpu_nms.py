@@ -363,3 +363,62 @@ def test_detect_head_padded_rows_equal_unpadded():
     for a, b in zip(res[True][2], res[False][2]):
         assert torch.equal(a, b)
     assert sum(len(d) for d in res[True][2]) > 0
+
+
+@pytest.mark.parametrize('single_cls', [False, True])
+def test_val_match_device_equals_host_process_batch(single_cls):
+    """`process_batch` + `scale_coords` of a whole batch on the device (dmay_val_match) against the host body that is
+    pinned to the executed reference (tests/golden/metrics.npz): same `correct` matrix, image by image — letterboxed
+    geometry, images without labels / without detections, labels of classes nobody predicts."""
+    from dma_yolo_b200 import val as PV
+    from dma_yolo_b200.utils.general import scale_coords, xywh2xyxy
+    g = torch.Generator().manual_seed(17)
+    B, max_det, nc, H, W = 5, 40, 4, 320, 416
+    iouv = torch.linspace(0.5, 0.95, 10)
+    shapes = [((240, 400), ((0.8, 0.8), (8.0, 64.0))), ((320, 416), ((1.0, 1.0), (0.0, 0.0))), ((640, 832), ((0.5, 0.5), (0.0, 0.0))),
+              ((300, 300), ((1.0666667, 1.0666667), (48.0, 0.0))), ((320, 416), ((1.0, 1.0), (0.0, 0.0)))]
+    targets, padded, counts = [], torch.zeros(B, max_det, 6), torch.zeros(B, dtype=torch.int32)
+    for b in range(B):
+        m = 0 if b == 1 else int(torch.randint(3, 12, (1,), generator=g))
+        cxy = torch.rand(m, 2, generator=g) * torch.tensor([W - 80., H - 80.]) + 40
+        wh = torch.rand(m, 2, generator=g) * 60 + 12
+        cls = torch.randint(0, nc, (m, 1), generator=g).float()
+        targets.append(torch.cat((torch.full((m, 1), float(b)), cls, cxy, wh), 1))
+        n = 0 if b == 3 else int(torch.randint(10, max_det, (1,), generator=g))
+        rows = []
+        for k in range(n):
+            if m and torch.rand(1, generator=g) < 0.7:
+                j = int(torch.randint(0, m, (1,), generator=g))
+                c = cxy[j] + torch.randn(2, generator=g) * 2.5
+                s = wh[j] * (0.85 + 0.3 * torch.rand(2, generator=g))
+                cl = cls[j, 0] if torch.rand(1, generator=g) < 0.8 else torch.randint(0, nc, (1,), generator=g).float()[0]
+            else:
+                c = torch.rand(2, generator=g) * torch.tensor([W * 1., H * 1.])
+                s = torch.rand(2, generator=g) * 50 + 6
+                cl = torch.randint(0, nc, (1,), generator=g).float()[0]
+            rows.append(torch.stack([c[0] - s[0] / 2, c[1] - s[1] / 2, c[0] + s[0] / 2, c[1] + s[1] / 2, torch.rand(1, generator=g)[0], cl]))
+        if n:
+            d = torch.stack(rows)
+            padded[b, :n] = d[d[:, 4].argsort(descending=True)]
+        counts[b] = n
+    targets = torch.cat(targets, 0)          # (image, cls, xywh in network-input pixels)
+    cor_d, tcls = PV.match_batch_device(padded.cuda(), counts.cuda(), targets, shapes, (H, W), iouv, single_cls)
+    cor_d = cor_d.cpu().bool()
+    for b in range(B):
+        n = int(counts[b])
+        pred = padded[b, :n].clone()
+        if single_cls:
+            pred[:, 5] = 0
+        labels = targets[targets[:, 0] == b, 1:]
+        assert tcls[b] == labels[:, 0].tolist()
+        if n == 0 or len(labels) == 0:
+            assert not cor_d[b].any()
+            continue
+        predn = pred.clone()
+        scale_coords((H, W), predn[:, :4], shapes[b][0], shapes[b][1])
+        tbox = xywh2xyxy(labels[:, 1:5])
+        scale_coords((H, W), tbox, shapes[b][0], shapes[b][1])
+        ref = PV.process_batch(predn, torch.cat((labels[:, 0:1], tbox), 1), iouv)
+        assert torch.equal(cor_d[b, :n], ref), b
+        assert not cor_d[b, n:].any()
+    assert cor_d.any()
