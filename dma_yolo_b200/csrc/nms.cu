@@ -525,31 +525,6 @@ constexpr int kRowsMaxNc = 96;
 //         odd number of 16-byte chunks: conflict-free LDS.128), and the multi-label scan reads four logits per load.
 // KIND 2: dense prediction [N, R, 5 + nc] (already decoded: utils/general.py's input when the caller holds a tensor):
 //         values are used as they are (no sigmoid, no grid decode); the tile is one contiguous run of memory.
-struct RowsTile {
-  int img, l, a, p0, np, npix;
-};
-__device__ __forceinline__ RowsTile rows_tile(const FuseArgs& fa, int tile_id) {
-  RowsTile r;
-  const int tiles_img = fa.tile0[fa.levels];
-  r.img = tile_id / tiles_img;
-  int t = tile_id - r.img * tiles_img;
-  int l = 0;
-  while (l + 1 < fa.levels && t >= fa.tile0[l + 1]) ++l;
-  t -= fa.tile0[l];
-  r.l = l;
-  r.a = t / fa.tpa[l];
-  const int ti = t - r.a * fa.tpa[l];
-  r.npix = fa.meta[l].ny * fa.meta[l].nx;
-  r.p0 = ti * kRowsThreads;
-  r.np = min(kRowsThreads, r.npix - r.p0);
-  return r;
-}
-
-// RESERVE = true additionally makes the CTAs persistent: the grid is two CTAs per SM, a CTA walks tiles blockIdx.x,
-// blockIdx.x + gridDim.x, ... (the reservation scheme does not care which CTA handles which tile) with TWO shared-memory
-// tile buffers, so the cp.async loads of the next tile are in flight while the current one is scanned.  ncu of the
-// one-tile-per-CTA form: 23 % warp occupancy (four 47 KB CTAs per SM), 28 % issue activity, 2.5 TB/s -- every CTA went
-// load -> wait -> scan -> write with nothing of its own to overlap.
 template <bool RESERVE, int KIND>
 __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
                                                                          const unsigned char* __restrict__ class_mask,
@@ -558,24 +533,31 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
                                                                          long long* __restrict__ img_offsets,
                                                                          unsigned long long* __restrict__ keys,
                                                                          float* __restrict__ cand) {
-  extern __shared__ float tile_all[];     // RESERVE: 2 x [rows][srow], otherwise [rows][srow]
+  extern __shared__ float tile[];     // [rows][no]
   __shared__ int warp_tot[kRowsThreads / 32];
   __shared__ long long base_s;
   __shared__ int tile_s;
-  const int nc = fa.nc, no = 5 + nc;
+  if (!RESERVE) {
+    if (threadIdx.x == 0) tile_s = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+  }
+  const int tile_id = RESERVE ? (int)blockIdx.x : tile_s;
+  const int tiles_img = fa.tile0[fa.levels];
+  const int img = tile_id / tiles_img;
+  int t = tile_id - img * tiles_img;
+  int l = 0;
+  while (l + 1 < fa.levels && t >= fa.tile0[l + 1]) ++l;
+  t -= fa.tile0[l];
+  const LevelMeta& m = fa.meta[l];
+  const int a = t / fa.tpa[l], ti = t - a * fa.tpa[l];
+  const int npix = m.ny * m.nx;
+  const int p0 = ti * kRowsThreads;
+  const int np = min(kRowsThreads, npix - p0);
+  const int nc = fa.nc, no = 5 + nc, ld = m.ld;
   const int pitch = KIND == 1 ? fa.pitch : no;              // global floats per anchor row
   const int srow = KIND == 1 ? fa.pitch + 4 : no;           // shared-memory words per row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float thr = fa.thr;
-  const int tiles_img = fa.tile0[fa.levels];
-  const int ntiles_all = fa.N * tiles_img;
-  const int buf_words = kRowsThreads * srow;
-
-  // issue (do not wait for) the copies of one tile into `tile`
-  auto stage = [&](int tile_id, float* tile) {
-    const RowsTile rt = rows_tile(fa, tile_id);
-    const LevelMeta& m = fa.meta[rt.l];
-    const int img = rt.img, l = rt.l, a = rt.a, p0 = rt.p0, np = rt.np, npix = rt.npix, ld = m.ld;
   {
     const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * pitch;
     const uint32_t tile_sm = (uint32_t)__cvta_generic_to_shared(tile);
@@ -619,32 +601,9 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
         g += gstep;
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  int tile_id;
-  if (RESERVE) {
-    tile_id = (int)blockIdx.x;
-    if (tile_id < ntiles_all) stage(tile_id, tile_all);
-  } else {
-    if (threadIdx.x == 0) tile_s = (int)atomicAdd(ticket, 1u);
-    __syncthreads();
-    tile_id = tile_s;
-    stage(tile_id, tile_all);
-  }
-  for (int it = 0; tile_id < ntiles_all; ++it, tile_id += (int)gridDim.x) {
-    float* tile = tile_all + (RESERVE ? (it & 1) * buf_words : 0);
-    if (RESERVE && tile_id + (int)gridDim.x < ntiles_all) {
-      stage(tile_id + (int)gridDim.x, tile_all + ((it + 1) & 1) * buf_words);   // next tile's loads fly during this scan
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const RowsTile rt = rows_tile(fa, tile_id);
-    const LevelMeta& m = fa.meta[rt.l];
-    const int img = rt.img, a = rt.a, p0 = rt.p0, np = rt.np;
+  __syncthreads();
 
   const int row = threadIdx.x;
   float* s = tile + row * srow;   // KIND 0 / 2: row stride 5 + nc words, conflict-free whenever it is odd (nc = 80, 10, ...)
@@ -802,7 +761,7 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
     }
   }
   __syncthreads();
-  if (cnt != 0) {
+  if (cnt == 0) return;
   long long g = base_s + before + inc - cnt;
   const unsigned long long img_hi = (unsigned long long)(unsigned)img << 32;
   if (fa.multi_label) {
@@ -829,10 +788,6 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
     cd[1] = make_float2(x2, y2);
     cd[2] = make_float2(bconf, (float)bcls);
     keys[g] = img_hi | (unsigned long long)(~__float_as_uint(bconf));
-  }
-  }
-    if (!RESERVE) break;
-    __syncthreads();   // every thread is done with this buffer (and with warp_tot / base_s) before it is refilled
   }
 }
 
@@ -1431,10 +1386,8 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
     void (*kern)(const FuseArgs, const unsigned char*, unsigned*, unsigned long long*, long long*, unsigned long long*, float*) =
         reserve ? (kind == 0 ? filter_fused_rows_kernel<true, 0> : kind == 1 ? filter_fused_rows_kernel<true, 1> : filter_fused_rows_kernel<true, 2>)
                 : (kind == 0 ? filter_fused_rows_kernel<false, 0> : kind == 1 ? filter_fused_rows_kernel<false, 1> : filter_fused_rows_kernel<false, 2>);
-    // reserve mode: persistent CTAs (two per SM) with two tile buffers each, the next tile's loads overlap the scan
-    const size_t smem_k = reserve ? 2 * smem : smem;
-    if (smem_k > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
     if (reserve) {
@@ -1444,10 +1397,8 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
       int* tile_cnt = (int*)(tile_base + tiles);
       long long* tile_off = (long long*)((char*)p->ws + 16 + ((12 * tiles + 7) & ~7LL));
       if (p->ws_bytes < 16 + ((12 * tiles + 7) & ~7LL) + 8 * tiles) return DMAY_ETOOBIG;
-      const long long slots = (long long)sm_count() * (smem_k <= 56 * 1024 ? 4 : 2);
-      kern<<<(int)(tiles < slots ? tiles : slots), kRowsThreads, smem_k, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
-                                                                             (long long*)p->img_offsets,
-                                                                             (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
+      kern<<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
+                                                  (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
       tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
                                           (int)(tiles / p->N), p->N);
       tile_gather_kernel<<<(int)tiles, 128, 0, s>>>(tile_base, tile_cnt, tile_off, (const unsigned long long*)p->keys_tmp,
