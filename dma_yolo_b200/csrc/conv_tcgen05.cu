@@ -273,6 +273,7 @@ struct __align__(64) ConvArgs {
   CUtensorMap tmY;   // bf16 output tile store: box = 32 channels x 32 rows (halo mode: 32 ch x 8 x 4 pixels)
   CUtensorMap tmR;   // residual / gate_x tile load, same geometry
   int opnd_stage;    // 1: the epilogue stages a residual / gate_x tile per item
+  int flags;         // tuning / A-B switches of the parameter struct (see include/dmayolo.h)
   int sb_floats;     // staged scale / bias entries (columns covered by all n-tiles, <= kMaxCout)
   int epi_warps;     // 8 or 16 (blockDim = 128 + 32 * epi_warps): 16 where the epilogue, not the MMA, paces the tile
   int epi_groups;    // 2: narrow tiles (block_n <= 64) — the 16 warps form two groups that take alternate tiles (one TMEM
@@ -371,6 +372,43 @@ __device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint32_t a_lo, uin
   if (PAIR) DMAY_MMA4("2");
   else DMAY_MMA4("1");
 #undef DMAY_MMA4
+}
+// All nine taps of one input patch (3x3 / stride 1, resident weights) in ONE asm block: KK MMAs per tap (KK = CK / 16).
+// ncu (r5g, 16->64 and 64->64 3x3 at 320x320): the issuing warp executed ~40 instructions per tap -- loop control, the
+// tap's address arithmetic (an IMAD fed by a constant-bank load), predicate and descriptor set-up -- ~2700 clk per 128 x 64
+// tile for 290 (stem) / 1150 (64 channels) clk of tensor work, and every other warp of the CTA waited for it.  Here the
+// tap offsets are immediates ((r * 10 + s) patch rows, t weight tiles), the invariant operands are named once, and the
+// block is straight-line code.
+//   a_lo / b_lo : descriptor low words of tap 0 (start address >> 4 | LBO); row16 = bytes of one patch pixel >> 4;
+//   b_step      : bytes of one tap's weight tile >> 4.
+#define DMAY_T9_MMA(CG, P) "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\ttcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %5, " P ";\n\t"
+#define DMAY_T9_NEXT "add.u32 al, al, 2;\n\tadd.u32 bl, bl, 2;\n\t"
+#define DMAY_T9_KK1(CG, P) DMAY_T9_MMA(CG, P)
+#define DMAY_T9_KK2(CG, P) DMAY_T9_MMA(CG, P) DMAY_T9_NEXT DMAY_T9_MMA(CG, "t")
+#define DMAY_T9_KK4(CG, P) DMAY_T9_MMA(CG, P) DMAY_T9_NEXT DMAY_T9_MMA(CG, "t") DMAY_T9_NEXT DMAY_T9_MMA(CG, "t") DMAY_T9_NEXT DMAY_T9_MMA(CG, "t")
+#define DMAY_T9_TAP(KKM, CG, T, AOFF, P) "mad.lo.u32 al, %7, " #AOFF ", %1;\n\tmad.lo.u32 bl, %8, " #T ", %3;\n\t" KKM(CG, P)
+#define DMAY_T9_ALL(KKM, CG)                                                                                              \
+  asm volatile("{\n\t.reg .pred p, t;\n\t.reg .b32 al, bl;\n\t.reg .b64 da, db;\n\t"                                       \
+               "setp.ne.b32 p, %6, 0;\n\tsetp.eq.u32 t, %6, %6;\n\t"                                                       \
+               DMAY_T9_TAP(KKM, CG, 0, 0, "p") DMAY_T9_TAP(KKM, CG, 1, 1, "t") DMAY_T9_TAP(KKM, CG, 2, 2, "t")             \
+               DMAY_T9_TAP(KKM, CG, 3, 10, "t") DMAY_T9_TAP(KKM, CG, 4, 11, "t") DMAY_T9_TAP(KKM, CG, 5, 12, "t")          \
+               DMAY_T9_TAP(KKM, CG, 6, 20, "t") DMAY_T9_TAP(KKM, CG, 7, 21, "t") DMAY_T9_TAP(KKM, CG, 8, 22, "t") "}"      \
+               ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(row16), "r"(b_step) \
+               : "memory")
+template <bool PAIR>
+__device__ __forceinline__ void umma_taps9(int kk_n, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate, uint32_t row16, uint32_t b_step) {
+  static_assert(kHaloTW + 2 == 10, "tap offsets below assume a 10-pixel patch pitch");
+  if (kk_n == 4) {
+    if (PAIR) DMAY_T9_ALL(DMAY_T9_KK4, "2");
+    else DMAY_T9_ALL(DMAY_T9_KK4, "1");
+  } else if (kk_n == 2) {
+    if (PAIR) DMAY_T9_ALL(DMAY_T9_KK2, "2");
+    else DMAY_T9_ALL(DMAY_T9_KK2, "1");
+  } else {
+    if (PAIR) DMAY_T9_ALL(DMAY_T9_KK1, "2");
+    else DMAY_T9_ALL(DMAY_T9_KK1, "1");
+  }
 }
 __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
   uint64_t r;
@@ -744,6 +782,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (a.b_resident == 1) {
       if (!(PAIR && crank != 0)) {   // CTA pair: the even CTA issues every MMA
       mbar_wait(full_bar, 0);   // resident weights have landed (both halves in pair mode)
+      // flags bit16 = the per-tap issue loop (A/B); CTA pairs keep it (the one-block issue measured slower there, r4k)
+      const bool taps9 = !PAIR && !(a.flags & 65536);
 #pragma unroll 1
       for (int st = cluster_id; st < total_super; st += num_clusters) {
         mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
@@ -757,6 +797,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           tc_fence_after();
           const uint32_t a_patch = abuf0 + ab * a.a_halo_bytes;
           if (elect_one()) {
+            const uint32_t hlo0 = ((a_patch >> 4) & 0x3FFFu) | (1u << 16);
+            if (taps9) {
+              // one straight-line block for the nine taps (see umma_taps9)
+              umma_taps9<PAIR>(kk_n, tmem_d, hlo0, desc_hi_halo, b_lo, desc_hi, a.idesc, accum, row_bytes >> 4, b_step);
+            } else {
 #pragma unroll 1
             for (int r = 0; r < 3; ++r)
 #pragma unroll 1
@@ -766,23 +811,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                 // (single-CTA tiles only: on the CTA-pair 128-channel layers the tighter issue measured the same for the
                 //  plain / gate epilogues and 14 % slower for the residual one, same box A/B r4k)
                 if (!PAIR && kk_n == 4) {
-                  umma_bf16_x4<PAIR>(tmem_d, hlo, desc_hi_halo, b_lo, desc_hi, a.idesc, accum);
+                  umma_bf16_x4<PAIR>(tmem_d, hlo, desc_hi_halo, b_lo + (uint32_t)(r * 3 + s2) * b_step, desc_hi, a.idesc, accum);
                   accum = 1;
                 } else {
 #pragma unroll 2
                   for (int kk = 0; kk < kk_n; ++kk) {
-                    if (PAIR) umma_bf16_2(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
-                    else umma_bf16(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(b_lo + kk * 2, desc_hi), a.idesc, accum);
+                    const uint32_t bl = b_lo + (uint32_t)(r * 3 + s2) * b_step + kk * 2;
+                    if (PAIR) umma_bf16_2(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(bl, desc_hi), a.idesc, accum);
+                    else umma_bf16(tmem_d, pack64(hlo + kk * 2, desc_hi_halo), pack64(bl, desc_hi), a.idesc, accum);
                     accum = 1;
                   }
                 }
-                b_lo += b_step;
               }
+            }
             if (PAIR) umma_commit_2(aempty_bar + ab * 8);
             else umma_commit(aempty_bar + ab * 8);
-          } else {
-            b_lo += 9u * b_step;   // keep the (uniform) running descriptor in step on the non-elected lanes
           }
+          b_lo += 9u * b_step;   // (uniform) running descriptor of the next channel chunk's weights
           accum = 1;
           __syncwarp();
           if (++ab == a.n_abuf) {
@@ -1426,6 +1471,7 @@ static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   a.g_sh = p->gHk > 0 ? (float)p->gHk / (float)p->Ho : 0.f;
   a.g_sw = p->gWk > 0 ? (float)p->gWk / (float)p->Wo : 0.f;
   a.act = p->act;
+  a.flags = p->flags;
   a.out_f32 = out_f32 ? 1 : 0;
   find_divisor(a.fd_nn, a.num_n_tiles);
   find_divisor(a.fd_pi, a.halo ? a.tiles_x * a.tiles_y : 1);
