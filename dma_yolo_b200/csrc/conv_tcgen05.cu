@@ -782,8 +782,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (a.b_resident == 1) {
       if (!(PAIR && crank != 0)) {   // CTA pair: the even CTA issues every MMA
       mbar_wait(full_bar, 0);   // resident weights have landed (both halves in pair mode)
-      // flags bit16 = the per-tap issue loop (A/B); CTA pairs keep it (the one-block issue measured slower there, r4k)
-      const bool taps9 = !PAIR && !(a.flags & 65536);
+      // flags bit16 = the per-tap issue loop (A/B)
+      // (CTA pairs too: r5h same-box A/B 128->128 plain 0.3425 -> 0.3016 ms @160, 0.0926 -> 0.0812 @80, residual / gate unchanged)
+      const bool taps9 = !(a.flags & 65536);
 #pragma unroll 1
       for (int st = cluster_id; st < total_super; st += num_clusters) {
         mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);

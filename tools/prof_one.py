@@ -17,6 +17,16 @@ if kind == 'conv':
     out = ops.empty_nhwc(B, cout, ho, ho, dev)
     for _ in range(3):
         ops.conv(x, pk, 1, out=out)
+elif kind == 'convres':
+    # Bottleneck cv2 with the residual add in the epilogue: python tools/prof_one.py convres 128 80
+    c, s_ = map(int, sys.argv[2:4])
+    B = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+    x = ops.empty_nhwc(B, c, s_, s_, dev).normal_()
+    r = ops.empty_nhwc(B, c, s_, s_, dev).normal_()
+    pk = ops.pack_conv(torch.randn(c, c, 3, 3) / (c * 9) ** 0.5, stride=1, pad=1, device=dev)
+    out = ops.empty_nhwc(B, c, s_, s_, dev)
+    for _ in range(3):
+        ops.conv(x, pk, 1, out=out, residual=r)
 elif kind == 'convgate':
     # SCConv k3 with the gate in the epilogue: k3(x) * sigmoid(x + up(k2))   python tools/prof_one.py convgate 64 320
     c, s = map(int, sys.argv[2:4])
