@@ -8,7 +8,7 @@ from dma_yolo_b200 import ops
 from tools.bench_kernels import timeit
 B, dev = 64, 'cuda'
 flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
-convs = [(128, 128, 160, 'plain'), (128, 128, 160, 'gate'), (128, 128, 80, 'plain'), (128, 128, 80, 'res'), (16, 64, 320, 'plain'), (64, 64, 320, 'plain'), (64, 64, 320, 'gate'), (64, 64, 160, 'res'), (64, 64, 160, 'plain'), (64, 64, 80, 'plain'),
+convs = [(128, 128, 160, 'plain'), (128, 128, 160, 'gate'), (128, 128, 80, 'plain'), (128, 128, 80, 'res'), (256, 256, 40, 'res'), (256, 256, 80, 'gate'), (512, 512, 20, 'res'), (64, 64, 160, 'res'), (64, 64, 320, 'gate'), (16, 64, 320, 'plain'), (64, 64, 320, 'plain'), (64, 64, 320, 'gate'), (64, 64, 160, 'res'), (64, 64, 160, 'plain'), (64, 64, 80, 'plain'),
          (32, 32, 320, 'plain'), (128, 128, 160, 'plain')]
 for cin, cout, ho, mode in convs:
     x = ops.empty_nhwc(B, cin, ho, ho, dev).normal_()
@@ -22,7 +22,7 @@ for cin, cout, ho, mode in convs:
     act = 0 if mode == 'gate' else 1
     row = dict(conv=f'{cin}->{cout} k3 @{ho} {mode}')
     outs = {}
-    for name, fl in (('loop', 65536), ('taps9', 131072)):
+    for name, fl in (('loop', int(sys.argv[1]) if len(sys.argv) > 1 else 65536), ('taps9', 0)):
         ms = timeit(lambda: ops.conv(x, pk, act, out=out, flags=fl, **kw), reps=7, flush=flush)
         row[name + '_ms'] = round(ms, 4)
         row[name + '_tflops'] = round(2 * B * ho * ho * cout * cin * 9 / ms / 1e9, 1)
