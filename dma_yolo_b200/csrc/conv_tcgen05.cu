@@ -538,7 +538,11 @@ __device__ __forceinline__ void epi_store8(const ConvArgs& a, const uint32_t* r,
 
 // PAIR is a template parameter (not a runtime flag): a kernel image that contains cta_group::2 instructions can only be
 // launched as a cluster (error 912 otherwise), so the single-CTA and the CTA-pair tile shapes are separate images.
-template <int MODE, bool PAIR>
+// T9 (plain SiLU layers with resident 3x3 weights only): the nine taps of a patch are issued as one straight-line asm block
+// (umma_taps9).  A separate image, because with those blocks in the function ptxas spills more in EVERY instantiation's
+// epilogue (residual / gate: 116 / 204 bytes instead of 32 / 84; plain: 20 instead of 0), which cost the other layers
+// 4-45 % in the network (same-box A/B r5k-r5m) -- they keep the image without the blocks.
+template <int MODE, bool PAIR, bool T9 = false>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -792,9 +796,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     if (a.b_resident == 1) {
       if (!(PAIR && crank != 0)) {   // CTA pair: the even CTA issues every MMA
       mbar_wait(full_bar, 0);   // resident weights have landed (both halves in pair mode)
-      // flags bit16 = the per-tap issue loop (A/B)
-      // (CTA pairs too: r5h same-box A/B 128->128 plain 0.3425 -> 0.3016 ms @160, 0.0926 -> 0.0812 @80, residual / gate unchanged)
-      const bool taps9 = !(a.flags & 65536);
+      // one-block issue of the nine taps (T9 images; flags bit16 selects the plain image: A/B).  Same-box A/B r5h: stem
+      // 16->64 @320 0.521 -> 0.280 ms, 128->128 plain (CTA pairs) 0.3425 -> 0.3016 ms @160, 0.0926 -> 0.0812 @80.
+      constexpr bool taps9 = T9;
 #pragma unroll 1
       for (int st = cluster_id; st < total_super; st += num_clusters) {
         mbar_wait(tempty_bar + acc * 8, acc_phase ^ 1u);
@@ -809,7 +813,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint32_t a_patch = abuf0 + ab * a.a_halo_bytes;
           if (elect_one()) {
             const uint32_t hlo0 = ((a_patch >> 4) & 0x3FFFu) | (1u << 16);
-            if (taps9) {
+            if constexpr (taps9) {
               // one straight-line block for the nine taps (see umma_taps9)
               umma_taps9<PAIR>(kk_n, tmem_d, hlo0, desc_hi_halo, b_lo, desc_hi, a.idesc, accum, row_bytes >> 4, b_step);
             } else {
@@ -989,15 +993,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t opnd_phase = 0;
     auto sidx = [](int r, int j) { return r * 4 + (j ^ ((r >> 1) & 3)); };   // 64-byte rows, TMA SWIZZLE_64B pattern
 
-    const bool release_hand_back = (a.flags & 262144) != 0;   // bit18: the release form of the arrive (A/B)
+    // (a relaxed arrive is legal here and measured 9-14 % faster on isolated CTA-pair residual / gate layers, r5i, but
+    //  3-6 % slower on the same layers inside the network, r5m: the release form stays)
     auto tmem_hand_back = [&](uint32_t bar) {
-      if (PAIR) {
-        if (release_hand_back) mbar_arrive_pair(bar);
-        else mbar_arrive_pair_relaxed(bar);
-      } else {
-        if (release_hand_back) mbar_arrive(bar);
-        else mbar_arrive_relaxed(bar);
-      }
+      if (PAIR) mbar_arrive_pair(bar);
+      else mbar_arrive(bar);
     };
     struct Item {
       int row;         // this thread's output row (pixel index), -1: not stored (beyond M / outside the image)
@@ -1243,6 +1243,7 @@ static int pow2ceil(int v) {
 struct ConvPlan {
   ConvArgs a;
   int mode;
+  int t9;
   int grid;
   int pdl;
   size_t smem;
@@ -1592,6 +1593,7 @@ static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   const long long max_clusters = sms / a.cs;
   pl.grid = (int)((supers < max_clusters ? supers : max_clusters) * a.cs);
   pl.mode = mode;
+  pl.t9 = (mode == EPI_SILU && a.b_resident == 1 && a.halo && !(p->flags & 65536)) ? 1 : 0;
   pl.smem = smem;
   pl.pdl = (p->flags & 128) ? 0 : 1;
   return DMAY_OK;
@@ -1636,6 +1638,40 @@ static int conv_issue(const ConvPlan& pl, cudaStream_t stream) {
                            : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE, false>, a);                            \
     if (e != cudaSuccess) return (int)e;                                                                            \
     break;                                                                                                          \
+  }
+  if (pl.t9) {   // plain SiLU, resident 3x3 weights: the image with the one-block tap issue
+    static std::atomic<unsigned long long> attr_mask9{0};
+    if (first_time_on_device(attr_mask9)) {
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<EPI_SILU, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(conv_gemm_kernel<EPI_SILU, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128 + 32 * a.epi_warps);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int nat = 0;
+    if (pl.pdl) {
+      at[nat].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[nat].val.programmaticStreamSerializationAllowed = 1;
+      ++nat;
+    }
+    if (a.cs > 1) {
+      at[nat].id = cudaLaunchAttributeClusterDimension;
+      at[nat].val.clusterDim.x = a.cs;
+      at[nat].val.clusterDim.y = 1;
+      at[nat].val.clusterDim.z = 1;
+      ++nat;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = nat;
+    cudaError_t e = a.pair ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<EPI_SILU, true, true>, a)
+                           : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<EPI_SILU, false, true>, a);
+    if (e != cudaSuccess) return (int)e;
+    return finish_launch();
   }
   switch (pl.mode) {
     DMAY_LAUNCH_MODE(EPI_SILU)

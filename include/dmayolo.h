@@ -81,8 +81,7 @@ const char* dmay_strerror(int code);
  *   for every staged operand (automatic only for CTA-pair layers with resident weights), bit14 = fp32 outputs of 1x1 convs
  *   (Detect heads) with direct per-lane stores instead of the staged tile + TMA store, bit15 = streamed halo mode with up
  *   to four input patches in flight (default: two, the rest of shared memory holds weight stages), bit16 = issue the nine
- *   taps of a resident-weight 3x3 layer with the per-tap loop instead of the one-block form, bit18 = release (instead of
- *   relaxed) mbarrier arrive when an epilogue warp hands its TMEM accumulator buffer back. */
+ *   taps of a resident-weight 3x3 layer with the per-tap loop instead of the one-block form. */
 typedef struct dmay_conv_params {
   const void* x;
   const void* w;
