@@ -285,6 +285,7 @@ struct FuseArgs {
   float thr;
   long long capacity;
   int pitch;           // floats between the rows of two anchors inside a pixel's channel vector (5 + nc, or padded to 4n)
+  const int* bin_thr;  // dense multi-label source: per-image score-key bin threshold of the pre-selection (nullptr: none)
 };
 
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
@@ -617,6 +618,7 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
       if (fa.multi_label) {
         if (KIND == 2) {
           // dense rows hold the class confidences themselves: the reference arithmetic is one multiply (general.py:677)
+          const unsigned bt = fa.bin_thr != nullptr ? (unsigned)fa.bin_thr[img] : 0xFFFFFFFFu;   // see dense_hist_kernel
 #pragma unroll
           for (int w = 0; w < 3; ++w) {
             uint32_t mk = 0u;
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
 #pragma unroll 8
             for (int cc = 0; cc < cend; ++cc) {
               const float conf = __fmul_rn(sc[cc], obj);
-              if (conf > thr && (class_mask == nullptr || class_mask[w * 32 + cc])) {
+              if (conf > thr && ((~__float_as_uint(conf)) >> 21) <= bt && (class_mask == nullptr || class_mask[w * 32 + cc])) {
                 sc[cc] = conf;
                 mk |= 1u << cc;
                 ++cnt;
@@ -789,6 +791,70 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
     cd[2] = make_float2(bconf, (float)bcls);
     keys[g] = img_hi | (unsigned long long)(~__float_as_uint(bconf));
   }
+}
+
+// ---- pre-selection for candidate-dense multi-label predictions --------------------------------------------------------
+// utils/general.py:702-703 keeps only the max_nms = 30000 best candidates of an image.  A dense multi-label prediction can
+// expand to 10x that (BASELINE cfg-5: 25,200 rows x 10 classes = 252 k candidates per image, 2 GB of candidate records per
+// batch of 256 for 0.39 GB of input), and seven eighths of what the filter writes is thrown away by the top-K selection.
+// Two cheap passes over the INPUT avoid that: a histogram of the top 11 bits of every candidate's score key per image
+// (dense_hist_kernel), the bin b* that contains the K-th best key (hist_threshold_kernel), and a filter that only writes
+// candidates whose key bin is <= b*.  Everything the exact top-K selection can keep (keys <= the K-th key, ties included)
+// has a bin <= b*, and the survivors keep their candidate order, so the selection / sort / greedy stages see a superset of
+// the top K in the same relative order and return the same detections bit for bit.
+constexpr int kHistBins = 2048;
+__global__ void __launch_bounds__(256) dense_hist_kernel(const float* __restrict__ pred, const unsigned char* __restrict__ class_mask,
+                                                         int* __restrict__ hist, int R, int nc, float thr, int rows_per_cta) {
+  __shared__ int h[kHistBins];
+  const int img = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, R);
+  for (int i = threadIdx.x; i < kHistBins; i += 256) h[i] = 0;
+  __syncthreads();
+  const int no = 5 + nc;
+  for (int r = r0 + threadIdx.x; r < r1; r += 256) {
+    const float* row = pred + ((long long)img * R + r) * no;
+    const float obj = row[4];
+    if (!(obj > thr)) continue;
+    for (int c = 0; c < nc; ++c) {
+      const float conf = __fmul_rn(row[5 + c], obj);
+      if (conf > thr && (class_mask == nullptr || class_mask[c])) atomicAdd(&h[(~__float_as_uint(conf)) >> 21], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kHistBins; i += 256)
+    if (h[i]) atomicAdd(&hist[(long long)img * kHistBins + i], h[i]);
+}
+
+// bin_thr[img] = first bin whose inclusive count reaches K (all bins when the image has at most K candidates)
+__global__ void __launch_bounds__(1024) hist_threshold_kernel(const int* __restrict__ hist, int* __restrict__ bin_thr, int K) {
+  __shared__ int warp_tot[32];
+  __shared__ int found;
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) found = kHistBins - 1;
+  const int h0 = hist[(long long)img * kHistBins + 2 * tid], h1 = hist[(long long)img * kHistBins + 2 * tid + 1];
+  int inc = h0 + h1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int v = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    warp_tot[lane] = v;   // inclusive over warps
+  }
+  __syncthreads();
+  const int excl = inc - (h0 + h1) + (warp > 0 ? warp_tot[warp - 1] : 0);
+  if (excl < K && excl + h0 >= K) found = 2 * tid;              // exactly one thread matches (prefix sums are monotone)
+  else if (excl + h0 < K && excl + h0 + h1 >= K) found = 2 * tid + 1;
+  __syncthreads();
+  if (tid == 0) bin_thr[img] = found;
 }
 
 // exclusive scan of the per-tile candidate counts (reference tile order == candidate order) -> tile_off[], img_offsets[]
@@ -1376,6 +1442,7 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   fa.thr = p->conf_thres;
   fa.capacity = p->capacity;
   fa.pitch = pitch;
+  fa.bin_thr = p->dense ? (const int*)p->bin_thr : nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned* ticket = (unsigned*)p->ws;
   unsigned long long* status = (unsigned long long*)((char*)p->ws + 16);
@@ -1418,6 +1485,18 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
                                                              (float*)p->cand);
   }
   img_counts_kernel<<<(p->N + 255) / 256, 256, 0, s>>>((const long long*)p->img_offsets, (int*)p->img_counts, p->N);
+  return finish_launch(2);
+}
+
+int dmay_nms_dense_prethreshold(const dmay_prethr_params* p, dmay_stream_t stream) {
+  if (!p || !p->pred || !p->hist || !p->bin_thr || p->N <= 0 || p->R <= 0 || p->nc <= 0 || p->K <= 0) return DMAY_EINVAL;
+  if (p->N > 65535) return DMAY_EUNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rows_per_cta = 2048;
+  dim3 grid((p->R + rows_per_cta - 1) / rows_per_cta, p->N);
+  dense_hist_kernel<<<grid, 256, 0, s>>>((const float*)p->pred, (const unsigned char*)p->class_mask, (int*)p->hist, p->R, p->nc,
+                                         p->conf_thres, rows_per_cta);
+  hist_threshold_kernel<<<p->N, 1024, 0, s>>>((const int*)p->hist, (int*)p->bin_thr, p->K);
   return finish_launch(2);
 }
 

@@ -539,7 +539,7 @@ def _nms_batched(pred, conf_thres, iou_thres, levels, na, nc, classes, agnostic,
         # dense prediction through the thread-per-row single-pass filter (one read of the tensor instead of the
         # count + write passes of the warp-per-row kernels)
         keys, cand, img_counts, img_offsets, offs_host, total = _fused_candidates(_dense_level(pred), 1, nc, conf_thres,
-                                                                                  multi_label, classes, dense=True)
+                                                                                  multi_label, classes, dense=True, max_nms=max_nms)
     else:
         keys, cand, img_counts, img_offsets, offs_host, total = _ordered_candidates(src, n, rows, nc, conf_thres, multi_label,
                                                                                     classes, dev, s)
@@ -656,7 +656,10 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     return out, out_counts, buf
 
 
-def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=False, reserve=None):
+PRETHRESHOLD = __import__('os').environ.get('DMAY_PRETHRESHOLD', '1') != '0'
+
+
+def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=False, reserve=None, max_nms=0):
     """Single-pass fused decode + filter + order-preserving compaction of the Detect logits (multi_label already
     reduced by `nc > 1`).  `dense`: `levels` is one pseudo level wrapping a dense prediction [N, R, 5 + nc] (values used
     as they are).  -> keys, cand, img_counts, img_offsets, img_offsets as a host list, total."""
@@ -672,6 +675,16 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=Fa
     cm = _class_mask(classes, nc, dev)
     key = (dev.index, n, rows, nc, multi_label, float(conf_thres), bool(dense))
     capacity = _FUSED_CAP.get(key, n * rows * (2 if multi_label else 1) // 2 + 4096)
+    bin_thr = None
+    if dense and multi_label and max_nms > 0 and PRETHRESHOLD and rows * nc > max_nms:
+        # an image may hold more than max_nms candidates: only those that the top-max_nms selection could keep are written
+        hist = torch.zeros((n, 2048), device=dev, dtype=torch.int32)
+        bin_thr = torch.empty(n, device=dev, dtype=torch.int32)
+        pf = dict(pred=levels[0].logits.data_ptr(), hist=hist.data_ptr(), bin_thr=bin_thr.data_ptr(), N=n, R=rows, nc=nc,
+                  K=int(max_nms), conf_thres=float(conf_thres))
+        if cm is not None:
+            pf["class_mask"] = cm.data_ptr()
+        call("dmay_nms_dense_prethreshold", s, **pf)
     img_counts = torch.empty(n, device=dev, dtype=torch.int32)
     img_offsets = torch.empty(n + 1, device=dev, dtype=torch.int64)
     while True:
@@ -686,9 +699,11 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=Fa
         # It moves every candidate twice more (32 B each way), so it is for sparse outputs: where most (row, class) pairs
         # become candidates (dense multi-label predictions: cfg-5 writes 2 GB of candidates for 0.39 GB of input) the
         # single-launch look-back form writes them once, in place.
+        if bin_thr is not None:
+            f["bin_thr"] = bin_thr.data_ptr()
         if dense and _DENSE_RESERVE is not None and reserve is None:
             reserve = _DENSE_RESERVE == '1'           # A/B switch
-        if reserve if reserve is not None else not (dense and multi_label):
+        if reserve if reserve is not None else (bin_thr is not None or not (dense and multi_label)):
             keys_tmp = torch.empty(capacity, device=dev, dtype=torch.int64)
             cand_tmp = torch.empty((capacity, 6), device=dev, dtype=torch.float32)
             f.update(keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr())

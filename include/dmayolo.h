@@ -433,7 +433,8 @@ int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream);
  *   then staged with 16-byte copies and scanned four logits per shared-memory load (ld and the base pointers must be
  *   16-byte multiples).
  * dense = 1: the source is a DENSE prediction [N, R, 5 + nc] (utils/general.py:633 input, already decoded) passed as
- *   lv_logits0 with one level {row0 0, ny 1, nx R, ld 5 + nc, na 1}: same kernels, values used as they are. */
+ *   lv_logits0 with one level {row0 0, ny 1, nx R, ld 5 + nc, na 1}: same kernels, values used as they are.
+ * bin_thr (dense multi-label only, optional): per-image key-bin threshold of dmay_nms_dense_prethreshold. */
 typedef struct dmay_filter_fused_params {
   const void* lv_logits0;
   const void* lv_logits1;
@@ -458,8 +459,28 @@ typedef struct dmay_filter_fused_params {
   void* cand_tmp;
   int row_pitch;
   int dense;
+  const void* bin_thr;
 } dmay_filter_fused_params;
 long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N);
+
+/* Pre-selection for candidate-dense MULTI-LABEL dense predictions (utils/general.py:702-703 keeps the max_nms best candidates
+ * of an image; a dense prediction can expand to many times that).  Per image: a 2048-bin histogram of the top 11 bits of every
+ * candidate's score key (~bits(conf)), then bin_thr[img] = the bin that holds the K-th best key (2047 when the image has at most
+ * K candidates).  dmay_nms_filter_fused (dense = 1, bin_thr given) then writes only candidates whose key bin is <= bin_thr:
+ * a superset of the top K, ties included, in candidate order -- the detections are unchanged.
+ * pred fp32 [N, R, 5 + nc]; hist: caller-ZEROED i32 [N, 2048]; bin_thr i32 [N]. */
+typedef struct dmay_prethr_params {
+  const void* pred;
+  const void* class_mask;
+  void* hist;
+  void* bin_thr;
+  int N;
+  int R;
+  int nc;
+  int K;
+  float conf_thres;
+} dmay_prethr_params;
+int dmay_nms_dense_prethreshold(const dmay_prethr_params* p, dmay_stream_t stream);
 int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t stream);
 
 /* stable sort of candidate keys (payload = candidate index).  CUB radix sort over the
