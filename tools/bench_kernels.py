@@ -145,6 +145,29 @@ def main():
     x, out = act(c, 20, 20), act(c, 20, 20)
     rec('coordatt c1024@20', timeit(lambda: ops.coordatt(x, pk, out=out), flush=flush), gbytes=2 * B * c * 400 * 2 / 1e9)
     del x, out
+    # a3 at the cfg-4b sizes (C3CASPD.yaml, 1280x1280: CoordAtt inside the CABottlenecks of its four C3CA stages), batch 32
+    for c, hw in ((64, 320), (128, 160), (256, 80), (512, 40)):
+        cm = max(8, c // 32)
+        conv1, bn1, ch, cw = nn.Conv2d(c, cm, 1), nn.BatchNorm2d(cm).eval(), nn.Conv2d(cm, c, 1), nn.Conv2d(cm, c, 1)
+        pk = ops.pack_coordatt(conv1, bn1, ch, cw, dev)
+        b4 = max(1, B // 2)
+        x, out = ops.empty_nhwc(b4, c, hw, hw, dev).normal_(), ops.empty_nhwc(b4, c, hw, hw, dev)
+        rec(f'coordatt c{c}@{hw} (cfg-4b, batch {b4})', timeit(lambda: ops.coordatt(x, pk, out=out), flush=flush),
+            gbytes=2 * b4 * c * hw * hw * 2 / 1e9)
+        del x, out
+    # a8 + a9 front end: fused decode + filter of the cfg-2 head logits (val-style threshold), bytes = logits read once
+    try:
+        lv = []
+        for (ny, st) in ((80, 8.), (40, 16.), (20, 32.)):
+            lg = torch.randn(B, ny, ny, 264, device=dev) * 2.0 - 4.0
+            lv.append(ops.DetectLevel(logits=lg, stride=st, anchors_px=[(st * 2, st * 3), (st * 4, st * 3), (st * 5, st * 8)], ny=ny, nx=ny,
+                                      ld=264, pitch=88))
+        ops.filter_candidates(None, 0.001, multi_label=True, levels=lv, na=3, nc=80)     # sizes the buffers once
+        rec('decode+filter (reserve, scan, gather) 3x88 logits', timeit(lambda: ops.filter_candidates(None, 0.001, multi_label=True, levels=lv, na=3, nc=80), flush=flush),
+            gbytes=sum(l.logits.numel() for l in lv) * 4 / 1e9)
+        del lv
+    except Exception as e:   # keep the table alive
+        print('filter bench skipped:', e)
     # a4 SPD (cfg-4 shape scaled to this batch)
     x = act(64, 320, 320)
     out = act(256, 160, 160)

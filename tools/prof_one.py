@@ -44,6 +44,21 @@ elif kind == 'gate':
                       ops.empty_nhwc(B, c, s // 4, s // 4, dev).normal_(), ops.empty_nhwc(B, c, s, s, dev))
     for _ in range(3):
         ops.scconv_gate(x, k3, k2, out=out)
+elif kind == 'nms5':
+    # BASELINE cfg-5: decode-less non_max_suppression on rand(256, 25200, 15), val style; second call profiled
+    import dma_yolo_b200 as D
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    pred = torch.rand(B, 25200, 15, generator=torch.Generator().manual_seed(1))
+    pred[..., :2] *= 640
+    pred[..., 2:4] = pred[..., 2:4] * 60 + 4
+    pred = pred.to(dev)
+    for it in range(3):
+        if it == 2:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+        D.non_max_suppression(pred, 0.001, 0.6, multi_label=True, max_det=300)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 elif kind == 'model':
     # whole hot path (forward + fused decode/filter + NMS) once warm, once profiled-range: for `ncu -k regex:...`
     import dma_yolo_b200 as D

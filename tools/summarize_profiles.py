@@ -32,8 +32,8 @@ def short(name):
     return n.split('(')[0][:70]
 
 
-def launches():
-    f = SRC / 'launches.csv'
+def launches(suffix='', what='cfg-2, batch 64, forward + fused decode/filter + NMS'):
+    f = SRC / f'launches{suffix}.csv'
     if not f.exists():
         return
     rows = read_ncu_csv(f.read_text())
@@ -56,7 +56,7 @@ def launches():
         a['rd'] += d.get('dram__bytes_read.sum', 0)
         a['wr'] += d.get('dram__bytes_write.sum', 0)
     tot = sum(a['us'] for a in agg.values())
-    out = [f'# {tag}: launch list of ONE warm step (cfg-2, batch 64, forward + fused decode/filter + NMS)', '',
+    out = [f'# {tag}{suffix}: launch list of ONE warm step ({what})', '',
            'Source: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none`',
            'around the second step of `tools/prof_one.py model` (profiler range). Times are serialised and cold-cache: read the',
            'SHARES, not the absolutes.', '',
@@ -65,13 +65,13 @@ def launches():
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['us']):
         gbs = (a['rd'] + a['wr']) / a['us'] / 1e3 if a['us'] else 0
         out.append(f"| `{k}` | {a['n']} | {a['us']:.1f} | {100 * a['us'] / tot:.1f}% | {a['rd'] / 1e6:.1f} | {a['wr'] / 1e6:.1f} | {gbs:.0f} |")
-    (DST / f'{tag}_launches.md').write_text('\n'.join(out) + '\n')
-    with open(DST / f'{tag}_launches.csv', 'w') as fo:
+    (DST / f'{tag}{suffix}_launches.md').write_text('\n'.join(out) + '\n')
+    with open(DST / f'{tag}{suffix}_launches.csv', 'w') as fo:
         fo.write('id,kernel,grid,block,us,dram_read_bytes,dram_write_bytes\n')
         for k, d in per.items():
             fo.write(f"{k},{d['name']},\"{d['grid']}\",\"{d['block']}\",{d.get('us', 0):.2f},{d.get('dram__bytes_read.sum', 0):.0f},{d.get('dram__bytes_write.sum', 0):.0f}\n")
-    json.dump({k: a for k, a in agg.items()}, open(DST / f'{tag}_launches.json', 'w'), indent=1)
-    print('\n'.join(out))
+    json.dump({k: a for k, a in agg.items()}, open(DST / f'{tag}{suffix}_launches.json', 'w'), indent=1)
+    print('\n'.join(out[:14]))
 
 
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -121,8 +121,13 @@ def full(rep):
 
 
 launches()
+launches('_cfg3', 'cfg-3 yolov5l-ca-sppfcspc-bifpn-scconv, 1536x1536, batch 8')
+launches('_cfg4a', 'cfg-4a spdconv, 1280x1280, batch 32')
+launches('_cfg4b', 'cfg-4b C3CASPD, 1280x1280, batch 32')
+launches('_cfg5', 'cfg-5 NMS stress: non_max_suppression(rand(256,25200,15)), val-style')
 for rep in sorted(SRC.glob('*.ncu-rep')):
     full(rep)
-for f in ('bench.json', 'bench_kernels.json', 'layers.json', 'gpu_check_summary.txt'):
+for f in ('bench.json', 'bench_cfg3.json', 'bench_cfg4a.json', 'bench_cfg4b.json', 'bench_cfg5.json', 'bench_kernels.json', 'layers.json',
+          'gpu_check_summary.txt', 'scale.json'):
     if (SRC / f).exists():
         (DST / f'{tag}_{f}').write_text((SRC / f).read_text())
