@@ -155,19 +155,6 @@ def main():
         rec(f'coordatt c{c}@{hw} (cfg-4b, batch {b4})', timeit(lambda: ops.coordatt(x, pk, out=out), flush=flush),
             gbytes=2 * b4 * c * hw * hw * 2 / 1e9)
         del x, out
-    # a8 + a9 front end: fused decode + filter of the cfg-2 head logits (val-style threshold), bytes = logits read once
-    try:
-        lv = []
-        for (ny, st) in ((80, 8.), (40, 16.), (20, 32.)):
-            lg = torch.randn(B, ny, ny, 264, device=dev) * 2.0 - 4.0
-            lv.append(ops.DetectLevel(logits=lg, stride=st, anchors_px=[(st * 2, st * 3), (st * 4, st * 3), (st * 5, st * 8)], ny=ny, nx=ny,
-                                      ld=264, pitch=88))
-        ops.filter_candidates(None, 0.001, multi_label=True, levels=lv, na=3, nc=80)     # sizes the buffers once
-        rec('decode+filter (reserve, scan, gather) 3x88 logits', timeit(lambda: ops.filter_candidates(None, 0.001, multi_label=True, levels=lv, na=3, nc=80), flush=flush),
-            gbytes=sum(l.logits.numel() for l in lv) * 4 / 1e9)
-        del lv
-    except Exception as e:   # keep the table alive
-        print('filter bench skipped:', e)
     # a4 SPD (cfg-4 shape scaled to this batch)
     x = act(64, 320, 320)
     out = act(256, 160, 160)
