@@ -419,3 +419,34 @@ def c3hb(x, sd, p, n=1, eps=1e-3):
     for i in range(n):
         y = horblock(y, sd, f'{p}m.{i}.', eps)
     return conv_bn_act(torch.cat((y, conv_bn_act(x, sd, p + 'cv2.', 1, eps=eps)), 1), sd, p + 'cv3.', 1, eps=eps)
+
+
+# ---- 8f-4: test-time augmentation (models/yolo.py:194-209, 241-275; scale_img utils/torch_utils.py:264-274) -----------
+def scale_img(img, ratio=1.0, gs=32):
+    """Bilinear resize by `ratio`, padded (value 0.447) to the next multiple of the grid size."""
+    if ratio == 1.0:
+        return img
+    h, w = img.shape[2:]
+    s = (int(h * ratio), int(w * ratio))
+    img = F.interpolate(img, size=s, mode='bilinear', align_corners=False)
+    hp, wp = (math.ceil(v * ratio / gs) * gs for v in (h, w))
+    return F.pad(img, [0, wp - s[1], 0, hp - s[0]], value=0.447)
+
+
+def forward_augment(cfg: dict, sd: dict, x: torch.Tensor, strides, nl: int):
+    """Model._forward_augment: six passes (scales 1 / 0.83 / 0.67, each plain and left-right flipped), predictions de-scaled
+    and de-flipped, the tail of the first pass (largest-stride level) and the head of the last pass (smallest-stride level)
+    clipped, everything concatenated along the row axis."""
+    img_h, img_w = x.shape[-2:]
+    ys = []
+    for si, fi in zip([1, 1, 0.83, 0.83, 0.67, 0.67], [None, 3, None, 3, None, 3]):
+        xi = scale_img(x.flip(fi) if fi else x, si, gs=int(max(strides)))
+        p = forward_model(cfg, sd, xi, strides)[0].clone()
+        p[..., :4] /= si
+        if fi == 3:
+            p[..., 0] = img_w - p[..., 0]
+        ys.append(p)
+    g = sum(4 ** k for k in range(nl))
+    ys[0] = ys[0][:, :-(ys[0].shape[1] // g)]
+    ys[-1] = ys[-1][:, (ys[-1].shape[1] // g) * 4 ** (nl - 1):]
+    return torch.cat(ys, 1)

@@ -57,6 +57,7 @@ def main():
     ap.add_argument('--lr', type=float, default=2e-3)
     ap.add_argument('--width', type=float, default=0.25)
     ap.add_argument('--depth', type=float, default=0.33)
+    ap.add_argument('--anchors', default='', help="'p2': replace a placeholder anchor COUNT by four real anchor triples (P2..P5)")
     args = ap.parse_args()
     from oracle import refshim
     R = refshim.load()
@@ -66,6 +67,8 @@ def main():
     S = args.size
     St = args.train_size or S
     cfgd = reduced_cfg(args.cfg, args.width, args.depth)
+    if args.anchors == 'p2':   # C3CASPD.yaml / spdconv.yaml say `anchors: 4` (placeholders 0..7: zero-size boxes, nothing to train on)
+        cfgd['anchors'] = [[5, 6, 8, 14, 15, 11], [10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]]
     torch.manual_seed(0)
     torch.set_num_threads(8)
     model = R.Model(cfgd, ch=3, nc=synth.NC)

@@ -474,3 +474,26 @@ def test_conditioned_free_running_parity(tag):
     print(f'confidence tensor rel-L2 {conf_rel:.5f}')
     assert max(rel) <= 1e-2, rel
     assert box_err <= 1e-2 and conf_rel <= 1e-2 and conf_err <= 2e-2, (box_err, conf_rel, conf_err)
+
+
+def test_tta_values_against_executed_reference():
+    """`model(x, augment=True)` on the kernel path against the SAME call of the executed reference (conditioned
+    checkpoint, two 256 x 320 images, tests/golden/tta_conditioned.npz): six scaled / flipped passes, de-scaling,
+    de-flipping, tail clipping and concatenation.  Boxes within 1e-2 of the image size, confidences within 1e-2 rel-L2 and
+    2e-2 absolute — the free-running bf16 bar of test_conditioned_free_running_parity."""
+    from pathlib import Path
+    gold = Path(__file__).parent / 'golden'
+    d = np.load(gold / 'tta_conditioned.npz')
+    m, cfg, info = _conditioned('ablation')
+    x = torch.from_numpy(d['x'])
+    ref = torch.from_numpy(d['out'])
+    mc = m.cuda().eval()
+    with torch.no_grad():
+        out = mc(x.cuda(), augment=True)[0].float().cpu()
+    assert out.shape == ref.shape
+    S = max(x.shape[-2:])
+    box_err = float(((out[..., :4] - ref[..., :4]).abs() / S).max())
+    conf_rel = float((out[..., 4:] - ref[..., 4:]).norm() / ref[..., 4:].norm())
+    conf_err = float((out[..., 4:] - ref[..., 4:]).abs().max())
+    print(f'TTA vs executed reference: box err {box_err:.5f} of the image size, confidence rel-L2 {conf_rel:.5f}, max {conf_err:.5f}')
+    assert box_err <= 1e-2 and conf_rel <= 1e-2 and conf_err <= 2e-2, (box_err, conf_rel, conf_err)

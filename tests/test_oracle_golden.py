@@ -246,3 +246,22 @@ def test_oracle_whole_path_map_equals_reference_val_run():
     mp, mr, map50, map_ = OM.evaluate(dets, labels, (S, S))
     assert abs(map_ - info['map']) < 1e-9 and abs(map50 - info['map50']) < 1e-9, (map_, info['map'])
     assert abs(mp - info['mp']) < 1e-6 and abs(mr - info['mr']) < 1e-9
+
+
+def test_oracle_tta_matches_reference_forward_augment():
+    """oracle.blocks.forward_augment against `model(x, augment=True)` of the executed reference (conditioned checkpoint,
+    two 256 x 320 images; tests/golden/tta_conditioned.npz, oracle/make_golden_tta.py): 1e-4 relative."""
+    from pathlib import Path
+
+    from oracle import blocks as O
+    gold = Path(__file__).parent / 'golden'
+    d = np.load(gold / 'tta_conditioned.npz')
+    ck = torch.load(gold / 'conditioned_ablation.pt', map_location='cpu')
+    sd = {k: (v.float() if v.is_floating_point() else v) for k, v in ck['state_dict'].items()}
+    x = torch.from_numpy(d['x'])
+    with torch.no_grad():
+        out = O.forward_augment(ck['cfg'], sd, x, ck['stride'], nl=len(ck['stride']))
+        plain = O.forward_model(ck['cfg'], sd, x, ck['stride'])[0]
+    assert tuple(out.shape) == d['out'].shape
+    assert np.allclose(plain.numpy(), d['plain'], atol=2e-3, rtol=1e-4)
+    assert np.allclose(out.numpy(), d['out'], atol=2e-3, rtol=1e-4)
