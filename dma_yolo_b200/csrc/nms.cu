@@ -512,8 +512,9 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
 // succeed is still evaluated) and runs the reference arithmetic -- fl(fl(sigmoid(c)) * obj) > thr -- only on those.
 // The passing classes are remembered as a 96-bit mask, so the write pass touches nothing else.  Candidate sets, order
 // and values are identical to the kernel above (tests compare both with the CPU restatement).
-constexpr int kRowsThreads = 128;   // rows (pixels of one anchor) per tile == threads per CTA
+constexpr int kRowsThreads = 128;   // rows (pixels of one anchor) per tile; threads per CTA = kRowsThreads * TPR
 constexpr int kRowsMaxNc = 96;
+constexpr bool kAnchorFastest = true;
 
 // RESERVE = false: tiles take a ticket and place their candidates with the decoupled look-back (final, ordered buffers).
 // RESERVE = true : no ordering inside this kernel -- a tile reserves its run in the TEMPORARY buffers with one atomicAdd
@@ -526,8 +527,13 @@ constexpr int kRowsMaxNc = 96;
 //         odd number of 16-byte chunks: conflict-free LDS.128), and the multi-label scan reads four logits per load.
 // KIND 2: dense prediction [N, R, 5 + nc] (already decoded: utils/general.py's input when the caller holds a tensor):
 //         values are used as they are (no sigmoid, no grid decode); the tile is one contiguous run of memory.
-template <bool RESERVE, int KIND>
-__global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
+// TPR = threads per row.  The warps in flight are bounded by shared memory (11.8 KB of staged logits per 32 rows: 16 warps
+// per SM with one thread per row -- ncu: 23 % occupancy, 28 % issue activity, the scan is a chain of dependent LDS).  With
+// TPR = 2 (KIND 1) two adjacent threads share a row: thread 2r scans the 16-byte chunks [1, 13), thread 2r + 1 the rest
+// (an offset of 12 chunks keeps the eight LDS.128 of a quarter-warp on distinct banks), twice the warps per staged byte.
+// Candidate order is unchanged: the CTA scan runs over (row, half) in thread order, and the lower half holds the lower classes.
+template <bool RESERVE, int KIND, int TPR = 1>
+__global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
                                                                          const unsigned char* __restrict__ class_mask,
                                                                          unsigned* __restrict__ ticket,
                                                                          unsigned long long* __restrict__ status,
@@ -535,22 +541,30 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
                                                                          unsigned long long* __restrict__ keys,
                                                                          float* __restrict__ cand) {
   extern __shared__ float tile[];     // [rows][no]
-  __shared__ int warp_tot[kRowsThreads / 32];
+  constexpr int kThreads = kRowsThreads * TPR;
+  __shared__ int warp_tot[kThreads / 32];
   __shared__ long long base_s;
   __shared__ int tile_s;
   if (!RESERVE) {
     if (threadIdx.x == 0) tile_s = (int)atomicAdd(ticket, 1u);
     __syncthreads();
   }
-  const int tile_id = RESERVE ? (int)blockIdx.x : tile_s;
   const int tiles_img = fa.tile0[fa.levels];
+  int tile_id = RESERVE ? (int)blockIdx.x : tile_s;
   const int img = tile_id / tiles_img;
   int t = tile_id - img * tiles_img;
   int l = 0;
   while (l + 1 < fa.levels && t >= fa.tile0[l + 1]) ++l;
   t -= fa.tile0[l];
   const LevelMeta& m = fa.meta[l];
-  const int a = t / fa.tpa[l], ti = t - a * fa.tpa[l];
+  int a = t / fa.tpa[l], ti = t - a * fa.tpa[l];
+  if (RESERVE && kAnchorFastest) {
+    // reservation does not care which CTA handles which tile: consecutive CTAs take the anchors of ONE pixel range, so the
+    // interleaved thirds of those pixels' channel vectors are fetched at about the same time
+    ti = t / m.na;
+    a = t - ti * m.na;
+    tile_id = img * tiles_img + fa.tile0[l] + a * fa.tpa[l] + ti;    // logical tile (reference order) for the scan / gather
+  }
   const int npix = m.ny * m.nx;
   const int p0 = ti * kRowsThreads;
   const int np = min(kRowsThreads, npix - p0);
@@ -567,9 +581,9 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
       const int cpr = pitch >> 2;
       uint32_t sdst = tile_sm + (uint32_t)(warp * srow) * 4u + (uint32_t)lane * 16u;
       const float* g = gsrc + (long long)warp * ld + lane * 4;
-      const uint32_t sstep = (uint32_t)(kRowsThreads / 32) * (uint32_t)srow * 4u;
-      const long long gstep = (long long)(kRowsThreads / 32) * ld;
-      for (int row = warp; row < np; row += kRowsThreads / 32) {
+      const uint32_t sstep = (uint32_t)(kThreads / 32) * (uint32_t)srow * 4u;
+      const long long gstep = (long long)(kThreads / 32) * ld;
+      for (int row = warp; row < np; row += kThreads / 32) {
         if (lane < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
         if (lane + 32 < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 512u), "l"(g + 128) : "memory");
         sdst += sstep;
@@ -579,7 +593,7 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
     } else if (KIND == 2) {   // the tile is contiguous: flat 16-byte copies when base and length allow
       const int words = np * no;
       if (((reinterpret_cast<uintptr_t>(gsrc) & 15u) == 0) && (words & 3) == 0) {
-        for (int i = threadIdx.x; i < (words >> 2); i += kRowsThreads)
+        for (int i = threadIdx.x; i < (words >> 2); i += kThreads)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_sm + (uint32_t)i * 16u), "l"(gsrc + i * 4) : "memory");
         staged = true;
       }
@@ -590,9 +604,9 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
       const uint32_t rem_off = (uint32_t)nfull * 128u;
       uint32_t sdst = tile_sm + (uint32_t)(warp * srow + lane) * 4u;
       const float* g = gsrc + (long long)warp * ld + lane;
-      const uint32_t sstep = (uint32_t)(kRowsThreads / 32) * (uint32_t)srow * 4u;
-      const long long gstep = (long long)(kRowsThreads / 32) * ld;
-      for (int row = warp; row < np; row += kRowsThreads / 32) {
+      const uint32_t sstep = (uint32_t)(kThreads / 32) * (uint32_t)srow * 4u;
+      const long long gstep = (long long)(kThreads / 32) * ld;
+      for (int row = warp; row < np; row += kThreads / 32) {
         // no <= 5 + kRowsMaxNc = 101: at most three full 32-lane copies; straight-line code with uniform predicates
         if (nfull > 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(g) : "memory");
         if (nfull > 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 128u), "l"(g + 32) : "memory");
@@ -606,12 +620,16 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
   }
   __syncthreads();
 
-  const int row = threadIdx.x;
+  const int row = TPR == 1 ? (int)threadIdx.x : (int)(threadIdx.x >> 1);
+  const int half = TPR == 1 ? 0 : (int)(threadIdx.x & 1);
   float* s = tile + row * srow;   // KIND 0 / 2: row stride 5 + nc words, conflict-free whenever it is odd (nc = 80, 10, ...)
   int cnt = 0;
   uint32_t pm[4] = {0u, 0u, 0u, 0u};  // passing classes (bit = class; KIND 1 indexes words 0..3 statically)
   float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, bconf = 0.f;
   int bcls = 0;
+  float bc_best = -INFINITY;       // best-class mode: this thread's (half) row maximum, combined after the branch
+  int bc_bi = 0x7fffffff;
+  bool bc_nan = false, bc_valid = false;
   if (row < np) {
     const float obj = KIND == 2 ? s[4] : sigmoid_dec(s[4]);
     if (obj > thr) {
@@ -644,9 +662,11 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
             // four logits per LDS.128; chunk k holds words 4k .. 4k+3 of the row, class c sits at word 5 + c
             const float4* s4 = reinterpret_cast<const float4*>(s);
             const int nchunk = (no + 3) >> 2;
+            const int k_lo = (TPR == 2 && half == 1) ? min(13, nchunk) : 1;
+            const int k_hi = (TPR == 2 && half == 0) ? min(13, nchunk) : nchunk;
 #pragma unroll
             for (int k = 1; k < (5 + kRowsMaxNc + 3) / 4; ++k) {
-              if (k < nchunk) {
+              if (k >= k_lo && k < k_hi) {
                 const float4 v4 = s4[k];
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
@@ -690,7 +710,8 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
         float best = -INFINITY;
         int bi = 0x7fffffff;
         bool has_nan = false;
-        for (int c = 0; c < nc; ++c) {
+        const int c_lo = (TPR == 2 && half == 1) ? (nc + 1) / 2 : 0, c_hi = (TPR == 2 && half == 0) ? (nc + 1) / 2 : nc;
+        for (int c = c_lo; c < c_hi; ++c) {
           const float conf = __fmul_rn(KIND == 2 ? s[5 + c] : sigmoid_dec(s[5 + c]), obj);
           if (conf != conf) has_nan = true;
           if (conf > best) {
@@ -698,35 +719,51 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
             bi = c;
           }
         }
-        if (!has_nan && best > thr && bi < nc && (class_mask == nullptr || class_mask[bi])) {
-          cnt = 1;
-          bconf = best;
-          bcls = bi;
-        }
-      }
-      if (cnt > 0) {
-        float x, y, w, h;
-        if (KIND == 2) {
-          x = s[0]; y = s[1]; w = s[2]; h = s[3];
-        } else {
-          const int pix = p0 + row;
-          const int gy = pix / m.nx, gx = pix - gy * m.nx;
-          const float sx = sigmoid_dec(s[0]), sy = sigmoid_dec(s[1]), sw = sigmoid_dec(s[2]), sh = sigmoid_dec(s[3]);
-          // models/yolo.py:91-97 operation order
-          x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), m.stride);
-          y = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.f), 0.5f), (float)gy), m.stride);
-          const float tw = __fmul_rn(sw, 2.f), th = __fmul_rn(sh, 2.f);
-          w = __fmul_rn(__fmul_rn(tw, tw), m.anchor[2 * a]);
-          h = __fmul_rn(__fmul_rn(th, th), m.anchor[2 * a + 1]);
-        }
-        // xywh2xyxy (utils/general.py:539-546)
-        const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
-        x1 = __fsub_rn(x, hw);
-        y1 = __fsub_rn(y, hh);
-        x2 = __fadd_rn(x, hw);
-        y2 = __fadd_rn(y, hh);
+        bc_best = best;
+        bc_bi = bi;
+        bc_nan = has_nan;
+        bc_valid = true;
       }
     }
+  }
+  if (!fa.multi_label) {   // warp-uniform: the two halves of a row meet here outside any divergent region
+    if (TPR == 2) {        // first maximum over the two halves of the row
+      const float ob = __shfl_xor_sync(0xffffffffu, bc_best, 1);
+      const int oi = __shfl_xor_sync(0xffffffffu, bc_bi, 1);
+      const bool on = __shfl_xor_sync(0xffffffffu, bc_nan ? 1 : 0, 1) != 0;
+      if (ob > bc_best || (ob == bc_best && oi < bc_bi)) {
+        bc_best = ob;
+        bc_bi = oi;
+      }
+      bc_nan = bc_nan || on;
+    }
+    if (bc_valid && half == 0 && !bc_nan && bc_best > thr && bc_bi < nc && (class_mask == nullptr || class_mask[bc_bi])) {
+      cnt = 1;
+      bconf = bc_best;
+      bcls = bc_bi;
+    }
+  }
+  if (cnt > 0) {
+    float x, y, w, h;
+    if (KIND == 2) {
+      x = s[0]; y = s[1]; w = s[2]; h = s[3];
+    } else {
+      const int pix = p0 + row;
+      const int gy = pix / m.nx, gx = pix - gy * m.nx;
+      const float sx = sigmoid_dec(s[0]), sy = sigmoid_dec(s[1]), sw = sigmoid_dec(s[2]), sh = sigmoid_dec(s[3]);
+      // models/yolo.py:91-97 operation order
+      x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), m.stride);
+      y = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.f), 0.5f), (float)gy), m.stride);
+      const float tw = __fmul_rn(sw, 2.f), th = __fmul_rn(sh, 2.f);
+      w = __fmul_rn(__fmul_rn(tw, tw), m.anchor[2 * a]);
+      h = __fmul_rn(__fmul_rn(th, th), m.anchor[2 * a + 1]);
+    }
+    // xywh2xyxy (utils/general.py:539-546)
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+    x1 = __fsub_rn(x, hw);
+    y1 = __fsub_rn(y, hh);
+    x2 = __fadd_rn(x, hw);
+    y2 = __fadd_rn(y, hh);
   }
   // ---- exclusive scan of the row counts over the CTA, then this tile's place among all tiles (warp 0) ----
   int inc = cnt;
@@ -739,7 +776,7 @@ __global__ void __launch_bounds__(kRowsThreads) filter_fused_rows_kernel(const _
   __syncthreads();
   int before = 0, total = 0;
 #pragma unroll
-  for (int w = 0; w < kRowsThreads / 32; ++w) {
+  for (int w = 0; w < kThreads / 32; ++w) {
     const int v = warp_tot[w];
     if (w < warp) before += v;
     total += v;
@@ -1450,9 +1487,14 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   const bool reserve = rows_kernel && p->keys_tmp != nullptr && p->cand_tmp != nullptr && !no_reserve;
   const int kind = p->dense ? 2 : (padded ? 1 : 0);
   if (rows_kernel) {
+    // two threads per row for the padded-logits layout (DMAY_FILTER_TPR=1: one thread per row, A/B)
+    static const bool tpr1 = [] { const char* e = getenv("DMAY_FILTER_TPR"); return e && e[0] == '1'; }();
+    const int tpr = (kind == 1 && !tpr1) ? 2 : 1;
     void (*kern)(const FuseArgs, const unsigned char*, unsigned*, unsigned long long*, long long*, unsigned long long*, float*) =
-        reserve ? (kind == 0 ? filter_fused_rows_kernel<true, 0> : kind == 1 ? filter_fused_rows_kernel<true, 1> : filter_fused_rows_kernel<true, 2>)
-                : (kind == 0 ? filter_fused_rows_kernel<false, 0> : kind == 1 ? filter_fused_rows_kernel<false, 1> : filter_fused_rows_kernel<false, 2>);
+        reserve ? (kind == 0 ? filter_fused_rows_kernel<true, 0> : kind == 2 ? filter_fused_rows_kernel<true, 2>
+                   : tpr == 2 ? filter_fused_rows_kernel<true, 1, 2> : filter_fused_rows_kernel<true, 1>)
+                : (kind == 0 ? filter_fused_rows_kernel<false, 0> : kind == 2 ? filter_fused_rows_kernel<false, 2>
+                   : tpr == 2 ? filter_fused_rows_kernel<false, 1, 2> : filter_fused_rows_kernel<false, 1>);
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
@@ -1464,8 +1506,8 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
       int* tile_cnt = (int*)(tile_base + tiles);
       long long* tile_off = (long long*)((char*)p->ws + 16 + ((12 * tiles + 7) & ~7LL));
       if (p->ws_bytes < 16 + ((12 * tiles + 7) & ~7LL) + 8 * tiles) return DMAY_ETOOBIG;
-      kern<<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
-                                                  (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
+      kern<<<(int)tiles, kRowsThreads * tpr, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
+                                                        (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
       tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
                                           (int)(tiles / p->N), p->N);
       tile_gather_kernel<<<(int)tiles, 128, 0, s>>>(tile_base, tile_cnt, tile_off, (const unsigned long long*)p->keys_tmp,
@@ -1473,8 +1515,8 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
                                                     p->capacity);
       return finish_launch(3);
     }
-    kern<<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
-                                                (unsigned long long*)p->keys, (float*)p->cand);
+    kern<<<(int)tiles, kRowsThreads * tpr, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
+                                                      (unsigned long long*)p->keys, (float*)p->cand);
   } else {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(filter_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
