@@ -286,6 +286,8 @@ struct FuseArgs {
   long long capacity;
   int pitch;           // floats between the rows of two anchors inside a pixel's channel vector (5 + nc, or padded to 4n)
   const int* bin_thr;  // dense multi-label source: per-image score-key bin threshold of the pre-selection (nullptr: none)
+  unsigned long long* img_ctr;   // reserve mode: one reservation counter per image (nullptr: one counter for the batch)
+  long long region;              // ... and the size of an image's region of the temporary buffers (capacity / N)
 };
 
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
@@ -665,6 +667,11 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
             const int k_lo = (TPR == 2 && half == 1) ? min(13, nchunk) : 1;
             const int k_hi = (TPR == 2 && half == 0) ? min(13, nchunk) : nchunk;
 #pragma unroll
+            // pass 1, branch-free: which class logits clear the conservative bound.  (Testing and evaluating in one loop made
+            // a warp run the ~40-instruction exact path for every class that ANY of its 32 rows cleared -- 60 % of the classes
+            // at a 2-3 % candidate rate -- a ~10 us dependent chain per tile that no amount of warps, staging width, tile order
+            // or load overlap moved; see profiles/r2_notes.md section 6.)
+            uint32_t pre[4] = {0u, 0u, 0u, 0u};
             for (int k = 1; k < (5 + kRowsMaxNc + 3) / 4; ++k) {
               if (k >= k_lo && k < k_hi) {
                 const float4 v4 = s4[k];
@@ -672,33 +679,41 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int c = 4 * k + e - 5;
-                  if (c >= 0 && c < nc && vv[e] > t_lo) {
-                    const float conf = __fmul_rn(sigmoid_dec(vv[e]), obj);
-                    if (conf > thr && (class_mask == nullptr || class_mask[c])) {
-                      s[5 + c] = conf;
-                      pm[c >> 5] |= 1u << (c & 31);
-                      ++cnt;
-                    }
-                  }
+                  if (c >= 0 && c < nc) pre[c >> 5] |= (vv[e] > t_lo ? 1u : 0u) << (c & 31);
+                }
+              }
+            }
+            // pass 2: the reference arithmetic for the survivors only (iterations = the busiest row of the warp)
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+              uint32_t mk = pre[w];
+              while (mk) {
+                const int c = w * 32 + __ffs(mk) - 1;
+                mk &= mk - 1;
+                const float conf = __fmul_rn(sigmoid_dec(s[5 + c]), obj);
+                if (conf > thr && (class_mask == nullptr || class_mask[c])) {
+                  s[5 + c] = conf;
+                  pm[w] |= 1u << (c & 31);
+                  ++cnt;
                 }
               }
             }
           } else {
 #pragma unroll
             for (int w = 0; w < 3; ++w) {   // 32 classes per mask word (static register indexing)
-              uint32_t mk = 0u;
+              uint32_t pre = 0u, mk = 0u;
               const int cend = min(32, nc - w * 32);
-              const float* sc = s + 5 + w * 32;
+              float* sc = s + 5 + w * 32;
 #pragma unroll 8
-              for (int cc = 0; cc < cend; ++cc) {
-                const float v = sc[cc];
-                if (v > t_lo) {
-                  const float conf = __fmul_rn(sigmoid_dec(v), obj);
-                  if (conf > thr && (class_mask == nullptr || class_mask[w * 32 + cc])) {
-                    s[5 + w * 32 + cc] = conf;
-                    mk |= 1u << cc;
-                    ++cnt;
-                  }
+              for (int cc = 0; cc < cend; ++cc) pre |= (sc[cc] > t_lo ? 1u : 0u) << cc;   // pass 1, branch-free (see KIND 1)
+              while (pre) {                                                               // pass 2: survivors only
+                const int cc = __ffs(pre) - 1;
+                pre &= pre - 1;
+                const float conf = __fmul_rn(sigmoid_dec(sc[cc]), obj);
+                if (conf > thr && (class_mask == nullptr || class_mask[w * 32 + cc])) {
+                  sc[cc] = conf;
+                  mk |= 1u << cc;
+                  ++cnt;
                 }
               }
               pm[w] = mk;
@@ -786,7 +801,11 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
       const long long ntiles = (long long)fa.N * tiles_img;
       long long* tile_base = reinterpret_cast<long long*>(status);
       int* tile_cnt = reinterpret_cast<int*>(tile_base + ntiles);
-      const long long b = total > 0 ? (long long)atomicAdd(reinterpret_cast<unsigned long long*>(ticket), (unsigned long long)total) : 0;
+      // one counter per image: 12,864 same-address atomics with a return value were the pacing item of this kernel
+      long long b = 0;
+      if (total > 0)
+        b = fa.img_ctr != nullptr ? (long long)img * fa.region + (long long)atomicAdd(fa.img_ctr + img, (unsigned long long)total)
+                                  : (long long)atomicAdd(reinterpret_cast<unsigned long long*>(ticket), (unsigned long long)total);
       tile_base[tile_id] = b;
       tile_cnt[tile_id] = total;
       base_s = b;
@@ -802,6 +821,7 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
   __syncthreads();
   if (cnt == 0) return;
   long long g = base_s + before + inc - cnt;
+  const long long g_lim = (RESERVE && fa.img_ctr != nullptr) ? (long long)(img + 1) * fa.region : fa.capacity;   // never past the image's region
   const unsigned long long img_hi = (unsigned long long)(unsigned)img << 32;
   if (fa.multi_label) {
 #pragma unroll
@@ -810,7 +830,7 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
       while (mk) {
         const int c = w * 32 + __ffs(mk) - 1;
         mk &= mk - 1;
-        if (g < fa.capacity) {
+        if (g < g_lim) {
           const float conf = s[5 + c];
           float2* cd = reinterpret_cast<float2*>(cand + g * 6);   // 24-byte rows: three aligned 8-byte stores
           cd[0] = make_float2(x1, y1);
@@ -821,12 +841,353 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
         ++g;
       }
     }
-  } else if (g < fa.capacity) {
+  } else if (g < g_lim) {
     float2* cd = reinterpret_cast<float2*>(cand + g * 6);
     cd[0] = make_float2(x1, y1);
     cd[1] = make_float2(x2, y2);
     cd[2] = make_float2(bconf, (float)bcls);
     keys[g] = img_hi | (unsigned long long)(~__float_as_uint(bconf));
+  }
+}
+
+// ---- persistent form of the reserve-mode kernel -------------------------------------------------------------------------
+// The one-tile-per-CTA kernel runs in lock-step waves: every CTA loads (DRAM busy, SMs idle), then scans and writes (SMs busy,
+// DRAM idle); ncu: 2.5 TB/s, and neither more warps per row nor another tile order moved it.  Here a CTA is persistent (grid =
+// resident CTAs), walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and keeps TWO tile buffers: the cp.async loads of the
+// next tile are in flight while the current one is scanned.  With two threads per row the two resident CTAs of an SM still
+// run 16 warps.  Same tiles, same reservation scheme, same outputs as filter_fused_rows_kernel<true, KIND, TPR>.
+template <int KIND, int TPR>
+__global__ void __launch_bounds__(kRowsThreads * TPR) filter_rows_persistent_kernel(const __grid_constant__ FuseArgs fa,
+                                                                                   const unsigned char* __restrict__ class_mask,
+                                                                                   unsigned* __restrict__ ticket,
+                                                                                   unsigned long long* __restrict__ status,
+                                                                                   long long* __restrict__ img_offsets,
+                                                                                   unsigned long long* __restrict__ keys,
+                                                                                   float* __restrict__ cand) {
+  constexpr bool RESERVE = true;
+  constexpr int kThreads = kRowsThreads * TPR;
+  extern __shared__ float tile_all[];     // 2 x [rows][srow]
+  __shared__ int warp_tot[kThreads / 32];
+  __shared__ long long base_s;
+  const int nc = fa.nc, no = 5 + nc;
+  const int pitch = KIND == 1 ? fa.pitch : no;
+  const int srow = KIND == 1 ? fa.pitch + 4 : no;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float thr = fa.thr;
+  const int tiles_img = fa.tile0[fa.levels];
+  const int ntiles_all = fa.N * tiles_img;
+  const int buf_words = kRowsThreads * srow;
+  struct TileIdx {
+    int img, l, a, p0, np, npix, tile_id;
+  };
+  auto decode = [&](int phys) {
+    TileIdx r;
+    r.img = phys / tiles_img;
+    int t = phys - r.img * tiles_img;
+    int l = 0;
+    while (l + 1 < fa.levels && t >= fa.tile0[l + 1]) ++l;
+    t -= fa.tile0[l];
+    const int na = fa.meta[l].na;
+    const int ti = t / na;                 // anchor fastest: neighbouring CTAs share a pixel range
+    r.a = t - ti * na;
+    r.l = l;
+    r.tile_id = r.img * tiles_img + fa.tile0[l] + r.a * fa.tpa[l] + ti;
+    r.npix = fa.meta[l].ny * fa.meta[l].nx;
+    r.p0 = ti * kRowsThreads;
+    r.np = min(kRowsThreads, r.npix - r.p0);
+    return r;
+  };
+  auto stage = [&](const TileIdx& ti_, float* tile) {   // issue (do not wait for) the copies of one tile
+    const int img = ti_.img, l = ti_.l, a = ti_.a, p0 = ti_.p0, np = ti_.np, npix = ti_.npix, ld = fa.meta[l].ld;
+  {
+    const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * pitch;
+    const uint32_t tile_sm = (uint32_t)__cvta_generic_to_shared(tile);
+    bool staged = false;
+    if (KIND == 1) {   // a warp copies whole rows, one 16-byte chunk per lane
+      const int cpr = pitch >> 2;
+      uint32_t sdst = tile_sm + (uint32_t)(warp * srow) * 4u + (uint32_t)lane * 16u;
+      const float* g = gsrc + (long long)warp * ld + lane * 4;
+      const uint32_t sstep = (uint32_t)(kThreads / 32) * (uint32_t)srow * 4u;
+      const long long gstep = (long long)(kThreads / 32) * ld;
+      for (int row = warp; row < np; row += kThreads / 32) {
+        if (lane < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
+        if (lane + 32 < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 512u), "l"(g + 128) : "memory");
+        sdst += sstep;
+        g += gstep;
+      }
+      staged = true;
+    } else if (KIND == 2) {   // the tile is contiguous: flat 16-byte copies when base and length allow
+      const int words = np * no;
+      if (((reinterpret_cast<uintptr_t>(gsrc) & 15u) == 0) && (words & 3) == 0) {
+        for (int i = threadIdx.x; i < (words >> 2); i += kThreads)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_sm + (uint32_t)i * 16u), "l"(gsrc + i * 4) : "memory");
+        staged = true;
+      }
+    }
+    if (!staged) {   // a warp copies whole rows (coalesced along the row; 4-byte cp.async, rows are only 4-byte aligned)
+      // per row: nfull unconditional copies (lane, lane + 32, ...) and one partial; addresses advance by constants
+      const int nfull = no >> 5, rem = no & 31;
+      const uint32_t rem_off = (uint32_t)nfull * 128u;
+      uint32_t sdst = tile_sm + (uint32_t)(warp * srow + lane) * 4u;
+      const float* g = gsrc + (long long)warp * ld + lane;
+      const uint32_t sstep = (uint32_t)(kThreads / 32) * (uint32_t)srow * 4u;
+      const long long gstep = (long long)(kThreads / 32) * ld;
+      for (int row = warp; row < np; row += kThreads / 32) {
+        // no <= 5 + kRowsMaxNc = 101: at most three full 32-lane copies; straight-line code with uniform predicates
+        if (nfull > 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(g) : "memory");
+        if (nfull > 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 128u), "l"(g + 32) : "memory");
+        if (nfull > 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 256u), "l"(g + 64) : "memory");
+        if (lane < rem) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + rem_off), "l"(g + nfull * 32) : "memory");
+        sdst += sstep;
+        g += gstep;
+      }
+    }
+  }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int phys = (int)blockIdx.x;
+  if (phys < ntiles_all) stage(decode(phys), tile_all);
+  for (int it = 0; phys < ntiles_all; ++it, phys += (int)gridDim.x) {
+    float* tile = tile_all + (it & 1) * buf_words;
+    if (phys + (int)gridDim.x < ntiles_all) {
+      stage(decode(phys + (int)gridDim.x), tile_all + ((it + 1) & 1) * buf_words);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const TileIdx cur = decode(phys);
+    const LevelMeta& m = fa.meta[cur.l];
+    const int img = cur.img, a = cur.a, p0 = cur.p0, np = cur.np, tile_id = cur.tile_id;
+
+  const int row = TPR == 1 ? (int)threadIdx.x : (int)(threadIdx.x >> 1);
+  const int half = TPR == 1 ? 0 : (int)(threadIdx.x & 1);
+  float* s = tile + row * srow;   // KIND 0 / 2: row stride 5 + nc words, conflict-free whenever it is odd (nc = 80, 10, ...)
+  int cnt = 0;
+  uint32_t pm[4] = {0u, 0u, 0u, 0u};  // passing classes (bit = class; KIND 1 indexes words 0..3 statically)
+  float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, bconf = 0.f;
+  int bcls = 0;
+  float bc_best = -INFINITY;       // best-class mode: this thread's (half) row maximum, combined after the branch
+  int bc_bi = 0x7fffffff;
+  bool bc_nan = false, bc_valid = false;
+  if (row < np) {
+    const float obj = KIND == 2 ? s[4] : sigmoid_dec(s[4]);
+    if (obj > thr) {
+      if (fa.multi_label) {
+        if (KIND == 2) {
+          // dense rows hold the class confidences themselves: the reference arithmetic is one multiply (general.py:677)
+          const unsigned bt = fa.bin_thr != nullptr ? (unsigned)fa.bin_thr[img] : 0xFFFFFFFFu;   // see dense_hist_kernel
+#pragma unroll
+          for (int w = 0; w < 3; ++w) {
+            uint32_t mk = 0u;
+            const int cend = min(32, nc - w * 32);
+            float* sc = s + 5 + w * 32;
+#pragma unroll 8
+            for (int cc = 0; cc < cend; ++cc) {
+              const float conf = __fmul_rn(sc[cc], obj);
+              if (conf > thr && ((~__float_as_uint(conf)) >> 21) <= bt && (class_mask == nullptr || class_mask[w * 32 + cc])) {
+                sc[cc] = conf;
+                mk |= 1u << cc;
+                ++cnt;
+              }
+            }
+            pm[w] = mk;
+          }
+        } else {
+          // conservative pre-filter on the raw logit (see the header comment); exact test only for survivors
+          const float q = (thr / obj) * (1.0f - 4e-6f);
+          float t_lo = -INFINITY;
+          if (q > 0.f) t_lo = q < 1.f ? fminf(__logf(q / (1.0f - q)) - 0.02f, 10.0f) : 10.0f;
+          if (KIND == 1) {
+            // four logits per LDS.128; chunk k holds words 4k .. 4k+3 of the row, class c sits at word 5 + c
+            const float4* s4 = reinterpret_cast<const float4*>(s);
+            const int nchunk = (no + 3) >> 2;
+            const int k_lo = (TPR == 2 && half == 1) ? min(13, nchunk) : 1;
+            const int k_hi = (TPR == 2 && half == 0) ? min(13, nchunk) : nchunk;
+#pragma unroll
+            // pass 1, branch-free: which class logits clear the conservative bound.  (Testing and evaluating in one loop made
+            // a warp run the ~40-instruction exact path for every class that ANY of its 32 rows cleared -- 60 % of the classes
+            // at a 2-3 % candidate rate -- a ~10 us dependent chain per tile that no amount of warps, staging width, tile order
+            // or load overlap moved; see profiles/r2_notes.md section 6.)
+            uint32_t pre[4] = {0u, 0u, 0u, 0u};
+            for (int k = 1; k < (5 + kRowsMaxNc + 3) / 4; ++k) {
+              if (k >= k_lo && k < k_hi) {
+                const float4 v4 = s4[k];
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int c = 4 * k + e - 5;
+                  if (c >= 0 && c < nc) pre[c >> 5] |= (vv[e] > t_lo ? 1u : 0u) << (c & 31);
+                }
+              }
+            }
+            // pass 2: the reference arithmetic for the survivors only (iterations = the busiest row of the warp)
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+              uint32_t mk = pre[w];
+              while (mk) {
+                const int c = w * 32 + __ffs(mk) - 1;
+                mk &= mk - 1;
+                const float conf = __fmul_rn(sigmoid_dec(s[5 + c]), obj);
+                if (conf > thr && (class_mask == nullptr || class_mask[c])) {
+                  s[5 + c] = conf;
+                  pm[w] |= 1u << (c & 31);
+                  ++cnt;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {   // 32 classes per mask word (static register indexing)
+              uint32_t pre = 0u, mk = 0u;
+              const int cend = min(32, nc - w * 32);
+              float* sc = s + 5 + w * 32;
+#pragma unroll 8
+              for (int cc = 0; cc < cend; ++cc) pre |= (sc[cc] > t_lo ? 1u : 0u) << cc;   // pass 1, branch-free (see KIND 1)
+              while (pre) {                                                               // pass 2: survivors only
+                const int cc = __ffs(pre) - 1;
+                pre &= pre - 1;
+                const float conf = __fmul_rn(sigmoid_dec(sc[cc]), obj);
+                if (conf > thr && (class_mask == nullptr || class_mask[w * 32 + cc])) {
+                  sc[cc] = conf;
+                  mk |= 1u << cc;
+                  ++cnt;
+                }
+              }
+              pm[w] = mk;
+            }
+          }
+        }
+      } else {
+        // best class: first maximum (torch.max on CPU); NaN anywhere -> no candidate
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        bool has_nan = false;
+        const int c_lo = (TPR == 2 && half == 1) ? (nc + 1) / 2 : 0, c_hi = (TPR == 2 && half == 0) ? (nc + 1) / 2 : nc;
+        for (int c = c_lo; c < c_hi; ++c) {
+          const float conf = __fmul_rn(KIND == 2 ? s[5 + c] : sigmoid_dec(s[5 + c]), obj);
+          if (conf != conf) has_nan = true;
+          if (conf > best) {
+            best = conf;
+            bi = c;
+          }
+        }
+        bc_best = best;
+        bc_bi = bi;
+        bc_nan = has_nan;
+        bc_valid = true;
+      }
+    }
+  }
+  if (!fa.multi_label) {   // warp-uniform: the two halves of a row meet here outside any divergent region
+    if (TPR == 2) {        // first maximum over the two halves of the row
+      const float ob = __shfl_xor_sync(0xffffffffu, bc_best, 1);
+      const int oi = __shfl_xor_sync(0xffffffffu, bc_bi, 1);
+      const bool on = __shfl_xor_sync(0xffffffffu, bc_nan ? 1 : 0, 1) != 0;
+      if (ob > bc_best || (ob == bc_best && oi < bc_bi)) {
+        bc_best = ob;
+        bc_bi = oi;
+      }
+      bc_nan = bc_nan || on;
+    }
+    if (bc_valid && half == 0 && !bc_nan && bc_best > thr && bc_bi < nc && (class_mask == nullptr || class_mask[bc_bi])) {
+      cnt = 1;
+      bconf = bc_best;
+      bcls = bc_bi;
+    }
+  }
+  if (cnt > 0) {
+    float x, y, w, h;
+    if (KIND == 2) {
+      x = s[0]; y = s[1]; w = s[2]; h = s[3];
+    } else {
+      const int pix = p0 + row;
+      const int gy = pix / m.nx, gx = pix - gy * m.nx;
+      const float sx = sigmoid_dec(s[0]), sy = sigmoid_dec(s[1]), sw = sigmoid_dec(s[2]), sh = sigmoid_dec(s[3]);
+      // models/yolo.py:91-97 operation order
+      x = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), m.stride);
+      y = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.f), 0.5f), (float)gy), m.stride);
+      const float tw = __fmul_rn(sw, 2.f), th = __fmul_rn(sh, 2.f);
+      w = __fmul_rn(__fmul_rn(tw, tw), m.anchor[2 * a]);
+      h = __fmul_rn(__fmul_rn(th, th), m.anchor[2 * a + 1]);
+    }
+    // xywh2xyxy (utils/general.py:539-546)
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+    x1 = __fsub_rn(x, hw);
+    y1 = __fsub_rn(y, hh);
+    x2 = __fadd_rn(x, hw);
+    y2 = __fadd_rn(y, hh);
+  }
+  // ---- exclusive scan of the row counts over the CTA, then this tile's place among all tiles (warp 0) ----
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int v = warp_tot[w];
+    if (w < warp) before += v;
+    total += v;
+  }
+  if (RESERVE) {
+    if (threadIdx.x == 0) {
+      const long long ntiles = (long long)fa.N * tiles_img;
+      long long* tile_base = reinterpret_cast<long long*>(status);
+      int* tile_cnt = reinterpret_cast<int*>(tile_base + ntiles);
+      // one counter per image: 12,864 same-address atomics with a return value were the pacing item of this kernel
+      long long b = 0;
+      if (total > 0)
+        b = fa.img_ctr != nullptr ? (long long)img * fa.region + (long long)atomicAdd(fa.img_ctr + img, (unsigned long long)total)
+                                  : (long long)atomicAdd(reinterpret_cast<unsigned long long*>(ticket), (unsigned long long)total);
+      tile_base[tile_id] = b;
+      tile_cnt[tile_id] = total;
+      base_s = b;
+    }
+  } else if (warp == 0) {
+    const long long excl = tile_lookback(status, tile_id, total, lane);
+    if (lane == 0) {
+      base_s = excl;
+      if (tile_id == img * tiles_img) img_offsets[img] = excl;                          // first tile of an image
+      if (tile_id == fa.N * tiles_img - 1) img_offsets[fa.N] = excl + total;            // last tile: batch total
+    }
+  }
+  __syncthreads();
+  if (cnt != 0) {
+  long long g = base_s + before + inc - cnt;
+  const long long g_lim = (RESERVE && fa.img_ctr != nullptr) ? (long long)(img + 1) * fa.region : fa.capacity;   // never past the image's region
+  const unsigned long long img_hi = (unsigned long long)(unsigned)img << 32;
+  if (fa.multi_label) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      uint32_t mk = pm[w];
+      while (mk) {
+        const int c = w * 32 + __ffs(mk) - 1;
+        mk &= mk - 1;
+        if (g < g_lim) {
+          const float conf = s[5 + c];
+          float2* cd = reinterpret_cast<float2*>(cand + g * 6);   // 24-byte rows: three aligned 8-byte stores
+          cd[0] = make_float2(x1, y1);
+          cd[1] = make_float2(x2, y2);
+          cd[2] = make_float2(conf, (float)c);
+          keys[g] = img_hi | (unsigned long long)(~__float_as_uint(conf));
+        }
+        ++g;
+      }
+    }
+  } else if (g < g_lim) {
+    float2* cd = reinterpret_cast<float2*>(cand + g * 6);
+    cd[0] = make_float2(x1, y1);
+    cd[1] = make_float2(x2, y2);
+    cd[2] = make_float2(bconf, (float)bcls);
+    keys[g] = img_hi | (unsigned long long)(~__float_as_uint(bconf));
+  }
+  }
+    __syncthreads();   // every thread is done with this buffer, warp_tot and base_s before they are reused
   }
 }
 
@@ -1433,7 +1794,7 @@ static long long fused_tiles_per_image(const LevelMeta* hm, int levels, FuseArgs
 
 long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N) {
   if (!lv_meta_host || levels <= 0 || levels > 5 || N <= 0) return DMAY_EINVAL;
-  return 16 + 24 * N * fused_tiles_per_image((const LevelMeta*)lv_meta_host, levels, nullptr);   // status words, or tile base / count / offset
+  return 16 + 24 * N * fused_tiles_per_image((const LevelMeta*)lv_meta_host, levels, nullptr) + 8LL * N + 8;   // status words, or tile base / count / offset; per-image reservation counters
 }
 
 int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t stream) {
@@ -1488,8 +1849,8 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   const int kind = p->dense ? 2 : (padded ? 1 : 0);
   if (rows_kernel) {
     // two threads per row for the padded-logits layout (DMAY_FILTER_TPR=1: one thread per row, A/B)
-    static const bool tpr1 = [] { const char* e = getenv("DMAY_FILTER_TPR"); return e && e[0] == '1'; }();
-    const int tpr = (kind == 1 && !tpr1) ? 2 : 1;
+    static const bool tpr2 = [] { const char* e = getenv("DMAY_FILTER_TPR"); return e && e[0] == '2'; }();
+    const int tpr = (kind == 1 && tpr2) ? 2 : 1;   // measured: 1 thread per row 176 us, 2 threads per row 281 us (r5y)
     void (*kern)(const FuseArgs, const unsigned char*, unsigned*, unsigned long long*, long long*, unsigned long long*, float*) =
         reserve ? (kind == 0 ? filter_fused_rows_kernel<true, 0> : kind == 2 ? filter_fused_rows_kernel<true, 2>
                    : tpr == 2 ? filter_fused_rows_kernel<true, 1, 2> : filter_fused_rows_kernel<true, 1>)
@@ -1506,8 +1867,27 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
       int* tile_cnt = (int*)(tile_base + tiles);
       long long* tile_off = (long long*)((char*)p->ws + 16 + ((12 * tiles + 7) & ~7LL));
       if (p->ws_bytes < 16 + ((12 * tiles + 7) & ~7LL) + 8 * tiles) return DMAY_ETOOBIG;
+      const long long ctr_off = (16 + ((12 * tiles + 7) & ~7LL) + 8 * tiles + 7) & ~7LL;
+      if (p->per_image_regions && p->ws_bytes >= ctr_off + 8LL * p->N && p->capacity / p->N > 0) {
+        fa.img_ctr = (unsigned long long*)((char*)p->ws + ctr_off);
+        fa.region = p->capacity / p->N;
+      }
+      static const int persist = [] { const char* e = getenv("DMAY_FILTER_PERSIST"); return e ? atoi(e) : 0; }();
+      if (persist && kind == 1 && 2 * smem <= 110 * 1024) {
+        // persistent CTAs, two tile buffers each (see filter_rows_persistent_kernel)
+        void (*pk)(const FuseArgs, const unsigned char*, unsigned*, unsigned long long*, long long*, unsigned long long*, float*) =
+            tpr == 2 ? filter_rows_persistent_kernel<1, 2> : filter_rows_persistent_kernel<1, 1>;
+        const size_t smem2 = 2 * smem;
+        cudaError_t e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return (int)e;
+        const long long slots = (long long)sm_count() * (227 * 1024 / (long long)(smem2 + 1024));
+        pk<<<(int)(tiles < slots ? tiles : slots), kRowsThreads * tpr, smem2, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status,
+                                                                                  (long long*)p->img_offsets,
+                                                                                  (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
+      } else {
       kern<<<(int)tiles, kRowsThreads * tpr, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
                                                         (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
+      }
       tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
                                           (int)(tiles / p->N), p->N);
       tile_gather_kernel<<<(int)tiles, 128, 0, s>>>(tile_base, tile_cnt, tile_off, (const unsigned long long*)p->keys_tmp,

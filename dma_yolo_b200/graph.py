@@ -102,13 +102,16 @@ class GraphedDetector:
             raise ops.DmayError('GraphedDetector runs on CUDA tensors only')
         e = self.replay_only(x)
         # ONE D2H carries the per-image counts and the true candidate total of this replay
-        host = torch.cat((e.counts.to(torch.int64), e.offsets[-1:])).tolist()
-        total = host[-1]
-        if total > e.capacity:                        # the static buffers were too small for this image: exact eager result,
+        host = torch.cat((e.counts.to(torch.int64), e.offsets)).tolist()
+        offs = host[e.n:]
+        total = offs[-1]
+        maxc = max(offs[i + 1] - offs[i] for i in range(e.n))
+        # (every image reserves inside its own region of capacity // n candidates, see ops.PER_IMAGE_REGIONS)
+        if total > e.capacity or maxc > e.capacity // e.n:   # the static buffers were too small: exact eager result,
             self.eager_fallbacks += 1                 # then a re-capture sized for it
             dets, _ = self._eager(x)
             key = (tuple(x.shape), x.dtype, x.device.index)
-            self._entries[key] = self._capture(x, total_hint=total)
+            self._entries[key] = self._capture(x, total_hint=max(total, e.n * maxc))
             return dets
         out, cnt, packed = e.out, e.counts, e.packed
         if self.clone_outputs:                        # the static buffers are overwritten by the next replay
@@ -117,6 +120,6 @@ class GraphedDetector:
             out, cnt = packed[:nd].view(e.n, self.kw['max_det'], 6), packed[nd:].view(torch.int32)
         d = Detections(out, cnt, packed)
         d._pending = False
-        for i, c in enumerate(host[:-1]):
+        for i, c in enumerate(host[:e.n]):
             list.__setitem__(d, i, out[i, :c])
         return d

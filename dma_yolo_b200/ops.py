@@ -657,6 +657,7 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
 
 
 PRETHRESHOLD = __import__('os').environ.get('DMAY_PRETHRESHOLD', '1') != '0'
+PER_IMAGE_REGIONS = __import__('os').environ.get('DMAY_FILTER_REGIONS', '1') != '0'   # one reservation counter per image
 
 
 def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=False, reserve=None, max_nms=0):
@@ -711,13 +712,17 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=Fa
             f[f"lv_logits{i}"] = lv.logits.data_ptr()
         if cm is not None:
             f["class_mask"] = cm.data_ptr()
+        f["per_image_regions"] = int(PER_IMAGE_REGIONS)
         call("dmay_nms_filter_fused", s, **f)
         offs_host = img_offsets.tolist()     # the one sizing sync of the batch (N+1 values)
         total = offs_host[-1]
-        if total <= capacity:
+        maxc = max(offs_host[i + 1] - offs_host[i] for i in range(n))
+        regions = PER_IMAGE_REGIONS and "keys_tmp" in f      # reserve mode: every image has capacity // n of the temporary buffers
+        if total <= capacity and (not regions or maxc <= capacity // n):
             break
-        capacity = total + total // 8 + 4096   # undersized guess: every candidate was counted, repeat once
-    _FUSED_CAP[key] = max(total + total // 4 + 4096, _FUSED_CAP.get(key, 0) // 2)
+        # undersized guess: every candidate was counted, repeat once
+        capacity = max(total + total // 8, (n * (maxc + maxc // 8)) if regions else 0) + 4096
+    _FUSED_CAP[key] = max(total + total // 4 + 4096, (n * (maxc + maxc // 4) + 4096) if regions else 0, _FUSED_CAP.get(key, 0) // 2)
     return keys, cand, img_counts, img_offsets, offs_host, total
 
 
@@ -754,7 +759,7 @@ def nms_fused_static(levels, na: int, nc: int, conf_thres: float, iou_thres: flo
              img_counts=img_counts.data_ptr(), img_offsets=img_offsets.data_ptr(), keys=keys.data_ptr(),
              cand=cand.data_ptr(), N=n, nc=nc, levels=len(levels), multi_label=int(multi_label), capacity=capacity,
              conf_thres=float(conf_thres), keys_tmp=keys_tmp.data_ptr(), cand_tmp=cand_tmp.data_ptr(),
-             row_pitch=levels[0].pitch)
+             row_pitch=levels[0].pitch, per_image_regions=int(PER_IMAGE_REGIONS))
     for i, lv in enumerate(levels):
         f[f"lv_logits{i}"] = lv.logits.data_ptr()
     if cm is not None:

@@ -434,7 +434,11 @@ int dmay_nms_filter(const dmay_filter_params* p, dmay_stream_t stream);
  *   16-byte multiples).
  * dense = 1: the source is a DENSE prediction [N, R, 5 + nc] (utils/general.py:633 input, already decoded) passed as
  *   lv_logits0 with one level {row0 0, ny 1, nx R, ld 5 + nc, na 1}: same kernels, values used as they are.
- * bin_thr (dense multi-label only, optional): per-image key-bin threshold of dmay_nms_dense_prethreshold. */
+ * bin_thr (dense multi-label only, optional): per-image key-bin threshold of dmay_nms_dense_prethreshold.
+ * per_image_regions = 1 (reserve mode): the temporary buffers are split into N regions of capacity / N candidates and every
+ *   image reserves in its own region with its own counter (one contended atomic address per image instead of one per batch).
+ *   An image then overflows when ITS count exceeds capacity / N: the caller checks max_i (img_offsets[i+1] - img_offsets[i])
+ *   against capacity / N as well as img_offsets[N] against capacity. */
 typedef struct dmay_filter_fused_params {
   const void* lv_logits0;
   const void* lv_logits1;
@@ -460,6 +464,7 @@ typedef struct dmay_filter_fused_params {
   int row_pitch;
   int dense;
   const void* bin_thr;
+  int per_image_regions;
 } dmay_filter_fused_params;
 long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N);
 
