@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
       const float* g = gsrc + (long long)warp * ld + lane * 4;
       const uint32_t sstep = (uint32_t)(kThreads / 32) * (uint32_t)srow * 4u;
       const long long gstep = (long long)(kThreads / 32) * ld;
+#pragma unroll 4
       for (int row = warp; row < np; row += kThreads / 32) {
         if (lane < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
         if (lane + 32 < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 512u), "l"(g + 128) : "memory");
@@ -909,6 +910,7 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_rows_persistent_ker
       const float* g = gsrc + (long long)warp * ld + lane * 4;
       const uint32_t sstep = (uint32_t)(kThreads / 32) * (uint32_t)srow * 4u;
       const long long gstep = (long long)(kThreads / 32) * ld;
+#pragma unroll 4
       for (int row = warp; row < np; row += kThreads / 32) {
         if (lane < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
         if (lane + 32 < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 512u), "l"(g + 128) : "memory");

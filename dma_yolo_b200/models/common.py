@@ -101,14 +101,22 @@ def _conv_supported(conv: nn.Conv2d) -> bool:
             and conv.padding_mode == 'zeros')
 
 
-def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device):
-    """Cached ConvPack for (conv, bn); rebuilt when any parameter/buffer changed (data_ptr/_version)."""
+def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device, colscale=None):
+    """Cached ConvPack for (conv, bn); rebuilt when any parameter/buffer changed (data_ptr/_version).
+    colscale = ((channels, weight), ...): the input-channel ranges of the weight are multiplied by `weight` in fp32 before
+    the bf16 rounding (the BiFPN weights of a virtual concat folded into its 1x1 consumer, see ops.VCat)."""
     key = (str(device),) + _ver(conv.weight, conv.bias, *((bn.weight, bn.bias, bn.running_mean, bn.running_var)
                                                           if bn is not None else ())) + ((bn.eps,) if bn is not None else ())
+    if colscale is not None:
+        key = key + (colscale,)
     cache = owner.__dict__.setdefault('_b200_packs', {})
     pk = cache.get(slot)
     if pk is None or pk.key != key:
-        pk = ops.pack_conv(conv.weight, bn=bn, conv_bias=conv.bias, stride=conv.stride[0], pad=conv.padding[0],
+        wt = conv.weight
+        if colscale is not None:
+            col = torch.cat([torch.full((c,), w, dtype=torch.float32) for c, w in colscale]).to(wt.device)
+            wt = wt.detach().float() * col.view(1, -1, 1, 1)
+        pk = ops.pack_conv(wt, bn=bn, conv_bias=conv.bias, stride=conv.stride[0], pad=conv.padding[0],
                            device=device)
         pk.key = key
         cache[slot] = pk
@@ -150,6 +158,15 @@ class Conv(_PackMixin, nn.Module):
     def forward_b200(self, x, out=None, residual=None):
         code = _act_code(self.act)
         bn = getattr(self, 'bn', None)
+        if isinstance(x, ops.VCat):   # a 1x1 layer reads the parts of a concat in place (weights folded into its columns)
+            c = self.conv
+            srcs = x.sources() if (code is not None and _conv_supported(c) and c.kernel_size == (1, 1) and c.stride == (1, 1)
+                                   and c.padding == (0, 0)) else None
+            if srcs is not None:
+                cs = x.colscale()
+                pk = get_conv_pack(self, 'conv@vcat' if cs is not None else 'conv', c, bn, srcs[0].device, cs)
+                return ops.conv(srcs, pk, code, out=out, residual=residual)
+            x = x.materialize()
         if not _conv_supported(self.conv):
             y = torch_body(self, (lambda t: self.act(bn(self.conv(t)))) if bn is not None else (lambda t: self.act(self.conv(t))), x)
             if residual is not None:
@@ -275,9 +292,10 @@ class C3(_PackMixin, nn.Module):
             return self.forward_b200(x)
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
 
-    def _merged_cv12(self, device):
+    def _merged_cv12(self, device, colscale=None):
         """cv1 and cv2 read the same x with the same geometry: ONE GEMM with their weights stacked along Cout
-        writes both halves of the concat slab (x is read once, one launch less).  None when they differ."""
+        writes both halves of the concat slab (x is read once, one launch less).  None when they differ.
+        colscale: per-part weights of a virtual concat input, folded into the weight columns (get_conv_pack)."""
         a, b = self.cv1, self.cv2
         if not (type(a) is Conv and type(b) is Conv and _conv_supported(a.conv) and _conv_supported(b.conv)):
             return None
@@ -286,25 +304,43 @@ class C3(_PackMixin, nn.Module):
         if (code is None or code != _act_code(b.act) or ca.weight.shape != cb.weight.shape or ca.stride != cb.stride
                 or ca.padding != cb.padding or ca.out_channels % 16 or (getattr(a, 'bn', None) is None) != (getattr(b, 'bn', None) is None)):
             return None
-        pa = get_conv_pack(a, 'conv', ca, getattr(a, 'bn', None), device)
-        pb = get_conv_pack(b, 'conv', cb, getattr(b, 'bn', None), device)
+        sfx = '' if colscale is None else '@vcat'
+        pa = get_conv_pack(a, 'conv' + sfx, ca, getattr(a, 'bn', None), device, colscale)
+        pb = get_conv_pack(b, 'conv' + sfx, cb, getattr(b, 'bn', None), device, colscale)
         cache = self.__dict__.setdefault('_b200_packs', {})
-        pk = cache.get('cv12')
+        pk = cache.get('cv12' + sfx)
         if pk is None or pk.key != (pa.key, pb.key):
             pk = ops.ConvPack(w=torch.cat((pa.w, pb.w), 0).contiguous(), scale=torch.cat((pa.scale, pb.scale)).contiguous(),
                               bias=torch.cat((pa.bias, pb.bias)).contiguous(), cin=pa.cin, cin_pad=pa.cin_pad,
                               cout=pa.cout + pb.cout, cout_pad=pa.cout_pad + pb.cout_pad, kh=pa.kh, kw=pa.kw,
                               stride=pa.stride, pad=pa.pad, key=(pa.key, pb.key))
-            cache['cv12'] = pk
+            cache['cv12' + sfx] = pk
         return pk, code
 
     def forward_b200(self, x, out=None):
         # cv1 -> bottlenecks write the first half of the concat slab, cv2 the second half: no torch.cat
-        x = ops.as_act(x)
+        srcs = None
+        if isinstance(x, ops.VCat):
+            # the input is a concat that was never written: cv1 | cv2 (1x1) walk its parts in their K loop
+            c = self.cv1.conv
+            if (isinstance(self.m, nn.Sequential) and c.kernel_size == (1, 1) and c.stride == (1, 1) and c.padding == (0, 0)
+                    and x.sources() is not None and self._merged_cv12(x.src.device, x.colscale()) is not None):
+                srcs, vc = x.sources(), x
+            else:
+                x = x.materialize()
+        if srcs is None:
+            x = ops.as_act(x)
         n, _, h, w = x.shape
+        dev = x.src.device if srcs is not None else x.device
         c_ = self.cv1.conv.out_channels
-        slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
+        slab = ops.empty_nhwc(n, 2 * c_, h, w, dev)
         first = slab[:, :c_]
+        if srcs is not None:
+            merged = self._merged_cv12(dev, vc.colscale())
+            ops.conv(srcs, merged[0], merged[1], out=slab)
+            if len(self.m) > 0:
+                _run_chain(self.m, first, first)
+            return self.cv3.forward_b200(slab, out=out)
         merged = self._merged_cv12(x.device) if isinstance(self.m, nn.Sequential) else None
         if merged is not None:
             ops.conv(x, merged[0], merged[1], out=slab)          # [cv1(x) | cv2(x)] in one launch
@@ -427,7 +463,7 @@ class Concat(nn.Module):
 
     def forward(self, x):
         if kernel_path(self, x) and self.d == 1 and all(_is_act_like(t) for t in x):
-            return ops.concat(x)
+            return ops.vcat(x, (1.0,) * len(x)) if 2 <= len(x) <= 3 else ops.concat(x)
         return torch.cat(_materialize(x), self.d)
 
 
@@ -465,7 +501,7 @@ class AdConcat2(_AdWeights, nn.Module):
 
     def forward(self, x):
         if kernel_path(self, x) and self.d == 1:
-            return ops.adconcat(x, self._norm_weights())
+            return ops.vcat(x, self._norm_weights())
         x = _materialize(x)
         w = self.w
         weight = w / (torch.sum(w, dim=0) + self.epsilon)
@@ -484,7 +520,7 @@ class AdConcat3(_AdWeights, nn.Module):
 
     def forward(self, x):
         if kernel_path(self, x) and self.d == 1:
-            return ops.adconcat(x, self._norm_weights())
+            return ops.vcat(x, self._norm_weights())
         x = _materialize(x)
         w = self.w
         weight = w / (torch.sum(w, dim=0) + self.epsilon)

@@ -239,6 +239,9 @@ class Model(nn.Module):
             fast = kernel_path(self, x)
         if fast and isinstance(m, nn.Upsample):
             return self._upsample_b200(m, x)
+        if fast and isinstance(x, ops.VCat) and getattr(type(m), 'forward_b200', None) in (_common.C3.forward_b200,
+                                                                                            _common.Conv.forward_b200):
+            return m(x)      # a 1x1 consumer reads the parts of the concat in place (ops.VCat)
         if fast and not isinstance(m, (_common.AdConcat2, _common.AdConcat3, _common.Concat)):
             x = _materialize(x)
         if fast and not _has_kernel_path(m):

@@ -184,8 +184,23 @@ def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor |
     """y = act(scale * conv(x, w) + bias) (+ residual) | (* sigmoid(gate_x + up(gate_k)))."""
     # uint8 images are normalised on the fly (x/255, the `img.float()/255` of val.py:199-202 folded into
     # the layout kernel) — an extension: the reference only accepts float images.
+    xs = None
+    if isinstance(x, (list, tuple)):
+        # virtual channel concat: the K loop of a 1x1 layer walks up to three tensors over the same pixels
+        xs = [as_act(t) for t in x]
+        x = xs[0]
+        if not (pk.kh == 1 and pk.kw == 1 and pk.stride == 1 and pk.pad == 0) or pk.stem_spd or not 1 <= len(xs) <= 3:
+            raise DmayError("conv: a list of inputs needs a 1x1 / stride-1 layer and at most three tensors")
+        if any(t.shape[1] % 64 or t.shape[0] != x.shape[0] or t.shape[2:] != x.shape[2:] for t in xs):
+            raise DmayError("conv: virtual concat parts need equal N, H, W and channel counts that are multiples of 64")
+        if sum(t.shape[1] for t in xs) != pk.cin or pk.cin != pk.cin_pad:
+            raise DmayError(f"conv: expected {pk.cin} input channels over all parts")
+        if len(xs) == 1:
+            xs = None
     mul = 1.0 / 255.0 if x.dtype == torch.uint8 else 1.0
-    if pk.stem_spd:
+    if xs is not None:
+        pass
+    elif pk.stem_spd:
         if x.shape[1] != pk.cin:
             raise DmayError(f"conv: expected {pk.cin} input channels, got {x.shape[1]}")
         x = input_prep(x, spd=True, cpad=pk.cin_pad, mul=mul)
@@ -214,6 +229,10 @@ def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor |
              N=n, H=h, W=w, Cin=pk.cin_pad, ldx=ld_of(x), Cout=cstore, Cout_pad=pk.cout_pad, kh=pk.kh, kw=pk.kw,
              stride=pk.stride, pad=pk.pad, Ho=ho, Wo=wo, ldy=ld_of(out), act=act,
              out_dtype=_DT[odt], block_n=block_n, num_sms=num_sms, flags=CONV_FLAGS if flags is None else flags)
+    if xs is not None:
+        f.update(x1=xs[1].data_ptr(), Cin1=xs[1].shape[1], ldx1=ld_of(xs[1]))
+        if len(xs) == 3:
+            f.update(x2=xs[2].data_ptr(), Cin2=xs[2].shape[1], ldx2=ld_of(xs[2]))
     if residual is not None:
         residual = as_act(residual)
         if tuple(residual.shape) != (n, pk.cout, ho, wo):
@@ -256,12 +275,51 @@ class Up:
         return upsample(self.src, 1 << self.log2f)
 
 
+class VCat(Up):
+    """cat([w_i * x_i], 1) that has not been materialised (AdConcat2 / AdConcat3 / Concat outputs).  A 1x1 consumer (C3's
+    cv1 | cv2, Conv) reads the parts in place -- `sources()`, the K loop of its GEMM walks them -- with w_i folded into the
+    matching columns of its weights (`colscale()`); every other consumer gets `materialize()` (the adconcat kernel, once)."""
+
+    def __init__(self, parts, weights):
+        self.parts = list(parts)
+        self.weights = tuple(float(w) for w in weights)
+        first = self.parts[0]
+        self.src, self.log2f = (first.src if isinstance(first, Up) else first), 0
+        self._mat = self._srcs = None
+
+    @property
+    def shape(self):
+        n, _, h, w = self.parts[0].shape
+        return torch.Size((n, sum(p.shape[1] for p in self.parts), h, w))
+
+    def materialize(self) -> torch.Tensor:
+        if self._mat is None:
+            self._mat = adconcat(self.parts, self.weights)
+        return self._mat
+
+    def sources(self):
+        """Same-resolution bf16 NHWC tensors for a virtual-concat GEMM (an `Up` part is replicated once), or None."""
+        if self._srcs is None:
+            if any(p.shape[1] % 64 for p in self.parts):
+                return None
+            self._srcs = [as_act(p.materialize() if isinstance(p, Up) else p) for p in self.parts]
+        return self._srcs
+
+    def colscale(self):
+        """((channels, weight), ...) per part; None when every weight is exactly 1 (plain Concat: nothing to fold)."""
+        if all(w == 1.0 for w in self.weights):
+            return None
+        return tuple((int(p.shape[1]), w) for p, w in zip(self.parts, self.weights))
+
+
 def adconcat(xs, weights, out: torch.Tensor | None = None) -> torch.Tensor:
     """cat([w_i * x_i], 1); x_i may be an `Up` (read at reduced resolution)."""
     if not 2 <= len(xs) <= 3:
         raise DmayError("adconcat takes 2 or 3 inputs")
     srcs, ups = [], []
     for t in xs:
+        if isinstance(t, VCat):
+            t = t.materialize()
         if isinstance(t, Up):
             srcs.append(as_act(t.src))
             ups.append(t.log2f)
@@ -295,6 +353,17 @@ def concat(xs, out=None):
     if len(xs) == 1:
         return xs[0].materialize() if isinstance(xs[0], Up) else xs[0]
     return adconcat(xs, (1.0,) * len(xs), out=out)
+
+
+VCAT = __import__('os').environ.get('DMAY_VCAT', '1') != '0'   # A/B switch: 0 = every concat is materialised (round-1 form)
+
+
+def vcat(xs, weights):
+    """Lazy cat([w_i * x_i], 1) when a 1x1 consumer could read the parts in place, else the materialised tensor."""
+    xs = [t.materialize() if isinstance(t, VCat) else t for t in xs]
+    if VCAT and 2 <= len(xs) <= 3 and all(t.shape[1] % 64 == 0 for t in xs):
+        return VCat(xs, weights)
+    return adconcat(xs, weights) if len(xs) <= 3 else concat(xs)
 
 
 def adapt_add(xs, weights, out=None) -> torch.Tensor:

@@ -115,6 +115,12 @@ typedef struct dmay_conv_params {
   int num_sms;
   int flags;
   int res_op;
+  const void* x1;
+  const void* x2;
+  int Cin1;
+  int Cin2;
+  int ldx1;
+  int ldx2;
 } dmay_conv_params;
 int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream);
 /* launch-plan cache of dmay_conv_bn_act (mode / tile decisions + encoded CUtensorMaps, keyed by the parameter struct and the

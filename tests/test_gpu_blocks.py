@@ -24,6 +24,10 @@ def test_block_kernel_path_matches_reference(name):
     with torch.no_grad():
         y = m([t.cuda() for t in ins] if len(ins) > 1 else ins[0].cuda())
     torch.cuda.synchronize()
+    from dma_yolo_b200 import ops
+    if isinstance(y, ops.Up):      # AdConcat / Concat return a lazy concat when a 1x1 consumer could read the parts in place
+        y = y.materialize()
+        torch.cuda.synchronize()
     assert D.launch_count() > n0, 'no kernel of libdmayolo.so was launched'
     y = y.float().cpu()
     if name == 'spd':
@@ -149,3 +153,78 @@ def test_dfl_decode_kernel_equals_reference_arithmetic(name, nc):
     assert y_k.shape == y_t.shape
     assert_close(y_k[:, :4], y_t[:, :4], atol=1e-3, rtol=1e-4, what='DFL boxes')
     assert_close(y_k[:, 4:], y_t[:, 4:], atol=1e-6, rtol=1e-5, what='class confidences')
+
+
+# ---- virtual concat: AdConcat2 / AdConcat3 / Concat feeding a 1x1 consumer without writing the concat -------------------
+def _vcat_parts(kind, n=2, hw=(24, 40), seed=0):
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    h, w = hw
+    mk = lambda c, hh, ww: ops.as_act(torch.randn(n, c, hh, ww, generator=g).cuda())
+    if kind == 'up2':        # [Up(low-res), same-res]: the head's top-down joins
+        return [ops.Up(mk(128, h // 2, w // 2), 1), mk(64, h, w)]
+    if kind == 'three':      # AdConcat3: three same-resolution parts of different widths, one a channel slice of a slab
+        slab = mk(256, h, w)
+        return [mk(64, h, w), slab[:, 64:192], mk(192, h, w)]
+    return [mk(128, h, w), mk(128, h, w)]
+
+
+@pytest.mark.parametrize('kind', ['up2', 'three', 'two'])
+def test_conv_over_virtual_concat_is_bit_identical_to_the_written_concat(kind):
+    """dmay_conv_bn_act with x / x1 / x2 (weights 1.0: nothing folded) against the same GEMM over the concat written by
+    the adconcat kernel: the K loop only changes where a 64-channel chunk is fetched from, so the outputs are EQUAL."""
+    from dma_yolo_b200 import ops
+    parts = _vcat_parts(kind)
+    vc = ops.vcat(parts, (1.0,) * len(parts))
+    assert isinstance(vc, ops.VCat) and vc.colscale() is None
+    cin = vc.shape[1]
+    g = torch.Generator().manual_seed(5)
+    for cout in (64, 264, 512):
+        pk = ops.pack_conv(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5, device='cuda')
+        y_virtual = ops.conv(vc.sources(), pk, ops.ACT_SILU)
+        y_written = ops.conv(vc.materialize(), pk, ops.ACT_SILU)
+        torch.cuda.synchronize()
+        assert torch.equal(y_virtual, y_written), (kind, cout)
+    with pytest.raises(ops.DmayError):       # 3x3 layers cannot walk parts
+        ops.conv(vc.sources(), ops.pack_conv(torch.randn(64, cin, 3, 3), pad=1, device='cuda'), ops.ACT_SILU)
+
+
+@pytest.mark.parametrize('mod', ['AdConcat2', 'AdConcat3', 'Concat'])
+def test_c3_reads_a_lazy_concat_in_place(mod):
+    """AdConcatN / Concat -> C3 through the layer loop's dispatch: the lazy form (parts read in place, BiFPN weights folded
+    into cv1 | cv2's columns in fp32 before the bf16 rounding) against the materialised form (adconcat kernel, then C3).
+    Concat folds nothing: equal.  AdConcat rounds w_i * W instead of w_i * x: 1e-2 relative to the output scale."""
+    import dma_yolo_b200 as D
+    from dma_yolo_b200 import ops
+    from dma_yolo_b200.models import common as C
+    from dma_yolo_b200.models import yolo as Y
+    torch.manual_seed(3)
+    parts = _vcat_parts('three' if mod == 'AdConcat3' else 'up2', seed=7)
+    cat = getattr(C, mod)(1).cuda().eval()
+    if mod != 'Concat':
+        cat.w.data = torch.tensor([0.7, 1.3, 0.4][:len(parts)]).cuda()
+    cin = sum(p.shape[1] for p in parts)
+    c3 = C.C3(cin, 128, n=1, shortcut=False).cuda().eval()
+    for m_ in c3.modules():
+        if isinstance(m_, torch.nn.BatchNorm2d):
+            m_.running_var.data.uniform_(0.5, 1.5)
+            m_.running_mean.data.normal_(0, 0.1)
+    run = Y.Model._run_layer
+    with torch.no_grad():
+        lazy = cat(parts)
+        assert isinstance(lazy, ops.VCat)
+        n0 = D.launch_count()
+        y_lazy = run(None, c3, lazy, True)
+        n_lazy = D.launch_count() - n0
+        assert lazy._mat is None, 'the concat was written although its consumer can read the parts'
+        n0 = D.launch_count()
+        y_mat = run(None, c3, ops.adconcat(parts, cat._norm_weights() if mod != 'Concat' else (1.0,) * len(parts)), True)
+        n_mat = D.launch_count() - n0
+    torch.cuda.synchronize()
+    a, b = y_lazy.float(), y_mat.float()
+    if mod == 'Concat':
+        assert torch.equal(a, b)
+    else:
+        rel = float((a - b).norm() / b.norm())
+        assert rel < 4e-3 and float((a - b).abs().max()) <= 1e-2 * float(b.abs().max()), rel
+    assert n_lazy <= n_mat    # the replicate of an `Up` part replaces the adconcat launch; same-resolution parts cost nothing
