@@ -514,7 +514,26 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
 // succeed is still evaluated) and runs the reference arithmetic -- fl(fl(sigmoid(c)) * obj) > thr -- only on those.
 // The passing classes are remembered as a 96-bit mask, so the write pass touches nothing else.  Candidate sets, order
 // and values are identical to the kernel above (tests compare both with the CPU restatement).
-constexpr int kRowsThreads = 128;   // rows (pixels of one anchor) per tile; threads per CTA = kRowsThreads * TPR
+// Build-time A/B switches of the rows kernel (tools/build_variant.sh + tools/ab_filter.sh, same box, cfg-2, us per launch):
+//   128-row tiles, CTA barrier after staging, loads consumed one by one ............ 174
+//   + DMAY_FILTER_GROUPED_LDS (six LDS.128 issued back to back) .................. 164
+//   + DMAY_FILTER_WARP_PRIVATE (a warp stages the rows it scans, __syncwarp only) . 158
+//   + DMAY_FILTER_ROWS 96 / 64 (35 / 23.5 KB tiles: 6 / 9 resident CTAs per SM) ... 145 / 138   <- default
+//   one survivor loop over the 96-bit set with two sigmoid chains per trip ....... 195 (removed)
+#ifndef DMAY_FILTER_WARP_PRIVATE
+#define DMAY_FILTER_WARP_PRIVATE 1
+#endif
+#ifndef DMAY_FILTER_GRP
+#define DMAY_FILTER_GRP 6
+#endif
+#ifndef DMAY_FILTER_ROWS
+#define DMAY_FILTER_ROWS 64
+#endif
+#ifndef DMAY_FILTER_GROUPED_LDS
+#define DMAY_FILTER_GROUPED_LDS 1
+#endif
+constexpr int kRowsThreads = DMAY_FILTER_ROWS;   // rows (pixels of one anchor) per tile; threads per CTA = kRowsThreads * TPR
+constexpr int kRowsWide = 128;      // tile of the unpadded / dense layouts
 constexpr int kRowsMaxNc = 96;
 constexpr bool kAnchorFastest = true;
 
@@ -534,8 +553,8 @@ constexpr bool kAnchorFastest = true;
 // TPR = 2 (KIND 1) two adjacent threads share a row: thread 2r scans the 16-byte chunks [1, 13), thread 2r + 1 the rest
 // (an offset of 12 chunks keeps the eight LDS.128 of a quarter-warp on distinct banks), twice the warps per staged byte.
 // Candidate order is unchanged: the CTA scan runs over (row, half) in thread order, and the lower half holds the lower classes.
-template <bool RESERVE, int KIND, int TPR = 1>
-__global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
+template <bool RESERVE, int KIND, int TPR = 1, int ROWS = kRowsThreads>
+__global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
                                                                          const unsigned char* __restrict__ class_mask,
                                                                          unsigned* __restrict__ ticket,
                                                                          unsigned long long* __restrict__ status,
@@ -543,7 +562,7 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
                                                                          unsigned long long* __restrict__ keys,
                                                                          float* __restrict__ cand) {
   extern __shared__ float tile[];     // [rows][no]
-  constexpr int kThreads = kRowsThreads * TPR;
+  constexpr int kThreads = ROWS * TPR;
   __shared__ int warp_tot[kThreads / 32];
   __shared__ long long base_s;
   __shared__ int tile_s;
@@ -568,8 +587,8 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
     tile_id = img * tiles_img + fa.tile0[l] + a * fa.tpa[l] + ti;    // logical tile (reference order) for the scan / gather
   }
   const int npix = m.ny * m.nx;
-  const int p0 = ti * kRowsThreads;
-  const int np = min(kRowsThreads, npix - p0);
+  const int p0 = ti * ROWS;
+  const int np = min(ROWS, npix - p0);
   const int nc = fa.nc, no = 5 + nc, ld = m.ld;
   const int pitch = KIND == 1 ? fa.pitch : no;              // global floats per anchor row
   const int srow = KIND == 1 ? fa.pitch + 4 : no;           // shared-memory words per row
@@ -581,12 +600,21 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
     bool staged = false;
     if (KIND == 1) {   // a warp copies whole rows, one 16-byte chunk per lane
       const int cpr = pitch >> 2;
-      uint32_t sdst = tile_sm + (uint32_t)(warp * srow) * 4u + (uint32_t)lane * 16u;
-      const float* g = gsrc + (long long)warp * ld + lane * 4;
-      const uint32_t sstep = (uint32_t)(kThreads / 32) * (uint32_t)srow * 4u;
-      const long long gstep = (long long)(kThreads / 32) * ld;
+#if DMAY_FILTER_WARP_PRIVATE
+      // a warp stages exactly the rows its own lanes scan (TPR == 1: rows [32 warp, 32 warp + 32)): no CTA barrier between the
+      // copies and the scan, the four warps of a tile drift apart and one warp's loads overlap another's arithmetic
+      const int row_first = TPR == 1 ? warp * 32 : warp;
+      const int row_last = TPR == 1 ? min(np, warp * 32 + 32) : np;
+      const int row_inc = TPR == 1 ? 1 : kThreads / 32;
+#else
+      const int row_first = warp, row_last = np, row_inc = kThreads / 32;
+#endif
+      uint32_t sdst = tile_sm + (uint32_t)(row_first * srow) * 4u + (uint32_t)lane * 16u;
+      const float* g = gsrc + (long long)row_first * ld + lane * 4;
+      const uint32_t sstep = (uint32_t)row_inc * (uint32_t)srow * 4u;
+      const long long gstep = (long long)row_inc * ld;
 #pragma unroll 4
-      for (int row = warp; row < np; row += kThreads / 32) {
+      for (int row = row_first; row < row_last; row += row_inc) {
         if (lane < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
         if (lane + 32 < cpr) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 512u), "l"(g + 128) : "memory");
         sdst += sstep;
@@ -621,7 +649,12 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   }
+#if DMAY_FILTER_WARP_PRIVATE
+  if (KIND == 1 && TPR == 1) __syncwarp();
+  else __syncthreads();
+#else
   __syncthreads();
+#endif
 
   const int row = TPR == 1 ? (int)threadIdx.x : (int)(threadIdx.x >> 1);
   const int half = TPR == 1 ? 0 : (int)(threadIdx.x & 1);
@@ -667,12 +700,35 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
             const int nchunk = (no + 3) >> 2;
             const int k_lo = (TPR == 2 && half == 1) ? min(13, nchunk) : 1;
             const int k_hi = (TPR == 2 && half == 0) ? min(13, nchunk) : nchunk;
-#pragma unroll
             // pass 1, branch-free: which class logits clear the conservative bound.  (Testing and evaluating in one loop made
             // a warp run the ~40-instruction exact path for every class that ANY of its 32 rows cleared -- 60 % of the classes
             // at a 2-3 % candidate rate -- a ~10 us dependent chain per tile that no amount of warps, staging width, tile order
             // or load overlap moved; see profiles/r2_notes.md section 6.)
             uint32_t pre[4] = {0u, 0u, 0u, 0u};
+#if DMAY_FILTER_GROUPED_LDS
+            // the LDS.128 of a group are issued back to back (ptxas kept 32 registers and consumed every load at once)
+            constexpr int kGrp = DMAY_FILTER_GRP;
+#pragma unroll
+            for (int k0 = 1; k0 < (5 + kRowsMaxNc + 3) / 4; k0 += kGrp) {
+              float4 v4[kGrp];
+#pragma unroll
+              for (int u = 0; u < kGrp; ++u) {
+                const int k = k0 + u;
+                v4[u] = (k >= k_lo && k < k_hi) ? s4[k] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+              }
+#pragma unroll
+              for (int u = 0; u < kGrp; ++u) {
+                const int k = k0 + u;
+                const float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int c = 4 * k + e - 5;
+                  if (c >= 0 && c < kRowsMaxNc) pre[c >> 5] |= ((c < nc && vv[e] > t_lo) ? 1u : 0u) << (c & 31);
+                }
+              }
+            }
+#else
+#pragma unroll
             for (int k = 1; k < (5 + kRowsMaxNc + 3) / 4; ++k) {
               if (k >= k_lo && k < k_hi) {
                 const float4 v4 = s4[k];
@@ -684,6 +740,7 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_fused_rows_kernel(c
                 }
               }
             }
+#endif
             // pass 2: the reference arithmetic for the survivors only (iterations = the busiest row of the warp)
 #pragma unroll
             for (int w = 0; w < 3; ++w) {
@@ -1006,12 +1063,12 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_rows_persistent_ker
             const int nchunk = (no + 3) >> 2;
             const int k_lo = (TPR == 2 && half == 1) ? min(13, nchunk) : 1;
             const int k_hi = (TPR == 2 && half == 0) ? min(13, nchunk) : nchunk;
-#pragma unroll
             // pass 1, branch-free: which class logits clear the conservative bound.  (Testing and evaluating in one loop made
             // a warp run the ~40-instruction exact path for every class that ANY of its 32 rows cleared -- 60 % of the classes
             // at a 2-3 % candidate rate -- a ~10 us dependent chain per tile that no amount of warps, staging width, tile order
             // or load overlap moved; see profiles/r2_notes.md section 6.)
             uint32_t pre[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
             for (int k = 1; k < (5 + kRowsMaxNc + 3) / 4; ++k) {
               if (k >= k_lo && k < k_hi) {
                 const float4 v4 = s4[k];
@@ -1827,9 +1884,12 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   // thread-per-row kernel for nc <= 96 (DMAY_FILTER_ROWS=0 keeps the warp-per-row one, for A/B runs and the tests)
   static const bool no_rows = [] { const char* e = getenv("DMAY_FILTER_ROWS"); return e && e[0] == '0'; }();
   const int srow = padded ? pitch + 4 : no;
-  const bool rows_kernel = (!no_rows || padded || p->dense) && p->nc <= kRowsMaxNc && (size_t)kRowsThreads * srow * sizeof(float) <= 100 * 1024;
+  // rows per tile: 64 for the padded Detect logits (352-byte rows: 23.5 KB tiles, nine CTAs per SM), 128 otherwise (the dense
+  // rows of cfg-5 are 60 bytes: same-box, 64-row tiles 1.46 ms per batch of 256 against 1.35 ms)
+  const int rows_tile = padded ? kRowsThreads : kRowsWide;
+  const bool rows_kernel = (!no_rows || padded || p->dense) && p->nc <= kRowsMaxNc && (size_t)rows_tile * srow * sizeof(float) <= 100 * 1024;
   if ((padded || p->dense) && !rows_kernel) return DMAY_EUNSUPPORTED;   // those layouts exist for the thread-per-row kernel only
-  const int P = rows_kernel ? kRowsThreads : kFuseP;
+  const int P = rows_kernel ? rows_tile : kFuseP;
   const long long tiles = (long long)p->N * fused_tiles_per_image(hm, p->levels, &fa, P);
   if (tiles > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
   if (p->ws_bytes < 16 + 8 * tiles) return DMAY_ETOOBIG;
@@ -1854,9 +1914,9 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
     static const bool tpr2 = [] { const char* e = getenv("DMAY_FILTER_TPR"); return e && e[0] == '2'; }();
     const int tpr = (kind == 1 && tpr2) ? 2 : 1;   // measured: 1 thread per row 176 us, 2 threads per row 281 us (r5y)
     void (*kern)(const FuseArgs, const unsigned char*, unsigned*, unsigned long long*, long long*, unsigned long long*, float*) =
-        reserve ? (kind == 0 ? filter_fused_rows_kernel<true, 0> : kind == 2 ? filter_fused_rows_kernel<true, 2>
+        reserve ? (kind == 0 ? filter_fused_rows_kernel<true, 0, 1, kRowsWide> : kind == 2 ? filter_fused_rows_kernel<true, 2, 1, kRowsWide>
                    : tpr == 2 ? filter_fused_rows_kernel<true, 1, 2> : filter_fused_rows_kernel<true, 1>)
-                : (kind == 0 ? filter_fused_rows_kernel<false, 0> : kind == 2 ? filter_fused_rows_kernel<false, 2>
+                : (kind == 0 ? filter_fused_rows_kernel<false, 0, 1, kRowsWide> : kind == 2 ? filter_fused_rows_kernel<false, 2, 1, kRowsWide>
                    : tpr == 2 ? filter_fused_rows_kernel<false, 1, 2> : filter_fused_rows_kernel<false, 1>);
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1887,7 +1947,7 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
                                                                                   (long long*)p->img_offsets,
                                                                                   (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
       } else {
-      kern<<<(int)tiles, kRowsThreads * tpr, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
+      kern<<<(int)tiles, P * tpr, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
                                                         (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
       }
       tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
@@ -1897,7 +1957,7 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
                                                     p->capacity);
       return finish_launch(3);
     }
-    kern<<<(int)tiles, kRowsThreads * tpr, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
+    kern<<<(int)tiles, P * tpr, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
                                                       (unsigned long long*)p->keys, (float*)p->cand);
   } else {
     if (smem > 48 * 1024) {
