@@ -177,12 +177,16 @@ def install_launch_timer(ops, torch):
         e0.record()
         real_call(fname, stream, **f)
         e1.record()
-        flops, shape = 0.0, None
+        flops, shape, nbytes = 0.0, None, 0.0
         if fname == 'dmay_conv_bn_act':
             flops = 2.0 * f['N'] * f['Ho'] * f['Wo'] * f['Cout'] * f['Cin'] * f['kh'] * f['kw']
             shape = (f['Cin'], f['Cout'], f['kh'], f['stride'], f['Ho'], f['Wo'], int(f.get('residual') is not None),
                      int(f.get('gate_x') is not None))
-        events.append((fname, e0, e1, flops, shape))
+            # algorithmic bytes of the launch: input + output once, + the residual / gate operand of its epilogue
+            opix = float(f['N'] * f['Ho'] * f['Wo'])
+            nbytes = (2.0 * f['N'] * f['H'] * f['W'] * f['Cin'] + opix * f['Cout'] * (4 if f.get('out_dtype') == 1 else 2)
+                      + 2.0 * opix * f['Cout'] * (int(f.get('residual') is not None) + int(f.get('gate_x') is not None)))
+        events.append((fname, e0, e1, flops, shape, nbytes))
     timed_call.on = False
     ops.call = timed_call
     return timed_call, events
@@ -191,7 +195,7 @@ def install_launch_timer(ops, torch):
 def summarize_launches(events, steps):
     """-> (per-entry-point table, conv ms, conv flops, n conv launches)"""
     per = {}
-    for fname, e0, e1, flops, _ in events:
+    for fname, e0, e1, *_ in events:
         d = per.setdefault(fname, dict(launches=0, ms=0.0))
         d['launches'] += 1
         d['ms'] += e0.elapsed_time(e1)
@@ -557,6 +561,10 @@ def main():
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
     peak_tf = float(pk.get('bf16_tflops_sustained', 1400.0))
+    # what the aggregate could reach: every conv launch at ITS OWN floor max(flops / tensor peak, algorithmic bytes / HBM peak)
+    # (the 1x1 layers are HBM-bound: 0.3-0.6 of the tensor peak is their ceiling)
+    floor_ms = sum(max(e[3] / (peak_tf * 1e12), e[5] / (float(pk.get('hbm_gbs', 6555.0)) * 1e9)) * 1e3
+                   for e in events if e[0] == 'dmay_conv_bn_act')
     in_mb = B * 3 * IMG * IMG * 4 >> 20
     line = dict(
         metric='images/sec', value=round(value, 1), unit='img/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -577,7 +585,11 @@ def main():
                       launches_per_step=n_conv // max(args.steps, 1), share_of_step=round(min(conv_ms / ms_rank, 1.0), 3),
                       measured_over=f'{args.steps} further steps of the same workload right after the timed region, one CUDA-event pair per launch',
                       peak_source=f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                      flops_per_step=conv_flops / max(args.steps, 1)),
+                      flops_per_step=conv_flops / max(args.steps, 1),
+                      ceiling_frac=round(conv_flops / (floor_ms / 1e3) / 1e12 / peak_tf, 3) if floor_ms > 0 else None,
+                      frac_of_layer_floors=round(floor_ms / conv_ms, 3) if conv_ms > 0 else None,
+                      ceiling_note='ceiling_frac: the aggregate if every launch ran at max(flops / tensor peak, algorithmic bytes / '
+                                   'HBM peak); frac_of_layer_floors = sum of those floors / measured conv time'),
         kernels=table,
     )
     if latency is not None:
