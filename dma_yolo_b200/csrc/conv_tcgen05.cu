@@ -275,6 +275,8 @@ enum EpiMode : int {
   EPI_LINEAR_RES = 6,  // bf16( s*acc + b + residual )              (Swin proj / fc2: Linear + shortcut)
   EPI_GELU = 7,        // bf16( gelu(s*acc + b) )                   (Swin mlp.fc1, exact erf GELU)
   EPI_LINEAR_MUL = 8,  // bf16( (s*acc + b) * operand )             (GnConv gating: pws_i(x) * dw_{i+1})
+  EPI_SILU_PRE = 9,    // bf16( silu(s*(acc + up(pre)) + b) )        (1x1 layer over [Up(x0) | x1]: W0.x0 comes in at low
+                       //                                             resolution as an fp32 partial sum, see ops.VCat)
 };
 
 struct __align__(64) ConvArgs {
@@ -296,6 +298,7 @@ struct __align__(64) ConvArgs {
   const __nv_bfloat16* residual;
   const __nv_bfloat16* gate_x;
   const __nv_bfloat16* gate_k;
+  const float* pre;    // EPI_SILU_PRE: fp32 [N, gHk, gWk, ldgk] partial pre-activation sums, nearest-upsampled to Ho x Wo
   void* y;
   int M, n_store, Cout_pad;
   int num_m_tiles, num_n_tiles;
@@ -463,7 +466,7 @@ __device__ __forceinline__ uint4 epi_compute8(const uint32_t* r, const float* sc
   float f[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(r[j]), s[j], b[j]);
-  if (MODE == EPI_SILU || MODE == EPI_SILU_RES) {
+  if (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_SILU_PRE) {
     // the staged scale / bias of these modes are pre-halved (exact), so f is already h = x/2: silu(x) = h + h*tanh(h)
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], tanh_approx(f[j]), f[j]);
@@ -615,7 +618,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   }
   // folded-BN scale / bias of every output channel, staged once (Cout_pad <= kMaxCout, checked on the host)
   // (SiLU modes keep them halved -- exact -- so the epilogue's FMA yields x/2 directly, see epi_compute8)
-  const float sb_mul = (MODE == EPI_SILU || MODE == EPI_SILU_RES) ? 0.5f : 1.0f;
+  const float sb_mul = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_SILU_PRE) ? 0.5f : 1.0f;
   for (int i = threadIdx.x; i < a.sb_floats; i += blockDim.x) {
     const bool in = i < a.Cout_pad;
     s_scale[i] = in ? sb_mul * a.scale[i] : 0.f;
@@ -992,7 +995,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int items = my_tiles * (cpw > 0 ? cpw : 1);                                  // cpw == 0: one "empty" item per tile
 
     constexpr bool kStaged = (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_LINEAR || MODE == EPI_GATE ||
-                              MODE == EPI_LINEAR_RES || MODE == EPI_GELU || MODE == EPI_LINEAR_MUL);
+                              MODE == EPI_LINEAR_RES || MODE == EPI_GELU || MODE == EPI_LINEAR_MUL || MODE == EPI_SILU_PRE);
     constexpr bool kOpnd = (MODE == EPI_SILU_RES || MODE == EPI_GATE || MODE == EPI_LINEAR_RES || MODE == EPI_LINEAR_MUL);
     const uint32_t out_stage = tail + (uint32_t)ew * (uint32_t)a.stage_tile;
     uint4* out_ptr = reinterpret_cast<uint4*>(tail_ptr + ew * a.stage_tile);
@@ -1016,7 +1019,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     };
     struct Item {
       int row;         // this thread's output row (pixel index), -1: not stored (beyond M / outside the image)
-      const __nv_bfloat16* gk_row;
+      const __nv_bfloat16* gk_row;   // EPI_GATE: this row's gate_k pixel; EPI_SILU_PRE: its fp32 `pre` pixel (reinterpreted)
       int n0, c0, width;
       int t1, t2, t3;  // TMA coordinates of the warp's 32-row box: 2-D {col, t1}; halo {col, t1 = w, t2 = h, t3 = n}
       bool first, last;
@@ -1058,7 +1061,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         it.t3 = hn;
       }
       it.gk_row = nullptr;
-      if (MODE == EPI_GATE && valid) {
+      if ((MODE == EPI_GATE || MODE == EPI_SILU_PRE) && valid) {
         int n_img, p, q;
         if (a.halo) {
           n_img = hn; p = hp; q = hq;
@@ -1069,7 +1072,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           q = rem - p * a.Wo;
         }
         const int hs = nearest_src(p, a.gHk, a.Ho, a.g_sh), ws = nearest_src(q, a.gWk, a.Wo, a.g_sw);
-        it.gk_row = a.gate_k + (((long long)n_img * a.gHk + hs) * a.gWk + ws) * a.ldgk;
+        const long long src_pix = ((long long)n_img * a.gHk + hs) * a.gWk + ws;
+        it.gk_row = MODE == EPI_GATE ? a.gate_k + src_pix * a.ldgk
+                                     : reinterpret_cast<const __nv_bfloat16*>(a.pre + src_pix * a.ldgk);
       }
       if (!valid) it.row = -1;
     };
@@ -1098,6 +1103,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         // 25 % of this kernel's warp samples in ncu) hit when the item is processed
         if (MODE == EPI_GATE && nxt.gk_row != nullptr)
           asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt.gk_row + nxt.n0 + nxt.c0));
+        if (MODE == EPI_SILU_PRE && nxt.gk_row != nullptr)   // the 128 bytes (32 fp32 columns) of the next item's partial sums
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float*>(nxt.gk_row) + nxt.n0 + nxt.c0));
       }
       if (cur.first) {
         mbar_wait(tfull_bar + acc * 8, acc_phase);
@@ -1147,6 +1154,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
           for (int v8 = 0; v8 < 4; ++v8) {
             uint4 gk = make_uint4(0, 0, 0, 0);
+            if (MODE == EPI_SILU_PRE) {   // acc += W0.x0 of the source pixel (two adjacent rows share it: one request)
+              const int c = cur.n0 + cur.c0 + v8 * 8;
+              if (cur.row >= 0 && v8 * 8 < cur.width && c + 8 <= a.n_store) {
+                const float4* pp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(cur.gk_row) + c);
+                const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+                uint32_t* rr = r + v8 * 8;
+                rr[0] = __float_as_uint(__uint_as_float(rr[0]) + p0.x);
+                rr[1] = __float_as_uint(__uint_as_float(rr[1]) + p0.y);
+                rr[2] = __float_as_uint(__uint_as_float(rr[2]) + p0.z);
+                rr[3] = __float_as_uint(__uint_as_float(rr[3]) + p0.w);
+                rr[4] = __float_as_uint(__uint_as_float(rr[4]) + p1.x);
+                rr[5] = __float_as_uint(__uint_as_float(rr[5]) + p1.y);
+                rr[6] = __float_as_uint(__uint_as_float(rr[6]) + p1.z);
+                rr[7] = __float_as_uint(__uint_as_float(rr[7]) + p1.w);
+              }
+            }
             if (MODE == EPI_GATE) {
               const int c = cur.n0 + cur.c0 + v8 * 8;
               if (cur.row >= 0 && v8 * 8 < cur.width && c + 8 <= a.n_store) gk = ld16(cur.gk_row + c);
@@ -1281,6 +1304,9 @@ static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   if (p->residual && (!aligned16(p->residual) || (p->ldr & 7) || p->ldr < p->Cout)) return DMAY_EINVAL;
   if (p->gate_x && (!p->gate_k || !aligned16(p->gate_x) || !aligned16(p->gate_k) || (p->ldgx & 7) || p->gHk <= 0 || p->gWk <= 0))
     return DMAY_EINVAL;
+  if (p->pre && (p->gate_x || p->residual || !aligned16(p->pre) || (p->ldpre & 3) || p->ldpre < p->Cout || p->preH <= 0 ||
+                 p->preW <= 0 || p->act != DMAY_ACT_SILU || p->out_dtype != DMAY_DT_BF16))
+    return DMAY_EINVAL;
   if ((p->Ho != (p->H + 2 * p->pad - p->kh) / p->stride + 1) || (p->Wo != (p->W + 2 * p->pad - p->kw) / p->stride + 1))
     return DMAY_EINVAL;
   if (p->pad > 127 || p->kh > 64 || p->kw > 64 || p->stride > 8) return DMAY_EUNSUPPORTED;
@@ -1316,7 +1342,8 @@ static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   a.im2col = !(p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0);
   int bn = p->block_n > 0 ? p->block_n : (p->Cout_pad < 256 ? p->Cout_pad : 256);
   int mode;
-  if (p->gate_x) mode = (!out_f32 && !p->residual) ? EPI_GATE : -1;
+  if (p->pre) mode = EPI_SILU_PRE;
+  else if (p->gate_x) mode = (!out_f32 && !p->residual) ? EPI_GATE : -1;
   else if (out_f32) mode = (p->act == DMAY_ACT_NONE && !p->residual) ? EPI_LINEAR_F32 : EPI_GENERIC;
   else if (p->act == DMAY_ACT_SILU) mode = p->residual ? EPI_SILU_RES : EPI_SILU;
   else if (p->res_op == 1) mode = (p->act == DMAY_ACT_NONE && p->residual) ? EPI_LINEAR_MUL : -1;
@@ -1325,7 +1352,7 @@ static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   else mode = EPI_GENERIC;
   if (mode < 0) return DMAY_EUNSUPPORTED;
   const bool staged = mode == EPI_SILU || mode == EPI_SILU_RES || mode == EPI_LINEAR || mode == EPI_GATE ||
-                      mode == EPI_LINEAR_RES || mode == EPI_GELU || mode == EPI_LINEAR_MUL;
+                      mode == EPI_LINEAR_RES || mode == EPI_GELU || mode == EPI_LINEAR_MUL || mode == EPI_SILU_PRE;
   a.opnd_stage = (mode == EPI_SILU_RES || mode == EPI_GATE || mode == EPI_LINEAR_RES || mode == EPI_LINEAR_MUL) ? 1 : 0;
   a.sb_floats = ((p->Cout_pad + bn - 1) / bn) * bn;
   if (a.sb_floats > kMaxCout) return DMAY_EUNSUPPORTED;
@@ -1504,6 +1531,7 @@ static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   a.residual = (const __nv_bfloat16*)p->residual;
   a.gate_x = (const __nv_bfloat16*)p->gate_x;
   a.gate_k = (const __nv_bfloat16*)p->gate_k;
+  a.pre = (const float*)p->pre;
   a.y = p->y;
   a.ldy = p->ldy;
   a.ldr = p->ldr;
@@ -1511,8 +1539,13 @@ static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   a.ldgk = p->Cout;  // k2 output is a dense [N,Hk,Wk,C] tensor
   a.gHk = p->gHk;
   a.gWk = p->gWk;
-  a.g_sh = p->gHk > 0 ? (float)p->gHk / (float)p->Ho : 0.f;
-  a.g_sw = p->gWk > 0 ? (float)p->gWk / (float)p->Wo : 0.f;
+  if (p->pre) {   // the partial sums use the gate_k geometry fields of the kernel arguments
+    a.ldgk = p->ldpre;
+    a.gHk = p->preH;
+    a.gWk = p->preW;
+  }
+  a.g_sh = a.gHk > 0 ? (float)a.gHk / (float)p->Ho : 0.f;
+  a.g_sw = a.gWk > 0 ? (float)a.gWk / (float)p->Wo : 0.f;
   a.act = p->act;
   a.flags = p->flags;
   a.out_f32 = out_f32 ? 1 : 0;
@@ -1715,6 +1748,7 @@ static int conv_issue(const ConvPlan& pl, cudaStream_t stream) {
     DMAY_LAUNCH_MODE(EPI_LINEAR_RES)
     DMAY_LAUNCH_MODE(EPI_GELU)
     DMAY_LAUNCH_MODE(EPI_LINEAR_MUL)
+    DMAY_LAUNCH_MODE(EPI_SILU_PRE)
   }
 #undef DMAY_LAUNCH_MODE
   return finish_launch();

@@ -101,14 +101,16 @@ def _conv_supported(conv: nn.Conv2d) -> bool:
             and conv.padding_mode == 'zeros')
 
 
-def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device, colscale=None):
+def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device, colscale=None, cols=None, plain=False):
     """Cached ConvPack for (conv, bn); rebuilt when any parameter/buffer changed (data_ptr/_version).
     colscale = ((channels, weight), ...): the input-channel ranges of the weight are multiplied by `weight` in fp32 before
-    the bf16 rounding (the BiFPN weights of a virtual concat folded into its 1x1 consumer, see ops.VCat)."""
+    the bf16 rounding (the BiFPN weights of a virtual concat folded into its 1x1 consumer, see ops.VCat).
+    cols = ((start, stop), ...): only these input-channel ranges are kept (the K segment of one group of concat parts);
+    plain: no BN / bias (scale 1, bias 0) -- the partial sums W0.x0 of ops.VCat.split."""
     key = (str(device),) + _ver(conv.weight, conv.bias, *((bn.weight, bn.bias, bn.running_mean, bn.running_var)
                                                           if bn is not None else ())) + ((bn.eps,) if bn is not None else ())
-    if colscale is not None:
-        key = key + (colscale,)
+    if colscale is not None or cols is not None or plain:
+        key = key + (colscale, cols, plain)
     cache = owner.__dict__.setdefault('_b200_packs', {})
     pk = cache.get(slot)
     if pk is None or pk.key != key:
@@ -116,8 +118,10 @@ def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device, cols
         if colscale is not None:
             col = torch.cat([torch.full((c,), w, dtype=torch.float32) for c, w in colscale]).to(wt.device)
             wt = wt.detach().float() * col.view(1, -1, 1, 1)
-        pk = ops.pack_conv(wt, bn=bn, conv_bias=conv.bias, stride=conv.stride[0], pad=conv.padding[0],
-                           device=device)
+        if cols is not None:
+            wt = torch.cat([wt[:, a:b] for a, b in cols], 1)
+        pk = ops.pack_conv(wt, bn=None if plain else bn, conv_bias=None if plain else conv.bias, stride=conv.stride[0],
+                           pad=conv.padding[0], device=device)
         pk.key = key
         cache[slot] = pk
     return pk
@@ -292,7 +296,7 @@ class C3(_PackMixin, nn.Module):
             return self.forward_b200(x)
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
 
-    def _merged_cv12(self, device, colscale=None):
+    def _merged_cv12(self, device, colscale=None, cols=None, plain=False):
         """cv1 and cv2 read the same x with the same geometry: ONE GEMM with their weights stacked along Cout
         writes both halves of the concat slab (x is read once, one launch less).  None when they differ.
         colscale: per-part weights of a virtual concat input, folded into the weight columns (get_conv_pack)."""
@@ -304,9 +308,9 @@ class C3(_PackMixin, nn.Module):
         if (code is None or code != _act_code(b.act) or ca.weight.shape != cb.weight.shape or ca.stride != cb.stride
                 or ca.padding != cb.padding or ca.out_channels % 16 or (getattr(a, 'bn', None) is None) != (getattr(b, 'bn', None) is None)):
             return None
-        sfx = '' if colscale is None else '@vcat'
-        pa = get_conv_pack(a, 'conv' + sfx, ca, getattr(a, 'bn', None), device, colscale)
-        pb = get_conv_pack(b, 'conv' + sfx, cb, getattr(b, 'bn', None), device, colscale)
+        sfx = ('' if colscale is None else '@vcat') + ('' if cols is None else '@lo' if plain else '@hi')
+        pa = get_conv_pack(a, 'conv' + sfx, ca, getattr(a, 'bn', None), device, colscale, cols, plain)
+        pb = get_conv_pack(b, 'conv' + sfx, cb, getattr(b, 'bn', None), device, colscale, cols, plain)
         cache = self.__dict__.setdefault('_b200_packs', {})
         pk = cache.get('cv12' + sfx)
         if pk is None or pk.key != (pa.key, pb.key):
@@ -324,8 +328,8 @@ class C3(_PackMixin, nn.Module):
             # the input is a concat that was never written: cv1 | cv2 (1x1) walk its parts in their K loop
             c = self.cv1.conv
             if (isinstance(self.m, nn.Sequential) and c.kernel_size == (1, 1) and c.stride == (1, 1) and c.padding == (0, 0)
-                    and x.sources() is not None and self._merged_cv12(x.src.device, x.colscale()) is not None):
-                srcs, vc = x.sources(), x
+                    and all(p.shape[1] % 64 == 0 for p in x.parts) and self._merged_cv12(x.src.device, x.colscale()) is not None):
+                srcs, vc = True, x
             else:
                 x = x.materialize()
         if srcs is None:
@@ -336,8 +340,18 @@ class C3(_PackMixin, nn.Module):
         slab = ops.empty_nhwc(n, 2 * c_, h, w, dev)
         first = slab[:, :c_]
         if srcs is not None:
-            merged = self._merged_cv12(dev, vc.colscale())
-            ops.conv(srcs, merged[0], merged[1], out=slab)
+            sp = vc.split() if _act_code(self.cv1.act) == ACT_SILU else None
+            if sp is not None:
+                # [Up(x0) | x1]: the x0 columns run at x0's own resolution into fp32 partial sums (a quarter of the pixels),
+                # the main GEMM walks the same-resolution parts only and adds up(partial) to its accumulators
+                lo, hi, (lo_cols, hi_cols) = sp
+                p_lo = self._merged_cv12(dev, vc.colscale(), lo_cols, True)[0]
+                p_hi = self._merged_cv12(dev, vc.colscale(), hi_cols, False)[0]
+                part = ops.conv(lo if len(lo) > 1 else lo[0], p_lo, ACT_NONE, out_fp32=True)
+                ops.conv(hi if len(hi) > 1 else hi[0], p_hi, ACT_SILU, out=slab, pre=part)
+            else:
+                merged = self._merged_cv12(dev, vc.colscale())
+                ops.conv(vc.sources(), merged[0], merged[1], out=slab)
             if len(self.m) > 0:
                 _run_chain(self.m, first, first)
             return self.cv3.forward_b200(slab, out=out)

@@ -180,8 +180,11 @@ CONV_FLAGS = int(__import__('os').environ.get('DMAY_CONV_FLAGS', '0'))   # defau
 
 def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor | None = None,
          residual: torch.Tensor | None = None, gate: tuple | None = None, out_fp32: bool = False,
-         block_n: int = 0, num_sms: int = 0, flags: int | None = None, res_mul: bool = False) -> torch.Tensor:
-    """y = act(scale * conv(x, w) + bias) (+ residual) | (* sigmoid(gate_x + up(gate_k)))."""
+         block_n: int = 0, num_sms: int = 0, flags: int | None = None, res_mul: bool = False,
+         pre: torch.Tensor | None = None) -> torch.Tensor:
+    """y = act(scale * conv(x, w) + bias) (+ residual) | (* sigmoid(gate_x + up(gate_k))).
+    x may be a list of up to three tensors (virtual channel concat, 1x1 layers).  pre: fp32 NHWC [N, Cout, h, w] partial
+    sums that are nearest-upsampled and added to the accumulator BEFORE scale / bias / SiLU (see VCat.split)."""
     # uint8 images are normalised on the fly (x/255, the `img.float()/255` of val.py:199-202 folded into
     # the layout kernel) — an extension: the reference only accepts float images.
     xs = None
@@ -238,6 +241,11 @@ def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor |
         if tuple(residual.shape) != (n, pk.cout, ho, wo):
             raise DmayError("conv: residual shape mismatch")
         f.update(residual=residual.data_ptr(), ldr=ld_of(residual), res_op=int(res_mul))
+    if pre is not None:
+        if (pre.dtype != torch.float32 or not is_nhwc(pre) or pre.shape[0] != n or pre.shape[1] != pk.cout or act != ACT_SILU
+                or out_fp32 or residual is not None or gate is not None):
+            raise DmayError("conv: `pre` needs fp32 NHWC partial sums of the output's channels and a plain SiLU bf16 layer")
+        f.update(pre=pre.data_ptr(), ldpre=ld_of(pre), preH=pre.shape[2], preW=pre.shape[3])
     if gate is not None:
         gx, gk = gate
         gx, gk = as_act(gx), as_act(gk)
@@ -311,6 +319,28 @@ class VCat(Up):
             return None
         return tuple((int(p.shape[1]), w) for p, w in zip(self.parts, self.weights))
 
+    def split(self):
+        """A 1x1 layer commutes with a nearest upsample: W.[up(x0) | x1] = up(W0.x0) + W1.x1.  -> (low, high, cols) with
+        low = the sources of the `Up` parts (all at ONE reduced resolution), high = the same-resolution parts, cols =
+        ((start, stop) column ranges of the low parts, ... of the high parts); None when the concat has no such split
+        (no `Up` part, nothing but `Up` parts, mixed factors, or channel counts that are not multiples of 64)."""
+        if not SPLIT_UP or any(p.shape[1] % 64 for p in self.parts):
+            return None
+        ups = [p for p in self.parts if isinstance(p, Up)]
+        if not ups or len(ups) == len(self.parts) or len({p.log2f for p in ups}) != 1 or any(isinstance(p, VCat) for p in ups):
+            return None
+        lo, hi, lo_cols, hi_cols, c0 = [], [], [], [], 0
+        for p in self.parts:
+            c = int(p.shape[1])
+            if isinstance(p, Up):
+                lo.append(as_act(p.src))
+                lo_cols.append((c0, c0 + c))
+            else:
+                hi.append(as_act(p))
+                hi_cols.append((c0, c0 + c))
+            c0 += c
+        return lo, hi, (tuple(lo_cols), tuple(hi_cols))
+
 
 def adconcat(xs, weights, out: torch.Tensor | None = None) -> torch.Tensor:
     """cat([w_i * x_i], 1); x_i may be an `Up` (read at reduced resolution)."""
@@ -356,6 +386,10 @@ def concat(xs, out=None):
 
 
 VCAT = __import__('os').environ.get('DMAY_VCAT', '1') != '0'   # A/B switch: 0 = every concat is materialised (round-1 form)
+# 1: the `Up` parts of a lazy concat are split off into a low-resolution partial GEMM whose fp32 sums the main GEMM's epilogue adds
+# (VCat.split, EPI_SILU_PRE).  Measured equal to replicating the part (same box, cfg-2: 12.87 vs 12.84 ms per step -- the two
+# consumers are L2 / HBM-bound 1x1 layers, the saved flops do not show and the fp32 partials cost what the replicate did): opt-in.
+SPLIT_UP = __import__('os').environ.get('DMAY_SPLIT_UP', '0') == '1'
 
 
 def vcat(xs, weights):

@@ -121,6 +121,10 @@ typedef struct dmay_conv_params {
   int Cin2;
   int ldx1;
   int ldx2;
+  const void* pre;
+  int ldpre;
+  int preH;
+  int preW;
 } dmay_conv_params;
 int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream);
 /* launch-plan cache of dmay_conv_bn_act (mode / tile decisions + encoded CUtensorMaps, keyed by the parameter struct and the

@@ -189,8 +189,9 @@ def test_conv_over_virtual_concat_is_bit_identical_to_the_written_concat(kind):
         ops.conv(vc.sources(), ops.pack_conv(torch.randn(64, cin, 3, 3), pad=1, device='cuda'), ops.ACT_SILU)
 
 
+@pytest.mark.parametrize('split', [False, True])
 @pytest.mark.parametrize('mod', ['AdConcat2', 'AdConcat3', 'Concat'])
-def test_c3_reads_a_lazy_concat_in_place(mod):
+def test_c3_reads_a_lazy_concat_in_place(mod, split, monkeypatch):
     """AdConcatN / Concat -> C3 through the layer loop's dispatch: the lazy form (parts read in place, BiFPN weights folded
     into cv1 | cv2's columns in fp32 before the bf16 rounding) against the materialised form (adconcat kernel, then C3).
     Concat folds nothing: equal.  AdConcat rounds w_i * W instead of w_i * x: 1e-2 relative to the output scale."""
@@ -198,6 +199,9 @@ def test_c3_reads_a_lazy_concat_in_place(mod):
     from dma_yolo_b200 import ops
     from dma_yolo_b200.models import common as C
     from dma_yolo_b200.models import yolo as Y
+    # split: the `Up` part runs as a low-resolution partial GEMM (fp32 sums) that the main GEMM's epilogue adds before
+    # scale / bias / SiLU (ops.VCat.split, opt-in) -- another summation order, so only Concat WITHOUT an Up part stays equal
+    monkeypatch.setattr(ops, 'SPLIT_UP', split)
     torch.manual_seed(3)
     parts = _vcat_parts('three' if mod == 'AdConcat3' else 'up2', seed=7)
     cat = getattr(C, mod)(1).cuda().eval()
@@ -222,9 +226,38 @@ def test_c3_reads_a_lazy_concat_in_place(mod):
         n_mat = D.launch_count() - n0
     torch.cuda.synchronize()
     a, b = y_lazy.float(), y_mat.float()
-    if mod == 'Concat':
+    if mod == 'Concat' and not split:
         assert torch.equal(a, b)
     else:
         rel = float((a - b).norm() / b.norm())
         assert rel < 4e-3 and float((a - b).abs().max()) <= 1e-2 * float(b.abs().max()), rel
     assert n_lazy <= n_mat    # the replicate of an `Up` part replaces the adconcat launch; same-resolution parts cost nothing
+
+
+@pytest.mark.parametrize('cout,hw,up', [(128, (24, 40), 2), (264, (20, 20), 2), (64, (16, 16), 4)])
+def test_conv_pre_add_epilogue_matches_torch(cout, hw, up):
+    """dmay_conv_bn_act with `pre` (EPI_SILU_PRE): y = silu(scale * (W.x + nearest_up(pre)) + bias) against torch fp32 on
+    the same bf16-rounded x / W and the same fp32 partial sums: atol = rtol = 1e-2 (single kernel)."""
+    import torch.nn.functional as F
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    h, w = hw
+    cin = 128
+    x = torch.randn(2, cin, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5).bfloat16().float()
+    bn = torch.nn.BatchNorm2d(cout).eval()
+    bn.weight.data.uniform_(0.5, 1.5, generator=g)
+    bn.bias.data.normal_(0, 0.2, generator=g)
+    bn.running_mean.data.normal_(0, 0.2, generator=g)
+    bn.running_var.data.uniform_(0.5, 1.5, generator=g)
+    pre = torch.randn(2, cout, h // up, w // up, generator=g)
+    with torch.no_grad():
+        ref = F.silu(bn(F.conv2d(x, wt) + F.interpolate(pre, scale_factor=up, mode='nearest')))
+    pk = ops.pack_conv(wt, bn=bn, device='cuda')
+    pre_d = ops.empty_nhwc(2, cout, h // up, w // up, 'cuda', torch.float32, c_alloc=(cout + 7) // 8 * 8)
+    pre_d.copy_(pre.cuda())
+    y = ops.conv(ops.as_act(x.cuda()), pk, ops.ACT_SILU, pre=pre_d)
+    torch.cuda.synchronize()
+    assert_close(y.float().cpu(), ref, atol=1e-2, rtol=1e-2, what=f'pre-add epilogue cout={cout}')
+    with pytest.raises(ops.DmayError):     # bf16 partial sums are not accepted
+        ops.conv(ops.as_act(x.cuda()), pk, ops.ACT_SILU, pre=pre_d.bfloat16())
