@@ -1320,10 +1320,13 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const int* __restrict__
                                                          long long ntiles, int tiles_img, int N) {
   __shared__ long long warp_sum[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long per = (ntiles + 1023) / 1024;
-  const long long t0 = (long long)tid * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+  // ntiles < 2^31 (checked by the caller): 32-bit indices, and the image boundary test is a running counter -- the 64-bit
+  // modulo per tile made this single CTA 23 us for the 25.7 k tiles of cfg-2
+  const int nt = (int)ntiles, per = (nt + 1023) / 1024;
+  const int t0 = min(tid * per, nt), t1 = min(t0 + per, nt);
   long long local = 0;
-  for (long long t = t0; t < t1; ++t) local += tile_cnt[t];
+#pragma unroll 4
+  for (int t = t0; t < t1; ++t) local += tile_cnt[t];
   long long inc = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -1343,9 +1346,14 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const int* __restrict__
   }
   __syncthreads();
   long long run = inc - local + (warp > 0 ? warp_sum[warp - 1] : 0);
-  for (long long t = t0; t < t1; ++t) {
+  int img = t0 / tiles_img, in_img = t0 - img * tiles_img;
+  for (int t = t0; t < t1; ++t) {
     tile_off[t] = run;
-    if (t % tiles_img == 0) img_offsets[t / tiles_img] = run;
+    if (in_img == 0) img_offsets[img] = run;
+    if (++in_img == tiles_img) {
+      in_img = 0;
+      ++img;
+    }
     run += tile_cnt[t];
   }
   if (tid == 1023) img_offsets[N] = warp_sum[31];

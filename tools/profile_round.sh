@@ -40,7 +40,7 @@ launch_list cfg5 nms5 256
 
 # full captures: memory-bound kernels of the warm step
 $NCU --profile-from-start off --set full -c 24 \
-    -k regex:'filter_|tile_|ca_|coordatt|pool_|adconcat|avgpool|nms_greedy|topk_|prep_kernel|img_' \
+    -k regex:'filter_|tile_|ca_|coordatt|pool_|adconcat|avgpool|upsample|nms_greedy|topk_|prep_kernel|img_' \
     -o $OUT/prof_membound -f python tools/prof_one.py model > $OUT/ncu_membound.log 2>&1
 
 # full captures: representative conv shapes (isolated, third launch)
