@@ -67,6 +67,14 @@ const char* dmay_strerror(int code);
  *   with nearest index hs=min(floor(p*gate_sh),gHk-1) — SCConv.forward models/common.py:1308-1316.
  * res_op: 0 = the residual operand is added after the activation (Bottleneck); 1 = act must be NONE and the result is
  *   MULTIPLIED by the residual operand: y = (scale*acc + bias) * residual  (GnConv recursive gating, common.py:1344).
+ * x1 / x2 (Cin1 / Cin2 > 0; 1x1, stride 1, pad 0 only): VIRTUAL channel concat -- the input is [x | x1 | x2] over the same
+ *   pixels, each part with its own base pointer and pixel pitch (ldx / ldx1 / ldx2), channel counts in multiples of 64;
+ *   Cin stays the TOTAL and w the weights of the concatenated input.  Replaces the torch.cat of Concat.forward
+ *   (models/common.py:656-664) and of AdConcat2/3.forward (models/common.py:1003-1008, 1021-1026; the BiFPN weights are
+ *   folded into the columns of w by the caller) in front of a 1x1 Conv / C3.cv1 | cv2.
+ * pre (fp32 [N, preH, preW, ldpre], act SiLU, bf16 output, no residual / gate): y = silu(scale * (acc + pre[n, hs, ws, co])
+ *   + bias) with the nearest source pixel of (p, q) -- a 1x1 layer commutes with nn.Upsample(nearest), so the columns
+ *   of an up-sampled concat part can be summed at ITS resolution and enter here.
  * block_n: 0 = auto, >0 = force the N tile, -2 = 2-CTA cluster multicast of the weight tile (experiment).
  * flags (tuning / A-B switches, 0 = auto): bit0 = never use the halo path (3x3 s1 p1 input patch loaded once
  *   per channel chunk, taps read shifted windows), bit1 = force it where legal, bit2 = never keep the weight

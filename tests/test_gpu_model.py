@@ -324,7 +324,9 @@ def test_graphed_detector_bit_identical_to_eager(kw):
 
 
 def test_conv_plan_cache_hits_in_steady_state():
-    """The second step of the same (batch, H, W) re-encodes no tensor map: every conv launch is a plan-cache hit."""
+    """Steady state of one (batch, H, W) re-encodes no tensor map: every conv launch is a plan-cache hit.  (The caching
+    allocator needs two to three steps to settle on the addresses it hands back -- measured 52 / 52 / 31 / 0 / 0 ... misses
+    per step on yolov5s -- so the check is made after six.)"""
     import dma_yolo_b200 as D
     from dma_yolo_b200 import _lib
     from dma_yolo_b200.utils.calib import build_calibrated
@@ -332,7 +334,7 @@ def test_conv_plan_cache_hits_in_steady_state():
     x = torch.rand(2, 3, 64, 64).cuda()
     L = _lib.lib()
     with torch.no_grad():
-        for _ in range(3):
+        for _ in range(6):
             a = m(x)[0].dense().clone()
         torch.cuda.synchronize()
         h0, m0 = L.dmay_conv_plan_stats(0), L.dmay_conv_plan_stats(1)
