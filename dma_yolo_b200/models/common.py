@@ -101,16 +101,18 @@ def _conv_supported(conv: nn.Conv2d) -> bool:
             and conv.padding_mode == 'zeros')
 
 
-def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device, colscale=None, cols=None, plain=False):
+def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device, colscale=None, cols=None, plain=False, spd=False):
     """Cached ConvPack for (conv, bn); rebuilt when any parameter/buffer changed (data_ptr/_version).
     colscale = ((channels, weight), ...): the input-channel ranges of the weight are multiplied by `weight` in fp32 before
     the bf16 rounding (the BiFPN weights of a virtual concat folded into its 1x1 consumer, see ops.VCat).
     cols = ((start, stop), ...): only these input-channel ranges are kept (the K segment of one group of concat parts);
-    plain: no BN / bias (scale 1, bias 0) -- the partial sums W0.x0 of ops.VCat.split."""
+    plain: no BN / bias (scale 1, bias 0) -- the partial sums W0.x0 of ops.VCat.split.
+    spd: the 1x1 weight over the 4C channels of a space_to_depth output re-laid as the 2x2 / stride-2 kernel over its C-channel
+    input (channel block q = dy + 2 dx, models/common.py:1457-1458; see ops.SPDView)."""
     key = (str(device),) + _ver(conv.weight, conv.bias, *((bn.weight, bn.bias, bn.running_mean, bn.running_var)
                                                           if bn is not None else ())) + ((bn.eps,) if bn is not None else ())
-    if colscale is not None or cols is not None or plain:
-        key = key + (colscale, cols, plain)
+    if colscale is not None or cols is not None or plain or spd:
+        key = key + (colscale, cols, plain, spd)
     cache = owner.__dict__.setdefault('_b200_packs', {})
     pk = cache.get(slot)
     if pk is None or pk.key != key:
@@ -120,8 +122,13 @@ def get_conv_pack(owner: nn.Module, slot: str, conv: nn.Conv2d, bn, device, cols
             wt = wt.detach().float() * col.view(1, -1, 1, 1)
         if cols is not None:
             wt = torch.cat([wt[:, a:b] for a, b in cols], 1)
-        pk = ops.pack_conv(wt, bn=None if plain else bn, conv_bias=None if plain else conv.bias, stride=conv.stride[0],
-                           pad=conv.padding[0], device=device)
+        stride, pad = conv.stride[0], conv.padding[0]
+        if spd:
+            co, c4 = wt.shape[:2]
+            wt = wt.detach().reshape(co, 2, 2, c4 // 4).permute(0, 3, 2, 1)   # [co, dx, dy, c] -> [co, c, kh = dy, kw = dx]
+            stride, pad = 2, 0
+        pk = ops.pack_conv(wt, bn=None if plain else bn, conv_bias=None if plain else conv.bias, stride=stride,
+                           pad=pad, device=device, allow_stem_spd=False if spd else True)
         pk.key = key
         cache[slot] = pk
     return pk
@@ -296,7 +303,7 @@ class C3(_PackMixin, nn.Module):
             return self.forward_b200(x)
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
 
-    def _merged_cv12(self, device, colscale=None, cols=None, plain=False):
+    def _merged_cv12(self, device, colscale=None, cols=None, plain=False, spd=False):
         """cv1 and cv2 read the same x with the same geometry: ONE GEMM with their weights stacked along Cout
         writes both halves of the concat slab (x is read once, one launch less).  None when they differ.
         colscale: per-part weights of a virtual concat input, folded into the weight columns (get_conv_pack)."""
@@ -308,9 +315,9 @@ class C3(_PackMixin, nn.Module):
         if (code is None or code != _act_code(b.act) or ca.weight.shape != cb.weight.shape or ca.stride != cb.stride
                 or ca.padding != cb.padding or ca.out_channels % 16 or (getattr(a, 'bn', None) is None) != (getattr(b, 'bn', None) is None)):
             return None
-        sfx = ('' if colscale is None else '@vcat') + ('' if cols is None else '@lo' if plain else '@hi')
-        pa = get_conv_pack(a, 'conv' + sfx, ca, getattr(a, 'bn', None), device, colscale, cols, plain)
-        pb = get_conv_pack(b, 'conv' + sfx, cb, getattr(b, 'bn', None), device, colscale, cols, plain)
+        sfx = ('' if colscale is None else '@vcat') + ('' if cols is None else '@lo' if plain else '@hi') + ('@spd' if spd else '')
+        pa = get_conv_pack(a, 'conv' + sfx, ca, getattr(a, 'bn', None), device, colscale, cols, plain, spd)
+        pb = get_conv_pack(b, 'conv' + sfx, cb, getattr(b, 'bn', None), device, colscale, cols, plain, spd)
         cache = self.__dict__.setdefault('_b200_packs', {})
         pk = cache.get('cv12' + sfx)
         if pk is None or pk.key != (pa.key, pb.key):
@@ -324,6 +331,21 @@ class C3(_PackMixin, nn.Module):
     def forward_b200(self, x, out=None):
         # cv1 -> bottlenecks write the first half of the concat slab, cv2 the second half: no torch.cat
         srcs = None
+        if isinstance(x, ops.SPDView):
+            # space_to_depth -> 1x1 == 2x2 / stride-2 over the un-shuffled tensor: cv1 | cv2 read it through the im2col maps
+            c = self.cv1.conv
+            merged = (self._merged_cv12(x.src.device, spd=True) if isinstance(self.m, nn.Sequential) and c.kernel_size == (1, 1)
+                      and c.stride == (1, 1) and c.padding == (0, 0) and x.src.shape[1] % 16 == 0 else None)
+            if merged is not None:
+                n, _, h, w = x.shape
+                c_ = c.out_channels
+                slab = ops.empty_nhwc(n, 2 * c_, h, w, x.src.device)
+                first = slab[:, :c_]
+                ops.conv(x.src, merged[0], merged[1], out=slab)
+                if len(self.m) > 0:
+                    _run_chain(self.m, first, first)
+                return self.cv3.forward_b200(slab, out=out)
+            x = x.materialize()
         if isinstance(x, ops.VCat):
             # the input is a concat that was never written: cv1 | cv2 (1x1) walk its parts in their K loop
             c = self.cv1.conv
@@ -1265,7 +1287,10 @@ class space_to_depth(nn.Module):
 
     def forward(self, x):
         if kernel_path(self, x) and x.shape[1] % 8 == 0:
-            return ops.spd(_materialize(x))
+            x = _materialize(x)
+            if ops.SPD_FOLD and x.dim() == 4 and x.shape[1] % 16 == 0 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+                return ops.SPDView(ops.as_act(x))     # folded into a C3 consumer's cv1 | cv2, else materialised on demand
+            return ops.spd(x)
         x = _materialize(x)
         return torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)
 

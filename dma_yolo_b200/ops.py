@@ -342,13 +342,37 @@ class VCat(Up):
         return lo, hi, (tuple(lo_cols), tuple(hi_cols))
 
 
+SPD_FOLD = __import__('os').environ.get('DMAY_SPD_FOLD', '1') != '0'   # A/B switch: 0 = space_to_depth always runs its kernel
+
+
+class SPDView(Up):
+    """A space_to_depth (SPD-Conv pixel unshuffle, models/common.py:1451-1458) that has not been materialised.  A 1x1 layer over
+    its output IS a 2x2 / stride-2 convolution over its input -- y[co] = sum_{dy,dx,c} W[co, (dy + 2 dx) C + c] x[2h+dy, 2w+dx, c]
+    -- so C3's cv1 | cv2 read `src` through the im2col maps with re-laid weights and the 4C-channel tensor is never written;
+    every other consumer gets `materialize()` (dmay_spd)."""
+
+    def __init__(self, src: torch.Tensor):
+        self.src, self.log2f = src, 0
+        self._mat = None
+
+    @property
+    def shape(self):
+        n, c, h, w = self.src.shape
+        return torch.Size((n, 4 * c, h // 2, w // 2))
+
+    def materialize(self) -> torch.Tensor:
+        if self._mat is None:
+            self._mat = spd(self.src)
+        return self._mat
+
+
 def adconcat(xs, weights, out: torch.Tensor | None = None) -> torch.Tensor:
     """cat([w_i * x_i], 1); x_i may be an `Up` (read at reduced resolution)."""
     if not 2 <= len(xs) <= 3:
         raise DmayError("adconcat takes 2 or 3 inputs")
     srcs, ups = [], []
     for t in xs:
-        if isinstance(t, VCat):
+        if isinstance(t, (VCat, SPDView)):
             t = t.materialize()
         if isinstance(t, Up):
             srcs.append(as_act(t.src))
@@ -377,7 +401,7 @@ def adconcat(xs, weights, out: torch.Tensor | None = None) -> torch.Tensor:
 
 def concat(xs, out=None):
     """torch.cat(xs, 1) for 2..3 inputs (weights 1.0: an exact copy); longer lists are folded pairwise."""
-    xs = list(xs)
+    xs = [t.materialize() if isinstance(t, (VCat, SPDView)) else t for t in xs]
     while len(xs) > 3:
         xs = [adconcat(xs[:3], (1.0, 1.0, 1.0))] + xs[3:]
     if len(xs) == 1:
@@ -394,7 +418,7 @@ SPLIT_UP = __import__('os').environ.get('DMAY_SPLIT_UP', '0') == '1'
 
 def vcat(xs, weights):
     """Lazy cat([w_i * x_i], 1) when a 1x1 consumer could read the parts in place, else the materialised tensor."""
-    xs = [t.materialize() if isinstance(t, VCat) else t for t in xs]
+    xs = [t.materialize() if isinstance(t, (VCat, SPDView)) else t for t in xs]
     if VCAT and 2 <= len(xs) <= 3 and all(t.shape[1] % 64 == 0 for t in xs):
         return VCat(xs, weights)
     return adconcat(xs, weights) if len(xs) <= 3 else concat(xs)

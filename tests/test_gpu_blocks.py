@@ -261,3 +261,37 @@ def test_conv_pre_add_epilogue_matches_torch(cout, hw, up):
     assert_close(y.float().cpu(), ref, atol=1e-2, rtol=1e-2, what=f'pre-add epilogue cout={cout}')
     with pytest.raises(ops.DmayError):     # bf16 partial sums are not accepted
         ops.conv(ops.as_act(x.cuda()), pk, ops.ACT_SILU, pre=pre_d.bfloat16())
+
+
+@pytest.mark.parametrize('c,hw', [(64, (32, 48)), (128, (20, 20)), (16, (8, 8))])
+def test_c3_folds_space_to_depth_into_a_stride2_gemm(c, hw):
+    """space_to_depth -> C3 through the layer loop's dispatch: cv1 | cv2 (1x1 over 4C channels) run as ONE 2x2 / stride-2 GEMM
+    over the un-shuffled tensor (ops.SPDView; the 4C-channel tensor is never written) against the materialised form (dmay_spd,
+    then the 1x1 GEMM).  Same products, another summation order over K: 4e-3 in rel-L2, 1e-2 of the output scale."""
+    import dma_yolo_b200 as D
+    from dma_yolo_b200 import ops
+    from dma_yolo_b200.models import common as C
+    from dma_yolo_b200.models import yolo as Y
+    torch.manual_seed(5)
+    h, w = hw
+    x = ops.as_act(torch.randn(2, c, h, w).cuda())
+    spd = C.space_to_depth().cuda().eval()
+    c3 = C.C3(4 * c, 64, n=1).cuda().eval()
+    for m_ in c3.modules():
+        if isinstance(m_, torch.nn.BatchNorm2d):
+            m_.running_var.data.uniform_(0.5, 1.5)
+            m_.running_mean.data.normal_(0, 0.1)
+    run = Y.Model._run_layer
+    with torch.no_grad():
+        lazy = run(None, spd, x, True)
+        assert isinstance(lazy, ops.SPDView) and tuple(lazy.shape) == (2, 4 * c, h // 2, w // 2)
+        y_lazy = run(None, c3, lazy, True)
+        assert lazy._mat is None, 'space_to_depth was written although its consumer folds it'
+        mat = lazy.materialize()
+        ref = torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)
+        assert torch.equal(mat, ref)                      # the lazy object still materialises to the reference's layout
+        y_mat = run(None, c3, mat, True)
+    torch.cuda.synchronize()
+    a, b = y_lazy.float(), y_mat.float()
+    rel = float((a - b).norm() / b.norm())
+    assert rel < 4e-3 and float((a - b).abs().max()) <= 1e-2 * float(b.abs().max()), rel
