@@ -328,61 +328,62 @@ class C3(_PackMixin, nn.Module):
             cache['cv12' + sfx] = pk
         return pk, code
 
-    def forward_b200(self, x, out=None):
-        # cv1 -> bottlenecks write the first half of the concat slab, cv2 the second half: no torch.cat
-        srcs = None
+    def _cv12_slab(self, x):
+        """[cv1(x) | cv2(x)] as ONE GEMM into a fresh concat slab -> (slab, x) ; (None, x as a tensor) when cv1 / cv2 cannot be
+        merged.  x may be lazy: an `ops.SPDView` (space_to_depth -> 1x1 == 2x2 / stride-2 over the un-shuffled tensor: the
+        GEMM reads it through the im2col maps) or an `ops.VCat` (a concat that was never written: the K loop walks its parts,
+        BiFPN weights folded into the weight columns); both are materialised when the merged GEMM does not apply."""
+        c = self.cv1.conv
+        one_by_one = c.kernel_size == (1, 1) and c.stride == (1, 1) and c.padding == (0, 0)
         if isinstance(x, ops.SPDView):
-            # space_to_depth -> 1x1 == 2x2 / stride-2 over the un-shuffled tensor: cv1 | cv2 read it through the im2col maps
-            c = self.cv1.conv
-            merged = (self._merged_cv12(x.src.device, spd=True) if isinstance(self.m, nn.Sequential) and c.kernel_size == (1, 1)
-                      and c.stride == (1, 1) and c.padding == (0, 0) and x.src.shape[1] % 16 == 0 else None)
+            merged = self._merged_cv12(x.src.device, spd=True) if one_by_one and x.src.shape[1] % 16 == 0 else None
             if merged is not None:
                 n, _, h, w = x.shape
-                c_ = c.out_channels
-                slab = ops.empty_nhwc(n, 2 * c_, h, w, x.src.device)
-                first = slab[:, :c_]
+                slab = ops.empty_nhwc(n, 2 * c.out_channels, h, w, x.src.device)
                 ops.conv(x.src, merged[0], merged[1], out=slab)
-                if len(self.m) > 0:
-                    _run_chain(self.m, first, first)
-                return self.cv3.forward_b200(slab, out=out)
+                return slab, x
             x = x.materialize()
         if isinstance(x, ops.VCat):
-            # the input is a concat that was never written: cv1 | cv2 (1x1) walk its parts in their K loop
-            c = self.cv1.conv
-            if (isinstance(self.m, nn.Sequential) and c.kernel_size == (1, 1) and c.stride == (1, 1) and c.padding == (0, 0)
-                    and all(p.shape[1] % 64 == 0 for p in x.parts) and self._merged_cv12(x.src.device, x.colscale()) is not None):
-                srcs, vc = True, x
-            else:
-                x = x.materialize()
-        if srcs is None:
-            x = ops.as_act(x)
+            dev = x.src.device
+            if one_by_one and all(p.shape[1] % 64 == 0 for p in x.parts) and self._merged_cv12(dev, x.colscale()) is not None:
+                n, _, h, w = x.shape
+                slab = ops.empty_nhwc(n, 2 * c.out_channels, h, w, dev)
+                sp = x.split() if _act_code(self.cv1.act) == ACT_SILU else None
+                if sp is not None:
+                    # [Up(x0) | x1]: the x0 columns run at x0's own resolution into fp32 partial sums (a quarter of the pixels),
+                    # the main GEMM walks the same-resolution parts only and adds up(partial) to its accumulators
+                    lo, hi, (lo_cols, hi_cols) = sp
+                    p_lo = self._merged_cv12(dev, x.colscale(), lo_cols, True)[0]
+                    p_hi = self._merged_cv12(dev, x.colscale(), hi_cols, False)[0]
+                    part = ops.conv(lo if len(lo) > 1 else lo[0], p_lo, ACT_NONE, out_fp32=True)
+                    ops.conv(hi if len(hi) > 1 else hi[0], p_hi, ACT_SILU, out=slab, pre=part)
+                else:
+                    merged = self._merged_cv12(dev, x.colscale())
+                    ops.conv(x.sources(), merged[0], merged[1], out=slab)
+                return slab, x
+            x = x.materialize()
+        x = ops.as_act(x)
+        merged = self._merged_cv12(x.device)
+        if merged is None:
+            return None, x
         n, _, h, w = x.shape
-        dev = x.src.device if srcs is not None else x.device
+        slab = ops.empty_nhwc(n, 2 * c.out_channels, h, w, x.device)
+        ops.conv(x, merged[0], merged[1], out=slab)          # [cv1(x) | cv2(x)] in one launch
+        return slab, x
+
+    def forward_b200(self, x, out=None):
+        # cv1 -> bottlenecks write the first half of the concat slab, cv2 the second half: no torch.cat
         c_ = self.cv1.conv.out_channels
-        slab = ops.empty_nhwc(n, 2 * c_, h, w, dev)
+        if isinstance(self.m, nn.Sequential):
+            slab, x = self._cv12_slab(x)
+            if slab is not None:
+                if len(self.m) > 0:
+                    _run_chain(self.m, slab[:, :c_], slab[:, :c_])   # the last block overwrites cv1(x) in place
+                return self.cv3.forward_b200(slab, out=out)
+        x = ops.as_act(_materialize(x))
+        n, _, h, w = x.shape
+        slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
         first = slab[:, :c_]
-        if srcs is not None:
-            sp = vc.split() if _act_code(self.cv1.act) == ACT_SILU else None
-            if sp is not None:
-                # [Up(x0) | x1]: the x0 columns run at x0's own resolution into fp32 partial sums (a quarter of the pixels),
-                # the main GEMM walks the same-resolution parts only and adds up(partial) to its accumulators
-                lo, hi, (lo_cols, hi_cols) = sp
-                p_lo = self._merged_cv12(dev, vc.colscale(), lo_cols, True)[0]
-                p_hi = self._merged_cv12(dev, vc.colscale(), hi_cols, False)[0]
-                part = ops.conv(lo if len(lo) > 1 else lo[0], p_lo, ACT_NONE, out_fp32=True)
-                ops.conv(hi if len(hi) > 1 else hi[0], p_hi, ACT_SILU, out=slab, pre=part)
-            else:
-                merged = self._merged_cv12(dev, vc.colscale())
-                ops.conv(vc.sources(), merged[0], merged[1], out=slab)
-            if len(self.m) > 0:
-                _run_chain(self.m, first, first)
-            return self.cv3.forward_b200(slab, out=out)
-        merged = self._merged_cv12(x.device) if isinstance(self.m, nn.Sequential) else None
-        if merged is not None:
-            ops.conv(x, merged[0], merged[1], out=slab)          # [cv1(x) | cv2(x)] in one launch
-            if len(self.m) > 0:
-                _run_chain(self.m, first, first)                 # the last block overwrites cv1(x) in place
-            return self.cv3.forward_b200(slab, out=out)
         if isinstance(self.m, nn.Sequential) and len(self.m) > 0:
             _run_chain(self.m, self.cv1.forward_b200(x), first)
         elif isinstance(self.m, nn.Sequential):
@@ -940,15 +941,13 @@ class C3STR(C3):
         self.m = SwinTransformerBlock(c_, c_, c_ // 32, n)
 
     def forward_b200(self, x, out=None):
-        x = ops.as_act(x)
-        n, _, h, w = x.shape
         c_ = self.cv1.conv.out_channels
-        slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
-        merged = self._merged_cv12(x.device)
-        if merged is not None:
-            ops.conv(x, merged[0], merged[1], out=slab)
+        slab, x = self._cv12_slab(x)                  # x may be a lazy concat / space_to_depth (see C3._cv12_slab)
+        if slab is not None:
             t = slab[:, :c_]
         else:
+            n, _, h, w = x.shape
+            slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
             t = self.cv1.forward_b200(x)
             self.cv2.forward_b200(x, out=slab[:, c_:])
         self.m.forward_b200(t, out=slab[:, :c_])      # the last Swin layer writes the first half of the concat slab
@@ -1129,17 +1128,16 @@ class C3HB(_PackMixin, nn.Module):
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
 
     _merged_cv12 = C3._merged_cv12
+    _cv12_slab = C3._cv12_slab
 
     def forward_b200(self, x, out=None):
-        x = ops.as_act(x)
-        n, _, h, w = x.shape
         c_ = self.cv1.conv.out_channels
-        slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
-        merged = self._merged_cv12(x.device)
-        if merged is not None:
-            ops.conv(x, merged[0], merged[1], out=slab)
+        slab, x = self._cv12_slab(x)                  # x may be a lazy concat / space_to_depth (see C3._cv12_slab)
+        if slab is not None:
             t = slab[:, :c_]
         else:
+            n, _, h, w = x.shape
+            slab = ops.empty_nhwc(n, 2 * c_, h, w, x.device)
             t = self.cv1.forward_b200(x)
             self.cv2.forward_b200(x, out=slab[:, c_:])
         _run_chain(self.m, t, slab[:, :c_])

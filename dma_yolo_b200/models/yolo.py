@@ -239,10 +239,11 @@ class Model(nn.Module):
             fast = kernel_path(self, x)
         if fast and isinstance(m, nn.Upsample):
             return self._upsample_b200(m, x)
-        if fast and isinstance(x, ops.VCat) and getattr(type(m), 'forward_b200', None) in (_common.C3.forward_b200,
-                                                                                            _common.Conv.forward_b200):
+        fb = getattr(type(m), 'forward_b200', None)
+        cv12 = (_common.C3.forward_b200, _common.C3STR.forward_b200, _common.C3HB.forward_b200)   # start with C3._cv12_slab
+        if fast and isinstance(x, ops.VCat) and fb in cv12 + (_common.Conv.forward_b200,):
             return m(x)      # a 1x1 consumer reads the parts of the concat in place (ops.VCat)
-        if fast and isinstance(x, ops.SPDView) and getattr(type(m), 'forward_b200', None) is _common.C3.forward_b200:
+        if fast and isinstance(x, ops.SPDView) and fb in cv12:
             return m(x)      # space_to_depth + cv1 | cv2 as one 2x2 / stride-2 GEMM (ops.SPDView)
         if fast and not isinstance(m, (_common.AdConcat2, _common.AdConcat3, _common.Concat)):
             x = _materialize(x)
