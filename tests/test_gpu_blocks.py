@@ -295,3 +295,30 @@ def test_c3_folds_space_to_depth_into_a_stride2_gemm(c, hw):
     a, b = y_lazy.float(), y_mat.float()
     rel = float((a - b).norm() / b.norm())
     assert rel < 4e-3 and float((a - b).abs().max()) <= 1e-2 * float(b.abs().max()), rel
+
+
+def test_conv1x1_reads_a_lazy_concat_and_others_materialise_it():
+    """A 1x1 `Conv` after AdConcat reads the parts in place (folded weights); a 3x3 `Conv` gets the written concat (once)."""
+    from dma_yolo_b200 import ops
+    from dma_yolo_b200.models import common as C
+    from dma_yolo_b200.models import yolo as Y
+    torch.manual_seed(9)
+    parts = _vcat_parts('three', seed=3)
+    cat = C.AdConcat3(1).cuda().eval()
+    cat.w.data = torch.tensor([1.1, 0.6, 0.9]).cuda()
+    cin = sum(p.shape[1] for p in parts)
+    run = Y.Model._run_layer
+    with torch.no_grad():
+        for k in (1, 3):
+            conv = C.Conv(cin, 96, k, 1).cuda().eval()
+            conv.bn.running_var.data.uniform_(0.5, 1.5)
+            lazy = cat(parts)
+            y_lazy = run(None, conv, lazy, True)
+            assert (lazy._mat is None) == (k == 1)
+            y_mat = run(None, conv, ops.adconcat(parts, cat._norm_weights()), True)
+            torch.cuda.synchronize()
+            a, b = y_lazy.float(), y_mat.float()
+            if k == 3:
+                assert torch.equal(a, b)
+            else:
+                assert float((a - b).norm() / b.norm()) < 4e-3
