@@ -286,6 +286,7 @@ struct FuseArgs {
   long long capacity;
   int pitch;           // floats between the rows of two anchors inside a pixel's channel vector (5 + nc, or padded to 4n)
   const int* bin_thr;  // dense multi-label source: per-image score-key bin threshold of the pre-selection (nullptr: none)
+  int* hist;           // HIST instantiation of the rows kernel: caller-zeroed [N][2048] score-key histogram (see dense_hist_kernel)
   unsigned long long* img_ctr;   // reserve mode: one reservation counter per image (nullptr: one counter for the batch)
   long long region;              // ... and the size of an image's region of the temporary buffers (capacity / N)
 };
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
 #define DMAY_FILTER_GROUPED_LDS 1
 #endif
 constexpr int kRowsThreads = DMAY_FILTER_ROWS;   // rows (pixels of one anchor) per tile; threads per CTA = kRowsThreads * TPR
+constexpr int kHistBins = 2048;     // score-key bins of the top-max_nms pre-selection (top 11 bits of ~bits(conf))
 constexpr int kRowsWide = 128;      // tile of the unpadded / dense layouts
 constexpr int kRowsMaxNc = 96;
 constexpr bool kAnchorFastest = true;
@@ -553,7 +555,10 @@ constexpr bool kAnchorFastest = true;
 // TPR = 2 (KIND 1) two adjacent threads share a row: thread 2r scans the 16-byte chunks [1, 13), thread 2r + 1 the rest
 // (an offset of 12 chunks keeps the eight LDS.128 of a quarter-warp on distinct banks), twice the warps per staged byte.
 // Candidate order is unchanged: the CTA scan runs over (row, half) in thread order, and the lower half holds the lower classes.
-template <bool RESERVE, int KIND, int TPR = 1, int ROWS = kRowsThreads>
+// HIST (KIND 1, multi-label): no candidate is written -- the exact confidences of the passing (row, class) pairs are binned
+// by the top 11 bits of their score key into fa.hist[img][2048] (per-CTA shared histogram, one global atomic per non-empty
+// bin): first pass of the top-max_nms pre-selection for candidate-rich Detect logits (dmay_nms_fused_prethreshold).
+template <bool RESERVE, int KIND, int TPR = 1, int ROWS = kRowsThreads, bool HIST = false>
 __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
                                                                          const unsigned char* __restrict__ class_mask,
                                                                          unsigned* __restrict__ ticket,
@@ -594,6 +599,9 @@ __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __g
   const int srow = KIND == 1 ? fa.pitch + 4 : no;           // shared-memory words per row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float thr = fa.thr;
+  int* hist_s = reinterpret_cast<int*>(tile + ROWS * srow);   // HIST: 2048 bins behind the staged tile
+  if (HIST)
+    for (int i = threadIdx.x; i < kHistBins; i += kThreads) hist_s[i] = 0;
   {
     const float* gsrc = fa.logits[l] + ((long long)img * npix + p0) * ld + a * pitch;
     const uint32_t tile_sm = (uint32_t)__cvta_generic_to_shared(tile);
@@ -650,7 +658,7 @@ __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __g
     asm volatile("cp.async.wait_all;" ::: "memory");
   }
 #if DMAY_FILTER_WARP_PRIVATE
-  if (KIND == 1 && TPR == 1) __syncwarp();
+  if (KIND == 1 && TPR == 1 && !HIST) __syncwarp();
   else __syncthreads();
 #else
   __syncthreads();
@@ -695,6 +703,7 @@ __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __g
           float t_lo = -INFINITY;
           if (q > 0.f) t_lo = q < 1.f ? fminf(__logf(q / (1.0f - q)) - 0.02f, 10.0f) : 10.0f;
           if (KIND == 1) {
+            const unsigned bt1 = (!HIST && fa.bin_thr != nullptr) ? (unsigned)fa.bin_thr[img] : 0xFFFFFFFFu;
             // four logits per LDS.128; chunk k holds words 4k .. 4k+3 of the row, class c sits at word 5 + c
             const float4* s4 = reinterpret_cast<const float4*>(s);
             const int nchunk = (no + 3) >> 2;
@@ -750,9 +759,14 @@ __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __g
                 mk &= mk - 1;
                 const float conf = __fmul_rn(sigmoid_dec(s[5 + c]), obj);
                 if (conf > thr && (class_mask == nullptr || class_mask[c])) {
-                  s[5 + c] = conf;
-                  pm[w] |= 1u << (c & 31);
-                  ++cnt;
+                  const unsigned kbin = (~__float_as_uint(conf)) >> 21;
+                  if (HIST) {
+                    atomicAdd(&hist_s[kbin], 1);
+                  } else if (kbin <= bt1) {   // pre-selection (when given): only what the top-max_nms selection can keep
+                    s[5 + c] = conf;
+                    pm[w] |= 1u << (c & 31);
+                    ++cnt;
+                  }
                 }
               }
             }
@@ -837,6 +851,12 @@ __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __g
     y1 = __fsub_rn(y, hh);
     x2 = __fadd_rn(x, hw);
     y2 = __fadd_rn(y, hh);
+  }
+  if (HIST) {   // flush the tile's histogram; nothing else to do
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistBins; i += kThreads)
+      if (hist_s[i]) atomicAdd(&fa.hist[(long long)img * kHistBins + i], hist_s[i]);
+    return;
   }
   // ---- exclusive scan of the row counts over the CTA, then this tile's place among all tiles (warp 0) ----
   int inc = cnt;
@@ -1259,7 +1279,6 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_rows_persistent_ker
 // candidates whose key bin is <= b*.  Everything the exact top-K selection can keep (keys <= the K-th key, ties included)
 // has a bin <= b*, and the survivors keep their candidate order, so the selection / sort / greedy stages see a superset of
 // the top K in the same relative order and return the same detections bit for bit.
-constexpr int kHistBins = 2048;
 __global__ void __launch_bounds__(256) dense_hist_kernel(const float* __restrict__ pred, const unsigned char* __restrict__ class_mask,
                                                          int* __restrict__ hist, int R, int nc, float thr, int rows_per_cta) {
   __shared__ int h[kHistBins];
@@ -1910,7 +1929,7 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
   fa.thr = p->conf_thres;
   fa.capacity = p->capacity;
   fa.pitch = pitch;
-  fa.bin_thr = p->dense ? (const int*)p->bin_thr : nullptr;
+  fa.bin_thr = (p->dense || padded) ? (const int*)p->bin_thr : nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned* ticket = (unsigned*)p->ws;
   unsigned long long* status = (unsigned long long*)((char*)p->ws + 16);
@@ -1977,6 +1996,51 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
                                                              (float*)p->cand);
   }
   img_counts_kernel<<<(p->N + 255) / 256, 256, 0, s>>>((const long long*)p->img_offsets, (int*)p->img_counts, p->N);
+  return finish_launch(2);
+}
+
+// Pre-selection for candidate-rich Detect LOGITS (padded anchor rows, multi-label): histogram pass of the rows kernel over the
+// same tiles, then the per-image bin threshold.  The following dmay_nms_filter_fused (same parameters + bin_thr) writes only
+// candidates whose key bin is <= bin_thr[img] -- a superset of the top K, ties included, in candidate order.
+int dmay_nms_fused_prethreshold(const dmay_filter_fused_params* p, dmay_stream_t stream) {
+  if (!p || p->N <= 0 || p->nc <= 0 || p->levels <= 0 || p->levels > 5) return DMAY_EINVAL;
+  if (!p->lv_meta_host || !p->lv_logits0 || !p->hist || !p->bin_thr || p->prethr_k <= 0) return DMAY_EINVAL;
+  if (p->dense || !p->multi_label || p->nc > kRowsMaxNc) return DMAY_EUNSUPPORTED;
+  FuseArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  const void* lg[5] = {p->lv_logits0, p->lv_logits1, p->lv_logits2, p->lv_logits3, p->lv_logits4};
+  const LevelMeta* hm = (const LevelMeta*)p->lv_meta_host;
+  const int no = 5 + p->nc, pitch = p->row_pitch;
+  if (pitch <= no || (pitch & 3)) return DMAY_EUNSUPPORTED;   // the padded-row layout only
+  long long rows = 0;
+  for (int l = 0; l < p->levels; ++l) {
+    const LevelMeta& m = hm[l];
+    if (!lg[l] || (reinterpret_cast<uintptr_t>(lg[l]) & 15u) || (m.ld & 3)) return DMAY_EUNSUPPORTED;
+    if (m.na <= 0 || m.na > 5 || m.ny <= 0 || m.nx <= 0 || m.ld < m.na * pitch || m.row0 != rows) return DMAY_EINVAL;
+    fa.logits[l] = (const float*)lg[l];
+    fa.meta[l] = m;
+    rows += (long long)m.na * m.ny * m.nx;
+  }
+  const int srow = pitch + 4;
+  const long long tiles = (long long)p->N * fused_tiles_per_image(hm, p->levels, &fa, kRowsThreads);
+  if (tiles > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
+  const size_t smem = (size_t)kRowsThreads * srow * sizeof(float) + kHistBins * sizeof(int);
+  if (smem > 200 * 1024) return DMAY_EUNSUPPORTED;
+  fa.levels = p->levels;
+  fa.nc = p->nc;
+  fa.multi_label = 1;
+  fa.N = p->N;
+  fa.thr = p->conf_thres;
+  fa.pitch = pitch;
+  fa.hist = (int*)p->hist;
+  cudaStream_t s = (cudaStream_t)stream;
+  auto kern = filter_fused_rows_kernel<true, 1, 1, kRowsThreads, true>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<(int)tiles, kRowsThreads, smem, s>>>(fa, (const unsigned char*)p->class_mask, nullptr, nullptr, nullptr, nullptr, nullptr);
+  hist_threshold_kernel<<<p->N, 1024, 0, s>>>((const int*)p->hist, (int*)p->bin_thr, p->prethr_k);
   return finish_launch(2);
 }
 

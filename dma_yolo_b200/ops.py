@@ -773,7 +773,8 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
     s = torch.cuda.current_stream(dev).cuda_stream
     multi_label = bool(multi_label) and nc > 1
     buf, out, out_counts = _det_buffers(n, max_det, dev)
-    keys, cand, img_counts, img_offsets, offs_host, total = _fused_candidates(levels, na, nc, conf_thres, multi_label, classes)
+    keys, cand, img_counts, img_offsets, offs_host, total = _fused_candidates(levels, na, nc, conf_thres, multi_label, classes,
+                                                                             max_nms=max_nms)
     if total == 0:
         return out, out_counts, buf
     idx, cnts, offs = _order_candidates(keys, offs_host, n, img_counts, img_offsets, max_nms, dev, s)
@@ -784,6 +785,10 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
 
 
 PRETHRESHOLD = __import__('os').environ.get('DMAY_PRETHRESHOLD', '1') != '0'
+# Detect-logits source: the histogram pre-selection costs one more pass over the logits, so it is switched on per (shape, threshold)
+# once a call has seen an image with more than this many times max_nms candidates (cfg-4a / cfg-4b: 1.7 M per image), 0 = never
+FUSED_PRETHR_RATIO = float(__import__('os').environ.get('DMAY_FUSED_PRETHR_RATIO', '4'))
+_FUSED_PRETHR = {}
 PER_IMAGE_REGIONS = __import__('os').environ.get('DMAY_FILTER_REGIONS', '1') != '0'   # one reservation counter per image
 
 
@@ -815,6 +820,19 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=Fa
         call("dmay_nms_dense_prethreshold", s, **pf)
     img_counts = torch.empty(n, device=dev, dtype=torch.int32)
     img_offsets = torch.empty(n + 1, device=dev, dtype=torch.int64)
+    fused_pre = (not dense and multi_label and max_nms > 0 and PRETHRESHOLD and _FUSED_PRETHR.get(key, False)
+                 and levels[0].pitch > 5 + nc and nc <= 96)
+    if fused_pre:
+        hist = torch.zeros((n, 2048), device=dev, dtype=torch.int32)
+        bin_thr = torch.empty(n, device=dev, dtype=torch.int32)
+        pf = dict(lv_meta_host=ctypes.addressof(meta_host), N=n, nc=nc, levels=len(levels), multi_label=1,
+                  conf_thres=float(conf_thres), row_pitch=levels[0].pitch, hist=hist.data_ptr(), bin_thr=bin_thr.data_ptr(),
+                  prethr_k=int(max_nms))
+        for i, lv in enumerate(levels):
+            pf[f"lv_logits{i}"] = lv.logits.data_ptr()
+        if cm is not None:
+            pf["class_mask"] = cm.data_ptr()
+        call("dmay_nms_fused_prethreshold", s, **pf)
     while True:
         ws = torch.zeros(ws_bytes // 8 + 1, device=dev, dtype=torch.int64)   # ticket + tile status words (zeroed)
         keys = torch.empty(capacity, device=dev, dtype=torch.int64)
@@ -850,6 +868,10 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=Fa
         # undersized guess: every candidate was counted, repeat once
         capacity = max(total + total // 8, (n * (maxc + maxc // 8)) if regions else 0) + 4096
     _FUSED_CAP[key] = max(total + total // 4 + 4096, (n * (maxc + maxc // 4) + 4096) if regions else 0, _FUSED_CAP.get(key, 0) // 2)
+    if (not dense and multi_label and max_nms > 0 and FUSED_PRETHR_RATIO > 0 and not fused_pre
+            and maxc > FUSED_PRETHR_RATIO * max_nms):
+        _FUSED_PRETHR[key] = True     # from the next call on: only what the top-max_nms selection can keep is written
+        _FUSED_CAP[key] = n * 2 * int(max_nms) + 4096
     return keys, cand, img_counts, img_offsets, offs_host, total
 
 

@@ -59,13 +59,14 @@ def xywh2xyxy(x: np.ndarray) -> np.ndarray:
 
 
 def non_max_suppression(prediction: np.ndarray, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
-                        multi_label=False, labels=(), max_det=300):
+                        multi_label=False, labels=(), max_det=300, max_nms=30000):
     """utils/general.py:633-725 on a [B, R, 5+nc] fp32 array -> list of (n,6) fp32 arrays.
     Deviations (documented): no wall-clock time_limit; the >max_nms truncation uses a
     STABLE descending sort (the reference's argsort is unstable, i.e. implementation-defined on ties)."""
     prediction = np.asarray(prediction, dtype=f32)
     nc = prediction.shape[2] - 5
-    max_wh, max_nms = 4096, 30000
+    max_wh = 4096          # max_nms: 30000 in the reference (utils/general.py:656); a parameter here so that tests can
+                           # exercise the truncation path on small inputs
     multi_label = bool(multi_label) and nc > 1
     thr = f32(conf_thres) if False else conf_thres  # comparisons: fp32 tensor vs python scalar -> fp32 compare
     out = []

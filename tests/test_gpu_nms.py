@@ -422,3 +422,37 @@ def test_val_match_device_equals_host_process_batch(single_cls):
         assert torch.equal(cor_d[b, :n], ref), b
         assert not cor_d[b, n:].any()
     assert cor_d.any()
+
+
+@pytest.mark.parametrize('maker,step', [('continuous', 0.0), ('quantised', 0.5)], ids=['continuous', 'massive-ties'])
+def test_fused_prethreshold_for_candidate_rich_logits_is_exact(maker, step):
+    """Detect logits (padded rows, multi-label) with many times max_nms candidates per image: after the first call has seen
+    that, the histogram pre-selection (dmay_nms_fused_prethreshold) makes the filter write only what the top-max_nms
+    selection can keep.  Detections must be IDENTICAL to the call without it and to the oracle -- also with massively tied
+    scores (every candidate of the threshold bin is kept) and with a class filter."""
+    from dma_yolo_b200 import ops
+    nc = 10
+    shapes = [(40, 24), (20, 12), (10, 6)]
+    if maker == 'continuous':
+        levels, na, no = _continuous_levels(3, nc, shapes, seed=31, scale=2.0)
+    else:
+        levels, na, no = _quantised_levels(3, nc, shapes, seed=32, step=step)
+    levels[0].logits[2] -= 9.0          # third image: (almost) no candidates on its largest level
+    padded = _pad_levels(levels, na, no)
+    dense = ops.detect_decode(levels, na, no)
+    for extra in (dict(), dict(classes=[1, 4, 6])):
+        kw = dict(multi_label=True, max_det=300, max_nms=400, **extra)
+        ops._FUSED_PRETHR.clear()
+        ops._FUSED_CAP.clear()
+        a, ac = ops.nms_batched(None, 0.001, 0.6, levels=padded, na=na, nc=nc, **kw)       # plain: sees > 4 x max_nms candidates
+        assert any(ops._FUSED_PRETHR.values()), 'the candidate-rich case was not detected'
+        n0 = ops.launch_count() if hasattr(ops, 'launch_count') else None
+        b, bc = ops.nms_batched(None, 0.001, 0.6, levels=padded, na=na, nc=nc, **kw)       # with the pre-selection
+        c, cc = ops.nms_batched(None, 0.001, 0.6, levels=padded, na=na, nc=nc, **kw)       # ... and with its own capacity guess
+        assert torch.equal(ac, bc) and torch.equal(a, b) and torch.equal(ac, cc) and torch.equal(a, c)
+        ref = ON.non_max_suppression(dense.cpu().numpy(), 0.001, 0.6, multi_label=True, max_det=300, max_nms=400,
+                                     **({'classes': extra['classes']} if extra else {}))
+        for i, r in enumerate(ref):
+            assert np.array_equal(b[i, :int(bc[i])].cpu().numpy(), r), i
+    ops._FUSED_PRETHR.clear()
+    ops._FUSED_CAP.clear()
