@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 #include <cstring>
 
 namespace dmay {
@@ -1385,6 +1387,30 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const int* __restrict__
   }
 }
 
+// Multi-CTA form of the scan above: CUB's single-pass decoupled look-back scan over the per-tile counts (int -> 64-bit offsets),
+// then the image boundaries.  The one-CTA kernel is 24 us for the 25.7 k tiles of cfg-2 and 264 us for the 278 k of cfg-4b.
+struct TileCntToLL {
+  __host__ __device__ __forceinline__ long long operator()(const int& v) const { return (long long)v; }
+};
+typedef cub::TransformInputIterator<long long, TileCntToLL, const int*> TileCntIter;
+static size_t tile_scan_temp_bytes(long long ntiles) {
+  size_t bytes = 0;
+  TileCntIter it((const int*)nullptr, TileCntToLL());
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, (long long*)nullptr, (int)ntiles, (cudaStream_t)0);
+  return (bytes + 255) & ~(size_t)255;
+}
+__global__ void __launch_bounds__(256) tile_img_offsets_kernel(const long long* __restrict__ tile_off, const int* __restrict__ tile_cnt,
+                                                               long long* __restrict__ img_offsets, int* __restrict__ img_counts,
+                                                               long long ntiles, int tiles_img, int N) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const long long a = tile_off[(long long)i * tiles_img];
+  const long long b = i + 1 < N ? tile_off[(long long)(i + 1) * tiles_img] : tile_off[ntiles - 1] + tile_cnt[ntiles - 1];
+  img_offsets[i] = a;
+  img_counts[i] = (int)(b - a);
+  if (i == N - 1) img_offsets[N] = b;
+}
+
 // move every tile's run from its reserved place in the temporary buffers to its ordered place
 __global__ void __launch_bounds__(128) tile_gather_kernel(const long long* __restrict__ tile_base, const int* __restrict__ tile_cnt,
                                                           const long long* __restrict__ tile_off,
@@ -1880,7 +1906,9 @@ static long long fused_tiles_per_image(const LevelMeta* hm, int levels, FuseArgs
 
 long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N) {
   if (!lv_meta_host || levels <= 0 || levels > 5 || N <= 0) return DMAY_EINVAL;
-  return 16 + 24 * N * fused_tiles_per_image((const LevelMeta*)lv_meta_host, levels, nullptr) + 8LL * N + 8;   // status words, or tile base / count / offset; per-image reservation counters
+  const long long tiles = (long long)N * fused_tiles_per_image((const LevelMeta*)lv_meta_host, levels, nullptr);
+  // status words, or tile base / count / offset; per-image reservation counters; temporary storage of the multi-CTA tile scan
+  return 16 + 24 * tiles + 8LL * N + 8 + 256 + (long long)tile_scan_temp_bytes(tiles);
 }
 
 int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t stream) {
@@ -1977,8 +2005,21 @@ int dmay_nms_filter_fused(const dmay_filter_fused_params* p, dmay_stream_t strea
       kern<<<(int)tiles, P * tpr, smem, s>>>(fa, (const unsigned char*)p->class_mask, ticket, status, (long long*)p->img_offsets,
                                                         (unsigned long long*)p->keys_tmp, (float*)p->cand_tmp);
       }
-      tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
-                                          (int)(tiles / p->N), p->N);
+      // scan of the per-tile counts: CUB's multi-CTA scan when the workspace holds its temporary storage, else one CTA
+      const long long scan_off = (ctr_off + 8LL * p->N + 8 + 255) & ~255LL;
+      size_t scan_bytes = tile_scan_temp_bytes(tiles);
+      static const bool one_cta_scan = [] { const char* e = getenv("DMAY_TILE_SCAN_CUB"); return e && e[0] == '0'; }();
+      if (!one_cta_scan && tiles >= 4096 && p->ws_bytes >= scan_off + (long long)scan_bytes &&
+          ((reinterpret_cast<uintptr_t>(p->ws) + scan_off) & 255) == 0) {
+        TileCntIter it((const int*)tile_cnt, TileCntToLL());
+        cudaError_t e = cub::DeviceScan::ExclusiveSum((char*)p->ws + scan_off, scan_bytes, it, tile_off, (int)tiles, s);
+        if (e != cudaSuccess) return (int)e;
+        tile_img_offsets_kernel<<<(p->N + 255) / 256, 256, 0, s>>>(tile_off, tile_cnt, (long long*)p->img_offsets, (int*)p->img_counts,
+                                                                   tiles, (int)(tiles / p->N), p->N);
+      } else {
+        tile_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tile_off, (long long*)p->img_offsets, (int*)p->img_counts, tiles,
+                                            (int)(tiles / p->N), p->N);
+      }
       tile_gather_kernel<<<(int)tiles, 128, 0, s>>>(tile_base, tile_cnt, tile_off, (const unsigned long long*)p->keys_tmp,
                                                     (const float*)p->cand_tmp, (unsigned long long*)p->keys, (float*)p->cand,
                                                     p->capacity);

@@ -786,7 +786,8 @@ def _nms_fused(levels, na, nc, conf_thres, iou_thres, classes, agnostic, multi_l
 
 PRETHRESHOLD = __import__('os').environ.get('DMAY_PRETHRESHOLD', '1') != '0'
 # Detect-logits source: the histogram pre-selection costs one more pass over the logits, so it is switched on per (shape, threshold)
-# once a call has seen an image with more than this many times max_nms candidates (cfg-4a / cfg-4b: 1.7 M per image), 0 = never
+# once a call has seen more than this many times max_nms candidates per image ON AVERAGE (cfg-4a / cfg-4b: 1.7 M per image; cfg-2
+# has single images above 120 k but pays 0.11 ms per step for the extra pass: same box 12.50 vs 12.62 ms), 0 = never
 FUSED_PRETHR_RATIO = float(__import__('os').environ.get('DMAY_FUSED_PRETHR_RATIO', '4'))
 _FUSED_PRETHR = {}
 PER_IMAGE_REGIONS = __import__('os').environ.get('DMAY_FILTER_REGIONS', '1') != '0'   # one reservation counter per image
@@ -869,7 +870,7 @@ def _fused_candidates(levels, na, nc, conf_thres, multi_label, classes, dense=Fa
         capacity = max(total + total // 8, (n * (maxc + maxc // 8)) if regions else 0) + 4096
     _FUSED_CAP[key] = max(total + total // 4 + 4096, (n * (maxc + maxc // 4) + 4096) if regions else 0, _FUSED_CAP.get(key, 0) // 2)
     if (not dense and multi_label and max_nms > 0 and FUSED_PRETHR_RATIO > 0 and not fused_pre
-            and maxc > FUSED_PRETHR_RATIO * max_nms):
+            and total > FUSED_PRETHR_RATIO * max_nms * n):
         _FUSED_PRETHR[key] = True     # from the next call on: only what the top-max_nms selection can keep is written
         _FUSED_CAP[key] = n * 2 * int(max_nms) + 4096
     return keys, cand, img_counts, img_offsets, offs_host, total
