@@ -536,7 +536,15 @@ __global__ void __launch_bounds__(kFuseThreads) filter_fused_kernel(const __grid
 #define DMAY_FILTER_GROUPED_LDS 1
 #endif
 constexpr int kRowsThreads = DMAY_FILTER_ROWS;   // rows (pixels of one anchor) per tile; threads per CTA = kRowsThreads * TPR
-constexpr int kHistBins = 2048;     // score-key bins of the top-max_nms pre-selection (top 11 bits of ~bits(conf))
+constexpr int kHistBins = 2048;     // score-key bins of the top-max_nms pre-selection
+// Bin of a confidence: monotone (non-decreasing) in the sort key ~bits(conf), i.e. better scores -> lower bins.  The key's top 15
+// bits (sign, exponent, 6 mantissa bits) minus those of conf = 1.0, clamped: confidences in (2^-21, 1] spread over 64 bins per binade
+// (~640 bins for a 0.001 threshold).  The first form -- the top 11 bits of the key, 4 bins per binade -- put cfg-4b's 55 M candidates
+// into ~40 bins: shared-memory atomics serialised on them, and the threshold bin alone held several times max_nms.
+__device__ __forceinline__ unsigned key_bin(float conf) {
+  const unsigned k = (~__float_as_uint(conf)) >> 17, base = (~0x3F800000u) >> 17;
+  return min(k > base ? k - base : 0u, (unsigned)(kHistBins - 1));
+}
 constexpr int kRowsWide = 128;      // tile of the unpadded / dense layouts
 constexpr int kRowsMaxNc = 96;
 constexpr bool kAnchorFastest = true;
@@ -558,7 +566,7 @@ constexpr bool kAnchorFastest = true;
 // (an offset of 12 chunks keeps the eight LDS.128 of a quarter-warp on distinct banks), twice the warps per staged byte.
 // Candidate order is unchanged: the CTA scan runs over (row, half) in thread order, and the lower half holds the lower classes.
 // HIST (KIND 1, multi-label): no candidate is written -- the exact confidences of the passing (row, class) pairs are binned
-// by the top 11 bits of their score key into fa.hist[img][2048] (per-CTA shared histogram, one global atomic per non-empty
+// by key_bin() of their score key into fa.hist[img][2048] (per-CTA shared histogram, one global atomic per non-empty
 // bin): first pass of the top-max_nms pre-selection for candidate-rich Detect logits (dmay_nms_fused_prethreshold).
 template <bool RESERVE, int KIND, int TPR = 1, int ROWS = kRowsThreads, bool HIST = false>
 __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __grid_constant__ FuseArgs fa,
@@ -691,7 +699,7 @@ __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __g
 #pragma unroll 8
             for (int cc = 0; cc < cend; ++cc) {
               const float conf = __fmul_rn(sc[cc], obj);
-              if (conf > thr && ((~__float_as_uint(conf)) >> 21) <= bt && (class_mask == nullptr || class_mask[w * 32 + cc])) {
+              if (conf > thr && key_bin(conf) <= bt && (class_mask == nullptr || class_mask[w * 32 + cc])) {
                 sc[cc] = conf;
                 mk |= 1u << cc;
                 ++cnt;
@@ -761,7 +769,7 @@ __global__ void __launch_bounds__(ROWS * TPR) filter_fused_rows_kernel(const __g
                 mk &= mk - 1;
                 const float conf = __fmul_rn(sigmoid_dec(s[5 + c]), obj);
                 if (conf > thr && (class_mask == nullptr || class_mask[c])) {
-                  const unsigned kbin = (~__float_as_uint(conf)) >> 21;
+                  const unsigned kbin = key_bin(conf);
                   if (HIST) {
                     atomicAdd(&hist_s[kbin], 1);
                   } else if (kbin <= bt1) {   // pre-selection (when given): only what the top-max_nms selection can keep
@@ -1066,7 +1074,7 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_rows_persistent_ker
 #pragma unroll 8
             for (int cc = 0; cc < cend; ++cc) {
               const float conf = __fmul_rn(sc[cc], obj);
-              if (conf > thr && ((~__float_as_uint(conf)) >> 21) <= bt && (class_mask == nullptr || class_mask[w * 32 + cc])) {
+              if (conf > thr && key_bin(conf) <= bt && (class_mask == nullptr || class_mask[w * 32 + cc])) {
                 sc[cc] = conf;
                 mk |= 1u << cc;
                 ++cnt;
@@ -1276,7 +1284,7 @@ __global__ void __launch_bounds__(kRowsThreads * TPR) filter_rows_persistent_ker
 // utils/general.py:702-703 keeps only the max_nms = 30000 best candidates of an image.  A dense multi-label prediction can
 // expand to 10x that (BASELINE cfg-5: 25,200 rows x 10 classes = 252 k candidates per image, 2 GB of candidate records per
 // batch of 256 for 0.39 GB of input), and seven eighths of what the filter writes is thrown away by the top-K selection.
-// Two cheap passes over the INPUT avoid that: a histogram of the top 11 bits of every candidate's score key per image
+// Two cheap passes over the INPUT avoid that: a histogram of key_bin() of every candidate's score key per image
 // (dense_hist_kernel), the bin b* that contains the K-th best key (hist_threshold_kernel), and a filter that only writes
 // candidates whose key bin is <= b*.  Everything the exact top-K selection can keep (keys <= the K-th key, ties included)
 // has a bin <= b*, and the survivors keep their candidate order, so the selection / sort / greedy stages see a superset of
@@ -1295,7 +1303,7 @@ __global__ void __launch_bounds__(256) dense_hist_kernel(const float* __restrict
     if (!(obj > thr)) continue;
     for (int c = 0; c < nc; ++c) {
       const float conf = __fmul_rn(row[5 + c], obj);
-      if (conf > thr && (class_mask == nullptr || class_mask[c])) atomicAdd(&h[(~__float_as_uint(conf)) >> 21], 1);
+      if (conf > thr && (class_mask == nullptr || class_mask[c])) atomicAdd(&h[key_bin(conf)], 1);
     }
   }
   __syncthreads();

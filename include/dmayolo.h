@@ -489,14 +489,14 @@ typedef struct dmay_filter_fused_params {
 long long dmay_nms_filter_fused_ws(const void* lv_meta_host, int levels, int N);
 /* Pre-selection for candidate-rich Detect logits (padded anchor rows, multi_label): utils/general.py:702-703 keeps the max_nms
  * best candidates of an image, a saturated head yields many times that (cfg-4a / cfg-4b at 0.001: 1.7 M per image).  One more pass
- * over the logits bins every candidate's exact confidence by the top 11 bits of its score key (hist: caller-ZEROED i32 [N, 2048])
+ * over the logits bins every candidate's exact confidence by a monotone 2048-bin function of its score key (64 bins per binade below 1.0; hist: caller-ZEROED i32 [N, 2048])
  * and writes bin_thr[img] = the bin holding the prethr_k-th best key; dmay_nms_filter_fused with the same parameters and that
  * bin_thr then writes only candidates of bins <= bin_thr: a superset of the top prethr_k, ties included, in candidate order --
  * the detections are unchanged. */
 int dmay_nms_fused_prethreshold(const dmay_filter_fused_params* p, dmay_stream_t stream);
 
 /* Pre-selection for candidate-dense MULTI-LABEL dense predictions (utils/general.py:702-703 keeps the max_nms best candidates
- * of an image; a dense prediction can expand to many times that).  Per image: a 2048-bin histogram of the top 11 bits of every
+ * of an image; a dense prediction can expand to many times that).  Per image: a 2048-bin histogram (key_bin: 64 bins per binade below 1.0) of every
  * candidate's score key (~bits(conf)), then bin_thr[img] = the bin that holds the K-th best key (2047 when the image has at most
  * K candidates).  dmay_nms_filter_fused (dense = 1, bin_thr given) then writes only candidates whose key bin is <= bin_thr:
  * a superset of the top K, ties included, in candidate order -- the detections are unchanged.
