@@ -204,6 +204,49 @@ __global__ void __launch_bounds__(256) ca_apply_kernel(const __nv_bfloat16* __re
   }
 }
 
+// ---- apply, tiled: CTA = (image, 64-channel group, 32 columns, band of kApplyRows rows).  thread = (channel vector v, column):
+// its a_w vector stays in registers for the whole band and a_h is one L1-resident 32-byte read per row, so the gate traffic
+// per activation vector drops from 64 bytes (ca_apply_kernel: the a_w row changes with every pixel) to ~32 / rows + 32 from L1.
+constexpr int kApplyRows = 32;
+__global__ void __launch_bounds__(256) ca_apply_tiled_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gates,
+                                                             __nv_bfloat16* __restrict__ y, int H, int W, int C, int ldx, int ldy,
+                                                             int wblocks, int hbands, int groups) {
+  int bid = blockIdx.x;
+  const int wb = bid % wblocks;
+  bid /= wblocks;
+  const int hb = bid % hbands;
+  bid /= hbands;
+  const int g = bid % groups, n = bid / groups;
+  const int v = g * 8 + (threadIdx.x & 7), w = wb * 32 + (threadIdx.x >> 3);
+  if (v >= (C >> 3) || w >= W) return;
+  const float* gbase = gates + (long long)n * (H + W) * C + v * 8;
+  const float4 w0 = reinterpret_cast<const float4*>(gbase + (long long)(H + w) * C)[0];
+  const float4 w1 = reinterpret_cast<const float4*>(gbase + (long long)(H + w) * C)[1];
+  const int h0 = hb * kApplyRows, h1 = min(h0 + kApplyRows, H);
+  const __nv_bfloat16* xp = x + (((long long)n * H + h0) * W + w) * ldx + v * 8;
+  __nv_bfloat16* yp = y + (((long long)n * H + h0) * W + w) * ldy + v * 8;
+  const long long xs = (long long)W * ldx, ys = (long long)W * ldy;
+  for (int h = h0; h < h1; h += 4) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = h + u < h1 ? ld_nc16(xp + u * xs) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (h + u < h1) {
+        const float4 a0 = reinterpret_cast<const float4*>(gbase + (long long)(h + u) * C)[0];
+        const float4 a1 = reinterpret_cast<const float4*>(gbase + (long long)(h + u) * C)[1];
+        float f[8];
+        unpack8(r[u], f);
+        f[0] = (f[0] * w0.x) * a0.x; f[1] = (f[1] * w0.y) * a0.y; f[2] = (f[2] * w0.z) * a0.z; f[3] = (f[3] * w0.w) * a0.w;
+        f[4] = (f[4] * w1.x) * a1.x; f[5] = (f[5] * w1.y) * a1.y; f[6] = (f[6] * w1.z) * a1.z; f[7] = (f[7] * w1.w) * a1.w;
+        st_na16(yp + u * ys, pack8(f));
+      }
+    }
+    xp += 4 * xs;
+    yp += 4 * ys;
+  }
+}
+
 // ---- fast path (plane of 64 channels fits in shared memory): TWO launches ---------------------------------
 // K1  ca_pool_hidden_kernel : CTA = (image, 64-channel group).  Stages its H x W x 64 plane (one coalesced read of x),
 //     reduces it to the pooled row / column means, multiplies them with its 64-row slice of W1 (partial hidden
@@ -1214,6 +1257,17 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
                                                   (const float*)p->wh, (const float*)p->bh, (const float*)p->ww,
                                                   (const float*)p->bw, p->H, p->W, p->C, p->Cm, p->C);
   // 3. apply
+  static const bool flat_apply = [] { const char* e = getenv("DMAY_CA_APPLY_TILED"); return e && e[0] == '0'; }();
+  {
+    const int wblocks = (p->W + 31) / 32, hbands = (p->H + kApplyRows - 1) / kApplyRows, groups = (cvec + 7) / 8;
+    const long long grid = (long long)p->N * groups * hbands * wblocks;
+    // tiled form wherever the 32-column blocks are reasonably full (W = 40: 62 %; measured below the flat kernel there)
+    if (!flat_apply && grid <= 0x7fffffffLL && p->W * 4 >= wblocks * 32 * 3) {
+      ca_apply_tiled_kernel<<<(int)grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, (const float*)p->gates, (__nv_bfloat16*)p->y, p->H,
+                                                      p->W, p->C, p->ldx, p->ldy, wblocks, hbands, groups);
+      return finish_launch(3);
+    }
+  }
   int vx = 1;
   while (vx * 2 <= cvec && vx < 32) vx *= 2;
   const dim3 blk(vx, 256 / vx);
