@@ -298,6 +298,8 @@ struct __align__(64) ConvArgs {
   const __nv_bfloat16* residual;
   const __nv_bfloat16* gate_x;
   const __nv_bfloat16* gate_k;
+  __nv_bfloat16* pool_out;   // T9 images: 4x4 average of the OUTPUT, [N, Ho/4, Wo/4, ldpool] (the AvgPool2d(4) of a following SCConv)
+  int ldpool;
   const float* pre;    // EPI_SILU_PRE: fp32 [N, gHk, gWk, ldgk] partial pre-activation sums, nearest-upsampled to Ho x Wo
   void* y;
   int M, n_store, Cout_pad;
@@ -1179,6 +1181,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           }
           fence_proxy_async();
           __syncwarp();   // every lane's staging writes are done, and its operand row has been consumed (own[] fed the math)
+          if (T9 && MODE == EPI_SILU && a.pool_out != nullptr && cur.width == 32) {
+            // AvgPool2d(4) of this layer's output as a by-product (SCConv k2 reads it: its kernel re-read the whole map).  The
+            // warp's 32 rows are a 4 x 8 pixel block of the 16 x 8 patch = two 4 x 4 windows; lane = channel of the 32-channel
+            // chunk, summed from the bf16 staging tile in (dy, dx) order, then * 1/16: bit-identical to avgpool_kernel.
+            const int cj = lane >> 3, ce = lane & 7;
+            const __nv_bfloat16* st = reinterpret_cast<const __nv_bfloat16*>(out_ptr);
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const float v = __bfloat162float(st[sidx(r, cj) * 8 + ce]);
+              if ((r & 7) < 4) sa += v;
+              else sb += v;
+            }
+            const int c = cur.n0 + cur.c0 + lane;
+            if (c < a.n_store && cur.t2 + 3 < a.Ho) {
+              __nv_bfloat16* po = a.pool_out + (((long long)cur.t3 * (a.Ho >> 2) + (cur.t2 >> 2)) * (a.Wo >> 2) + (cur.t1 >> 2)) * a.ldpool + c;
+              if (cur.t1 + 3 < a.Wo) po[0] = __float2bfloat16_rn(sa * 0.0625f);
+              if (cur.t1 + 7 < a.Wo) po[a.ldpool] = __float2bfloat16_rn(sb * 0.0625f);
+            }
+          }
           if (lane == 0) {
             if (a.halo) tma_store_4d(&a.tmY, out_stage, cur.n0 + cur.c0, cur.t1, cur.t2, cur.t3);
             else tma_store_2d(&a.tmY, out_stage, cur.n0 + cur.c0, cur.t1);
@@ -1659,6 +1681,11 @@ static int conv_plan(const dmay_conv_params* p, ConvPlan& pl) {
   pl.grid = (int)((supers < max_clusters ? supers : max_clusters) * a.cs);
   pl.mode = mode;
   pl.t9 = (mode == EPI_SILU && a.b_resident == 1 && a.halo && !(p->flags & 65536)) ? 1 : 0;
+  if (p->pool4_out) {   // only the T9 images carry the pooling epilogue; the caller falls back to dmay_avgpool otherwise
+    if (!pl.t9 || (p->Ho & 3) || (p->Wo & 3) || (p->ldpool4 & 7) || p->ldpool4 < p->Cout || (bn & 31) || out_f32) return DMAY_EUNSUPPORTED;
+    a.pool_out = (__nv_bfloat16*)p->pool4_out;
+    a.ldpool = p->ldpool4;
+  }
   pl.smem = smem;
   pl.pdl = (p->flags & 128) ? 0 : 1;
   return DMAY_OK;

@@ -166,7 +166,8 @@ class Conv(_PackMixin, nn.Module):
             return self.forward_b200(x)
         return self.act(self.conv(x))
 
-    def forward_b200(self, x, out=None, residual=None):
+    def forward_b200(self, x, out=None, residual=None, pool4=False):
+        """pool4: the next layer is an SCConv with AvgPool2d(4): ask the kernel for the pooled output as a by-product."""
         code = _act_code(self.act)
         bn = getattr(self, 'bn', None)
         if isinstance(x, ops.VCat):   # a 1x1 layer reads the parts of a concat in place (weights folded into its columns)
@@ -196,7 +197,7 @@ class Conv(_PackMixin, nn.Module):
                 out.copy_(y)
                 return out
             return y
-        return ops.conv(x, pk, code, out=out, residual=residual)
+        return ops.conv(x, pk, code, out=out, residual=residual, pool4=pool4 and residual is None)
 
 
 class DWConv(Conv):
@@ -1264,7 +1265,10 @@ class SCConv(_PackMixin, nn.Module):
             self._unsupported()
         x = ops.as_act(x)
         r = self.k2[0].kernel_size if isinstance(self.k2[0].kernel_size, int) else self.k2[0].kernel_size[0]
-        k2o = ops.conv(ops.avgpool(x, r), get_conv_pack(self, 'k2', self.k2[1], self.k2[2], x.device), ACT_NONE)
+        pooled = getattr(x, '_dmay_pool4', None) if r == 4 else None     # by-product of the producing conv's epilogue
+        if pooled is None or tuple(pooled.shape) != (x.shape[0], x.shape[1], x.shape[2] // 4, x.shape[3] // 4):
+            pooled = ops.avgpool(x, r)
+        k2o = ops.conv(pooled, get_conv_pack(self, 'k2', self.k2[1], self.k2[2], x.device), ACT_NONE)
         pk3 = get_conv_pack(self, 'k3', self.k3[0], self.k3[1], x.device)
         if _State.fuse_scconv_gate:
             g = ops.conv(x, pk3, ACT_NONE, gate=(x, k2o))       # k3(x) * sigmoid(x + up(k2)) in the epilogue

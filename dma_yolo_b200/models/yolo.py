@@ -226,7 +226,12 @@ class Model(nn.Module):
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
             if profile:
                 self._profile_one_layer(m, x, dt)
-            x = self._run_layer(m, x, fast)
+            nxt = self.model[m.i + 1] if fast and m.i + 1 < len(self.model) else None
+            if (nxt is not None and isinstance(nxt, _common.SCConv) and nxt.f == -1 and not isinstance(x, (list, tuple, Up))
+                    and getattr(type(m), 'forward_b200', None) is _common.Conv.forward_b200):
+                x = m.forward_b200(x, pool4=True)      # the SCConv's AvgPool2d(4) input comes out of this conv's epilogue
+            else:
+                x = self._run_layer(m, x, fast)
             y.append(x if m.i in self.save else None)
             tr = self.__dict__.get('_trace')
             if tr is not None:  # test/debug hook: per-layer outputs (incl. layers that bypass nn.Module.__call__)

@@ -175,16 +175,19 @@ def pack_conv(weight: torch.Tensor, bn=None, conv_bias=None, stride=1, pad=0, de
                     kh=kh, kw=kw, stride=stride, pad=pad, stem_spd=stem)
 
 
+POOL4_FUSE = __import__('os').environ.get('DMAY_POOL4_FUSE', '1') != '0'   # A/B: 0 = SCConv always runs its AvgPool2d kernel
 CONV_FLAGS = int(__import__('os').environ.get('DMAY_CONV_FLAGS', '0'))   # default tuning flags (see include/dmayolo.h)
 
 
 def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor | None = None,
          residual: torch.Tensor | None = None, gate: tuple | None = None, out_fp32: bool = False,
          block_n: int = 0, num_sms: int = 0, flags: int | None = None, res_mul: bool = False,
-         pre: torch.Tensor | None = None) -> torch.Tensor:
+         pre: torch.Tensor | None = None, pool4: bool = False) -> torch.Tensor:
     """y = act(scale * conv(x, w) + bias) (+ residual) | (* sigmoid(gate_x + up(gate_k))).
     x may be a list of up to three tensors (virtual channel concat, 1x1 layers).  pre: fp32 NHWC [N, Cout, h, w] partial
-    sums that are nearest-upsampled and added to the accumulator BEFORE scale / bias / SiLU (see VCat.split)."""
+    sums that are nearest-upsampled and added to the accumulator BEFORE scale / bias / SiLU (see VCat.split).
+    pool4: also produce AvgPool2d(4)(y) in the epilogue where the kernel can (plain SiLU 3x3 layers with resident weights); the
+    pooled tensor is attached to the result as `y._dmay_pool4` (absent when the layer does not qualify)."""
     # uint8 images are normalised on the fly (x/255, the `img.float()/255` of val.py:199-202 folded into
     # the layout kernel) — an extension: the reference only accepts float images.
     xs = None
@@ -252,6 +255,14 @@ def conv(x: torch.Tensor, pk: ConvPack, act: int = ACT_SILU, out: torch.Tensor |
         if tuple(gx.shape) != (n, pk.cout, ho, wo) or gk.shape[1] != pk.cout or ld_of(gk) != pk.cout:
             raise DmayError("conv: gate shape mismatch")
         f.update(gate_x=gx.data_ptr(), gate_k=gk.data_ptr(), ldgx=ld_of(gx), gHk=gk.shape[2], gWk=gk.shape[3])
+    if pool4 and POOL4_FUSE and act == ACT_SILU and not out_fp32 and ho % 4 == 0 and wo % 4 == 0 and pk.kh == 3 and pk.stride == 1:
+        pooled = empty_nhwc(n, pk.cout, ho // 4, wo // 4, x.device)
+        try:
+            call("dmay_conv_bn_act", _stream(x), pool4_out=pooled.data_ptr(), ldpool4=ld_of(pooled), **f)
+            out._dmay_pool4 = pooled
+            return out
+        except DmayError:       # not a layer whose kernel image carries the pooling epilogue: plain launch below
+            pass
     call("dmay_conv_bn_act", _stream(x), **f)
     return out
 

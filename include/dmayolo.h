@@ -75,6 +75,9 @@ const char* dmay_strerror(int code);
  * pre (fp32 [N, preH, preW, ldpre], act SiLU, bf16 output, no residual / gate): y = silu(scale * (acc + pre[n, hs, ws, co])
  *   + bias) with the nearest source pixel of (p, q) -- a 1x1 layer commutes with nn.Upsample(nearest), so the columns
  *   of an up-sampled concat part can be summed at ITS resolution and enter here.
+ * pool4_out (bf16 [N, Ho/4, Wo/4, ldpool4]; plain SiLU 3x3 stride-1 layers with resident weights only, else DMAY_EUNSUPPORTED):
+ *   additionally writes AvgPool2d(4, 4) of y -- the k2 branch input of a following SCConv (models/common.py:1281-1287), whose
+ *   pooling kernel would re-read the whole map.  Bit-identical to dmay_avgpool(y, 4).
  * block_n: 0 = auto, >0 = force the N tile, -2 = 2-CTA cluster multicast of the weight tile (experiment).
  * flags (tuning / A-B switches, 0 = auto): bit0 = never use the halo path (3x3 s1 p1 input patch loaded once
  *   per channel chunk, taps read shifted windows), bit1 = force it where legal, bit2 = never keep the weight
@@ -133,6 +136,8 @@ typedef struct dmay_conv_params {
   int ldpre;
   int preH;
   int preW;
+  void* pool4_out;
+  int ldpool4;
 } dmay_conv_params;
 int dmay_conv_bn_act(const dmay_conv_params* p, dmay_stream_t stream);
 /* launch-plan cache of dmay_conv_bn_act (mode / tile decisions + encoded CUtensorMaps, keyed by the parameter struct and the

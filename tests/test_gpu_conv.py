@@ -269,3 +269,26 @@ def test_conv_fp32_output_staged_equals_direct(shape):
     assert y.dtype == torch.float32 and y.shape[1] == cout and torch.equal(y, y0)
     ref = F.conv2d(back(x), wt, bias)
     assert_close(y.cpu(), ref, atol=2e-4, rtol=2e-4, what=f'fp32 head {shape}')
+
+
+@pytest.mark.parametrize('cin,cout,hw', [(16, 64, (64, 48)), (64, 64, (40, 24)), (32, 32, (44, 28))])
+def test_conv_epilogue_avgpool4_byproduct_is_bit_identical(cin, cout, hw):
+    """pool4_out of dmay_conv_bn_act (plain SiLU 3x3 layers with resident weights: the stem in front of an SCConv): the 4x4
+    average of the layer's OWN bf16 output, written from the epilogue's staging tile, equals dmay_avgpool of that output bit
+    for bit -- also where the 16 x 8 patches overhang the map (44 x 28) -- and the output itself is unchanged."""
+    from dma_yolo_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout)
+    h, w = hw
+    x = ops.as_act(torch.randn(48, cin, h, w, generator=g).cuda())      # >= 2 x 148 patches: the halo / resident-weight plan
+    pk = ops.pack_conv(torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5, stride=1, pad=1, device='cuda')
+    y_plain = ops.conv(x, pk, ops.ACT_SILU)
+    y = ops.conv(x, pk, ops.ACT_SILU, pool4=True)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_plain)
+    pooled = getattr(y, '_dmay_pool4', None)
+    assert pooled is not None, 'the layer qualifies for the pooling epilogue (T9 image) but fell back'
+    assert torch.equal(pooled, ops.avgpool(y, 4))
+    # a layer that does not qualify (residual epilogue) silently runs the plain launch
+    r = ops.as_act(torch.randn(48, cout, h, w, generator=g).cuda())
+    y2 = ops.conv(x, pk, ops.ACT_SILU, residual=r, pool4=True)
+    assert getattr(y2, '_dmay_pool4', None) is None and torch.equal(y2, ops.conv(x, pk, ops.ACT_SILU, residual=r))
