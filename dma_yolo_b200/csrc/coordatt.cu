@@ -1219,7 +1219,7 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
   // 1. pool
   // plane-in-shared-memory pool only when a CTA can take all the channel vectors of a 64-channel group (>= 128 contiguous bytes
   // per pixel): with 1 / 4 vectors per CTA (80x80 / 40x40 planes at cfg-4b) its loads use half of every sector and ran at
-  // 0.85 TB/s (ncu r7z: 373 us for four launches); the direct kernel below reads 128 bytes per pixel (4.4 TB/s at the larger sizes)
+  // 0.85 TB/s (ncu: 373 us for four launches); the direct kernel below reads 128 bytes per pixel (4.4 TB/s at the larger sizes)
   int VL = 0;
   for (int cand : {8, 4, 2, 1}) {
     if (cand > cvec && cand != 1) continue;
