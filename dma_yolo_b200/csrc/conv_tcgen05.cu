@@ -259,6 +259,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
+#ifndef DMAY_EPI_F2
+#define DMAY_EPI_F2 1
+#endif
 constexpr int BLOCK_M = 128;
 constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 16;                      // up to four warps per TMEM lane quadrant (8 or 16 per launch)
@@ -466,6 +469,22 @@ __device__ __forceinline__ uint4 epi_compute8(const uint32_t* r, const float* sc
   const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
   const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float f[8];
+#if DMAY_EPI_F2
+  // packed fp32x2 FMAs (same IEEE roundings as the scalar form: outputs bit-identical): 4 FFMA2 for scale / bias and 4 for
+  // h + h * tanh(h) instead of 8 + 8 FFMA per 8 columns.  Same-box A/B (cfg-2): 12.33 / 12.34 -> 12.16 / 12.26 ms per step.
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f32x2_t h2 = f2_fma(f2_pack(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])), f2_pack(s[2 * k], s[2 * k + 1]),
+                        f2_pack(b[2 * k], b[2 * k + 1]));
+    if (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_SILU_PRE) {
+      // the staged scale / bias of these modes are pre-halved (exact), so h2 is already h = x/2: silu(x) = h + h*tanh(h)
+      float h0, h1;
+      f2_unpack(h2, h0, h1);
+      h2 = f2_fma(h2, f2_pack(tanh_approx(h0), tanh_approx(h1)), h2);
+    }
+    f2_unpack(h2, f[2 * k], f[2 * k + 1]);
+  }
+#else
 #pragma unroll
   for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(r[j]), s[j], b[j]);
   if (MODE == EPI_SILU || MODE == EPI_SILU_RES || MODE == EPI_SILU_PRE) {
@@ -473,6 +492,7 @@ __device__ __forceinline__ uint4 epi_compute8(const uint32_t* r, const float* sc
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], tanh_approx(f[j]), f[j]);
   }
+#endif
   if (MODE == EPI_GELU) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
