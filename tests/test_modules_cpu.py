@@ -177,3 +177,56 @@ def test_every_reference_yaml_builds_like_the_reference(name):
     assert sum(p.numel() for p in m.parameters()) == g['params']
     assert len(m.state_dict()) == g['keys']
     assert state_digest(m.state_dict()) == g['digest']
+
+
+# ---- host logic of the lazy concat / space_to_depth folds (weights only; the GEMMs are -m gpu) ---------------------------
+def _unpacked_weight(pk):
+    """ConvPack.w [Cout_pad][kh][kw][Cin_pad] bf16 -> torch conv weight [Cout, Cin, kh, kw] fp32."""
+    return pk.w.float()[:pk.cout, :, :, :pk.cin].permute(0, 3, 1, 2).contiguous()
+
+
+def test_space_to_depth_fold_weights_are_the_stride2_kernel():
+    """get_conv_pack(spd=True): the 1x1 weight over the 4C channels of space_to_depth(x) re-laid as a 2x2 / stride-2 kernel
+    over x gives the same convolution (models/common.py:1457-1458 channel order: block q = dy + 2 dx)."""
+    import torch.nn.functional as F
+    from dma_yolo_b200.models import common as C
+    torch.manual_seed(0)
+    c, co = 16, 32
+    conv = C.Conv(4 * c, co, 1, 1).eval()
+    conv.conv.weight.data = conv.conv.weight.data.bfloat16().float()
+    x = torch.randn(2, c, 12, 10)
+    spd = torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)
+    pk = C.get_conv_pack(conv, 'conv@spd', conv.conv, conv.bn, torch.device('cpu'), spd=True)
+    assert (pk.kh, pk.kw, pk.stride, pk.pad, pk.cin) == (2, 2, 2, 0, c)
+    ref = F.conv2d(spd, conv.conv.weight)
+    got = F.conv2d(x, _unpacked_weight(pk), stride=2)
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+    plain = C.get_conv_pack(conv, 'conv', conv.conv, conv.bn, torch.device('cpu'))
+    assert torch.equal(pk.scale, plain.scale) and torch.equal(pk.bias, plain.bias)     # the folded BN is untouched
+
+
+def test_lazy_concat_weight_folding_and_column_split():
+    """get_conv_pack(colscale=..., cols=..., plain=...): BiFPN weights folded into the input-channel ranges of a 1x1 weight
+    (fp32, before the bf16 rounding) and the column split of VCat.split -- W.cat(w_i x_i) == sum_i (w_i W_i).x_i."""
+    import torch.nn.functional as F
+    from dma_yolo_b200.models import common as C
+    torch.manual_seed(1)
+    cs, co = (64, 128, 64), 48
+    conv = C.Conv(sum(cs), co, 1, 1).eval()
+    ws = (0.7, 1.3, 0.4)
+    colscale = tuple(zip(cs, ws))
+    xs = [torch.randn(1, c, 6, 5) for c in cs]
+    ref = F.conv2d(torch.cat([w * x for w, x in zip(ws, xs)], 1), conv.conv.weight)
+    pk = C.get_conv_pack(conv, 'conv@vcat', conv.conv, conv.bn, torch.device('cpu'), colscale)
+    got = F.conv2d(torch.cat(xs, 1), _unpacked_weight(pk))
+    assert torch.allclose(got, ref, atol=2e-2, rtol=2e-2)                   # bf16 rounding of the folded weights
+    # split: first part at its own (low) resolution without BN, the rest with it
+    lo = C.get_conv_pack(conv, 'conv@lo', conv.conv, conv.bn, torch.device('cpu'), colscale, ((0, 64),), True)
+    hi = C.get_conv_pack(conv, 'conv@hi', conv.conv, conv.bn, torch.device('cpu'), colscale, ((64, 192), (192, 256)), False)
+    assert lo.cin == 64 and hi.cin == 192
+    assert torch.all(lo.scale[:co] == 1) and torch.all(lo.bias == 0) and torch.equal(hi.scale, pk.scale) and torch.equal(hi.bias, pk.bias)
+    both = F.conv2d(xs[0], _unpacked_weight(lo)) + F.conv2d(torch.cat(xs[1:], 1), _unpacked_weight(hi))
+    assert torch.allclose(both, got, atol=1e-5, rtol=1e-5)
+    # the cache is keyed by the fold: another weight tuple rebuilds the pack
+    pk2 = C.get_conv_pack(conv, 'conv@vcat', conv.conv, conv.bn, torch.device('cpu'), tuple(zip(cs, (1.0, 1.0, 2.0))))
+    assert not torch.equal(pk2.w, pk.w)
