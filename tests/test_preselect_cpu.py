@@ -9,10 +9,11 @@ KBINS = 2048
 
 def key_bin(conf):
     """csrc/nms.cu key_bin(): top 15 bits of ~bits(conf) minus those of 1.0, clamped to [0, 2047]."""
-    bits = np.asarray(conf, dtype=np.float32).view(np.uint32)
-    k = (~bits) >> np.uint32(17)
-    base = (~np.uint32(0x3F800000)) >> np.uint32(17)
-    return np.minimum(np.where(k > base, k - base, 0), KBINS - 1).astype(np.int64)
+    bits = np.atleast_1d(np.asarray(conf, dtype=np.float32)).view(np.uint32)
+    k = ((~bits) >> np.uint32(17)).astype(np.int64)
+    base = int((~np.uint32(0x3F800000)) >> np.uint32(17))
+    out = np.clip(k - base, 0, KBINS - 1)
+    return out if np.ndim(conf) else int(out[0])
 
 
 def bin_threshold(bins, K):
