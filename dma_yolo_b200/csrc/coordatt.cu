@@ -108,6 +108,110 @@ __global__ void __launch_bounds__(256) ca_pool_kernel(const __nv_bfloat16* __res
   }
 }
 
+// ---- pool, ONE pass over x for planes that do not fit in shared memory (W <= 320).  ca_pool_kernel above reads x twice (row
+// means, then column means: ncu shows 825 MB of DRAM reads for the 419 MB map of c64@320).  Here CTA (n, g, b) owns the row
+// band b of a 64-channel group: thread = (slot, lane) walks the columns slot, slot + 32, ... of every row of the band, adds each
+// 16-byte vector to the row's sum AND to its own per-column accumulator (registers, <= 10 columns x 8 channels).  Row sums are
+// combined over the 32 slots through shared memory in slot order; the band's column sums go to `colpart` and are reduced over
+// the bands in band order by ca_colreduce_kernel -- every sum has a fixed order (no atomics).
+constexpr int kPoolCols = 10;    // columns per thread: W <= 32 * kPoolCols
+constexpr int kPoolRowChunk = 4;
+__global__ void __launch_bounds__(256) ca_pool_onepass_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ pooled,
+                                                              float* __restrict__ colpart, int H, int W, int C, int ldx, int bands,
+                                                              int rows_per_band) {
+  __shared__ float rs[32][kPoolRowChunk][64];
+  const int cvec = C >> 3;
+  const int groups = (cvec + 7) >> 3;
+  int bid = blockIdx.x;
+  const int b = bid % bands;
+  bid /= bands;
+  const int g = bid % groups;
+  const int n = bid / groups;
+  const int lane = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const int v = g * 8 + lane;
+  const bool active = v < cvec;
+  const int h0 = b * rows_per_band, h1 = min(H, h0 + rows_per_band);
+  const __nv_bfloat16* xb = x + (long long)n * H * W * ldx + v * 8;
+  float* pb = pooled + (long long)n * (H + W) * C;
+  const float invW = 1.0f / (float)W;
+  float cacc[kPoolCols][8];
+#pragma unroll
+  for (int k = 0; k < kPoolCols; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cacc[k][j] = 0.f;
+  for (int hc = h0; hc < h1; hc += kPoolRowChunk) {
+#pragma unroll
+    for (int r = 0; r < kPoolRowChunk; ++r) {
+      float racc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) racc[j] = 0.f;
+      const int h = hc + r;
+      if (h < h1 && active) {
+        const __nv_bfloat16* row = xb + (long long)h * W * ldx;
+        uint4 raw[kPoolCols];
+#pragma unroll
+        for (int k = 0; k < kPoolCols; ++k) {
+          const int w = slot + 32 * k;
+          raw[k] = w < W ? ld_nc16(row + (long long)w * ldx) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < kPoolCols; ++k) {
+          float f[8];
+          unpack8(raw[k], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            racc[j] += f[j];
+            cacc[k][j] += f[j];
+          }
+        }
+      }
+      float4* o = reinterpret_cast<float4*>(&rs[slot][r][lane * 8]);
+      o[0] = make_float4(racc[0], racc[1], racc[2], racc[3]);
+      o[1] = make_float4(racc[4], racc[5], racc[6], racc[7]);
+    }
+    __syncthreads();
+    {
+      const int r = threadIdx.x >> 6, ch = threadIdx.x & 63, h = hc + r;
+      if (h < h1 && g * 64 + ch < C) {
+        float sum = 0.f;
+#pragma unroll 8
+        for (int sl = 0; sl < 32; ++sl) sum += rs[sl][r][ch];
+        pb[(long long)h * C + g * 64 + ch] = sum * invW;
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    float* cp = colpart + (((long long)n * bands + b) * W) * C + v * 8;
+#pragma unroll
+    for (int k = 0; k < kPoolCols; ++k) {
+      const int w = slot + 32 * k;
+      if (w < W) {
+        float4* o = reinterpret_cast<float4*>(cp + (long long)w * C);
+        o[0] = make_float4(cacc[k][0], cacc[k][1], cacc[k][2], cacc[k][3]);
+        o[1] = make_float4(cacc[k][4], cacc[k][5], cacc[k][6], cacc[k][7]);
+      }
+    }
+  }
+}
+// pooled[n, H + w, c] = (1 / H) * sum over the bands, in band order
+__global__ void __launch_bounds__(256) ca_colreduce_kernel(const float* __restrict__ colpart, float* __restrict__ pooled, int N, int H,
+                                                           int W, int C, int bands) {
+  const long long items = (long long)N * W * (C >> 2);
+  const float invH = 1.0f / (float)H;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < items; i += (long long)gridDim.x * 256) {
+    const int c4 = (int)(i % (C >> 2));
+    const long long t = i / (C >> 2);
+    const int w = (int)(t % W), n = (int)(t / W);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < bands; ++b) {
+      const float4 q = reinterpret_cast<const float4*>(colpart + (((long long)n * bands + b) * W + w) * C)[c4];
+      a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+    }
+    reinterpret_cast<float4*>(pooled + ((long long)n * (H + W) + H + w) * C)[c4] = make_float4(a.x * invH, a.y * invH, a.z * invH, a.w * invH);
+  }
+}
+
 // ---- mlp.  grid = N * (ceil(H/PG) + ceil(W/PG)); a CTA handles PG consecutive positions of one image that
 // all lie in the H part or all in the W part (so it needs only one of Wh / Ww).
 // w1T: [C][Cm] fp32, whT / wwT: [Cm][Cout] fp32 (transposed: consecutive threads read consecutive floats).
@@ -1113,10 +1217,18 @@ __global__ void __launch_bounds__(256) ca_fused_mma_kernel(const __nv_bfloat16* 
 
 using namespace dmay;
 
+static int ca_pool_bands(int N, int groups, int H, int W, int sms) {
+  int bands = 1;
+  while ((long long)N * groups * bands < 2LL * sms && bands * 2 <= (H < W ? H : W)) bands *= 2;
+  return bands;
+}
+
 extern "C" long long dmay_coordatt_ws(int N, int H, int W, int C, int Cm) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cm <= 0) return DMAY_EINVAL;
   const long long G = (C / 8 + kCaVL - 1) / kCaVL, P = H + W;
-  return ((long long)N * G * P * Cm + (long long)N * P * Cm) * 4 + ((long long)3 * N + 2) * 4;   // partial, y, sync words
+  const long long fast = ((long long)N * G * P * Cm + (long long)N * P * Cm) * 4 + ((long long)3 * N + 2) * 4;   // partial, y, sync words
+  const long long onepass = W <= 32 * kPoolCols ? (long long)N * ca_pool_bands(N, (C / 8 + 7) / 8, H, W, sm_count()) * W * C * 4 : 0;   // colpart
+  return fast > onepass ? fast : onepass;
 }
 
 
@@ -1217,6 +1329,7 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
   }
   if (!p->pooled || !p->gates) return DMAY_EINVAL;   // the three-launch path needs both workspaces
   // 1. pool
+  int extra_launches = 0;
   // plane-in-shared-memory pool only when a CTA can take all the channel vectors of a 64-channel group (>= 128 contiguous bytes
   // per pixel): with 1 / 4 vectors per CTA (80x80 / 40x40 planes at cfg-4b) its loads use half of every sector and ran at
   // 0.85 TB/s (ncu: 373 us for four launches); the direct kernel below reads 128 bytes per pixel (4.4 TB/s at the larger sizes)
@@ -1237,12 +1350,27 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
                                                           p->C, p->ldx, VL);
   } else {
     const int groups = (cvec + 7) / 8;
-    int bands = 1;
-    while ((long long)p->N * groups * bands < 2LL * sms && bands * 2 <= (p->H < p->W ? p->H : p->W)) bands *= 2;
+    const int bands = ca_pool_bands(p->N, groups, p->H, p->W, sms);
     long long g1 = (long long)p->N * groups * bands;
     if (g1 > 0x7fffffffLL) return DMAY_EUNSUPPORTED;
-    ca_pool_kernel<<<(int)g1, 256, 0, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, p->H, p->W, p->C, p->ldx,
-                                           bands);
+    static const bool two_pass = [] { const char* e = getenv("DMAY_CA_POOL_ONEPASS"); return e && e[0] == '0'; }();
+    const long long cp_bytes = (long long)p->N * bands * p->W * p->C * 4;
+    // (measured, batch 32: c64@320 0.345 -> 0.296 ms for the whole CoordAtt; with fewer than eight columns per thread -- W = 160 / 80 /
+    //  40 -- most of a thread's load slots are empty and it loses: 0.187 -> 0.195, 0.113 -> 0.140, 0.078 -> 0.124 ms)
+    if (!two_pass && p->W <= 32 * kPoolCols && p->W >= 32 * 8 && p->ws != nullptr && aligned16(p->ws) && p->ws_bytes >= cp_bytes && (p->C & 3) == 0) {
+      // one pass over x: row means + per-band column sums, then the reduction over the bands
+      const int rpb = (p->H + bands - 1) / bands;
+      ca_pool_onepass_kernel<<<(int)g1, 256, 0, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, (float*)p->ws, p->H, p->W, p->C,
+                                                     p->ldx, bands, rpb);
+      const long long items = (long long)p->N * p->W * (p->C >> 2);
+      const long long blocks = (items + 255) / 256;
+      ca_colreduce_kernel<<<(int)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8), 256, 0, s>>>(
+          (const float*)p->ws, (float*)p->pooled, p->N, p->H, p->W, p->C, bands);
+      extra_launches = 1;
+    } else {
+      ca_pool_kernel<<<(int)g1, 256, 0, s>>>((const __nv_bfloat16*)p->x, (float*)p->pooled, p->H, p->W, p->C, p->ldx,
+                                             bands);
+    }
   }
   // 2. mlp
   const int pgroups = (p->H + PG - 1) / PG + (p->W + PG - 1) / PG;
@@ -1265,7 +1393,7 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
     if (!flat_apply && grid <= 0x7fffffffLL && p->W * 4 >= wblocks * 32 * 3) {
       ca_apply_tiled_kernel<<<(int)grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, (const float*)p->gates, (__nv_bfloat16*)p->y, p->H,
                                                       p->W, p->C, p->ldx, p->ldy, wblocks, hbands, groups);
-      return finish_launch(3);
+      return finish_launch(3 + extra_launches);
     }
   }
   int vx = 1;
@@ -1276,5 +1404,5 @@ extern "C" int dmay_coordatt(const dmay_coordatt_params* p, dmay_stream_t stream
   ca_apply_kernel<<<(int)(need < cap ? need : cap), blk, 0, s>>>((const __nv_bfloat16*)p->x, (const float*)p->gates,
                                                                  (__nv_bfloat16*)p->y, (unsigned)npix, p->H, p->W, p->C,
                                                                  p->ldx, p->ldy);
-  return finish_launch(3);
+  return finish_launch(3 + extra_launches);
 }

@@ -55,9 +55,10 @@ def test_coordatt_golden(name):
     assert_close(back(y), d['out'], atol=1e-2, rtol=1e-2, what=name)
 
 
-@pytest.mark.parametrize('shape', [(2, 1024, 20, 20), (1, 64, 48, 40), (1, 128, 160, 96)])
+@pytest.mark.parametrize('shape', [(2, 1024, 20, 20), (1, 64, 48, 40), (1, 128, 160, 96), (2, 72, 44, 300), (1, 64, 320, 320)])
 def test_coordatt_stages_vs_oracle(shape):
-    """pooled means and gates (fp32 side outputs) against the restatement, H != W and large planes."""
+    """pooled means and gates (fp32 side outputs) against the restatement, H != W and large planes (W >= 256: the one-pass
+    pool with per-band column partials; 72 channels: a partial last channel group)."""
     from dma_yolo_b200 import ops
     from dma_yolo_b200.models import common as C
     n, c, h, w = shape
